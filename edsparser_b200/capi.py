@@ -1,0 +1,244 @@
+"""ctypes binding of include/edsparser_b200.h.
+
+Plumbing for tests/, bench.py and __graft_entry__ only: the product's host side is the C++17 layer
+under edsparser_b200/host/ (same signatures as the reference's transforms/ headers). The library
+has no CPU path: `load()` raises if libedsparser_b200.so has not been built, and every transform
+raises EdsError(status=EDS_ERR_CUDA) when no CUDA device is usable.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PRODUCT_SO = os.path.join(HERE, "libedsparser_b200.so")
+
+EDS_OK = 0
+EDS_ERR_INVALID_ARGUMENT = 1
+EDS_ERR_RUNTIME = 2
+EDS_ERR_OUT_OF_RANGE = 3
+EDS_ERR_CUDA = 4
+EDS_ERR_BAD_MSA = 5
+EDS_ERR_BUDGET = 6
+EDS_ERR_HALO = 7
+
+EXPORTS = [
+    "eds_last_error", "eds_version", "eds_ctx_create", "eds_ctx_destroy", "eds_ctx_synchronize",
+    "eds_ctx_set_tuning", "eds_ctx_set_profiling", "eds_ctx_kernel_times", "eds_msa_index_host",
+    "eds_msa_index_free", "eds_msa_transform_device", "eds_msa_transform_host", "eds_msa_conserved_bits",
+    "eds_msa_synth_device", "eds_msa_synth_free", "eds_buffer_free_host", "eds_leds_merge_host",
+]
+
+
+class EdsError(Exception):
+    def __init__(self, status, message):
+        super().__init__(f"[eds_status {status}] {message}")
+        self.status = status
+        self.message = message
+
+
+class MsaIndex(ctypes.Structure):
+    _fields_ = [("row_start", ctypes.POINTER(ctypes.c_uint64)), ("n_rows", ctypes.c_uint32),
+                ("n_cols", ctypes.c_uint64), ("line_width", ctypes.c_uint32), ("row_bytes", ctypes.c_uint64)]
+
+
+class MsaView(ctypes.Structure):
+    _fields_ = [("text", ctypes.c_void_p), ("text_bytes", ctypes.c_uint64),
+                ("row_start", ctypes.POINTER(ctypes.c_uint64)), ("n_rows", ctypes.c_uint32),
+                ("line_width", ctypes.c_uint32), ("total_cols", ctypes.c_uint64), ("col_begin", ctypes.c_uint64),
+                ("col_count", ctypes.c_uint64), ("own_begin", ctypes.c_uint64), ("own_end", ctypes.c_uint64)]
+
+
+class Buffer(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("bytes", ctypes.c_uint64)]
+
+
+class MsaStats(ctypes.Structure):
+    _fields_ = [("n_variable_cols", ctypes.c_uint64), ("n_runs", ctypes.c_uint64), ("n_symbols", ctypes.c_uint64),
+                ("n_variable", ctypes.c_uint64), ("n_alternatives", ctypes.c_uint64),
+                ("first_open_col", ctypes.c_uint64), ("eds_bytes", ctypes.c_uint64), ("seds_bytes", ctypes.c_uint64),
+                ("eds_lead_bytes", ctypes.c_uint64), ("tail_open_common", ctypes.c_uint32),
+                ("gpu_launches", ctypes.c_uint32), ("retries", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+class Library:
+    """One loaded copy of the C ABI."""
+
+    def __init__(self, path=PRODUCT_SO):
+        if not os.path.exists(path):
+            raise ImportError(f"{path} is not built (run `make` or __graft_entry__.build()); there is no CPU fallback")
+        self.path = path
+        L = ctypes.CDLL(path)
+        vp, u8p = ctypes.c_void_p, ctypes.c_char_p
+        u32, u64, i32 = ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int
+        P = ctypes.POINTER
+        L.eds_last_error.restype = ctypes.c_char_p
+        L.eds_version.restype = ctypes.c_char_p
+        L.eds_ctx_create.argtypes = [i32, vp, P(vp)]
+        L.eds_ctx_destroy.argtypes = [vp]
+        L.eds_ctx_destroy.restype = None
+        L.eds_ctx_synchronize.argtypes = [vp]
+        L.eds_ctx_set_tuning.argtypes = [vp, u32, u32]
+        L.eds_ctx_set_profiling.argtypes = [vp, i32]
+        L.eds_ctx_kernel_times.argtypes = [vp, P(ctypes.c_char_p), P(ctypes.c_float), u32]
+        L.eds_ctx_kernel_times.restype = u32
+        L.eds_msa_index_host.argtypes = [vp, u64, P(MsaIndex)]
+        L.eds_msa_index_free.argtypes = [P(MsaIndex)]
+        L.eds_msa_index_free.restype = None
+        L.eds_msa_transform_device.argtypes = [vp, P(MsaView), u32, i32, P(Buffer), P(Buffer), P(MsaStats)]
+        L.eds_msa_transform_host.argtypes = [vp, vp, u64, u32, i32, P(Buffer), P(Buffer), P(MsaStats)]
+        L.eds_msa_conserved_bits.argtypes = [vp, P(MsaView), vp, u64]
+        L.eds_msa_synth_device.argtypes = [vp, u32, u64, u32, u64, u64, u64, u32, P(MsaView)]
+        L.eds_msa_synth_free.argtypes = [vp]
+        L.eds_msa_synth_free.restype = None
+        L.eds_buffer_free_host.argtypes = [P(Buffer)]
+        L.eds_buffer_free_host.restype = None
+        L.eds_leds_merge_host.argtypes = [vp, vp, u64, vp, u64, u32, i32, u64, P(Buffer), P(Buffer), P(u32)]
+        self.L = L
+        _ = u8p
+
+    def version(self):
+        return self.L.eds_version().decode()
+
+    def check(self, rc):
+        if rc != EDS_OK:
+            raise EdsError(rc, self.L.eds_last_error().decode("latin-1"))
+
+    def context(self, device=0, stream=None):
+        return Context(self, device, stream)
+
+
+def _host_bytes(lib, buf):
+    data = ctypes.string_at(buf.data, buf.bytes) if buf.data and buf.bytes else b""
+    lib.L.eds_buffer_free_host(ctypes.byref(buf))
+    return data
+
+
+def _as_pointer(data):
+    """(address, length, keepalive) of bytes / bytearray / numpy / torch host data."""
+    if isinstance(data, (bytes, bytearray)):
+        arr = (ctypes.c_char * len(data)).from_buffer_copy(data) if isinstance(data, bytes) else (
+            ctypes.c_char * len(data)).from_buffer(data)
+        return ctypes.addressof(arr), len(data), arr
+    if hasattr(data, "data_ptr"):  # torch tensor (host, uint8)
+        return data.data_ptr(), data.numel() * data.element_size(), data
+    if hasattr(data, "ctypes"):  # numpy
+        return data.ctypes.data, data.nbytes, data
+    raise TypeError(type(data))
+
+
+class Context:
+    def __init__(self, lib, device=0, stream=None):
+        self.lib = lib
+        self.handle = ctypes.c_void_p()
+        lib.check(lib.L.eds_ctx_create(device, ctypes.c_void_p(stream) if stream else None,
+                                       ctypes.byref(self.handle)))
+
+    def close(self):
+        if self.handle:
+            self.lib.L.eds_ctx_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_tuning(self, partitions=0, scan_blocks_per_sm=0):
+        self.lib.check(self.lib.L.eds_ctx_set_tuning(self.handle, partitions, scan_blocks_per_sm))
+
+    def set_profiling(self, on):
+        self.lib.check(self.lib.L.eds_ctx_set_profiling(self.handle, 1 if on else 0))
+
+    def kernel_times(self):
+        cap = 64
+        names = (ctypes.c_char_p * cap)()
+        ms = (ctypes.c_float * cap)()
+        n = min(cap, self.lib.L.eds_ctx_kernel_times(self.handle, names, ms, cap))
+        return [(names[i].decode(), float(ms[i])) for i in range(n) if names[i]]
+
+    def synchronize(self):
+        self.lib.check(self.lib.L.eds_ctx_synchronize(self.handle))
+
+    # -- MSA ------------------------------------------------------------------------------
+    def msa_index(self, text):
+        addr, n, keep = _as_pointer(text)
+        idx = MsaIndex()
+        self.lib.check(self.lib.L.eds_msa_index_host(addr, n, ctypes.byref(idx)))
+        out = {"row_start": [idx.row_start[i] for i in range(idx.n_rows)], "n_rows": idx.n_rows,
+               "n_cols": idx.n_cols, "line_width": idx.line_width, "row_bytes": idx.row_bytes}
+        self.lib.L.eds_msa_index_free(ctypes.byref(idx))
+        del keep
+        return out
+
+    def msa_transform_host(self, text, l=0, leds=None):
+        """bytes of a .msa file -> (eds bytes, seds bytes, stats dict); l == 0 and leds None -> plain EDS."""
+        if leds is None:
+            leds = l > 0
+        addr, n, keep = _as_pointer(text)
+        e, s, st = Buffer(), Buffer(), MsaStats()
+        self.lib.check(self.lib.L.eds_msa_transform_host(self.handle, addr, n, l, 1 if leds else 0, ctypes.byref(e),
+                                                         ctypes.byref(s), ctypes.byref(st)))
+        del keep
+        return _host_bytes(self.lib, e), _host_bytes(self.lib, s), st.as_dict()
+
+    def msa_transform_device(self, view, l=0, leds=None):
+        """view: MsaView over device memory -> (eds Buffer, seds Buffer, stats dict); buffers stay on the device."""
+        if leds is None:
+            leds = l > 0
+        e, s, st = Buffer(), Buffer(), MsaStats()
+        self.lib.check(self.lib.L.eds_msa_transform_device(self.handle, ctypes.byref(view), l, 1 if leds else 0,
+                                                           ctypes.byref(e), ctypes.byref(s), ctypes.byref(st)))
+        return e, s, st.as_dict()
+
+    def msa_conserved_bits(self, view):
+        n = (view.col_count + 7) // 8
+        out = ctypes.create_string_buffer(n)
+        self.lib.check(self.lib.L.eds_msa_conserved_bits(self.handle, ctypes.byref(view), out, n))
+        return out.raw
+
+    def msa_synth(self, n_rows, total_cols, line_width=80, col_begin=0, col_count=None, seed=1, variable_ppm=10000):
+        if col_count is None:
+            col_count = total_cols - col_begin
+        v = MsaView()
+        self.lib.check(self.lib.L.eds_msa_synth_device(self.handle, n_rows, total_cols, line_width, col_begin,
+                                                       col_count, seed, variable_ppm, ctypes.byref(v)))
+        return v
+
+    def msa_synth_free(self):
+        self.lib.L.eds_msa_synth_free(self.handle)
+
+    # -- l-EDS merge ------------------------------------------------------------------------
+    def leds_merge_host(self, eds, seds, l, compact=True, max_output_bytes=0):
+        """seds None -> CARTESIAN. Returns (leds bytes, seds bytes or None, rounds)."""
+        ea, en, k1 = _as_pointer(eds)
+        if seds is not None:
+            sa, sn, k2 = _as_pointer(seds)
+        else:
+            sa, sn, k2 = None, 0, None
+        o, so, rounds = Buffer(), Buffer(), ctypes.c_uint32()
+        self.lib.check(self.lib.L.eds_leds_merge_host(self.handle, ea, en, sa, sn, l, 1 if compact else 0,
+                                                      max_output_bytes, ctypes.byref(o), ctypes.byref(so),
+                                                      ctypes.byref(rounds)))
+        del k1, k2
+        out, sout = _host_bytes(self.lib, o), _host_bytes(self.lib, so)
+        return out, (sout if seds is not None else None), rounds.value
+
+
+_product = None
+
+
+def load():
+    """The product library (nvcc build). Raises ImportError when it has not been built."""
+    global _product
+    if _product is None:
+        _product = Library(PRODUCT_SO)
+    return _product

@@ -1,0 +1,321 @@
+// C ABI of libedsparser_b200.so (include/edsparser_b200.h): context management, the host-side MSA
+// loader, and exception -> status mapping around the pipelines. No CPU compute path lives here.
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "ctx.h"
+#include "leds.h"
+#include "msa.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+template <typename F>
+eds_status guarded(F&& body) {
+    try {
+        body();
+        return EDS_OK;
+    } catch (const edsb::BadMsa& e) {
+        g_last_error = e.what();
+        return EDS_ERR_BAD_MSA;
+    } catch (const edsb::HaloError& e) {
+        g_last_error = e.what();
+        return EDS_ERR_HALO;
+    } catch (const edsb::BudgetError& e) {
+        g_last_error = e.what();
+        return EDS_ERR_BUDGET;
+    } catch (const edsb::CudaError& e) {
+        g_last_error = e.what();
+        return EDS_ERR_CUDA;
+    } catch (const std::invalid_argument& e) {
+        g_last_error = e.what();
+        return EDS_ERR_INVALID_ARGUMENT;
+    } catch (const std::out_of_range& e) {
+        g_last_error = e.what();
+        return EDS_ERR_OUT_OF_RANGE;
+    } catch (const std::bad_alloc&) {
+        g_last_error = "out of host memory";
+        return EDS_ERR_RUNTIME;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return EDS_ERR_RUNTIME;
+    }
+}
+
+void use_device(eds_ctx* ctx) {
+    if (!ctx) throw std::invalid_argument("null eds_ctx");
+    EDSB_CUDA(cudaSetDevice(ctx->device));
+}
+
+uint8_t* to_host(eds_ctx* ctx, const eds_buffer& dev) {
+    uint8_t* h = static_cast<uint8_t*>(malloc(dev.bytes ? dev.bytes : 1));
+    if (!h) throw std::bad_alloc();
+    if (dev.bytes) {
+        cudaError_t e = cudaMemcpyAsync(h, dev.data, dev.bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            free(h);
+            throw edsb::CudaError(std::string("device to host copy: ") + cudaGetErrorString(e));
+        }
+    }
+    return h;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* eds_last_error(void) { return g_last_error.c_str(); }
+
+const char* eds_version(void) {
+#ifdef EDSB_EMU
+    return "edsparser_b200 0.1.0 emulated (test build, not a product path)";
+#else
+    return "edsparser_b200 0.1.0 sm_100a";
+#endif
+}
+
+eds_status eds_ctx_create(int device, void* stream, eds_ctx** out) {
+    return guarded([&] {
+        if (!out) throw std::invalid_argument("eds_ctx_create: null out");
+        *out = nullptr;
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0)
+            throw edsb::CudaError(std::string("no usable CUDA device (this library has no CPU fallback): ") +
+                                  cudaGetErrorString(e));
+        if (device < 0 || device >= n) throw std::invalid_argument("eds_ctx_create: no such device");
+        EDSB_CUDA(cudaSetDevice(device));
+        eds_ctx* ctx = new eds_ctx();
+        ctx->device = device;
+        cudaDeviceProp prop;
+        EDSB_CUDA(cudaGetDeviceProperties(&prop, device));
+        ctx->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+        ctx->smem_optin = prop.sharedMemPerBlockOptin ? prop.sharedMemPerBlockOptin : 48 * 1024;
+        if (stream) {
+            ctx->stream = static_cast<cudaStream_t>(stream);
+        } else {
+            EDSB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+            ctx->own_stream = true;
+        }
+        ctx->clock.stream = ctx->stream;
+        if (const char* hm = getenv("EDSB_DEBUG_HASH_MASK")) ctx->hash_mask = strtoull(hm, nullptr, 0);
+        ctx->msa = new edsb::MsaPipeline(ctx);
+        ctx->leds = new edsb::LedsPipeline(ctx);
+        *out = ctx;
+    });
+}
+
+void eds_ctx_destroy(eds_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    delete ctx->msa;
+    delete ctx->leds;
+    ctx->synth_text.release();
+    ctx->file_buf.release();
+    ctx->clock.release();
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+eds_status eds_ctx_synchronize(eds_ctx* ctx) {
+    return guarded([&] {
+        use_device(ctx);
+        EDSB_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+eds_status eds_ctx_set_tuning(eds_ctx* ctx, uint32_t partitions, uint32_t scan_blocks_per_sm) {
+    return guarded([&] {
+        if (!ctx) throw std::invalid_argument("null eds_ctx");
+        ctx->partitions = partitions;
+        ctx->scan_blocks_per_sm = scan_blocks_per_sm;
+    });
+}
+
+eds_status eds_ctx_set_profiling(eds_ctx* ctx, int on) {
+    return guarded([&] {
+        if (!ctx) throw std::invalid_argument("null eds_ctx");
+        ctx->clock.on = on != 0;
+    });
+}
+
+uint32_t eds_ctx_kernel_times(eds_ctx* ctx, const char** names, float* ms, uint32_t cap) {
+    if (!ctx) return 0;
+    const uint32_t n = (uint32_t)ctx->clock.names.size();
+    for (uint32_t i = 0; i < n && i < cap; ++i) {
+        if (names) names[i] = ctx->clock.names[i];
+        if (ms) ms[i] = i < ctx->clock.ms.size() ? ctx->clock.ms[i] : 0.f;
+    }
+    return ctx->clock.on ? n : ctx->clock.launches;
+}
+
+// MSAMetadata of msa_transforms.cpp:18-24 without touching the residues of rows 1..R-1:
+// row 0 fixes C and the wrap width, every other row is located from its header.
+eds_status eds_msa_index_host(const uint8_t* text, uint64_t n, eds_msa_index* out) {
+    return guarded([&] {
+        if (!text || !out) throw std::invalid_argument("eds_msa_index_host: null argument");
+        memset(out, 0, sizeof(*out));
+        std::vector<uint64_t> rows;
+        uint64_t p = 0;
+        while (p < n && text[p] == '\n') ++p;
+        if (p >= n || text[p] != '>') throw edsb::BadMsa("not a FASTA alignment: expected '>'");
+        const uint8_t* nl = static_cast<const uint8_t*>(memchr(text + p, '\n', n - p));
+        if (!nl) throw edsb::BadMsa("header without sequence data");
+        p = (uint64_t)(nl - text) + 1;
+        const uint64_t start0 = p;
+        uint64_t C = 0, lw = 0, row_end = p;
+        bool short_seen = false;
+        while (p < n && text[p] != '>' && text[p] != '\n') {
+            const uint8_t* e = static_cast<const uint8_t*>(memchr(text + p, '\n', n - p));
+            const uint64_t len = e ? (uint64_t)(e - (text + p)) : n - p;
+            if (lw == 0) lw = len;
+            if (short_seen || len > lw) throw edsb::BadMsa("first row is not wrapped at a uniform width");
+            if (len < lw) short_seen = true;
+            C += len;
+            row_end = p + len;
+            p = e ? (uint64_t)(e - text) + 1 : n;
+        }
+        if (C == 0) throw edsb::BadMsa("first row is empty");
+        if (lw > 0xffffffffull) throw edsb::BadMsa("line too long");
+        const uint64_t row_bytes = row_end - start0;
+        rows.push_back(start0);
+        p = row_end;
+        for (;;) {
+            while (p < n && text[p] == '\n') ++p;
+            if (p >= n) break;
+            if (text[p] != '>') throw edsb::BadMsa("row longer than the first row, or blank line inside a record");
+            const uint8_t* he = static_cast<const uint8_t*>(memchr(text + p, '\n', n - p));
+            if (!he) throw edsb::BadMsa("header without sequence data");
+            const uint64_t start = (uint64_t)(he - text) + 1;
+            if (start + row_bytes > n) throw edsb::BadMsa("row shorter than the first row");
+            if (start + row_bytes < n && text[start + row_bytes] != '\n')
+                throw edsb::BadMsa("row longer than the first row (or differently wrapped)");
+            if (rows.size() >= 0xffffffffull) throw edsb::BadMsa("too many rows");
+            rows.push_back(start);
+            p = start + row_bytes;
+        }
+        if (rows.size() < 2)
+            throw edsb::BadMsa("alignment needs at least 2 rows (undefined in the reference, msa_transforms.cpp:53-57)");
+        out->row_start = static_cast<uint64_t*>(malloc(rows.size() * sizeof(uint64_t)));
+        if (!out->row_start) throw std::bad_alloc();
+        memcpy(out->row_start, rows.data(), rows.size() * sizeof(uint64_t));
+        out->n_rows = (uint32_t)rows.size();
+        out->n_cols = C;
+        out->line_width = (uint32_t)lw;
+        out->row_bytes = row_bytes;
+    });
+}
+
+void eds_msa_index_free(eds_msa_index* idx) {
+    if (!idx) return;
+    free(idx->row_start);
+    memset(idx, 0, sizeof(*idx));
+}
+
+eds_status eds_msa_transform_device(eds_ctx* ctx, const eds_msa_view* view, uint32_t l, int leds, eds_buffer* eds_out,
+                                    eds_buffer* seds_out, eds_msa_stats* stats) {
+    return guarded([&] {
+        use_device(ctx);
+        if (!view) throw std::invalid_argument("eds_msa_transform_device: null view");
+        ctx->msa->transform(*view, l, leds, eds_out, seds_out, stats);
+    });
+}
+
+eds_status eds_msa_transform_host(eds_ctx* ctx, const uint8_t* file, uint64_t file_bytes, uint32_t l, int leds,
+                                  eds_buffer* eds_out, eds_buffer* seds_out, eds_msa_stats* stats) {
+    eds_msa_index idx;
+    memset(&idx, 0, sizeof(idx));
+    eds_status rc = guarded([&] {
+        use_device(ctx);
+        if (!file || !eds_out || !seds_out) throw std::invalid_argument("eds_msa_transform_host: null argument");
+        eds_out->data = seds_out->data = nullptr;
+        eds_out->bytes = seds_out->bytes = 0;
+        const eds_status irc = eds_msa_index_host(file, file_bytes, &idx);
+        if (irc != EDS_OK) throw edsb::BadMsa(g_last_error);
+        ctx->file_buf.reserve(file_bytes + 64);
+        EDSB_CUDA(cudaMemcpyAsync(ctx->file_buf.p, file, file_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        eds_msa_view v;
+        memset(&v, 0, sizeof(v));
+        v.text = ctx->file_buf.as<uint8_t>();
+        v.text_bytes = file_bytes;
+        v.row_start = idx.row_start;
+        v.n_rows = idx.n_rows;
+        v.line_width = idx.line_width;
+        v.total_cols = idx.n_cols;
+        v.col_begin = 0;
+        v.col_count = idx.n_cols;
+        v.own_begin = 0;
+        v.own_end = idx.n_cols;
+        eds_buffer de, ds;
+        ctx->msa->transform(v, l, leds, &de, &ds, stats);
+        eds_out->data = to_host(ctx, de);
+        eds_out->bytes = de.bytes;
+        seds_out->data = to_host(ctx, ds);
+        seds_out->bytes = ds.bytes;
+    });
+    eds_msa_index_free(&idx);
+    if (rc != EDS_OK) {
+        if (eds_out) eds_buffer_free_host(eds_out);
+        if (seds_out) eds_buffer_free_host(seds_out);
+    }
+    return rc;
+}
+
+eds_status eds_msa_conserved_bits(eds_ctx* ctx, const eds_msa_view* view, uint8_t* out_bits, uint64_t out_bytes) {
+    return guarded([&] {
+        use_device(ctx);
+        if (!view || !out_bits) throw std::invalid_argument("eds_msa_conserved_bits: null argument");
+        ctx->msa->conserved_bits(*view, out_bits, out_bytes);
+    });
+}
+
+eds_status eds_msa_synth_device(eds_ctx* ctx, uint32_t n_rows, uint64_t total_cols, uint32_t line_width,
+                                uint64_t col_begin, uint64_t col_count, uint64_t seed, uint32_t variable_ppm,
+                                eds_msa_view* view) {
+    return guarded([&] {
+        use_device(ctx);
+        if (!view) throw std::invalid_argument("eds_msa_synth_device: null view");
+        edsb::msa_synth(ctx, n_rows, total_cols, line_width, col_begin, col_count, seed, variable_ppm, view);
+    });
+}
+
+void eds_msa_synth_free(eds_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    ctx->synth_text.release();
+    ctx->synth_rows.clear();
+}
+
+void eds_buffer_free_host(eds_buffer* buf) {
+    if (!buf) return;
+    free(buf->data);
+    buf->data = nullptr;
+    buf->bytes = 0;
+}
+
+eds_status eds_leds_merge_host(eds_ctx* ctx, const uint8_t* eds_in, uint64_t eds_bytes, const uint8_t* seds_in,
+                               uint64_t seds_bytes, uint32_t l, int compact, uint64_t max_output_bytes,
+                               eds_buffer* leds_out, eds_buffer* seds_out, uint32_t* rounds_out) {
+    eds_status rc = guarded([&] {
+        use_device(ctx);
+        if (!eds_in || !leds_out || !seds_out) throw std::invalid_argument("eds_leds_merge_host: null argument");
+        leds_out->data = seds_out->data = nullptr;
+        leds_out->bytes = seds_out->bytes = 0;
+        ctx->leds->merge_host(eds_in, eds_bytes, seds_in, seds_bytes, l, compact != 0, max_output_bytes, leds_out,
+                              seds_out, rounds_out);
+    });
+    if (rc != EDS_OK) {
+        if (leds_out) eds_buffer_free_host(leds_out);
+        if (seds_out) eds_buffer_free_host(seds_out);
+    }
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// The library context behind eds_ctx (include/edsparser_b200.h): device, stream, launch knobs,
+// per-kernel event timing, and the per-path pipelines with their grow-only device buffers.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/edsparser_b200.h"
+#include "common.cuh"
+
+namespace edsb {
+class MsaPipeline;
+class LedsPipeline;
+
+// One event pair per launch when profiling is on; resolved to milliseconds after the stream syncs.
+struct KernelClock {
+    bool on = false;
+    cudaStream_t stream = nullptr;
+    std::vector<const char*> names;
+    std::vector<cudaEvent_t> pool;  // 2 per launch
+    std::vector<float> ms;
+    uint32_t launches = 0;
+
+    void reset() {
+        names.clear();
+        ms.clear();
+        launches = 0;
+    }
+    void begin(const char* name) {
+        ++launches;
+        if (!on) return;
+        size_t i = names.size();
+        names.push_back(name);
+        while (pool.size() < 2 * (i + 1)) {
+            cudaEvent_t e;
+            EDSB_CUDA(cudaEventCreate(&e));
+            pool.push_back(e);
+        }
+        EDSB_CUDA(cudaEventRecord(pool[2 * i], stream));
+    }
+    void end() {
+        if (!on) return;
+        EDSB_CUDA(cudaEventRecord(pool[2 * (names.size() - 1) + 1], stream));
+    }
+    void resolve() {
+        ms.assign(names.size(), 0.f);
+        if (!on) return;
+        for (size_t i = 0; i < names.size(); ++i) EDSB_CUDA(cudaEventElapsedTime(&ms[i], pool[2 * i], pool[2 * i + 1]));
+    }
+    void release() {
+        for (cudaEvent_t e : pool) cudaEventDestroy(e);
+        pool.clear();
+    }
+};
+}  // namespace edsb
+
+struct eds_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    size_t smem_optin = 227 * 1024;
+    uint32_t partitions = 0;          // 0 = default
+    uint32_t scan_blocks_per_sm = 0;  // 0 = default
+    uint64_t hash_mask = ~0ull;       // tests narrow it (EDSB_HASH_MASK) to exercise the exact-compare fallback
+    edsb::KernelClock clock;
+    edsb::MsaPipeline* msa = nullptr;
+    edsb::LedsPipeline* leds = nullptr;
+    // synthetic alignment (eds_msa_synth_device)
+    edsb::DevBuf synth_text;
+    edsb::DevBuf file_buf;  // eds_msa_transform_host: the .msa bytes on the device
+    std::vector<uint64_t> synth_rows;
+};

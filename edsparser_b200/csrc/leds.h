@@ -1,0 +1,29 @@
+// Host-side launcher of the l-EDS merge kernels (leds.cu): eds_to_leds_linear / eds_to_leds_cartesian.
+#pragma once
+#include <stdexcept>
+
+#include "ctx.h"
+
+namespace edsb {
+
+struct BudgetError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+class LedsPipeline {
+   public:
+    explicit LedsPipeline(eds_ctx* ctx);
+    ~LedsPipeline();
+    LedsPipeline(const LedsPipeline&) = delete;
+    LedsPipeline& operator=(const LedsPipeline&) = delete;
+
+    // Host text in, malloc'd host text out.
+    void merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const uint8_t* seds_in, uint64_t seds_bytes, uint32_t l,
+                    bool compact, uint64_t max_output_bytes, eds_buffer* leds_out, eds_buffer* seds_out,
+                    uint32_t* rounds_out);
+
+   private:
+    eds_ctx* ctx_;
+};
+
+}  // namespace edsb

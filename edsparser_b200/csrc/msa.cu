@@ -1,0 +1,1220 @@
+// MSA -> EDS / l-EDS on the GPU: the kernels behind eds_msa_transform_device.
+//
+// Reference behaviour (draessld/EDSParser, src/cpp/lib/transforms/msa_transforms.cpp):
+//   pass 1  parse_msa_and_build_variant_bv :36-90   -> k_scan, k_colbits
+//   pass 2  build_eds_boundaries :101-115 / build_leds_boundaries :133-190
+//                                                   -> k_compact, k_sym_count, k_sym_scatter, k_finalize
+//   pass 3  generate_output :200-324                -> k_stash, k_group, k_size_*, k_emit_*
+// Nothing here is derived from the reference's code: the reference walks the file with getline /
+// seekg / std::map; this is a column-parallel formulation whose output bytes are identical.
+//
+// Data flow (all in HBM, one stream, no host round trip until the final status copy):
+//   text (FASTA rows, any alignment) --k_scan--> mismatch bits in row-0-aligned byte space
+//   --k_colbits--> variable-column bits V, run-start bits T, row 0 in column space
+//   --k_compact--> variable-column list + rank directory, run list
+//   --k_stash--> stash[k][r]: the R residues of every variable column, column-major (the only
+//                re-read of the alignment: R bytes per variable column)
+//   --k_sym_*--> symbol list (runs that open a symbol), --k_finalize--> owned range / shard edges
+//   --k_group--> per variable symbol: hash rows, exact dedup, alternative ids, sizes
+//   --k_size_*--> output offsets, --k_emit_*--> EDS and SEDS text.
+#include "msa.h"
+
+#include <string.h>
+
+#include <algorithm>
+
+namespace edsb {
+
+// ---------------------------------------------------------------------------------------------
+// k_scan: column-conservation scan (msa_transforms.cpp:69-84).
+// One thread owns one 16-byte chunk of p-space and walks all rows: acc |= row ^ row0. A row whose
+// start is not congruent to row 0's mod 16 is read as two aligned vectors and funnel-shifted.
+// Algorithmic bytes: R * row_bytes read once; writes 2 bytes per chunk.
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanUnroll = 8;
+constexpr int kRowCache = 2048;
+
+__global__ void __launch_bounds__(kScanThreads) k_scan(MsaGeom g, uint16_t* mism16, MsaStatus* st) {
+    __shared__ long long s_d[kRowCache];
+    const uint32_t nrc = g.R < (uint32_t)kRowCache ? g.R : (uint32_t)kRowCache;
+    for (uint32_t i = threadIdx.x; i < nrc; i += blockDim.x) s_d[i] = (long long)g.row_off[i] - (long long)g.a0;
+    __syncthreads();
+
+    const uint4* vec = reinterpret_cast<const uint4*>(g.text);
+    const long long vmax = (long long)g.n_vec - 1;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t wpb = blockDim.x >> 5;
+    const uint32_t n_tiles = (g.n_chunks + 31) / 32;
+    uint32_t bad = 0;
+
+    for (uint32_t tile = blockIdx.x * wpb + (threadIdx.x >> 5); tile < n_tiles; tile += gridDim.x * wpb) {
+        const uint32_t j = tile * 32 + lane;
+        if (j >= g.n_chunks) continue;
+        const long long jj = (long long)j;
+        const long long d0 = s_d[0];
+        long long v0 = jj + (d0 >> 4);
+        v0 = v0 < 0 ? 0 : (v0 > vmax ? vmax : v0);
+        const uint4 ref = ldg_nc(vec + v0);
+        uint4 acc = make_uint4(0, 0, 0, 0);
+
+        for (uint32_t r = 1; r < g.R; r += kScanUnroll) {
+            uint4 lo[kScanUnroll], hi[kScanUnroll];
+            uint32_t sh[kScanUnroll];
+#pragma unroll
+            for (int u = 0; u < kScanUnroll; ++u) {
+                const uint32_t rr = (r + u < g.R) ? r + u : 0;  // row 0 against itself: no effect
+                const long long d = rr < nrc ? s_d[rr] : (long long)g.row_off[rr] - (long long)g.a0;
+                long long vi = jj + (d >> 4);
+                sh[u] = (uint32_t)(d & 15);
+                long long va = vi < 0 ? 0 : (vi > vmax ? vmax : vi);
+                lo[u] = ldg_nc(vec + va);
+                if (sh[u]) {
+                    long long vb = vi + 1;
+                    vb = vb < 0 ? 0 : (vb > vmax ? vmax : vb);
+                    hi[u] = ldg_nc(vec + vb);
+                } else {
+                    hi[u] = lo[u];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kScanUnroll; ++u) {
+                const uint4 x = realign16(lo[u], hi[u], sh[u]);
+                acc.x |= x.x ^ ref.x;
+                acc.y |= x.y ^ ref.y;
+                acc.z |= x.z ^ ref.z;
+                acc.w |= x.w ^ ref.w;
+            }
+        }
+
+        // bytes of this chunk that belong to the row segment
+        const uint64_t p0 = (uint64_t)j * 16u;
+        const uint64_t pend = (uint64_t)g.a0 + g.row_bytes;
+        const uint32_t vlo = p0 >= g.a0 ? 0u : (uint32_t)(g.a0 - p0);
+        const uint32_t vhi = pend >= p0 + 16u ? 16u : (pend > p0 ? (uint32_t)(pend - p0) : 0u);
+        const uint32_t valid = low_bits(vhi) & ~low_bits(vlo);
+        // where line breaks must be: u % (lw + 1) == lw
+        uint32_t expect = 0;
+        {
+            const uint64_t u_first = g.u_begin + (p0 + vlo - g.a0);
+            uint32_t rem = (uint32_t)(u_first % (uint64_t)(g.lw + 1u));
+            for (uint32_t i = vlo; i < vhi; ++i) {
+                if (rem == g.lw) expect |= 1u << i;
+                rem = (rem == g.lw) ? 0u : rem + 1u;
+            }
+        }
+        uint32_t mism = nonzero_bytes16(acc) | eq_bytes16(ref, 0x2d2d2d2du);  // differs from row 0, or row 0 is '-'
+        const uint32_t nl = eq_bytes16(ref, 0x0a0a0a0au);
+        if (((nl ^ expect) | (nonzero_bytes16(acc) & expect)) & valid) bad = 1;
+        mism &= valid & ~expect;
+        mism16[j] = (uint16_t)mism;
+    }
+    if (bad) atomicOr(&st->bad_msa, (uint32_t)kBadNewlineLayout);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_colbits: p-space mismatch bits -> column-space V (variable) and T (run start) words, row 0 in
+// column space, per-partition counts. Thread per 32-column word.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPartThreads = 256;
+
+__device__ __forceinline__ uint32_t get_bits(const uint32_t* m, uint64_t p, uint32_t n) {
+    const uint64_t wi = p >> 5;
+    const uint32_t v = __funnelshift_r(m[wi], m[wi + 1], (uint32_t)(p & 31u));
+    return v & low_bits(n);
+}
+
+__global__ void __launch_bounds__(kPartThreads) k_colbits(MsaGeom g, const uint32_t* mism, uint32_t* vbits,
+                                                          uint32_t* tbits, uint8_t* refc, uint2* part_cnt) {
+    __shared__ unsigned long long s_red[33];
+    const uint32_t P = gridDim.x;
+    const uint32_t wpp = (g.n_words + P - 1) / P;
+    const uint32_t w_begin = min(g.n_words, blockIdx.x * wpp);
+    const uint32_t w_end = min(g.n_words, w_begin + wpp);
+    const uint8_t* row0 = g.text + g.row_off[0];
+    unsigned long long cnt = 0;
+    for (uint32_t w = w_begin + threadIdx.x; w < w_end; w += blockDim.x) {
+        const uint32_t c0 = w * 32u;
+        const uint32_t nvalid = min(32u, g.ncols - c0);
+        const uint64_t gc = g.col_begin + c0;
+        const uint64_t q = gc / g.lw;
+        uint32_t rem = (uint32_t)(gc - q * g.lw);
+        uint64_t u = gc + q - g.u_begin;  // byte offset inside the row segment
+        uint32_t V = 0, filled = 0;
+        uint32_t chars[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        while (filled < nvalid) {
+            const uint32_t n = min(nvalid - filled, g.lw - rem);
+            V |= get_bits(mism, u + g.a0, n) << filled;
+            for (uint32_t i = 0; i < n; ++i) {
+                const uint32_t at = filled + i;
+                chars[at >> 2] |= (uint32_t)row0[u + i] << ((at & 3u) * 8u);
+            }
+            filled += n;
+            u += n + 1u;  // skip the line break
+            rem = 0;
+        }
+        uint32_t prev;
+        if (c0 == 0) {
+            prev = (~V) & 1u;  // a run always starts at the first held column
+        } else {
+            const uint64_t gp = gc - 1;
+            const uint64_t up = gp + gp / g.lw - g.u_begin;
+            prev = get_bits(mism, up + g.a0, 1);
+        }
+        const uint32_t T = (V ^ ((V << 1) | prev)) & low_bits(nvalid);
+        vbits[w] = V;
+        tbits[w] = T;
+        uint4* dst = reinterpret_cast<uint4*>(refc + (size_t)c0);
+        dst[0] = make_uint4(chars[0], chars[1], chars[2], chars[3]);
+        dst[1] = make_uint4(chars[4], chars[5], chars[6], chars[7]);
+        cnt += (unsigned long long)__popc(V) | ((unsigned long long)__popc(T) << 32);
+    }
+    const unsigned long long tot = block_sum(cnt, s_red);
+    if (threadIdx.x == 0) part_cnt[blockIdx.x] = uint2{(uint32_t)tot, (uint32_t)(tot >> 32)};
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_compact: stream compaction of V into the variable-column list (+ rank directory) and of T into
+// the run list. Each block first sums the counts of the partitions before it.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPartThreads) k_compact(MsaGeom g, MsaBufs b) {
+    __shared__ unsigned long long s_scan[33];
+    const uint32_t P = gridDim.x;
+    const uint32_t wpp = (g.n_words + P - 1) / P;
+    const uint32_t w_begin = min(g.n_words, blockIdx.x * wpp);
+    const uint32_t w_end = min(g.n_words, w_begin + wpp);
+    unsigned long long mine = 0;
+    for (uint32_t q = threadIdx.x; q < blockIdx.x; q += blockDim.x) {
+        const uint2 c = b.part_cnt[q];
+        mine += (unsigned long long)c.x | ((unsigned long long)c.y << 32);
+    }
+    const unsigned long long base = block_sum(mine, s_scan);
+    uint32_t base_var = (uint32_t)base, base_run = (uint32_t)(base >> 32);
+    for (uint32_t w0 = w_begin; w0 < w_end; w0 += blockDim.x) {
+        const uint32_t w = w0 + threadIdx.x;
+        uint32_t V = 0, T = 0;
+        if (w < w_end) {
+            V = b.vbits[w];
+            T = b.tbits[w];
+        }
+        const unsigned long long cnt = (unsigned long long)__popc(V) | ((unsigned long long)__popc(T) << 32);
+        unsigned long long total;
+        const unsigned long long ex = block_exclusive_scan(cnt, s_scan, total);
+        if (w < w_end) {
+            uint32_t iv = base_var + (uint32_t)ex, ir = base_run + (uint32_t)(ex >> 32);
+            b.rankdir[w] = iv;
+            for (uint32_t bits = V; bits; bits &= bits - 1) {
+                const uint32_t bit = (uint32_t)__ffs((int)bits) - 1u;
+                if (iv < b.cap_var) b.varcol[iv] = w * 32u + bit;
+                ++iv;
+            }
+            for (uint32_t bits = T; bits; bits &= bits - 1) {
+                const uint32_t bit = (uint32_t)__ffs((int)bits) - 1u;
+                if (ir < b.cap_runs) b.runs[ir] = (w * 32u + bit) | (((V >> bit) & 1u) ? 0u : kCommonFlag);
+                ++ir;
+            }
+        }
+        base_var += (uint32_t)total;
+        base_run += (uint32_t)(total >> 32);
+    }
+    if (blockIdx.x == P - 1 && threadIdx.x == 0) {
+        MsaStatus* st = b.status;
+        st->n_var = base_var;
+        st->n_runs = base_run;
+        st->need_var = base_var;
+        st->need_runs = base_run;
+        if (base_run <= b.cap_runs) b.runs[base_run] = g.ncols;  // sentinel (cap_runs + 1 entries allocated)
+        if (base_var > b.cap_var)
+            st->abort = kAbortVarCap;
+        else if (base_run > b.cap_runs)
+            st->abort = kAbortRunsCap;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_stash: gather the R residues of every variable column into stash[k * Rp + r] (lanes over rows,
+// coalesced writes; the reads are one sector per (column, row) and are the pipeline's only re-read).
+// ---------------------------------------------------------------------------------------------
+constexpr int kStashCols = 8;
+
+__global__ void k_stash(MsaGeom g, MsaBufs b) {
+    MsaStatus* st = b.status;
+    if (st->abort) return;
+    const uint32_t n_var = st->n_var;
+    uint32_t bad = 0;
+    for (uint32_t k0 = blockIdx.x * kStashCols; k0 < n_var; k0 += gridDim.x * kStashCols) {
+        uint64_t uoff[kStashCols];
+#pragma unroll
+        for (int kk = 0; kk < kStashCols; ++kk) {
+            const uint32_t k = min(k0 + kk, n_var - 1);
+            const uint64_t gc = g.col_begin + b.varcol[k];
+            uoff[kk] = gc + gc / g.lw - g.u_begin;
+        }
+        for (uint32_t r = threadIdx.x; r < g.R; r += blockDim.x) {
+            const uint8_t* row = g.text + g.row_off[r];
+            uint8_t ch[kStashCols];
+#pragma unroll
+            for (int kk = 0; kk < kStashCols; ++kk) ch[kk] = row[uoff[kk]];
+#pragma unroll
+            for (int kk = 0; kk < kStashCols; ++kk) {
+                if (k0 + kk < n_var) {
+                    b.stash[(size_t)(k0 + kk) * g.Rp + r] = ch[kk];
+                    bad |= (ch[kk] == (uint8_t)'\n');
+                }
+            }
+        }
+    }
+    if (bad) atomicOr(&st->bad_msa, (uint32_t)kBadResidueByte);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Symbol boundaries. Plain EDS (msa_transforms.cpp:101-115): every run opens a symbol.
+// l-EDS (msa_transforms.cpp:133-190): a conserved run is standalone when it is at least l long or
+// touches an end of the alignment; run k opens a symbol iff run k or run k-1 is standalone (or k is
+// the first run of the alignment). At a window edge that is not an alignment end a short conserved
+// run is of unknown length: it is treated as not standalone and k_finalize decides whether that
+// matters for the owned range.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool run_standalone(const MsaGeom& g, const uint32_t* runs, uint32_t k) {
+    const uint32_t e = runs[k];
+    if (!(e & kCommonFlag)) return false;
+    const uint32_t s = e & kColMask, en = runs[k + 1] & kColMask;
+    if (en - s >= g.l) return true;
+    return (g.col_begin + s == 0) || (g.col_begin + en == g.total_cols);
+}
+
+__device__ __forceinline__ bool run_opens(const MsaGeom& g, const uint32_t* runs, uint32_t k) {
+    if (!g.leds || g.l == 0) return true;
+    if (k == 0) return g.col_begin == 0 ? true : run_standalone(g, runs, 0);
+    return run_standalone(g, runs, k) || run_standalone(g, runs, k - 1);
+}
+
+__global__ void __launch_bounds__(kPartThreads) k_sym_count(MsaGeom g, MsaBufs b) {
+    __shared__ uint32_t s_red[33];
+    const MsaStatus* st = b.status;
+    if (st->abort) return;
+    const uint32_t n = st->n_runs, P = gridDim.x;
+    const uint32_t per = (n + P - 1) / P;
+    const uint32_t k_begin = min(n, blockIdx.x * per), k_end = min(n, k_begin + per);
+    uint32_t cnt = 0;
+    for (uint32_t k = k_begin + threadIdx.x; k < k_end; k += blockDim.x) cnt += run_opens(g, b.runs, k) ? 1u : 0u;
+    const uint32_t tot = block_sum(cnt, s_red);
+    if (threadIdx.x == 0) b.part_sym[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(kPartThreads) k_sym_scatter(MsaGeom g, MsaBufs b) {
+    __shared__ uint32_t s_scan[33];
+    MsaStatus* st = b.status;
+    if (st->abort) return;
+    const uint32_t n = st->n_runs, P = gridDim.x;
+    const uint32_t per = (n + P - 1) / P;
+    const uint32_t k_begin = min(n, blockIdx.x * per), k_end = min(n, k_begin + per);
+    uint32_t mine = 0;
+    for (uint32_t q = threadIdx.x; q < blockIdx.x; q += blockDim.x) mine += b.part_sym[q];
+    uint32_t base = block_sum(mine, s_scan);
+    for (uint32_t k0 = k_begin; k0 < k_end; k0 += blockDim.x) {
+        const uint32_t k = k0 + threadIdx.x;
+        const bool open = k < k_end && run_opens(g, b.runs, k);
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan(open ? 1u : 0u, s_scan, total);
+        if (open) b.sym[base + ex] = b.runs[k];  // an opening conserved run is a whole common symbol
+        base += total;
+    }
+    if (blockIdx.x == P - 1 && threadIdx.x == 0) {
+        st->n_syms = base;
+        b.sym[base] = g.ncols;
+    }
+}
+
+__device__ __forceinline__ uint32_t sym_lower_bound(const uint32_t* sym, uint32_t n, uint32_t col) {
+    uint32_t lo = 0, hi = n;  // first k with start(sym[k]) >= col
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((sym[mid] & kColMask) < col)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// k_finalize: owned symbol range and what happens at the shard's two edges (one thread).
+__global__ void k_finalize(MsaGeom g, MsaBufs b) {
+    MsaStatus* st = b.status;
+    if (st->abort || threadIdx.x != 0 || blockIdx.x != 0) return;
+    const uint32_t n_runs = st->n_runs, n_syms = st->n_syms;
+    const uint32_t* sym = b.sym;
+    const uint32_t* runs = b.runs;
+    const bool leds = g.leds && g.l > 0;
+    const bool right_open = g.col_begin + g.ncols < g.total_cols;  // the alignment continues past the window
+    uint32_t fail = 0;
+    const uint32_t k_lo = sym_lower_bound(sym, n_syms, g.own_lo);
+    const uint32_t k_hi = sym_lower_bound(sym, n_syms, g.own_hi);
+    uint32_t lead_lo = 0, lead_hi = 0, lead_close = 0, tail_open = 0;
+
+    if (leds && g.col_begin > 0 && n_runs > 0) {
+        // run 0 is cut by the window: conserved and short => its true length is unknown
+        const uint32_t e0 = runs[0], end0 = runs[1] & kColMask;
+        const bool uncertain = (e0 & kCommonFlag) && end0 < g.l && !(g.col_begin + end0 == g.total_cols);
+        if (uncertain && g.own_lo <= end0) fail = 1;
+    }
+    if (g.own_lo < g.own_hi) {
+        const bool at_start = k_lo < n_syms && (sym[k_lo] & kColMask) == g.own_lo;
+        if (!at_start && k_lo > 0 && (sym[k_lo - 1] & kCommonFlag)) {
+            const uint32_t end = sym[k_lo] & kColMask;  // sentinel = ncols
+            lead_lo = g.own_lo;
+            lead_hi = min(end, g.own_hi);
+            lead_close = end <= g.own_hi ? 1u : 0u;
+        }
+        if (k_hi > k_lo) {
+            const uint32_t last = sym[k_hi - 1], end = sym[k_hi] & kColMask;
+            if (last & kCommonFlag) {
+                tail_open = end > g.own_hi ? 1u : 0u;
+            } else if (k_hi == n_syms && right_open) {
+                fail = 1;  // the last owned variable symbol does not close inside the window
+            }
+        }
+    }
+    st->k_lo = k_lo;
+    st->k_hi = k_hi;
+    st->lead_lo = lead_lo;
+    st->lead_hi = lead_hi;
+    st->lead_close = lead_close;
+    st->tail_open = tail_open;
+    st->halo_fail = fail;
+    st->first_open_col = k_lo < k_hi ? g.col_begin + (sym[k_lo] & kColMask) : ~0ull;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Walking one row's characters across the columns of a variable symbol: conserved columns read
+// row 0 (column space), variable columns read the stash; '-' is dropped (msa_transforms.cpp:281-286).
+// ---------------------------------------------------------------------------------------------
+struct RowWalk {
+    const uint32_t* vbits;
+    const uint8_t* refc;
+    const uint8_t* stash;
+    uint32_t Rp;
+};
+
+__device__ __forceinline__ int next_char(const RowWalk& w, uint32_t r, uint32_t& c, uint32_t e, uint32_t& slot) {
+    while (c < e) {
+        const uint32_t v = (w.vbits[c >> 5] >> (c & 31u)) & 1u;
+        uint8_t ch;
+        if (v) {
+            ch = w.stash[(size_t)slot * w.Rp + r];
+            ++slot;
+        } else {
+            ch = w.refc[c];
+        }
+        ++c;
+        if (ch != (uint8_t)'-') return (int)ch;
+    }
+    return -1;
+}
+
+__device__ bool rows_equal(const RowWalk& w, uint32_t r1, uint32_t r2, uint32_t s, uint32_t e, uint32_t slot0) {
+    uint32_t c1 = s, c2 = s, s1 = slot0, s2 = slot0;
+    for (;;) {
+        const int a = next_char(w, r1, c1, e, s1);
+        const int bch = next_char(w, r2, c2, e, s2);
+        if (a != bch) return false;
+        if (a < 0) return true;
+    }
+}
+
+__device__ __forceinline__ uint32_t first_slot(const MsaBufs& b, uint32_t s) {
+    return b.rankdir[s >> 5] + (uint32_t)__popc(b.vbits[s >> 5] & low_bits(s & 31u));
+}
+
+__device__ __forceinline__ void store_alt(const MsaGeom& g, void* altid, size_t i, uint32_t a) {
+    if (g.alt32)
+        reinterpret_cast<uint32_t*>(altid)[i] = a;
+    else
+        reinterpret_cast<uint16_t*>(altid)[i] = (uint16_t)a;
+}
+__device__ __forceinline__ uint32_t load_alt(const MsaGeom& g, const void* altid, size_t i) {
+    return g.alt32 ? reinterpret_cast<const uint32_t*>(altid)[i] : (uint32_t)reinterpret_cast<const uint16_t*>(altid)[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_group: one warp per owned variable symbol (generate_output's variant branch,
+// msa_transforms.cpp:259-318). Rows are hashed (FNV-1a over the gap-stripped string), grouped through
+// a per-warp open-addressing table that keeps the smallest row of each hash class, and every row is
+// then compared byte for byte with that row; a true hash collision switches the symbol to an exact
+// quadratic search. Alternatives are numbered by first row (insertion_order, :263,290-292).
+// Per-warp scratch (shared memory, or global when R is large): h[Rq] u64, len[Rq], lead[Rq], tab[T].
+// ---------------------------------------------------------------------------------------------
+__global__ void k_group(MsaGeom g, MsaBufs b, uint32_t Rq, uint32_t T, uint32_t use_global) {
+    MsaStatus* st = b.status;
+    if (st->abort || st->halo_fail) return;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const size_t per_warp = (size_t)Rq * 16u + (size_t)T * 4u;
+    unsigned char* base = use_global ? b.group_ws + ((size_t)blockIdx.x * wpb + warp) * per_warp
+                                     : EDSB_DYN_SMEM() + (size_t)warp * per_warp;
+    unsigned long long* hrow = reinterpret_cast<unsigned long long*>(base);
+    uint32_t* len = reinterpret_cast<uint32_t*>(hrow + Rq);
+    uint32_t* lead = len + Rq;
+    uint32_t* tab = lead + Rq;
+    const RowWalk w{b.vbits, b.refc, b.stash, g.Rp};
+    const uint32_t k_lo = st->k_lo, k_hi = st->k_hi;
+    unsigned long long alts_here = 0;
+    uint32_t var_here = 0;
+
+    for (uint32_t k = k_lo + blockIdx.x * wpb + warp; k < k_hi; k += gridDim.x * wpb) {
+        const uint32_t e = b.sym[k];
+        if (e & kCommonFlag) continue;  // warp-uniform
+        const uint32_t s = e & kColMask, en = b.sym[k + 1] & kColMask;
+        const uint32_t slot0 = first_slot(b, s);
+
+        for (uint32_t i = lane; i < T; i += 32) tab[i] = kEmptySlot;
+        for (uint32_t r = lane; r < g.R; r += 32) {
+            uint32_t c = s, slot = slot0, n = 0;
+            unsigned long long h = 14695981039346656037ull;
+            int ch;
+            while ((ch = next_char(w, r, c, en, slot)) >= 0) {
+                h = (h ^ (unsigned long long)ch) * 1099511628211ull;
+                ++n;
+            }
+            h = (h ^ ((unsigned long long)n * 0x9e3779b97f4a7c15ull)) & g.hash_mask;
+            hrow[r] = h;
+            len[r] = n;
+        }
+        __syncwarp();
+        for (uint32_t r = lane; r < g.R; r += 32) {
+            const unsigned long long h = hrow[r];
+            uint32_t slot = (uint32_t)(h ^ (h >> 32)) & (T - 1u);
+            for (;;) {
+                const uint32_t cur = atomicCAS(&tab[slot], kEmptySlot, r);
+                if (cur == kEmptySlot) break;
+                if (hrow[cur] == h) {
+                    atomicMin(&tab[slot], r);
+                    break;
+                }
+                slot = (slot + 1u) & (T - 1u);
+            }
+            lead[r] = slot;
+        }
+        __syncwarp();
+        uint32_t collided = 0;
+        for (uint32_t r = lane; r < g.R; r += 32) {
+            const uint32_t m = tab[lead[r]];
+            if (m != r && (len[m] != len[r] || !rows_equal(w, m, r, s, en, slot0))) collided = 1;
+            lead[r] = m;
+        }
+        collided = __any_sync(0xffffffffu, collided);
+        __syncwarp();
+        if (collided) {
+            // exact fallback: first earlier row with the same string
+            for (uint32_t r = lane; r < g.R; r += 32) {
+                uint32_t m = r;
+                for (uint32_t r2 = 0; r2 < r; ++r2) {
+                    if (len[r2] == len[r] && hrow[r2] == hrow[r] && rows_equal(w, r2, r, s, en, slot0)) {
+                        m = r2;
+                        break;
+                    }
+                }
+                lead[r] = m;
+            }
+            __syncwarp();
+        }
+        // number the alternatives by first row; tab[0..R) is reused as "alternative of leader row"
+        uint32_t nalts = 0;
+        unsigned long long lensum = 0;
+        for (uint32_t r0 = 0; r0 < g.R; r0 += 32) {
+            const uint32_t r = r0 + lane;
+            const bool isl = r < g.R && lead[r] == r;
+            const uint32_t mask = __ballot_sync(0xffffffffu, isl);
+            if (isl) {
+                tab[r] = nalts + (uint32_t)__popc(mask & lanemask_lt());
+                lensum += len[r];
+            }
+            if (lane == 0) b.leadmask[(size_t)slot0 * (g.Rp >> 5) + (r0 >> 5)] = mask;
+            nalts += (uint32_t)__popc(mask);
+        }
+        __syncwarp();
+        for (uint32_t r = lane; r < g.R; r += 32) store_alt(g, b.altid, (size_t)slot0 * g.Rp + r, tab[lead[r]]);
+        lensum = warp_sum(lensum);
+        if (lane == 0) {
+            b.sym_nalts[k] = nalts;
+            b.sym_edsz[k] = 2ull + lensum + (unsigned long long)(nalts - 1u);
+            alts_here += nalts;
+            var_here += 1;
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && var_here) {
+        atomicAdd(&st->n_alts, alts_here);
+        atomicAdd(&st->n_var_syms, var_here);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Output sizes -> offsets. Symbol k emits (eds, seds) bytes:
+//   common   : '{' + its own columns (+ '}' when it ends inside the owned range), "{0}"
+//   variable : 2 + sum(len) + (nalts - 1),  nalts + sum_id_width + R
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void symbol_sizes(const MsaGeom& g, const MsaBufs& b, const MsaStatus* st, uint32_t k,
+                                             unsigned long long& eds, unsigned long long& seds) {
+    eds = 0;
+    seds = 0;
+    if (k < st->k_lo || k >= st->k_hi) return;
+    const uint32_t e = b.sym[k];
+    const uint32_t s = e & kColMask, en = b.sym[k + 1] & kColMask;
+    if (e & kCommonFlag) {
+        const uint32_t endc = min(en, g.own_hi);
+        eds = 1ull + (endc - s) + (en <= g.own_hi ? 1u : 0u);
+        seds = 3;
+    } else {
+        eds = b.sym_edsz[k];
+        seds = (unsigned long long)b.sym_nalts[k] + g.sum_id_width + g.R;
+    }
+}
+
+__global__ void __launch_bounds__(kPartThreads) k_size_count(MsaGeom g, MsaBufs b) {
+    __shared__ unsigned long long s_red[33];
+    const MsaStatus* st = b.status;
+    if (st->abort || st->halo_fail) return;
+    const uint32_t n = st->n_syms, P = gridDim.x;
+    const uint32_t per = (n + P - 1) / P;
+    const uint32_t k_begin = min(n, blockIdx.x * per), k_end = min(n, k_begin + per);
+    unsigned long long se = 0, ss = 0;
+    for (uint32_t k = k_begin + threadIdx.x; k < k_end; k += blockDim.x) {
+        unsigned long long a, c;
+        symbol_sizes(g, b, st, k, a, c);
+        se += a;
+        ss += c;
+    }
+    se = block_sum(se, s_red);
+    ss = block_sum(ss, s_red);
+    if (threadIdx.x == 0) {
+        b.part_sz[2 * blockIdx.x] = se;
+        b.part_sz[2 * blockIdx.x + 1] = ss;
+    }
+}
+
+__global__ void __launch_bounds__(kPartThreads) k_size_scatter(MsaGeom g, MsaBufs b) {
+    __shared__ unsigned long long s_scan[33];
+    MsaStatus* st = b.status;
+    if (st->abort || st->halo_fail) return;
+    const uint32_t n = st->n_syms, P = gridDim.x;
+    const uint32_t per = (n + P - 1) / P;
+    const uint32_t k_begin = min(n, blockIdx.x * per), k_end = min(n, k_begin + per);
+    unsigned long long me = 0, ms = 0;
+    for (uint32_t q = threadIdx.x; q < blockIdx.x; q += blockDim.x) {
+        me += b.part_sz[2 * q];
+        ms += b.part_sz[2 * q + 1];
+    }
+    unsigned long long base_e = block_sum(me, s_scan) + (st->lead_hi - st->lead_lo) + st->lead_close;
+    unsigned long long base_s = block_sum(ms, s_scan);
+    for (uint32_t k0 = k_begin; k0 < k_end; k0 += blockDim.x) {
+        const uint32_t k = k0 + threadIdx.x;
+        unsigned long long a = 0, c = 0;
+        if (k < k_end) symbol_sizes(g, b, st, k, a, c);
+        unsigned long long ta, tc;
+        const unsigned long long ea = block_exclusive_scan(a, s_scan, ta);
+        const unsigned long long ec = block_exclusive_scan(c, s_scan, tc);
+        if (k < k_end) {
+            b.eds_off[k] = base_e + ea;
+            b.seds_off[k] = base_s + ec;
+        }
+        base_e += ta;
+        base_s += tc;
+    }
+    if (blockIdx.x == P - 1 && threadIdx.x == 0) {
+        st->eds_total = base_e;
+        st->seds_total = base_s;
+        st->need_eds = base_e;
+        st->need_seds = base_s;
+        if (base_e > b.cap_eds)
+            st->abort = kAbortEdsCap;
+        else if (base_s > b.cap_seds)
+            st->abort = kAbortSedsCap;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_emit_common: conserved text. A thread owns 16 consecutive window columns, finds the symbol of
+// the first by binary search and walks on from there; bytes of common symbols (and of the leading
+// continuation of a lower shard's symbol) go to eds_off[k] + 1 + (c - start). The same kernel
+// writes each owned common symbol's braces and its "{0}".
+// ---------------------------------------------------------------------------------------------
+__global__ void k_emit_common(MsaGeom g, MsaBufs b) {
+    const MsaStatus* st = b.status;
+    if (st->abort || st->halo_fail) return;
+    const uint32_t n_syms = st->n_syms, k_lo = st->k_lo, k_hi = st->k_hi;
+    const uint32_t lead_lo = st->lead_lo, lead_hi = st->lead_hi;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+
+    // braces and {0}
+    for (uint32_t k = k_lo + tid; k < k_hi; k += nth) {
+        const uint32_t e = b.sym[k];
+        if (!(e & kCommonFlag)) continue;
+        const uint32_t en = b.sym[k + 1] & kColMask;
+        const unsigned long long off = b.eds_off[k];
+        b.eds_out[off] = '{';
+        if (en <= g.own_hi) b.eds_out[off + 1 + (en - (e & kColMask))] = '}';
+        uint8_t* sd = b.seds_out + b.seds_off[k];
+        sd[0] = '{';
+        sd[1] = '0';
+        sd[2] = '}';
+    }
+    if (tid == 0 && st->lead_close) b.eds_out[lead_hi - lead_lo] = '}';
+
+    // text
+    const uint32_t g_lo = g.own_lo >> 4, g_hi = (g.own_hi + 15u) >> 4;
+    for (uint32_t grp = g_lo + tid; grp < g_hi; grp += nth) {
+        const uint32_t c_first = max(grp * 16u, g.own_lo), c_last = min(grp * 16u + 16u, g.own_hi);
+        if (c_first >= c_last) continue;
+        // symbol containing c_first: last k with start <= c_first (may not exist)
+        uint32_t k = sym_lower_bound(b.sym, n_syms, c_first + 1u);  // first start > c_first
+        uint32_t next_start = b.sym[k] & kColMask;                  // sentinel at n_syms
+        bool have = k > 0;
+        if (have) --k;
+        uint32_t cur = have ? b.sym[k] : 0u;
+        unsigned long long off = (have && k >= k_lo && k < k_hi) ? b.eds_off[k] : 0ull;
+        for (uint32_t c = c_first; c < c_last; ++c) {
+            while (c >= next_start) {  // step into the next symbol
+                k = have ? k + 1 : 0;
+                have = true;
+                cur = b.sym[k];
+                next_start = b.sym[k + 1] & kColMask;
+                off = (k >= k_lo && k < k_hi) ? b.eds_off[k] : 0ull;
+            }
+            if (c >= lead_lo && c < lead_hi) {
+                b.eds_out[c - lead_lo] = b.refc[c];
+            } else if (have && (cur & kCommonFlag) && k >= k_lo && k < k_hi) {
+                b.eds_out[off + 1u + (c - (cur & kColMask))] = b.refc[c];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_emit_var: one warp per owned variable symbol writes "{alt0,alt1,...}" and one "{ids}" per
+// alternative (msa_transforms.cpp:297-317). SEDS ids are 1-based rows in ascending order; a row's
+// byte offset is  base(alt) + bytes of lower rows of the same alternative, obtained per 32-row chunk
+// from __match_any_sync plus per-alternative running totals. Within a chunk decimal widths take at
+// most two values, so the in-chunk prefix is two popcounts.
+// Per-warp scratch: altw[Rq], altbase[Rq], running[Rq] (uint32).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_emit_var(MsaGeom g, MsaBufs b, uint32_t Rq, uint32_t use_global) {
+    const MsaStatus* st = b.status;
+    if (st->abort || st->halo_fail) return;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const size_t per_warp = (size_t)Rq * 12u;
+    unsigned char* base = use_global ? b.group_ws + ((size_t)blockIdx.x * wpb + warp) * per_warp
+                                     : EDSB_DYN_SMEM() + (size_t)warp * per_warp;
+    uint32_t* altw = reinterpret_cast<uint32_t*>(base);
+    uint32_t* altbase = altw + Rq;
+    uint32_t* running = altbase + Rq;
+    const RowWalk w{b.vbits, b.refc, b.stash, g.Rp};
+    const uint32_t k_lo = st->k_lo, k_hi = st->k_hi;
+    const uint32_t lt = lanemask_lt();
+
+    for (uint32_t k = k_lo + blockIdx.x * wpb + warp; k < k_hi; k += gridDim.x * wpb) {
+        const uint32_t e = b.sym[k];
+        if (e & kCommonFlag) continue;  // warp-uniform
+        const uint32_t s = e & kColMask, en = b.sym[k + 1] & kColMask;
+        const uint32_t slot0 = first_slot(b, s);
+        const uint32_t nalts = b.sym_nalts[k];
+        uint8_t* eds = b.eds_out + b.eds_off[k];
+        uint8_t* seds = b.seds_out + b.seds_off[k];
+
+        // ---- EDS: '{' alt0 ',' alt1 ... '}' in leader-row order
+        unsigned long long run = 1;
+        uint32_t a_base = 0;
+        for (uint32_t r0 = 0; r0 < g.R; r0 += 32) {
+            const uint32_t r = r0 + lane;
+            const uint32_t mask = b.leadmask[(size_t)slot0 * (g.Rp >> 5) + (r0 >> 5)];
+            const bool isl = (mask >> lane) & 1u;
+            uint32_t n = 0;
+            if (isl) {
+                uint32_t c = s, slot = slot0;
+                while (next_char(w, r, c, en, slot) >= 0) ++n;
+            }
+            const unsigned long long contrib = isl ? (unsigned long long)n + 1ull : 0ull;
+            const unsigned long long inc = warp_inclusive_scan(contrib);
+            if (isl) {
+                const unsigned long long pos = run + inc - contrib;
+                const uint32_t a = a_base + (uint32_t)__popc(mask & lt);
+                eds[pos - 1] = a == 0 ? '{' : ',';
+                uint32_t c = s, slot = slot0;
+                unsigned long long at = pos;
+                int ch;
+                while ((ch = next_char(w, r, c, en, slot)) >= 0) eds[at++] = (uint8_t)ch;
+            }
+            run += __shfl_sync(0xffffffffu, inc, 31);
+            a_base += (uint32_t)__popc(mask);
+        }
+        if (lane == 0) eds[run - 1] = '}';
+
+        // ---- SEDS pass 1: bytes per alternative (each id costs separator + digits)
+        for (uint32_t i = lane; i < nalts; i += 32) {
+            altw[i] = 0;
+            running[i] = 0;
+        }
+        __syncwarp();
+        for (uint32_t r0 = 0; r0 < g.R; r0 += 32) {
+            const uint32_t r = r0 + lane;
+            const bool valid = r < g.R;
+            const uint32_t a = valid ? load_alt(g, b.altid, (size_t)slot0 * g.Rp + r) : kEmptySlot;
+            const uint32_t wd = decimal_width(r + 1u) + 1u;
+            const uint32_t wfirst = __shfl_sync(0xffffffffu, wd, 0);
+            const uint32_t mA = __ballot_sync(0xffffffffu, wd == wfirst);
+            const uint32_t peers = __match_any_sync(0xffffffffu, a);
+            if (valid && lane == (uint32_t)__ffs((int)peers) - 1u)
+                altw[a] += (uint32_t)__popc(peers & mA) * wfirst + (uint32_t)__popc(peers & ~mA) * (wfirst + 1u);
+            __syncwarp();
+        }
+        // exclusive scan over alternatives; every finished alternative adds its '}'
+        uint32_t carry = 0;
+        for (uint32_t i0 = 0; i0 < nalts; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            const uint32_t v = i < nalts ? altw[i] + 1u : 0u;
+            const uint32_t inc = warp_inclusive_scan(v);
+            if (i < nalts) altbase[i] = carry + inc - v;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        __syncwarp();
+        // ---- SEDS pass 2: place every id
+        for (uint32_t r0 = 0; r0 < g.R; r0 += 32) {
+            const uint32_t r = r0 + lane;
+            const bool valid = r < g.R;
+            const uint32_t a = valid ? load_alt(g, b.altid, (size_t)slot0 * g.Rp + r) : kEmptySlot;
+            const uint32_t wd = decimal_width(r + 1u) + 1u;
+            const uint32_t wfirst = __shfl_sync(0xffffffffu, wd, 0);
+            const uint32_t mA = __ballot_sync(0xffffffffu, wd == wfirst);
+            const uint32_t peers = __match_any_sync(0xffffffffu, a);
+            const uint32_t below = peers & lt;
+            const uint32_t pre = (uint32_t)__popc(below & mA) * wfirst + (uint32_t)__popc(below & ~mA) * (wfirst + 1u);
+            uint32_t done = 0;
+            if (valid) {
+                done = running[a] + pre;
+                uint8_t* dst = seds + altbase[a] + done;
+                dst[0] = done == 0 ? '{' : ',';
+                write_decimal(dst + 1, r + 1u, wd - 1u);
+                if (done + wd == altw[a]) dst[wd] = '}';
+            }
+            __syncwarp();
+            if (valid && lane == 31u - (uint32_t)__clz((int)peers)) running[a] = done + wd;
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_synth: the synthetic alignment of BASELINE.json configs 2 / 4, written as FASTA text straight
+// into HBM. Keyed hashing (splitmix64 of seed, row, column) makes any column window of the same
+// alignment reproducible on any rank.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+
+__device__ __forceinline__ uint8_t synth_residue(uint64_t seed, uint32_t r, uint64_t col, uint32_t variable_ppm) {
+    const uint64_t hc = mix64(seed ^ mix64(col));
+    const uint8_t base0 = (uint8_t)"ACGT"[hc & 3u];
+    if (r == 0) return base0;
+    const bool variable = ((hc >> 8) % 1000000ull) < variable_ppm;
+    if (!variable) return base0;
+    const uint64_t hr = mix64(hc ^ mix64(((uint64_t)r << 1) | 1ull));
+    const uint32_t roll = (uint32_t)((hr >> 8) % 100ull);
+    if (roll < 30) return (uint8_t)"ACGT"[hr & 3u];  // substitution (may equal row 0)
+    if (roll < 40) return (uint8_t)'-';
+    return base0;
+}
+
+__global__ void k_synth(uint8_t* text, const uint64_t* row_off, uint32_t R, uint32_t lw, uint64_t u_begin,
+                        uint64_t row_bytes, uint64_t seed, uint32_t variable_ppm) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint32_t r = blockIdx.y; r < R; r += gridDim.y) {
+        uint8_t* row = text + row_off[r];
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < row_bytes; i += stride) {
+            const uint64_t u = u_begin + i;
+            const uint64_t line = u / (lw + 1u);
+            const uint32_t rem = (uint32_t)(u - line * (lw + 1u));
+            row[i] = rem == lw ? (uint8_t)'\n' : synth_residue(seed, r, line * lw + rem, variable_ppm);
+        }
+    }
+}
+
+// =============================================================================================
+// Host side
+// =============================================================================================
+
+static uint32_t pow2_ceil(uint32_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+static uint64_t sum_decimal_widths(uint32_t R) {
+    uint64_t total = 0, lo = 1, width = 1;
+    while (lo <= R) {
+        const uint64_t hi = std::min<uint64_t>(R, lo * 10 - 1);
+        total += (hi - lo + 1) * width;
+        lo *= 10;
+        ++width;
+    }
+    return total;
+}
+
+MsaPipeline::MsaPipeline(eds_ctx* ctx) : ctx_(ctx) {
+    EDSB_CUDA(cudaMallocHost(&h_status_, sizeof(MsaStatus)));
+    d_status_.reserve(sizeof(MsaStatus));
+}
+
+MsaPipeline::~MsaPipeline() {
+    DevBuf* all[] = {&d_rows_, &d_mism_, &d_vbits_, &d_tbits_, &d_rank_, &d_refc_, &d_part_, &d_varcol_, &d_runs_,
+                     &d_sym_, &d_stash_, &d_altid_, &d_leadmask_, &d_symmeta_, &d_eds_, &d_seds_, &d_ws_, &d_status_};
+    for (DevBuf* d : all) d->release();
+    if (h_status_) cudaFreeHost(h_status_);
+}
+
+uint32_t MsaPipeline::partitions() const {
+    uint32_t p = ctx_->partitions ? ctx_->partitions : 592u;  // 4 blocks per SM on 148 SMs
+    return std::max(1u, std::min(p, 4096u));
+}
+
+void MsaPipeline::prepare(const eds_msa_view& v, uint32_t l, int leds) {
+    if (!v.text || !v.row_start) throw std::invalid_argument("eds_msa_view: null text or row_start");
+    if (reinterpret_cast<uintptr_t>(v.text) & 15u) throw std::invalid_argument("eds_msa_view: text must be 16-byte aligned");
+    if (v.n_rows < 2) throw BadMsa("alignment needs at least 2 rows (undefined in the reference, msa_transforms.cpp:53-57)");
+    if (v.line_width == 0 || v.total_cols == 0 || v.col_count == 0) throw BadMsa("empty alignment");
+    if (v.col_begin + v.col_count > v.total_cols) throw std::invalid_argument("eds_msa_view: window exceeds the alignment");
+    if (v.col_count >= 0x7fffffffull - 64) throw std::invalid_argument("eds_msa_view: col_count must be < 2^31 - 64");
+    const uint64_t win_end = v.col_begin + v.col_count;
+    if (v.own_begin < v.col_begin || v.own_end > win_end || v.own_begin > v.own_end)
+        throw std::invalid_argument("eds_msa_view: owned range outside the window");
+    if (v.own_begin < v.own_end) {
+        if (v.col_begin > 0 && v.own_begin == v.col_begin)
+            throw std::invalid_argument("eds_msa_view: a shard that does not start the alignment needs a left halo");
+        if (win_end < v.total_cols && v.own_end == win_end)
+            throw std::invalid_argument("eds_msa_view: a shard that does not end the alignment needs a right halo");
+    }
+    MsaGeom& g = geom_;
+    memset(&g, 0, sizeof(g));
+    g.text = v.text;
+    g.n_vec = (v.text_bytes + 15) / 16;
+    g.total_cols = v.total_cols;
+    g.col_begin = v.col_begin;
+    g.lw = v.line_width;
+    g.u_begin = v.col_begin + v.col_begin / v.line_width;
+    const uint64_t last = win_end - 1;
+    g.row_bytes = last + last / v.line_width - g.u_begin + 1;
+    g.R = v.n_rows;
+    g.Rp = (v.n_rows + 31u) & ~31u;
+    g.ncols = (uint32_t)v.col_count;
+    g.own_lo = (uint32_t)(v.own_begin - v.col_begin);
+    g.own_hi = (uint32_t)(v.own_end - v.col_begin);
+    g.a0 = (uint32_t)(v.row_start[0] & 15u);
+    const uint64_t chunks = (g.a0 + g.row_bytes + 15) / 16;
+    if (chunks >= 0xffffffffull) throw std::invalid_argument("eds_msa_view: window too large");
+    g.n_chunks = (uint32_t)chunks;
+    g.n_words = (g.ncols + 31u) / 32u;
+    g.l = l;
+    g.leds = leds ? 1u : 0u;
+    g.alt32 = v.n_rows > 65535u ? 1u : 0u;
+    g.sum_id_width = sum_decimal_widths(v.n_rows);
+    g.hash_mask = ctx_->hash_mask;
+    for (uint32_t r = 0; r < v.n_rows; ++r)
+        if (v.row_start[r] + g.row_bytes > v.text_bytes) throw BadMsa("a row runs past the end of the buffer (rows of unequal length?)");
+
+    cudaStream_t s = ctx_->stream;
+    d_rows_.reserve((size_t)v.n_rows * 8);
+    EDSB_CUDA(cudaMemcpyAsync(d_rows_.p, v.row_start, (size_t)v.n_rows * 8, cudaMemcpyHostToDevice, s));
+    g.row_off = d_rows_.as<uint64_t>();
+
+    const uint32_t P = partitions();
+    d_mism_.reserve(((size_t)g.n_chunks / 2 + 4) * 4);
+    d_vbits_.reserve((size_t)(g.n_words + 1) * 4);
+    d_tbits_.reserve((size_t)(g.n_words + 1) * 4);
+    d_rank_.reserve((size_t)(g.n_words + 1) * 4);
+    d_refc_.reserve((size_t)g.n_words * 32 + 32);
+    d_part_.reserve((size_t)P * (8 + 4 + 16));
+}
+
+void MsaPipeline::bind(MsaBufs& b) {
+    const uint32_t P = partitions();
+    const MsaGeom& g = geom_;
+    memset(&b, 0, sizeof(b));
+    b.mism = d_mism_.as<uint32_t>();
+    b.vbits = d_vbits_.as<uint32_t>();
+    b.tbits = d_tbits_.as<uint32_t>();
+    b.rankdir = d_rank_.as<uint32_t>();
+    b.refc = d_refc_.as<uint8_t>();
+    unsigned char* part = d_part_.as<unsigned char>();
+    b.part_sz = reinterpret_cast<unsigned long long*>(part);
+    b.part_cnt = reinterpret_cast<uint2*>(part + (size_t)P * 16);
+    b.part_sym = reinterpret_cast<uint32_t*>(part + (size_t)P * 24);
+
+    d_varcol_.reserve((size_t)cap_var_ * 4);
+    d_runs_.reserve((size_t)(cap_runs_ + 2) * 4);
+    d_sym_.reserve((size_t)(cap_runs_ + 2) * 4);
+    d_stash_.reserve((size_t)cap_var_ * g.Rp);
+    d_altid_.reserve((size_t)cap_var_ * g.Rp * (g.alt32 ? 4 : 2));
+    d_leadmask_.reserve((size_t)cap_var_ * (g.Rp / 32) * 4);
+    d_symmeta_.reserve((size_t)(cap_runs_ + 2) * (4 + 8 + 8 + 8));
+    d_eds_.reserve(cap_eds_);
+    d_seds_.reserve(cap_seds_);
+    b.varcol = d_varcol_.as<uint32_t>();
+    b.runs = d_runs_.as<uint32_t>();
+    b.sym = d_sym_.as<uint32_t>();
+    b.stash = d_stash_.as<uint8_t>();
+    b.altid = d_altid_.p;
+    b.leadmask = d_leadmask_.as<uint32_t>();
+    unsigned char* meta = d_symmeta_.as<unsigned char>();
+    const size_t n = (size_t)cap_runs_ + 2;
+    b.sym_edsz = reinterpret_cast<unsigned long long*>(meta);
+    b.eds_off = reinterpret_cast<unsigned long long*>(meta + n * 8);
+    b.seds_off = reinterpret_cast<unsigned long long*>(meta + n * 16);
+    b.sym_nalts = reinterpret_cast<uint32_t*>(meta + n * 24);
+    b.eds_out = d_eds_.as<uint8_t>();
+    b.seds_out = d_seds_.as<uint8_t>();
+    b.group_ws = d_ws_.as<uint8_t>();
+    b.status = d_status_.as<MsaStatus>();
+    b.cap_var = cap_var_;
+    b.cap_runs = cap_runs_;
+    b.cap_eds = cap_eds_;
+    b.cap_seds = cap_seds_;
+}
+
+void MsaPipeline::launch_scan(const MsaBufs& b) {
+    const MsaGeom& g = geom_;
+    cudaStream_t s = ctx_->stream;
+    const uint32_t per_sm = ctx_->scan_blocks_per_sm ? ctx_->scan_blocks_per_sm : 4u;
+    const uint32_t tiles = (g.n_chunks + 31) / 32;
+    const uint32_t blocks = std::max(1u, std::min((tiles + 7) / 8, (uint32_t)ctx_->sm_count * per_sm));
+    ctx_->clock.begin("k_scan");
+    EDSB_LAUNCH(k_scan, blocks, kScanThreads, 0, s, g, reinterpret_cast<uint16_t*>(b.mism), b.status);
+    ctx_->clock.end();
+    ctx_->clock.begin("k_colbits");
+    EDSB_LAUNCH(k_colbits, partitions(), kPartThreads, 0, s, g, b.mism, b.vbits, b.tbits, b.refc, b.part_cnt);
+    ctx_->clock.end();
+}
+
+void MsaPipeline::run_once(MsaBufs& b) {
+    const MsaGeom& g = geom_;
+    cudaStream_t s = ctx_->stream;
+    const uint32_t P = partitions();
+    const uint32_t sms = (uint32_t)ctx_->sm_count;
+    EDSB_CUDA(cudaMemsetAsync(b.status, 0, sizeof(MsaStatus), s));
+    launch_scan(b);
+
+    ctx_->clock.begin("k_compact");
+    EDSB_LAUNCH(k_compact, P, kPartThreads, 0, s, g, b);
+    ctx_->clock.end();
+
+    const uint32_t stash_threads = g.R <= 128 ? 128u : 256u;
+    ctx_->clock.begin("k_stash");
+    EDSB_LAUNCH(k_stash, sms * 16u, stash_threads, 0, s, g, b);
+    ctx_->clock.end();
+
+    ctx_->clock.begin("k_sym_count");
+    EDSB_LAUNCH(k_sym_count, P, kPartThreads, 0, s, g, b);
+    ctx_->clock.end();
+    ctx_->clock.begin("k_sym_scatter");
+    EDSB_LAUNCH(k_sym_scatter, P, kPartThreads, 0, s, g, b);
+    ctx_->clock.end();
+    ctx_->clock.begin("k_finalize");
+    EDSB_LAUNCH(k_finalize, 1, 32, 0, s, g, b);
+    ctx_->clock.end();
+
+    // per-warp scratch: shared memory while it fits, else a global workspace
+    const uint32_t Rq = std::max(32u, pow2_ceil(g.R));
+    const uint32_t T = 2u * Rq;
+    const size_t group_per_warp = (size_t)Rq * 16 + (size_t)T * 4;
+    const size_t emit_per_warp = (size_t)Rq * 12;
+    const size_t smem_budget = std::min<size_t>(ctx_->smem_optin, 200 * 1024);
+    uint32_t gw = 8;  // warps per block
+    while (gw > 1 && gw * group_per_warp > smem_budget / 2) gw >>= 1;
+    const bool group_global = gw * group_per_warp > smem_budget;
+    uint32_t ew = 8;
+    while (ew > 1 && ew * emit_per_warp > smem_budget / 2) ew >>= 1;
+    const bool emit_global = ew * emit_per_warp > smem_budget;
+    const uint32_t group_blocks = sms * (group_global ? 2u : std::max(1u, 32u / gw));
+    const uint32_t emit_blocks = sms * (emit_global ? 2u : std::max(1u, 32u / ew));
+    if (group_global || emit_global) {
+        const size_t need = std::max(group_global ? (size_t)group_blocks * gw * group_per_warp : 0,
+                                     emit_global ? (size_t)emit_blocks * ew * emit_per_warp : 0);
+        d_ws_.reserve(need);
+        b.group_ws = d_ws_.as<uint8_t>();
+    }
+    const size_t group_smem = group_global ? 0 : gw * group_per_warp;
+    const size_t emit_smem = emit_global ? 0 : ew * emit_per_warp;
+#ifndef EDSB_EMU
+    if (group_smem > 48 * 1024)
+        EDSB_CUDA(cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)group_smem));
+    if (emit_smem > 48 * 1024)
+        EDSB_CUDA(cudaFuncSetAttribute(k_emit_var, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
+#endif
+    ctx_->clock.begin("k_group");
+    EDSB_LAUNCH(k_group, group_blocks, gw * 32u, group_smem, s, g, b, Rq, T, group_global ? 1u : 0u);
+    ctx_->clock.end();
+
+    ctx_->clock.begin("k_size_count");
+    EDSB_LAUNCH(k_size_count, P, kPartThreads, 0, s, g, b);
+    ctx_->clock.end();
+    ctx_->clock.begin("k_size_scatter");
+    EDSB_LAUNCH(k_size_scatter, P, kPartThreads, 0, s, g, b);
+    ctx_->clock.end();
+
+    ctx_->clock.begin("k_emit_common");
+    EDSB_LAUNCH(k_emit_common, sms * 8u, 256, 0, s, g, b);
+    ctx_->clock.end();
+    ctx_->clock.begin("k_emit_var");
+    EDSB_LAUNCH(k_emit_var, emit_blocks, ew * 32u, emit_smem, s, g, b, Rq, emit_global ? 1u : 0u);
+    ctx_->clock.end();
+
+    EDSB_CUDA(cudaMemcpyAsync(h_status_, b.status, sizeof(MsaStatus), cudaMemcpyDeviceToHost, s));
+    EDSB_CUDA(cudaStreamSynchronize(s));
+    EDSB_CUDA(cudaGetLastError());
+}
+
+void MsaPipeline::transform(const eds_msa_view& view, uint32_t l, int leds, eds_buffer* eds_out, eds_buffer* seds_out,
+                            eds_msa_stats* stats) {
+    ctx_->clock.reset();
+    prepare(view, l, leds);
+    const MsaGeom& g = geom_;
+    // first guesses; a stage that runs out of room reports what it needs and the pipeline is re-run
+    cap_var_ = std::max<uint32_t>(cap_var_, std::max<uint32_t>(1024u, g.ncols / 64u));
+    cap_runs_ = std::max<uint32_t>(cap_runs_, 2u * cap_var_ + 2u);
+    cap_eds_ = std::max<uint64_t>(cap_eds_, (uint64_t)g.ncols + g.ncols / 4 + 4096);
+    cap_seds_ = std::max<uint64_t>(cap_seds_, 1u << 20);
+    uint32_t retries = 0;
+    MsaStatus st;
+    for (;;) {
+        MsaBufs b;
+        bind(b);
+        run_once(b);
+        st = *h_status_;
+        if (st.bad_msa & kBadNewlineLayout)
+            throw BadMsa("line breaks are not at the same positions in every row (unequal row lengths or wrap widths)");
+        if (st.bad_msa & kBadResidueByte) throw BadMsa("a row is shorter than the first row (line break inside a residue column)");
+        if (st.abort == kAbortNone) break;
+        if (++retries > 8) throw std::runtime_error("edsparser_b200: buffer sizing did not converge");
+        if (st.abort == kAbortVarCap || st.abort == kAbortRunsCap) {
+            cap_var_ = std::max<uint32_t>(cap_var_, (uint32_t)std::min<uint64_t>(st.need_var + st.need_var / 16 + 64, 0x7fffffffu));
+            cap_runs_ = std::max<uint32_t>(cap_runs_, (uint32_t)std::min<uint64_t>(st.need_runs + st.need_runs / 16 + 64, 0xfffffff0u));
+        } else {
+            cap_eds_ = std::max<uint64_t>(cap_eds_, st.need_eds + st.need_eds / 16 + 4096);
+            cap_seds_ = std::max<uint64_t>(cap_seds_, st.need_seds + st.need_seds / 16 + 4096);
+        }
+    }
+    if (st.halo_fail) throw HaloError("a symbol of the owned range does not resolve inside the window; widen the halo");
+    ctx_->clock.resolve();
+    if (eds_out) {
+        eds_out->data = d_eds_.as<uint8_t>();
+        eds_out->bytes = st.eds_total;
+    }
+    if (seds_out) {
+        seds_out->data = d_seds_.as<uint8_t>();
+        seds_out->bytes = st.seds_total;
+    }
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->n_variable_cols = st.n_var;
+        stats->n_runs = st.n_runs;
+        stats->n_symbols = st.k_hi - st.k_lo;
+        stats->n_variable = st.n_var_syms;
+        stats->n_alternatives = st.n_alts;
+        stats->first_open_col = st.first_open_col;
+        stats->eds_bytes = st.eds_total;
+        stats->seds_bytes = st.seds_total;
+        stats->eds_lead_bytes = (uint64_t)(st.lead_hi - st.lead_lo) + st.lead_close;
+        stats->tail_open_common = st.tail_open;
+        stats->gpu_launches = ctx_->clock.launches;
+        stats->retries = retries;
+    }
+}
+
+void MsaPipeline::conserved_bits(const eds_msa_view& view, uint8_t* out_bits, uint64_t out_bytes) {
+    ctx_->clock.reset();
+    prepare(view, 0, 0);
+    const MsaGeom& g = geom_;
+    const uint64_t need = ((uint64_t)g.ncols + 7) / 8;
+    if (out_bytes < need) throw std::invalid_argument("eds_msa_conserved_bits: output too small");
+    MsaBufs b;
+    bind(b);
+    cudaStream_t s = ctx_->stream;
+    EDSB_CUDA(cudaMemsetAsync(b.status, 0, sizeof(MsaStatus), s));
+    launch_scan(b);
+    std::vector<uint32_t> words(g.n_words);
+    EDSB_CUDA(cudaMemcpyAsync(words.data(), b.vbits, (size_t)g.n_words * 4, cudaMemcpyDeviceToHost, s));
+    EDSB_CUDA(cudaMemcpyAsync(h_status_, b.status, sizeof(MsaStatus), cudaMemcpyDeviceToHost, s));
+    EDSB_CUDA(cudaStreamSynchronize(s));
+    EDSB_CUDA(cudaGetLastError());
+    if (h_status_->bad_msa) throw BadMsa("line breaks are not at the same positions in every row");
+    for (uint64_t i = 0; i < need; ++i) {
+        const uint32_t w = words[i / 4];
+        uint8_t v = (uint8_t)~(w >> ((i & 3u) * 8u));
+        const uint64_t first = i * 8;
+        if (first + 8 > g.ncols) v &= (uint8_t)((1u << (g.ncols - first)) - 1u);
+        out_bits[i] = v;
+    }
+}
+
+// Synthetic alignment text for a column window, laid out like a FASTA file of that window:
+// ">seq<r+1>\n" + row segment + "\n" per row (so rows start at arbitrary byte offsets).
+void msa_synth(eds_ctx* ctx, uint32_t n_rows, uint64_t total_cols, uint32_t lw, uint64_t col_begin, uint64_t col_count,
+               uint64_t seed, uint32_t variable_ppm, eds_msa_view* view) {
+    if (n_rows < 2 || lw == 0 || col_count == 0 || col_begin + col_count > total_cols)
+        throw std::invalid_argument("eds_msa_synth_device: bad shape");
+    const uint64_t u_begin = col_begin + col_begin / lw;
+    const uint64_t last = col_begin + col_count - 1;
+    const uint64_t row_bytes = last + last / lw - u_begin + 1;
+    std::vector<uint64_t>& rows = ctx->synth_rows;
+    rows.assign(n_rows, 0);
+    std::string headers;
+    uint64_t at = 0;
+    std::vector<uint64_t> header_at(n_rows);
+    for (uint32_t r = 0; r < n_rows; ++r) {
+        const std::string h = ">seq" + std::to_string(r + 1) + "\n";
+        header_at[r] = at;
+        at += h.size();
+        rows[r] = at;
+        at += row_bytes + 1;
+        headers += h;
+    }
+    const uint64_t total = at;
+    ctx->synth_text.reserve(total + 64);
+    uint8_t* text = ctx->synth_text.as<uint8_t>();
+    cudaStream_t s = ctx->stream;
+    // headers and the line break after each row: small strided copies from one host staging string
+    {
+        size_t hpos = 0;
+        static const uint8_t nl = '\n';
+        for (uint32_t r = 0; r < n_rows; ++r) {
+            const size_t hl = (size_t)(rows[r] - header_at[r]);
+            EDSB_CUDA(cudaMemcpyAsync(text + header_at[r], headers.data() + hpos, hl, cudaMemcpyHostToDevice, s));
+            EDSB_CUDA(cudaMemcpyAsync(text + rows[r] + row_bytes, &nl, 1, cudaMemcpyHostToDevice, s));
+            hpos += hl;
+        }
+        EDSB_CUDA(cudaStreamSynchronize(s));  // `headers` goes out of scope
+    }
+    DevBuf d_rows;
+    d_rows.reserve((size_t)n_rows * 8);
+    EDSB_CUDA(cudaMemcpyAsync(d_rows.p, rows.data(), (size_t)n_rows * 8, cudaMemcpyHostToDevice, s));
+    const uint32_t bx = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((row_bytes + 1023) / 1024, 4096));
+    EDSB_LAUNCH(k_synth, dim3(bx, std::min(n_rows, 65535u), 1), dim3(256, 1, 1), 0, s, text, d_rows.as<uint64_t>(), n_rows, lw, u_begin,
+                row_bytes, seed, variable_ppm);
+    EDSB_CUDA(cudaStreamSynchronize(s));
+    EDSB_CUDA(cudaGetLastError());
+    d_rows.release();
+    memset(view, 0, sizeof(*view));
+    view->text = text;
+    view->text_bytes = total;
+    view->row_start = rows.data();
+    view->n_rows = n_rows;
+    view->line_width = lw;
+    view->total_cols = total_cols;
+    view->col_begin = col_begin;
+    view->col_count = col_count;
+    view->own_begin = col_begin;
+    view->own_end = col_begin + col_count;
+}
+
+}  // namespace edsb

@@ -1,0 +1,48 @@
+// Host-side launcher of the MSA -> EDS / l-EDS kernels (msa.cu).
+#pragma once
+#include <stdexcept>
+
+#include "ctx.h"
+#include "msa_kernels.cuh"
+
+namespace edsb {
+
+struct BadMsa : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+struct HaloError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+class MsaPipeline {
+   public:
+    explicit MsaPipeline(eds_ctx* ctx);
+    ~MsaPipeline();
+    MsaPipeline(const MsaPipeline&) = delete;
+    MsaPipeline& operator=(const MsaPipeline&) = delete;
+
+    // Outputs point into buffers owned by this object (valid until the next call).
+    void transform(const eds_msa_view& view, uint32_t l, int leds, eds_buffer* eds_out, eds_buffer* seds_out,
+                   eds_msa_stats* stats);
+    void conserved_bits(const eds_msa_view& view, uint8_t* out_bits, uint64_t out_bytes);
+
+   private:
+    uint32_t partitions() const;
+    void prepare(const eds_msa_view& view, uint32_t l, int leds);
+    void bind(MsaBufs& b);
+    void launch_scan(const MsaBufs& b);
+    void run_once(MsaBufs& b);
+
+    eds_ctx* ctx_;
+    MsaGeom geom_;
+    MsaStatus* h_status_ = nullptr;  // pinned
+    DevBuf d_rows_, d_mism_, d_vbits_, d_tbits_, d_rank_, d_refc_, d_part_, d_varcol_, d_runs_, d_sym_, d_stash_,
+        d_altid_, d_leadmask_, d_symmeta_, d_eds_, d_seds_, d_ws_, d_status_;
+    uint32_t cap_var_ = 0, cap_runs_ = 0;
+    uint64_t cap_eds_ = 0, cap_seds_ = 0;
+};
+
+void msa_synth(eds_ctx* ctx, uint32_t n_rows, uint64_t total_cols, uint32_t lw, uint64_t col_begin, uint64_t col_count,
+               uint64_t seed, uint32_t variable_ppm, eds_msa_view* view);
+
+}  // namespace edsb

@@ -1,0 +1,165 @@
+/*
+ * edsparser_b200 — C ABI of the B200-native EDSParser hot path (libedsparser_b200.so).
+ *
+ * Plain C, POD structs, status codes, no exceptions and no torch types across the boundary.
+ * The reference (draessld/EDSParser) has no FFI of its own: its boundary for this path is the
+ * public C++ API in src/cpp/lib/transforms/ + src/cpp/lib/formats/. Each entry point below names
+ * the reference interface it stands behind; edsparser_b200/host/ holds the C++17 wrappers that
+ * keep those signatures and call this ABI.
+ *
+ * There is NO CPU fallback: every transform entry point needs a CUDA device and returns
+ * EDS_ERR_CUDA when none is usable.
+ */
+#ifndef EDSPARSER_B200_H
+#define EDSPARSER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status codes map 1:1 onto the exception classes the reference throws on this path
+ * (SURVEY.md §8b): the C++ wrappers rethrow them with eds_last_error() as what(). */
+typedef enum eds_status {
+    EDS_OK = 0,
+    EDS_ERR_INVALID_ARGUMENT = 1, /* std::invalid_argument (eds_transforms.cpp:322-324,388-390,395-397) */
+    EDS_ERR_RUNTIME = 2,          /* std::runtime_error   (eds.cpp:80-82,123-131,278-349,1513-1519)   */
+    EDS_ERR_OUT_OF_RANGE = 3,     /* std::out_of_range    (std::stoi overflow in eds.cpp:302,322)      */
+    EDS_ERR_CUDA = 4,             /* CUDA runtime failure or no device (no CPU fallback exists)        */
+    EDS_ERR_BAD_MSA = 5,          /* input outside the reference's well-defined MSA domain (C.2)       */
+    EDS_ERR_BUDGET = 6,           /* output larger than the caller's max_output_bytes                  */
+    EDS_ERR_HALO = 7              /* a symbol cannot be resolved inside the shard's window: widen it   */
+} eds_status;
+
+typedef struct eds_ctx eds_ctx; /* one per (device, stream); owns scratch + output buffers; not thread-safe */
+
+/* Thread-local message of the last failing call on this thread. */
+const char* eds_last_error(void);
+/* "edsparser_b200 <version> sm_100a" */
+const char* eds_version(void);
+
+/* stream: a cudaStream_t to launch on (e.g. the caller's current stream), or NULL = the library
+ * creates its own non-blocking stream. */
+eds_status eds_ctx_create(int device, void* stream, eds_ctx** out);
+void eds_ctx_destroy(eds_ctx* ctx);
+eds_status eds_ctx_synchronize(eds_ctx* ctx);
+
+/* Launch-shape knobs (tests sweep them; results never depend on them).
+ * partitions: blocks used by the scan/compaction kernels (0 = default). */
+eds_status eds_ctx_set_tuning(eds_ctx* ctx, uint32_t partitions, uint32_t scan_blocks_per_sm);
+
+/* Per-kernel device times of the LAST transform on this ctx, measured with CUDA events on the
+ * ctx's stream when profiling is on (adds one event pair per launch; leave off for throughput runs).
+ * eds_ctx_kernel_times fills up to cap entries and returns the number of kernels launched. */
+eds_status eds_ctx_set_profiling(eds_ctx* ctx, int on);
+uint32_t eds_ctx_kernel_times(eds_ctx* ctx, const char** names, float* ms, uint32_t cap);
+
+/* ------------------------------------------------------------------------------------------
+ * MSA loader (host side): locate the rows of a gapped-FASTA alignment.
+ * Replaces the bookkeeping half of parse_msa_and_build_variant_bv (msa_transforms.cpp:36-90):
+ * MSAMetadata{start_positions, n_sequences, seq_length, line_width} (msa_transforms.cpp:18-24).
+ * Cost is O(first row + rows x header length); the byte comparison itself runs on the GPU.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct eds_msa_index {
+    uint64_t* row_start; /* malloc'd, n_rows entries: offset of the first residue of each row */
+    uint32_t n_rows;     /* R */
+    uint64_t n_cols;     /* C (residues per row, gaps included) */
+    uint32_t line_width; /* residues per text line */
+    uint64_t row_bytes;  /* bytes from a row's first to last residue, inner newlines included */
+} eds_msa_index;
+
+eds_status eds_msa_index_host(const uint8_t* text, uint64_t text_bytes, eds_msa_index* out);
+void eds_msa_index_free(eds_msa_index* idx);
+
+/* A column window of an alignment held in ONE device buffer. Residue (r, c),
+ * col_begin <= c < col_begin + col_count, lives at
+ *     text[row_start[r] + (c + c / line_width) - (col_begin + col_begin / line_width)]
+ * i.e. each row segment is a verbatim slice of the FASTA text, inner '\n' included, rows may start
+ * at any byte offset. `text` itself must be 16-byte aligned and readable up to the next 16-byte
+ * boundary past text_bytes (any cudaMalloc'd buffer is).
+ * A whole file is the window col_begin = 0, col_count = total_cols, own = [0, total_cols).
+ * A shard owns the symbols that START in [own_begin, own_end) plus the conserved text of its own
+ * columns, and holds a halo on both sides: >= 1 column (EDS) or >= l + 1 columns (l-EDS) on a side
+ * that is not an end of the alignment, and far enough to the right to contain the end of its last
+ * variable symbol (else EDS_ERR_HALO). Concatenating the shards' outputs in column order gives the
+ * whole-alignment output byte for byte. col_count < 2^31 - 64. */
+typedef struct eds_msa_view {
+    const uint8_t* text;
+    uint64_t text_bytes;
+    const uint64_t* row_start; /* HOST array, n_rows entries */
+    uint32_t n_rows;
+    uint32_t line_width;
+    uint64_t total_cols;
+    uint64_t col_begin, col_count;
+    uint64_t own_begin, own_end;
+} eds_msa_view;
+
+typedef struct eds_buffer {
+    uint8_t* data; /* device memory owned by the ctx (valid until the next transform on it), or malloc'd host memory */
+    uint64_t bytes;
+} eds_buffer;
+
+typedef struct eds_msa_stats {
+    uint64_t n_variable_cols; /* non-conserved columns in the window                              */
+    uint64_t n_runs;          /* maximal runs of conserved / variable columns in the window       */
+    uint64_t n_symbols;       /* symbols that start in the owned range                            */
+    uint64_t n_variable;      /* ... of which variable (degenerate or single-haplotype)           */
+    uint64_t n_alternatives;  /* strings in those variable symbols                                */
+    uint64_t first_open_col;  /* global column of the first owned symbol (UINT64_MAX if none)     */
+    uint64_t eds_bytes, seds_bytes; /* bytes this shard emits                                     */
+    uint64_t eds_lead_bytes;  /* of which continue a conserved symbol opened by a lower shard      */
+    uint32_t tail_open_common; /* 1: the last owned symbol is conserved and continues in the next shard */
+    uint32_t gpu_launches;    /* kernels launched by this call (retries included)                 */
+    uint32_t retries;         /* pipeline re-runs after a scratch/output buffer had to grow       */
+    uint32_t reserved;
+} eds_msa_stats;
+
+/* Whole pipeline on one device, input already in device memory.
+ * leds = 0: parse_msa_to_eds_streaming  (msa_transforms.cpp:334-345)
+ * leds = 1: parse_msa_to_leds_streaming (msa_transforms.cpp:351-365) with context_length = l
+ * Outputs are byte-identical to the reference's pair<string,string> (for a shard: to this shard's
+ * slice of it); they stay in device memory owned by the ctx. The call returns after the stream
+ * has been synchronised (the output sizes are needed on the host). */
+eds_status eds_msa_transform_device(eds_ctx* ctx, const eds_msa_view* view, uint32_t l, int leds,
+                                    eds_buffer* eds_out, eds_buffer* seds_out, eds_msa_stats* stats);
+
+/* Same, from the bytes of a .msa file in host memory (pinned memory copies fastest) to malloc'd
+ * host strings: index on the host, H2D, transform, D2H. This is what the C++ wrappers and the CLI
+ * call. Free the outputs with eds_buffer_free_host. */
+eds_status eds_msa_transform_host(eds_ctx* ctx, const uint8_t* file, uint64_t file_bytes, uint32_t l, int leds,
+                                  eds_buffer* eds_out, eds_buffer* seds_out, eds_msa_stats* stats);
+
+/* Conserved-column bit vector B of msa_transforms.cpp:36-90 for the window: out_bits[c / 8] bit
+ * (c % 8) = 1 iff window column c is conserved; out_bytes >= ceil(col_count / 8). For tests. */
+eds_status eds_msa_conserved_bits(eds_ctx* ctx, const eds_msa_view* view, uint8_t* out_bits, uint64_t out_bytes);
+
+/* Synthetic alignment of BASELINE.json configs 2 and 4, generated directly in
+ * device memory as FASTA text for the column window [col_begin, col_begin + col_count):
+ * headers ">seq<r+1>", wrap `line_width`, counter-based RNG keyed on (seed, row, column) so any
+ * window of the same (seed, R, C) alignment agrees with the whole. The buffer is owned by the ctx
+ * until eds_msa_synth_free / ctx destruction; `view` is filled in (own range = the whole window;
+ * callers narrow it), view->row_start points at ctx-owned host memory.
+ * variable_ppm: probability (per million) that a column is variable. */
+eds_status eds_msa_synth_device(eds_ctx* ctx, uint32_t n_rows, uint64_t total_cols, uint32_t line_width,
+                                uint64_t col_begin, uint64_t col_count, uint64_t seed, uint32_t variable_ppm,
+                                eds_msa_view* view);
+void eds_msa_synth_free(eds_ctx* ctx);
+
+void eds_buffer_free_host(eds_buffer* buf);
+
+/* ------------------------------------------------------------------------------------------
+ * l-EDS merge: eds_to_leds_linear (eds_transforms.cpp:313-373) when seds_in != NULL,
+ * eds_to_leds_cartesian (eds_transforms.cpp:381-426) when seds_in == NULL.
+ * Host text in, malloc'd host text out (EDS::save / save_sources dialect, eds.cpp:600-659).
+ * max_output_bytes = 0 means no limit (the reference has none); otherwise EDS_ERR_BUDGET.
+ * ------------------------------------------------------------------------------------------ */
+eds_status eds_leds_merge_host(eds_ctx* ctx, const uint8_t* eds_in, uint64_t eds_bytes, const uint8_t* seds_in,
+                               uint64_t seds_bytes, uint32_t l, int compact, uint64_t max_output_bytes,
+                               eds_buffer* leds_out, eds_buffer* seds_out, uint32_t* rounds_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDSPARSER_B200_H */
