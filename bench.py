@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — msa2eds -l 10 on the synthetic alignment of BASELINE.json (config 2 per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path (eds_msa_transform_device) over one resident alignment window.
+N = 1: config 2 (100 sequences x 10 Mbp, 1 % variable columns, wrap 80, l = 10).
+N > 1 (torchrun, one rank per GPU): weak scaling — the alignment is 100 x (N * 10 Mbp), rank g holds
+the column window [g * 10 Mbp, (g + 1) * 10 Mbp) plus a halo, transforms it, and the ranks all-gather
+their (eds, seds) byte counts over NCCL to get the file offsets of their slices (the path's only
+exchange step). value = total cells / max-over-ranks device time.
+
+The JSON line carries: value (device-resident), e2e (host buffers through eds_msa_transform_host, H2D
+and D2H inside the timed region), roofline (k_scan, the dominant kernel: algorithmic bytes R * C per
+launch / CUDA-event time, against MEASURED_PEAKS.json), cpu_baseline (the UNMODIFIED reference library
+oracle/_ref/ref_driver, or the oracle port, on a bounded sample of the same alignment).
+
+--impl reference: the reference's own CPU implementation (oracle/_ref/ref_driver msa2eds, single
+threaded by construction: msa2eds has no thread option) on a bounded sample per step.
+"""
+import argparse
+import ctypes
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+R = 100
+C_PER_GPU = 10_000_000
+WRAP = 80
+L = 10
+SEED = 1
+PPM = 10_000
+HALO = 4096
+SAMPLE_COLS = 2_000_000  # CPU legs: 100 x 2 Mbp = 2e8 cells, a few seconds of reference time per pass
+METRIC = "MSA cells/s (msa2eds -l 10)"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram read+write bytes per k_scan launch from the committed ncu capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get("k_scan_dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def write_sample_file(cols):
+    from edsparser_b200 import synth
+
+    text = synth.fasta_window(R, cols, WRAP, seed=SEED, variable_ppm=PPM)
+    fd, path = tempfile.mkstemp(suffix=".msa", prefix="edsb_sample_")
+    with os.fdopen(fd, "wb") as f:
+        f.write(text)
+    return path, len(text)
+
+
+def reference_pass(path, workdir):
+    """One msa2eds -l 10 pass of the reference's own library over `path`. Returns (seconds, kind)."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    eds, seds = os.path.join(workdir, "o.leds"), os.path.join(workdir, "o.seds")
+    if os.path.exists(ref):
+        out = subprocess.run([ref, "msa2eds", path, str(L), eds, seds], check=True, capture_output=True, text=True).stdout
+        return float(re.search(r"seconds=([0-9.eE+-]+)", out).group(1)), "reference"
+    port = os.path.join(ROOT, "oracle", "eds_oracle")
+    if not os.path.exists(port):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "restatement"], stdout=subprocess.DEVNULL)
+    t0 = time.perf_counter()
+    subprocess.run([port, "msa2eds", path, str(L), eds, seds], check=True)
+    return time.perf_counter() - t0, "port"
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    path, nbytes = write_sample_file(SAMPLE_COLS)
+    cells = R * SAMPLE_COLS
+    with tempfile.TemporaryDirectory() as wd:
+        kind = "reference"
+        for _ in range(args.warmup):
+            _, kind = reference_pass(path, wd)
+        times = []
+        for _ in range(args.steps):
+            t, kind = reference_pass(path, wd)
+            times.append(t)
+    os.unlink(path)
+    total = sum(times)
+    value = cells * args.steps / total
+    sample = f"{R} seq x {SAMPLE_COLS} columns of the config-2 generator (seed {SEED}), msa2eds -l {L}, in-memory library call"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": 1, "kind": kind, "sample": sample,
+                         "host_cores": os.cpu_count()},
+        "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n):
+    return {"workload": f"config 2 per GPU: synthetic MSA {R} seq x {C_PER_GPU} columns, 1% variable columns, "
+                        f"wrap {WRAP}, msa2eds -l {L}" + ("" if n == 1 else f"; {n} column shards of a {R} x {n * C_PER_GPU} alignment, halo {HALO}"),
+            "rows": R, "cols_per_gpu": C_PER_GPU, "context_length": L, "seed": SEED,
+            "l2": "inputs larger than L2 (1.01 GB window per GPU vs 126 MB L2), no explicit flush",
+            "parallelism": f"column-sharded x{n}" if n > 1 else "single GPU"}
+
+
+def run_ours(args, rank, world):
+    import torch
+    import torch.distributed as dist
+
+    import edsparser_b200 as E
+
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = E.load()  # raises if the CUDA library is missing: there is no CPU fallback
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = lib.context(local, stream)
+
+    total_cols = C_PER_GPU * world
+    lo, hi = C_PER_GPU * rank, C_PER_GPU * (rank + 1)
+    wb, we = max(0, lo - HALO), min(total_cols, hi + HALO)
+    view = ctx.msa_synth(R, total_cols, WRAP, col_begin=wb, col_count=we - wb, seed=SEED, variable_ppm=PPM)
+    view.own_begin, view.own_end = lo, hi
+    counts = torch.zeros(2, dtype=torch.int64, device=dev)
+    gathered = torch.zeros(2 * world, dtype=torch.int64, device=dev)
+
+    def step():
+        e, s, st = ctx.msa_transform_device(view, L)
+        if world > 1:  # file offsets of this rank's slices: all-gather of the byte counts
+            counts[0], counts[1] = int(e.bytes), int(s.bytes)
+            dist.all_gather_into_tensor(gathered, counts)
+        return e, s, st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        e, s, st = step()
+    launches_per_step = st["gpu_launches"]
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        e, s, st = step()
+    ev1.record()
+    barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clocks = sampler.stop() if sampler else None
+    cells_step = R * C_PER_GPU * world
+    value = cells_step * args.steps / (ms_total / 1e3)
+    out_bytes = int(e.bytes) + int(s.bytes)
+
+    # ---- per-kernel times (CUDA events on the launch stream) for the roofline of the dominant kernel
+    ctx.set_profiling(True)
+    acc = {}
+    prof_steps = min(args.steps, 5)
+    for _ in range(prof_steps):
+        ctx.msa_transform_device(view, L)
+        for name, t in ctx.kernel_times():
+            acc[name] = acc.get(name, 0.0) + t
+    ctx.set_profiling(False)
+    kern = {k: v / prof_steps for k, v in acc.items()}
+    peak, peak_src = peaks()
+    scan_ms = kern.get("k_scan", 0.0)
+    row_bytes = (we - 1) + (we - 1) // WRAP - (wb + wb // WRAP) + 1
+    scan_bytes = R * row_bytes  # every cell of the window read once (newlines ride along)
+    achieved = scan_bytes / (scan_ms / 1e3) / 1e9 if scan_ms > 0 else 0.0
+    step_alg_bytes = R * (hi - lo) + out_bytes
+    roofline = {"bound": "hbm", "kernel": "k_scan", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                "kernel_ms": scan_ms, "algorithmic_bytes_per_launch": scan_bytes,
+                "step": {"algorithmic_bytes": step_alg_bytes,
+                         "achieved_gbs": step_alg_bytes * args.steps / (ms_total / 1e3) / 1e9,
+                         "frac": step_alg_bytes * args.steps / (ms_total / 1e3) / 1e9 / peak},
+                "kernels_ms": {k: round(v, 4) for k, v in kern.items()}}
+
+    # ---- end to end: .msa bytes in pinned host memory -> eds_msa_transform_host -> host strings
+    text = ctx.download(E.Buffer(view.text, view.text_bytes)) if world == 1 else None
+    e2e = None
+    if world == 1:
+        pinned = torch.empty(len(text), dtype=torch.uint8).pin_memory()
+        pinned.copy_(torch.frombuffer(bytearray(text), dtype=torch.uint8))
+        ctx.msa_synth_free()
+        e2e_steps = max(1, min(args.steps, 5))
+        for _ in range(2):
+            he, hs, _ = ctx.msa_transform_host(pinned, L)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            he, hs, _ = ctx.msa_transform_host(pinned, L)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": cells_step * e2e_steps / dt, "unit": "cells/s", "h2d_bytes_per_step": len(text),
+               "d2h_bytes_per_step": len(he) + len(hs), "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
+               "api": "eds_msa_transform_host (index + H2D + kernels + D2H), pinned input"}
+    else:
+        # per-rank shard from pinned host memory, same call; slowest rank decides
+        shard_text = ctx.download(E.Buffer(view.text, view.text_bytes))
+        pinned = torch.empty(len(shard_text), dtype=torch.uint8).pin_memory()
+        pinned.copy_(torch.frombuffer(bytearray(shard_text), dtype=torch.uint8))
+        dtext = torch.empty(len(shard_text) + 64, dtype=torch.uint8, device=dev)
+        hview = E.MsaView()
+        ctypes.memmove(ctypes.byref(hview), ctypes.byref(view), ctypes.sizeof(view))
+        hview.text = dtext.data_ptr()
+        e2e_steps = max(1, min(args.steps, 5))
+
+        def e2e_step():
+            dtext[: len(shard_text)].copy_(pinned, non_blocking=True)
+            ee, ss, _ = ctx.msa_transform_device(hview, L)
+            a, b = ctx.download(ee), ctx.download(ss)
+            counts[0], counts[1] = len(a), len(b)
+            dist.all_gather_into_tensor(gathered, counts)
+            return len(a) + len(b)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            nout = e2e_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": cells_step * e2e_steps / float(dt.item()), "unit": "cells/s",
+               "h2d_bytes_per_step": len(shard_text) * world, "d2h_bytes_per_step": nout * world,
+               "ms_per_step": 1e3 * float(dt.item()) / e2e_steps, "steps": e2e_steps,
+               "api": "per rank: pinned H2D + eds_msa_transform_device + D2H + NCCL all-gather of offsets"}
+
+    # ---- CPU baseline: the reference library on a bounded sample (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        path, _ = write_sample_file(SAMPLE_COLS)
+        with tempfile.TemporaryDirectory() as wd:
+            reference_pass(path, wd)
+            ts = []
+            kind = "reference"
+            t_begin = time.perf_counter()
+            while len(ts) < 3 and time.perf_counter() - t_begin < 25:
+                t, kind = reference_pass(path, wd)
+                ts.append(t)
+        os.unlink(path)
+        cpu = {"value": R * SAMPLE_COLS / min(ts), "unit": "cells/s", "cores": 1, "kind": kind,
+               "sample": f"{R} seq x {SAMPLE_COLS} columns of the same generator (seed {SEED}), msa2eds -l {L}, "
+                         f"best of {len(ts)} in-memory library calls; msa2eds is single-threaded by construction",
+               "host_cores": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(world), "gb_per_s": value / 1e9, "e2e": e2e, "roofline": roofline,
+            "cpu_baseline": cpu, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+            "output_bytes_per_step": out_bytes, "library": lib.version(),
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-launch under it
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

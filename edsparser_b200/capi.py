@@ -24,7 +24,7 @@ EXPORTS = [
     "eds_last_error", "eds_version", "eds_ctx_create", "eds_ctx_destroy", "eds_ctx_synchronize",
     "eds_ctx_set_tuning", "eds_ctx_set_profiling", "eds_ctx_kernel_times", "eds_msa_index_host",
     "eds_msa_index_free", "eds_msa_transform_device", "eds_msa_transform_host", "eds_msa_conserved_bits",
-    "eds_msa_synth_device", "eds_msa_synth_free", "eds_buffer_free_host", "eds_leds_merge_host",
+    "eds_msa_synth_device", "eds_msa_synth_free", "eds_buffer_to_host", "eds_buffer_free_host", "eds_leds_merge_host",
 ]
 
 
@@ -92,6 +92,7 @@ class Library:
         L.eds_msa_synth_device.argtypes = [vp, u32, u64, u32, u64, u64, u64, u32, P(MsaView)]
         L.eds_msa_synth_free.argtypes = [vp]
         L.eds_msa_synth_free.restype = None
+        L.eds_buffer_to_host.argtypes = [vp, P(Buffer), P(Buffer)]
         L.eds_buffer_free_host.argtypes = [P(Buffer)]
         L.eds_buffer_free_host.restype = None
         L.eds_leds_merge_host.argtypes = [vp, vp, u64, vp, u64, u32, i32, u64, P(Buffer), P(Buffer), P(u32)]
@@ -198,6 +199,14 @@ class Context:
         self.lib.check(self.lib.L.eds_msa_transform_device(self.handle, ctypes.byref(view), l, 1 if leds else 0,
                                                            ctypes.byref(e), ctypes.byref(s), ctypes.byref(st)))
         return e, s, st.as_dict()
+
+    def download(self, device_buf):
+        """bytes of a device-resident Buffer (an output of msa_transform_device, or any (ptr, n) pair)."""
+        if not device_buf.bytes:
+            return b""
+        h = Buffer()
+        self.lib.check(self.lib.L.eds_buffer_to_host(self.handle, ctypes.byref(device_buf), ctypes.byref(h)))
+        return _host_bytes(self.lib, h)
 
     def msa_conserved_bits(self, view):
         n = (view.col_count + 7) // 8

@@ -293,6 +293,15 @@ void eds_msa_synth_free(eds_ctx* ctx) {
     ctx->synth_rows.clear();
 }
 
+eds_status eds_buffer_to_host(eds_ctx* ctx, const eds_buffer* device_buf, eds_buffer* host_out) {
+    return guarded([&] {
+        use_device(ctx);
+        if (!device_buf || !host_out) throw std::invalid_argument("eds_buffer_to_host: null argument");
+        host_out->data = to_host(ctx, *device_buf);
+        host_out->bytes = device_buf->bytes;
+    });
+}
+
 void eds_buffer_free_host(eds_buffer* buf) {
     if (!buf) return;
     free(buf->data);

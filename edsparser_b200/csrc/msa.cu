@@ -31,7 +31,11 @@ namespace edsb {
 // start is not congruent to row 0's mod 16 is read as two aligned vectors and funnel-shifted.
 // Algorithmic bytes: R * row_bytes read once; writes 2 bytes per chunk.
 // ---------------------------------------------------------------------------------------------
+#ifdef EDSB_EMU
+constexpr int kScanThreads = 64;
+#else
 constexpr int kScanThreads = 256;
+#endif
 constexpr int kScanUnroll = 8;
 constexpr int kRowCache = 2048;
 
@@ -116,7 +120,11 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(MsaGeom g, uint16_t* mism
 // k_colbits: p-space mismatch bits -> column-space V (variable) and T (run start) words, row 0 in
 // column space, per-partition counts. Thread per 32-column word.
 // ---------------------------------------------------------------------------------------------
+#ifdef EDSB_EMU
+constexpr int kPartThreads = 64;  // fewer OS threads per emulated block; results do not depend on it
+#else
 constexpr int kPartThreads = 256;
+#endif
 
 __device__ __forceinline__ uint32_t get_bits(const uint32_t* m, uint64_t p, uint32_t n) {
     const uint64_t wi = p >> 5;
@@ -1063,7 +1071,7 @@ void MsaPipeline::run_once(MsaBufs& b) {
     ctx_->clock.end();
 
     ctx_->clock.begin("k_emit_common");
-    EDSB_LAUNCH(k_emit_common, sms * 8u, 256, 0, s, g, b);
+    EDSB_LAUNCH(k_emit_common, sms * 8u, kPartThreads, 0, s, g, b);
     ctx_->clock.end();
     ctx_->clock.begin("k_emit_var");
     EDSB_LAUNCH(k_emit_var, emit_blocks, ew * 32u, emit_smem, s, g, b, Rq, emit_global ? 1u : 0u);

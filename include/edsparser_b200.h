@@ -147,6 +147,8 @@ eds_status eds_msa_synth_device(eds_ctx* ctx, uint32_t n_rows, uint64_t total_co
                                 eds_msa_view* view);
 void eds_msa_synth_free(eds_ctx* ctx);
 
+/* Copy a device-resident output (eds_msa_transform_device) into malloc'd host memory. */
+eds_status eds_buffer_to_host(eds_ctx* ctx, const eds_buffer* device_buf, eds_buffer* host_out);
 void eds_buffer_free_host(eds_buffer* buf);
 
 /* ------------------------------------------------------------------------------------------

@@ -1,0 +1,60 @@
+"""CPU tier: the MSA kernels' logic, stepped through the test-only CUDA emulator build, against the
+oracle and the reference's golden vectors. (Parity proper is tests/test_msa_gpu.py on a B200.)"""
+import pytest
+
+import emu_lib
+import msa_checks
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = emu_lib.lib().context()
+    c.set_tuning(3, 1)  # few partitions: every scan crosses partition edges even on tiny inputs
+    yield c
+    c.close()
+
+
+def test_reference_unit_strings(ctx):
+    msa_checks.check_reference_unit_strings(ctx)
+
+
+def test_golden_subset(ctx):
+    assert msa_checks.check_golden(ctx, stride=16) >= 35
+
+
+def test_random_against_oracle(ctx):
+    msa_checks.check_random_against_oracle(ctx, seed=1, n_cases=40, max_cols=120)
+
+
+def test_leds_flag_with_l0(ctx):
+    msa_checks.check_leds_flag_with_l0(ctx)
+
+
+def test_conserved_bits(ctx):
+    msa_checks.check_conserved_bits(ctx, on_gpu=False, n_cases=4)
+
+
+def test_bad_inputs(ctx):
+    msa_checks.check_bad_inputs(ctx)
+
+
+def test_hash_collision_fallback():
+    msa_checks.check_hash_collision_fallback(emu_lib.lib(), n_cases=10)
+
+
+def test_shards(ctx):
+    msa_checks.check_shards(ctx, on_gpu=False, seed=2, n_cases=12, max_cols=150)
+
+
+def test_synth_small(ctx):
+    msa_checks.check_synth(ctx, n_rows=5, n_cols=900, wrap=80, l=10, variable_ppm=40000, shards=1)
+
+
+def test_partition_count_does_not_matter():
+    c = emu_lib.lib().context()
+    try:
+        for parts in (1, 2, 7):
+            c.set_tuning(parts, 1)
+            msa_checks.check_random_against_oracle(c, seed=9, n_cases=5, max_cols=150)
+    finally:
+        c.close()

@@ -1,0 +1,79 @@
+"""GPU tier (-m gpu): byte parity of the sm_100a MSA path with the oracle, through the C ABI."""
+import pytest
+
+import edsparser_b200
+import msa_checks
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return edsparser_b200.load()  # raises when the CUDA library is not built: no CPU fallback
+
+
+@pytest.fixture(scope="module")
+def ctx(lib):
+    c = lib.context(0)
+    yield c
+    c.close()
+
+
+def test_reference_unit_strings(ctx):
+    msa_checks.check_reference_unit_strings(ctx)
+
+
+def test_golden_all(ctx):
+    assert msa_checks.check_golden(ctx) > 500
+
+
+def test_random_against_oracle(ctx):
+    msa_checks.check_random_against_oracle(ctx, seed=1, n_cases=300, max_cols=400)
+    msa_checks.check_random_against_oracle(ctx, seed=2, n_cases=40, max_rows=150, max_cols=3000)
+
+
+def test_leds_flag_with_l0(ctx):
+    msa_checks.check_leds_flag_with_l0(ctx)
+
+
+def test_conserved_bits(ctx):
+    msa_checks.check_conserved_bits(ctx, on_gpu=True, n_cases=20)
+
+
+def test_bad_inputs(ctx):
+    msa_checks.check_bad_inputs(ctx)
+
+
+def test_hash_collision_fallback(lib):
+    msa_checks.check_hash_collision_fallback(lib, n_cases=60)
+
+
+def test_shards(ctx):
+    msa_checks.check_shards(ctx, on_gpu=True, seed=2, n_cases=80, max_cols=2000)
+
+
+def test_partition_count_does_not_matter(lib):
+    c = lib.context(0)
+    try:
+        for parts in (1, 3, 64, 1024):
+            c.set_tuning(parts, 0)
+            msa_checks.check_random_against_oracle(c, seed=9, n_cases=15, max_cols=2000)
+    finally:
+        c.close()
+
+
+def test_synth_config2_shape_small(ctx):
+    # BASELINE config 2 shape (100 rows, 1% variable columns, wrap 80, l = 10) at 200 kbp
+    st = msa_checks.check_synth(ctx, n_rows=100, n_cols=200_000, wrap=80, l=10, shards=4)
+    assert st["n_variable_cols"] > 1000
+
+
+def test_synth_many_rows(ctx):
+    # config 4 shape: 1000 rows (shared-memory budget of k_group changes), plain EDS and l-EDS
+    msa_checks.check_synth(ctx, n_rows=1000, n_cols=30_000, wrap=80, l=10, shards=2)
+    msa_checks.check_synth(ctx, n_rows=1000, n_cols=10_000, wrap=60, l=0)
+
+
+def test_synth_wide_rows(ctx):
+    # R > 4096: per-warp scratch moves to global memory; R > 65535 would switch ids to uint32
+    msa_checks.check_synth(ctx, n_rows=5000, n_cols=3_000, wrap=70, l=5, variable_ppm=20000)
