@@ -105,6 +105,7 @@ eds_status eds_ctx_create(int device, void* stream, eds_ctx** out) {
         }
         ctx->clock.stream = ctx->stream;
         if (const char* hm = getenv("EDSB_DEBUG_HASH_MASK")) ctx->hash_mask = strtoull(hm, nullptr, 0);
+        if (const char* no = getenv("EDSB_DEBUG_NARROW_OFF")) ctx->narrow_off = atoi(no) != 0;
         ctx->msa = new edsb::MsaPipeline(ctx);
         ctx->leds = new edsb::LedsPipeline(ctx);
         *out = ctx;

@@ -70,13 +70,9 @@ extern __shared__ __align__(16) unsigned char edsb_dyn_smem_[];
 // purpose: a row that is not 16-byte aligned is read as two overlapping aligned vectors and the
 // second one is an L1 hit.
 __device__ __forceinline__ uint4 ldg_nc(const uint4* p) {
-#if defined(__CUDA_ARCH__)
-    uint4 v;
-    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-#else
-    return *p;
-#endif
+    // __ldg = ld.global.nc; as an intrinsic (not opaque inline asm) the compiler knows it is a long-latency
+    // load and keeps an unrolled batch of them in flight instead of interleaving each with its use.
+    return __ldg(p);
 }
 
 // bit k of the result = (byte k of w != 0), k = 0..3

@@ -36,14 +36,92 @@ constexpr int kScanThreads = 64;
 #else
 constexpr int kScanThreads = 256;
 #endif
-constexpr int kScanUnroll = 8;
+#ifndef EDSB_SCAN_MINB
+#define EDSB_SCAN_MINB 3
+#endif
+#ifndef EDSB_SCAN_UNROLL
+#define EDSB_SCAN_UNROLL 8
+#endif
+constexpr int kScanUnroll = EDSB_SCAN_UNROLL;
 constexpr int kRowCache = 2048;
 
-__global__ void __launch_bounds__(kScanThreads) k_scan(MsaGeom g, uint16_t* mism16, MsaStatus* st) {
-    __shared__ long long s_d[kRowCache];
-    const uint32_t nrc = g.R < (uint32_t)kRowCache ? g.R : (uint32_t)kRowCache;
-    for (uint32_t i = threadIdx.x; i < nrc; i += blockDim.x) s_d[i] = (long long)g.row_off[i] - (long long)g.a0;
-    __syncthreads();
+// row_pack: for every row r >= 1, the address of the aligned 16-byte vector that holds p-space byte 0 of
+// the row, with the row's byte shift (0..15) in the low 4 bits; sorted on the host by word shift
+// (shift >> 2) so that each class runs with a compile-time word selection and only the bit shift is a
+// run-time operand of the funnel shifts (g.cls[c]..g.cls[c+1] = rows of class c). Entry 0 is row 0.
+template <int WS>
+__device__ __forceinline__ void xor_acc(const uint4& lo, const uint4& hi, uint32_t bs, const uint4& ref, uint4& acc) {
+    uint32_t w0, w1, w2, w3, w4;
+    if (WS == 0) { w0 = lo.x; w1 = lo.y; w2 = lo.z; w3 = lo.w; w4 = hi.x; }
+    else if (WS == 1) { w0 = lo.y; w1 = lo.z; w2 = lo.w; w3 = hi.x; w4 = hi.y; }
+    else if (WS == 2) { w0 = lo.z; w1 = lo.w; w2 = hi.x; w3 = hi.y; w4 = hi.z; }
+    else { w0 = lo.w; w1 = hi.x; w2 = hi.y; w3 = hi.z; w4 = hi.w; }
+    acc.x |= __funnelshift_r(w0, w1, bs) ^ ref.x;
+    acc.y |= __funnelshift_r(w1, w2, bs) ^ ref.y;
+    acc.z |= __funnelshift_r(w2, w3, bs) ^ ref.z;
+    acc.w |= __funnelshift_r(w3, w4, bs) ^ ref.w;
+}
+
+template <int WS>
+__device__ __forceinline__ void scan_class(const unsigned long long* pk, uint32_t n, long long jj, const uint4& ref,
+                                           uint4& acc) {
+    uint32_t r = 0;
+    for (; r + kScanUnroll <= n; r += kScanUnroll) {
+        uint4 lo[kScanUnroll], hi[kScanUnroll];
+        uint32_t bs[kScanUnroll];
+#pragma unroll
+        for (int u = 0; u < kScanUnroll; ++u) {
+            const unsigned long long v = pk[r + u];
+            const uint4* p = reinterpret_cast<const uint4*>(v & ~15ull) + jj;
+            bs[u] = ((uint32_t)v & 3u) * 8u;
+            lo[u] = ldg_nc(p);
+            hi[u] = ldg_nc(p + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < kScanUnroll; ++u) xor_acc<WS>(lo[u], hi[u], bs[u], ref, acc);
+    }
+    for (; r < n; ++r) {
+        const unsigned long long v = pk[r];
+        const uint4* p = reinterpret_cast<const uint4*>(v & ~15ull) + jj;
+        const uint4 lo = ldg_nc(p), hi = ldg_nc(p + 1);
+        xor_acc<WS>(lo, hi, ((uint32_t)v & 3u) * 8u, ref, acc);
+    }
+}
+
+// every row starts on a 16-byte boundary relative to row 0 (e.g. a pitched copy): one load per row
+__device__ __forceinline__ void scan_aligned(const unsigned long long* pk, uint32_t n, long long jj, const uint4& ref,
+                                             uint4& acc) {
+    uint32_t r = 0;
+    for (; r + kScanUnroll <= n; r += kScanUnroll) {
+        uint4 lo[kScanUnroll];
+#pragma unroll
+        for (int u = 0; u < kScanUnroll; ++u) lo[u] = ldg_nc(reinterpret_cast<const uint4*>(pk[r + u]) + jj);
+#pragma unroll
+        for (int u = 0; u < kScanUnroll; ++u) {
+            acc.x |= lo[u].x ^ ref.x;
+            acc.y |= lo[u].y ^ ref.y;
+            acc.z |= lo[u].z ^ ref.z;
+            acc.w |= lo[u].w ^ ref.w;
+        }
+    }
+    for (; r < n; ++r) {
+        const uint4 lo = ldg_nc(reinterpret_cast<const uint4*>(pk[r]) + jj);
+        acc.x |= lo.x ^ ref.x;
+        acc.y |= lo.y ^ ref.y;
+        acc.z |= lo.z ^ ref.z;
+        acc.w |= lo.w ^ ref.w;
+    }
+}
+
+template <bool CACHED>
+__global__ void __launch_bounds__(kScanThreads, EDSB_SCAN_MINB) k_scan(MsaGeom g, const unsigned long long* row_pack, uint16_t* mism16,
+                                                       MsaStatus* st) {
+    __shared__ unsigned long long s_pk[CACHED ? kRowCache : 1];
+    if (CACHED) {
+        for (uint32_t i = threadIdx.x; i < g.R; i += blockDim.x) s_pk[i] = row_pack[i];
+        __syncthreads();
+    }
+    const unsigned long long* pk = CACHED ? s_pk : row_pack;
 
     const uint4* vec = reinterpret_cast<const uint4*>(g.text);
     const long long vmax = (long long)g.n_vec - 1;
@@ -54,36 +132,36 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(MsaGeom g, uint16_t* mism
 
     for (uint32_t tile = blockIdx.x * wpb + (threadIdx.x >> 5); tile < n_tiles; tile += gridDim.x * wpb) {
         const uint32_t j = tile * 32 + lane;
+        const long long j0 = (long long)tile * 32;
+        // interior tile: every vector any lane touches (and its right neighbour) lies inside the buffer
+        const bool interior = j0 + 31 < (long long)g.n_chunks && j0 + g.d_min_vec >= 0 && j0 + 32 + g.d_max_vec <= vmax;
         if (j >= g.n_chunks) continue;
         const long long jj = (long long)j;
-        const long long d0 = s_d[0];
-        long long v0 = jj + (d0 >> 4);
-        v0 = v0 < 0 ? 0 : (v0 > vmax ? vmax : v0);
-        const uint4 ref = ldg_nc(vec + v0);
-        uint4 acc = make_uint4(0, 0, 0, 0);
-
-        for (uint32_t r = 1; r < g.R; r += kScanUnroll) {
-            uint4 lo[kScanUnroll], hi[kScanUnroll];
-            uint32_t sh[kScanUnroll];
-#pragma unroll
-            for (int u = 0; u < kScanUnroll; ++u) {
-                const uint32_t rr = (r + u < g.R) ? r + u : 0;  // row 0 against itself: no effect
-                const long long d = rr < nrc ? s_d[rr] : (long long)g.row_off[rr] - (long long)g.a0;
-                long long vi = jj + (d >> 4);
-                sh[u] = (uint32_t)(d & 15);
-                long long va = vi < 0 ? 0 : (vi > vmax ? vmax : vi);
-                lo[u] = ldg_nc(vec + va);
-                if (sh[u]) {
-                    long long vb = vi + 1;
-                    vb = vb < 0 ? 0 : (vb > vmax ? vmax : vb);
-                    hi[u] = ldg_nc(vec + vb);
-                } else {
-                    hi[u] = lo[u];
-                }
+        uint4 ref, acc = make_uint4(0, 0, 0, 0);
+        if (interior) {
+            ref = ldg_nc(reinterpret_cast<const uint4*>(pk[0]) + jj);
+            if (g.all_aligned) {
+                scan_aligned(pk + 1, g.R - 1, jj, ref, acc);
+            } else {
+                scan_class<0>(pk + g.cls[0], g.cls[1] - g.cls[0], jj, ref, acc);
+                scan_class<1>(pk + g.cls[1], g.cls[2] - g.cls[1], jj, ref, acc);
+                scan_class<2>(pk + g.cls[2], g.cls[3] - g.cls[2], jj, ref, acc);
+                scan_class<3>(pk + g.cls[3], g.cls[4] - g.cls[3], jj, ref, acc);
             }
-#pragma unroll
-            for (int u = 0; u < kScanUnroll; ++u) {
-                const uint4 x = realign16(lo[u], hi[u], sh[u]);
+        } else {
+            // edge tile: clamp every vector index into the buffer (bytes outside the row are masked below)
+            const long long d0 = (long long)g.row_off[0] - (long long)g.a0;
+            long long v0 = jj + (d0 >> 4);
+            v0 = v0 < 0 ? 0 : (v0 > vmax ? vmax : v0);
+            ref = ldg_nc(vec + v0);
+            for (uint32_t r = 1; r < g.R; ++r) {
+                const long long d = (long long)g.row_off[r] - (long long)g.a0;
+                const long long vi = jj + (d >> 4);
+                const uint32_t sh = (uint32_t)(d & 15);
+                const long long va = vi < 0 ? 0 : (vi > vmax ? vmax : vi);
+                long long vb = vi + 1;
+                vb = vb < 0 ? 0 : (vb > vmax ? vmax : vb);
+                const uint4 x = realign16(ldg_nc(vec + va), ldg_nc(vec + vb), sh);
                 acc.x |= x.x ^ ref.x;
                 acc.y |= x.y ^ ref.y;
                 acc.z |= x.z ^ ref.z;
@@ -243,34 +321,45 @@ __global__ void __launch_bounds__(kPartThreads) k_compact(MsaGeom g, MsaBufs b) 
 // k_stash: gather the R residues of every variable column into stash[k * Rp + r] (lanes over rows,
 // coalesced writes; the reads are one sector per (column, row) and are the pipeline's only re-read).
 // ---------------------------------------------------------------------------------------------
-constexpr int kStashCols = 8;
+#ifdef EDSB_EMU
+constexpr int kStashThreads = 64;
+#else
+constexpr int kStashThreads = 256;
+#endif
 
-__global__ void k_stash(MsaGeom g, MsaBufs b) {
+__global__ void __launch_bounds__(kStashThreads) k_stash(MsaGeom g, MsaBufs b) {
+    __shared__ uint8_t tile[32][36];
     MsaStatus* st = b.status;
     if (st->abort) return;
     const uint32_t n_var = st->n_var;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint32_t tiles_r = (g.R + 31) / 32, tiles_c = (n_var + 31) / 32;
+    const uint64_t n_tiles = (uint64_t)tiles_r * tiles_c;
     uint32_t bad = 0;
-    for (uint32_t k0 = blockIdx.x * kStashCols; k0 < n_var; k0 += gridDim.x * kStashCols) {
-        uint64_t uoff[kStashCols];
-#pragma unroll
-        for (int kk = 0; kk < kStashCols; ++kk) {
-            const uint32_t k = min(k0 + kk, n_var - 1);
+    for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const uint32_t tc = (uint32_t)(t / tiles_r), tr = (uint32_t)(t % tiles_r);
+        // read: a warp instruction reads 32 variable columns of ONE row (one page, nearby sectors)
+        const uint32_t k = tc * 32 + lane;
+        uint64_t uoff = 0;
+        if (k < n_var) {
             const uint64_t gc = g.col_begin + b.varcol[k];
-            uoff[kk] = gc + gc / g.lw - g.u_begin;
+            uoff = gc + gc / g.lw - g.u_begin;
         }
-        for (uint32_t r = threadIdx.x; r < g.R; r += blockDim.x) {
-            const uint8_t* row = g.text + g.row_off[r];
-            uint8_t ch[kStashCols];
-#pragma unroll
-            for (int kk = 0; kk < kStashCols; ++kk) ch[kk] = row[uoff[kk]];
-#pragma unroll
-            for (int kk = 0; kk < kStashCols; ++kk) {
-                if (k0 + kk < n_var) {
-                    b.stash[(size_t)(k0 + kk) * g.Rp + r] = ch[kk];
-                    bad |= (ch[kk] == (uint8_t)'\n');
-                }
+        for (uint32_t rl = warp; rl < 32; rl += nw) {
+            const uint32_t r = tr * 32 + rl;
+            if (r < g.R && k < n_var) {
+                const uint8_t ch = g.text[g.row_off[r] + uoff];
+                tile[rl][lane] = ch;
+                bad |= (ch == (uint8_t)'\n');
             }
         }
+        __syncthreads();
+        // write: lanes over rows, 32 consecutive bytes of one stash column
+        for (uint32_t cl = warp; cl < 32; cl += nw) {
+            const uint32_t k2 = tc * 32 + cl, r = tr * 32 + lane;
+            if (k2 < n_var && r < g.R) b.stash[(size_t)k2 * g.Rp + r] = tile[lane][cl];
+        }
+        __syncthreads();
     }
     if (bad) atomicOr(&st->bad_msa, (uint32_t)kBadResidueByte);
 }
@@ -297,40 +386,48 @@ __device__ __forceinline__ bool run_opens(const MsaGeom& g, const uint32_t* runs
     return run_standalone(g, runs, k) || run_standalone(g, runs, k - 1);
 }
 
+// The two kernels also list the variable symbols (varsym[v] = symbol index), the work list of k_group /
+// k_emit_var: counts are packed as opens | variable opens << 32.
 __global__ void __launch_bounds__(kPartThreads) k_sym_count(MsaGeom g, MsaBufs b) {
-    __shared__ uint32_t s_red[33];
+    __shared__ unsigned long long s_red[33];
     const MsaStatus* st = b.status;
     if (st->abort) return;
     const uint32_t n = st->n_runs, P = gridDim.x;
     const uint32_t per = (n + P - 1) / P;
     const uint32_t k_begin = min(n, blockIdx.x * per), k_end = min(n, k_begin + per);
-    uint32_t cnt = 0;
-    for (uint32_t k = k_begin + threadIdx.x; k < k_end; k += blockDim.x) cnt += run_opens(g, b.runs, k) ? 1u : 0u;
-    const uint32_t tot = block_sum(cnt, s_red);
+    unsigned long long cnt = 0;
+    for (uint32_t k = k_begin + threadIdx.x; k < k_end; k += blockDim.x)
+        if (run_opens(g, b.runs, k)) cnt += (b.runs[k] & kCommonFlag) ? 1ull : (1ull | (1ull << 32));
+    const unsigned long long tot = block_sum(cnt, s_red);
     if (threadIdx.x == 0) b.part_sym[blockIdx.x] = tot;
 }
 
 __global__ void __launch_bounds__(kPartThreads) k_sym_scatter(MsaGeom g, MsaBufs b) {
-    __shared__ uint32_t s_scan[33];
+    __shared__ unsigned long long s_scan[33];
     MsaStatus* st = b.status;
     if (st->abort) return;
     const uint32_t n = st->n_runs, P = gridDim.x;
     const uint32_t per = (n + P - 1) / P;
     const uint32_t k_begin = min(n, blockIdx.x * per), k_end = min(n, k_begin + per);
-    uint32_t mine = 0;
+    unsigned long long mine = 0;
     for (uint32_t q = threadIdx.x; q < blockIdx.x; q += blockDim.x) mine += b.part_sym[q];
-    uint32_t base = block_sum(mine, s_scan);
+    unsigned long long base = block_sum(mine, s_scan);
     for (uint32_t k0 = k_begin; k0 < k_end; k0 += blockDim.x) {
         const uint32_t k = k0 + threadIdx.x;
         const bool open = k < k_end && run_opens(g, b.runs, k);
-        uint32_t total;
-        const uint32_t ex = block_exclusive_scan(open ? 1u : 0u, s_scan, total);
-        if (open) b.sym[base + ex] = b.runs[k];  // an opening conserved run is a whole common symbol
+        const uint32_t e = open ? b.runs[k] : kCommonFlag;
+        const bool var = open && !(e & kCommonFlag);
+        unsigned long long total;
+        const unsigned long long ex = block_exclusive_scan((open ? 1ull : 0ull) | (var ? 1ull << 32 : 0ull), s_scan, total);
+        const uint32_t ks = (uint32_t)(base + ex);
+        if (open) b.sym[ks] = e;  // an opening conserved run is a whole common symbol
+        if (var) b.varsym[(uint32_t)((base + ex) >> 32)] = ks;
         base += total;
     }
     if (blockIdx.x == P - 1 && threadIdx.x == 0) {
-        st->n_syms = base;
-        b.sym[base] = g.ncols;
+        st->n_syms = (uint32_t)base;
+        st->n_varsyms_window = (uint32_t)(base >> 32);
+        b.sym[(uint32_t)base] = g.ncols;
     }
 }
 
@@ -383,6 +480,22 @@ __global__ void k_finalize(MsaGeom g, MsaBufs b) {
             }
         }
     }
+    // owned slice of the variable-symbol list
+    {
+        const uint32_t nv = st->n_varsyms_window;
+        uint32_t lo = 0, hi = nv;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (b.varsym[mid] < k_lo) lo = mid + 1; else hi = mid;
+        }
+        st->v_lo = lo;
+        hi = nv;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (b.varsym[mid] < k_hi) lo = mid + 1; else hi = mid;
+        }
+        st->v_hi = lo;
+    }
     st->k_lo = k_lo;
     st->k_hi = k_hi;
     st->lead_lo = lead_lo;
@@ -402,9 +515,27 @@ struct RowWalk {
     const uint8_t* refc;
     const uint8_t* stash;
     uint32_t Rp;
+    // staged mode: the symbol's columns are described in shared memory (cdesc[i]: 0x100 | index of the
+    // variable column inside the staged block, or the conserved character) and its stash block is a copy
+    // in shared memory; every warp lane walks without touching global memory.
+    const uint16_t* cdesc;
+    const uint8_t* stage;
+    uint32_t s0;
+    bool staged;
 };
 
+constexpr uint32_t kStageCols = 64;  // widest symbol the staged path takes
+
 __device__ __forceinline__ int next_char(const RowWalk& w, uint32_t r, uint32_t& c, uint32_t e, uint32_t& slot) {
+    if (w.staged) {
+        while (c < e) {
+            const uint32_t d = w.cdesc[c - w.s0];
+            ++c;
+            const uint8_t ch = (d & 0x100u) ? w.stage[(d & 0xffu) * w.Rp + r] : (uint8_t)d;
+            if (ch != (uint8_t)'-') return (int)ch;
+        }
+        return -1;
+    }
     while (c < e) {
         const uint32_t v = (w.vbits[c >> 5] >> (c & 31u)) & 1u;
         uint8_t ch;
@@ -418,6 +549,31 @@ __device__ __forceinline__ int next_char(const RowWalk& w, uint32_t r, uint32_t&
         if (ch != (uint8_t)'-') return (int)ch;
     }
     return -1;
+}
+
+// Warp-cooperative: describe columns [s, en) in cdesc and copy the symbol's stash block (its variable
+// columns are consecutive slots from slot0) into `stage`. False (warp-uniform) when the symbol is too
+// wide or its block does not fit; the caller then walks global memory.
+__device__ __forceinline__ bool stage_symbol(const MsaGeom& g, const MsaBufs& b, uint32_t s, uint32_t en, uint32_t slot0,
+                                             uint16_t* cdesc, uint8_t* stage, uint32_t stage_bytes) {
+    const uint32_t lane = threadIdx.x & 31, width = en - s;
+    if (stage_bytes == 0 || width > kStageCols) return false;
+    uint32_t nv = 0;
+    for (uint32_t i0 = 0; i0 < width; i0 += 32) {
+        const uint32_t i = i0 + lane, c = s + i;
+        const bool in = i < width;
+        const uint32_t v = in ? (b.vbits[c >> 5] >> (c & 31u)) & 1u : 0u;
+        const uint32_t m = __ballot_sync(0xffffffffu, v);
+        if (in) cdesc[i] = v ? (uint16_t)(0x100u | (nv + (uint32_t)__popc(m & lanemask_lt()))) : (uint16_t)b.refc[c];
+        nv += (uint32_t)__popc(m);
+    }
+    if (nv > 255u || nv * g.Rp > stage_bytes) return false;
+    const uint4* src = reinterpret_cast<const uint4*>(b.stash + (size_t)slot0 * g.Rp);
+    uint4* dst = reinterpret_cast<uint4*>(stage);
+    const uint32_t n16 = nv * g.Rp / 16u;
+    for (uint32_t i = lane; i < n16; i += 32) dst[i] = src[i];
+    __syncwarp();
+    return true;
 }
 
 __device__ bool rows_equal(const RowWalk& w, uint32_t r1, uint32_t r2, uint32_t s, uint32_t e, uint32_t slot0) {
@@ -445,115 +601,243 @@ __device__ __forceinline__ uint32_t load_alt(const MsaGeom& g, const void* altid
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_group: one warp per owned variable symbol (generate_output's variant branch,
-// msa_transforms.cpp:259-318). Rows are hashed (FNV-1a over the gap-stripped string), grouped through
-// a per-warp open-addressing table that keeps the smallest row of each hash class, and every row is
-// then compared byte for byte with that row; a true hash collision switches the symbol to an exact
-// quadratic search. Alternatives are numbered by first row (insertion_order, :263,290-292).
-// Per-warp scratch (shared memory, or global when R is large): h[Rq] u64, len[Rq], lead[Rq], tab[T].
+// Grouping of a variable symbol's rows into alternatives (generate_output's variant branch,
+// msa_transforms.cpp:259-318). Two shapes of work:
+//
+//  * narrow: the symbol is ONE variable column (the common case: ~80 % of the variable symbols of an
+//    l = 10 run at 1 % variability, ~99 % in plain EDS). A LANE owns the symbol and walks its stash column
+//    serially; the distinct residues, in order of first row, live in two registers (up to 8; more, or a
+//    NUL byte, demotes the symbol to the wide path). 32 symbols per warp, ~10 instructions per row.
+//  * wide: a WARP owns the symbol. Rows are keyed by the gap-stripped string — packed exactly into 64 bits
+//    when the symbol is at most 7 columns wide, else FNV-1a hashed — grouped through a per-warp
+//    open-addressing table that keeps the smallest row of each key; hashed keys are then verified byte for
+//    byte, and a true collision switches the symbol to an exact quadratic search.
+// Alternatives are numbered by first row (insertion_order, :263,290-292).
+// Per-warp scratch of the wide path (shared memory, or global when R is large): h[Rq] u64, len[Rq],
+// lead[Rq], tab[T], then the stage of stage_symbol.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_group(MsaGeom g, MsaBufs b, uint32_t Rq, uint32_t T, uint32_t use_global) {
-    MsaStatus* st = b.status;
-    if (st->abort || st->halo_fail) return;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const size_t per_warp = (size_t)Rq * 16u + (size_t)T * 4u;
-    unsigned char* base = use_global ? b.group_ws + ((size_t)blockIdx.x * wpb + warp) * per_warp
-                                     : EDSB_DYN_SMEM() + (size_t)warp * per_warp;
-    unsigned long long* hrow = reinterpret_cast<unsigned long long*>(base);
-    uint32_t* len = reinterpret_cast<uint32_t*>(hrow + Rq);
-    uint32_t* lead = len + Rq;
-    uint32_t* tab = lead + Rq;
-    const RowWalk w{b.vbits, b.refc, b.stash, g.Rp};
-    const uint32_t k_lo = st->k_lo, k_hi = st->k_hi;
-    unsigned long long alts_here = 0;
-    uint32_t var_here = 0;
+struct Seen {
+    uint32_t lo, hi, n;
+};
 
-    for (uint32_t k = k_lo + blockIdx.x * wpb + warp; k < k_hi; k += gridDim.x * wpb) {
-        const uint32_t e = b.sym[k];
-        if (e & kCommonFlag) continue;  // warp-uniform
-        const uint32_t s = e & kColMask, en = b.sym[k + 1] & kColMask;
-        const uint32_t slot0 = first_slot(b, s);
+// index of byte ch (non-zero) among the seen bytes, appending it if new; n == 9 signals overflow
+__device__ __forceinline__ uint32_t seen_index(Seen& sn, uint32_t ch) {
+    const uint32_t sp = ch * 0x01010101u;
+    uint32_t x = sn.lo ^ sp;
+    uint32_t z = (x - 0x01010101u) & ~x & 0x80808080u;  // lowest flagged byte is a true zero byte
+    if (z) return ((uint32_t)__ffs((int)z) - 1u) >> 3;
+    x = sn.hi ^ sp;
+    z = (x - 0x01010101u) & ~x & 0x80808080u;
+    if (z) return 4u + (((uint32_t)__ffs((int)z) - 1u) >> 3);
+    const uint32_t a = sn.n;
+    if (a < 4u)
+        sn.lo |= ch << (8u * a);
+    else if (a < 8u)
+        sn.hi |= ch << (8u * (a - 4u));
+    sn.n = a + 1u;
+    return a;
+}
 
-        for (uint32_t i = lane; i < T; i += 32) tab[i] = kEmptySlot;
-        for (uint32_t r = lane; r < g.R; r += 32) {
-            uint32_t c = s, slot = slot0, n = 0;
-            unsigned long long h = 14695981039346656037ull;
-            int ch;
+__device__ __forceinline__ uint32_t seen_byte(const Seen& sn, uint32_t a) {
+    return ((a < 4u ? sn.lo >> (8u * a) : sn.hi >> (8u * (a - 4u)))) & 0xffu;
+}
+
+// Lane-serial pass over one stash column: distinct residues in first-row order. False on overflow.
+__device__ __forceinline__ bool narrow_scan(const uint8_t* col, uint32_t R, Seen& sn) {
+    sn.lo = sn.hi = sn.n = 0;
+    for (uint32_t r0 = 0; r0 < R; r0 += 4) {
+        uint32_t word = *reinterpret_cast<const uint32_t*>(col + r0);
+        const uint32_t lim = min(4u, R - r0);
+        for (uint32_t i = 0; i < lim; ++i) {
+            const uint32_t ch = word & 0xffu;
+            word >>= 8;
+            if (ch == 0u) return false;
+            seen_index(sn, ch);
+            if (sn.n > 8u) return false;
+        }
+    }
+    return true;
+}
+
+struct GroupScratch {
+    unsigned long long* hrow;
+    uint32_t* len;
+    uint32_t* lead;
+    uint32_t* tab;
+    uint8_t* stage;
+    uint16_t* cdesc;
+    uint32_t T, stage_bytes;
+};
+
+__device__ void group_wide(const MsaGeom& g, const MsaBufs& b, const GroupScratch& sc, uint32_t k) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t T = sc.T;
+    unsigned long long* hrow = sc.hrow;
+    uint32_t *len = sc.len, *lead = sc.lead, *tab = sc.tab;
+    const uint32_t e = b.sym[k];
+    const uint32_t s = e & kColMask, en = b.sym[k + 1] & kColMask;
+    const uint32_t slot0 = first_slot(b, s);
+    RowWalk w{b.vbits, b.refc, b.stash, g.Rp, sc.cdesc, sc.stage, s, false};
+    w.staged = stage_symbol(g, b, s, en, slot0, sc.cdesc, sc.stage, sc.stage_bytes);
+    const bool exact = (en - s) <= 7u && g.hash_mask == ~0ull;  // the key IS the string: no verification needed
+
+    for (uint32_t i = lane; i < T; i += 32) tab[i] = kEmptySlot;
+    for (uint32_t r = lane; r < g.R; r += 32) {
+        uint32_t c = s, slot = slot0, n = 0;
+        unsigned long long h;
+        int ch;
+        if (exact) {
+            h = 0;
+            while ((ch = next_char(w, r, c, en, slot)) >= 0) {
+                h |= (unsigned long long)ch << (8u * n);
+                ++n;
+            }
+            h |= (unsigned long long)n << 56;
+        } else {
+            h = 14695981039346656037ull;
             while ((ch = next_char(w, r, c, en, slot)) >= 0) {
                 h = (h ^ (unsigned long long)ch) * 1099511628211ull;
                 ++n;
             }
             h = (h ^ ((unsigned long long)n * 0x9e3779b97f4a7c15ull)) & g.hash_mask;
-            hrow[r] = h;
-            len[r] = n;
         }
-        __syncwarp();
+        hrow[r] = h;
+        len[r] = n;
+    }
+    __syncwarp();
+    for (uint32_t r = lane; r < g.R; r += 32) {
+        const unsigned long long h = hrow[r];
+        uint32_t slot = (uint32_t)((h ^ (h >> 32)) * 0x9e3779b1u >> 7) & (T - 1u);
+        for (;;) {
+            const uint32_t cur = atomicCAS(&tab[slot], kEmptySlot, r);
+            if (cur == kEmptySlot) break;
+            if (hrow[cur] == h) {
+                atomicMin(&tab[slot], r);
+                break;
+            }
+            slot = (slot + 1u) & (T - 1u);
+        }
+        lead[r] = slot;
+    }
+    __syncwarp();
+    uint32_t collided = 0;
+    for (uint32_t r = lane; r < g.R; r += 32) {
+        const uint32_t m = tab[lead[r]];
+        if (!exact && m != r && (len[m] != len[r] || !rows_equal(w, m, r, s, en, slot0))) collided = 1;
+        lead[r] = m;
+    }
+    collided = __any_sync(0xffffffffu, collided);
+    __syncwarp();
+    if (collided) {
+        // exact fallback: first earlier row with the same string
         for (uint32_t r = lane; r < g.R; r += 32) {
-            const unsigned long long h = hrow[r];
-            uint32_t slot = (uint32_t)(h ^ (h >> 32)) & (T - 1u);
-            for (;;) {
-                const uint32_t cur = atomicCAS(&tab[slot], kEmptySlot, r);
-                if (cur == kEmptySlot) break;
-                if (hrow[cur] == h) {
-                    atomicMin(&tab[slot], r);
+            uint32_t m = r;
+            for (uint32_t r2 = 0; r2 < r; ++r2) {
+                if (len[r2] == len[r] && hrow[r2] == hrow[r] && rows_equal(w, r2, r, s, en, slot0)) {
+                    m = r2;
                     break;
                 }
-                slot = (slot + 1u) & (T - 1u);
             }
-            lead[r] = slot;
-        }
-        __syncwarp();
-        uint32_t collided = 0;
-        for (uint32_t r = lane; r < g.R; r += 32) {
-            const uint32_t m = tab[lead[r]];
-            if (m != r && (len[m] != len[r] || !rows_equal(w, m, r, s, en, slot0))) collided = 1;
             lead[r] = m;
         }
-        collided = __any_sync(0xffffffffu, collided);
-        __syncwarp();
-        if (collided) {
-            // exact fallback: first earlier row with the same string
-            for (uint32_t r = lane; r < g.R; r += 32) {
-                uint32_t m = r;
-                for (uint32_t r2 = 0; r2 < r; ++r2) {
-                    if (len[r2] == len[r] && hrow[r2] == hrow[r] && rows_equal(w, r2, r, s, en, slot0)) {
-                        m = r2;
-                        break;
-                    }
-                }
-                lead[r] = m;
-            }
-            __syncwarp();
-        }
-        // number the alternatives by first row; tab[0..R) is reused as "alternative of leader row"
-        uint32_t nalts = 0;
-        unsigned long long lensum = 0;
-        for (uint32_t r0 = 0; r0 < g.R; r0 += 32) {
-            const uint32_t r = r0 + lane;
-            const bool isl = r < g.R && lead[r] == r;
-            const uint32_t mask = __ballot_sync(0xffffffffu, isl);
-            if (isl) {
-                tab[r] = nalts + (uint32_t)__popc(mask & lanemask_lt());
-                lensum += len[r];
-            }
-            if (lane == 0) b.leadmask[(size_t)slot0 * (g.Rp >> 5) + (r0 >> 5)] = mask;
-            nalts += (uint32_t)__popc(mask);
-        }
-        __syncwarp();
-        for (uint32_t r = lane; r < g.R; r += 32) store_alt(g, b.altid, (size_t)slot0 * g.Rp + r, tab[lead[r]]);
-        lensum = warp_sum(lensum);
-        if (lane == 0) {
-            b.sym_nalts[k] = nalts;
-            b.sym_edsz[k] = 2ull + lensum + (unsigned long long)(nalts - 1u);
-            alts_here += nalts;
-            var_here += 1;
-        }
         __syncwarp();
     }
-    if (lane == 0 && var_here) {
-        atomicAdd(&st->n_alts, alts_here);
-        atomicAdd(&st->n_var_syms, var_here);
+    // number the alternatives by first row; tab[0..R) is reused as "alternative of leader row"
+    uint32_t nalts = 0;
+    unsigned long long lensum = 0;
+    for (uint32_t r0 = 0; r0 < g.R; r0 += 32) {
+        const uint32_t r = r0 + lane;
+        const bool isl = r < g.R && lead[r] == r;
+        const uint32_t mask = __ballot_sync(0xffffffffu, isl);
+        if (isl) {
+            tab[r] = nalts + (uint32_t)__popc(mask & lanemask_lt());
+            lensum += len[r];
+        }
+        if (lane == 0) b.leadmask[(size_t)slot0 * (g.Rp >> 5) + (r0 >> 5)] = mask;
+        nalts += (uint32_t)__popc(mask);
     }
+    __syncwarp();
+    for (uint32_t r = lane; r < g.R; r += 32) store_alt(g, b.altid, (size_t)slot0 * g.Rp + r, tab[lead[r]]);
+    lensum = warp_sum(lensum);
+    if (lane == 0) {
+        b.sym_nalts[k] = nalts;
+        b.sym_edsz[k] = 2ull + lensum + (unsigned long long)(nalts - 1u);
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void list_append(uint32_t* list, uint32_t* counter, bool mine, uint32_t k) {
+    const uint32_t m = __ballot_sync(0xffffffffu, mine);
+    if (!m) return;
+    uint32_t base = 0;
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(counter, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (mine) list[base + (uint32_t)__popc(m & lanemask_lt())] = k;
+}
+
+// k_group: single-column symbols, lane per symbol (registers only); everything else is queued for k_group2
+// (two variable columns already give up to 25 alternatives, more than a lane's register list holds).
+__global__ void k_group(MsaGeom g, MsaBufs b, uint32_t narrow_ok) {
+    MsaStatus* st = b.status;
+    if (st->abort || st->halo_fail) return;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const uint32_t v_lo = st->v_lo, v_hi = st->v_hi;
+    unsigned long long alts_here = 0;
+    for (uint32_t v0 = v_lo + (blockIdx.x * wpb + warp) * 32u; v0 < v_hi; v0 += gridDim.x * wpb * 32u) {
+        const uint32_t v = v0 + lane;
+        const bool have = v < v_hi;
+        const uint32_t k = have ? b.varsym[v] : 0u;
+        uint32_t s = 0, en = 0;
+        if (have) {
+            s = b.sym[k] & kColMask;
+            en = b.sym[k + 1] & kColMask;
+        }
+        uint32_t cls = !have ? 0u : ((narrow_ok && en - s == 1u) ? 1u : 3u);
+        if (cls == 1u) {
+            Seen sn;
+            if (narrow_scan(b.stash + (size_t)first_slot(b, s) * g.Rp, g.R, sn)) {
+                // alternative = the residue, or the empty string for '-'
+                uint32_t chars = 0;
+                for (uint32_t a = 0; a < sn.n; ++a) chars += seen_byte(sn, a) != (uint32_t)'-';
+                b.sym_nalts[k] = sn.n;
+                b.sym_edsz[k] = 2ull + chars + (sn.n - 1u);
+                alts_here += sn.n;
+            } else {
+                cls = 3u;
+            }
+        }
+        list_append(b.widelist, &st->n_wide, cls == 3u, k);
+    }
+    alts_here = warp_sum(alts_here);
+    if (lane == 0 && alts_here) atomicAdd(&st->n_alts, alts_here);
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->n_var_syms = v_hi - v_lo;
+}
+
+// k_group2: the queued symbols, warp per symbol, evenly strided over the list.
+__global__ void k_group2(MsaGeom g, MsaBufs b, uint32_t Rq, uint32_t T, uint32_t use_global, uint32_t stage_bytes,
+                         uint32_t per_warp_smem) {
+    MsaStatus* st = b.status;
+    if (st->abort || st->halo_fail) return;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    unsigned char* smem = EDSB_DYN_SMEM() + (size_t)warp * per_warp_smem;
+    unsigned char* base = use_global ? b.group_ws + ((size_t)blockIdx.x * wpb + warp) * ((size_t)Rq * 16u + (size_t)T * 4u) : smem;
+    GroupScratch sc;
+    sc.hrow = reinterpret_cast<unsigned long long*>(base);
+    sc.len = reinterpret_cast<uint32_t*>(sc.hrow + Rq);
+    sc.lead = sc.len + Rq;
+    sc.tab = sc.lead + Rq;
+    sc.stage = reinterpret_cast<uint8_t*>(sc.tab + T);  // only when the scratch is in shared memory
+    sc.cdesc = reinterpret_cast<uint16_t*>(sc.stage + stage_bytes);
+    sc.T = T;
+    sc.stage_bytes = use_global ? 0u : stage_bytes;
+    const uint32_t n_wide = st->n_wide;
+    unsigned long long alts_here = 0;
+    for (uint32_t item = blockIdx.x * wpb + warp; item < n_wide; item += gridDim.x * wpb) {
+        const uint32_t kw = b.widelist[item];
+        group_wide(g, b, sc, kw);
+        if (lane == 0) alts_here += b.sym_nalts[kw];
+    }
+    if (lane == 0 && alts_here) atomicAdd(&st->n_alts, alts_here);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -698,116 +982,284 @@ __global__ void k_emit_common(MsaGeom g, MsaBufs b) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_emit_var: one warp per owned variable symbol writes "{alt0,alt1,...}" and one "{ids}" per
-// alternative (msa_transforms.cpp:297-317). SEDS ids are 1-based rows in ascending order; a row's
-// byte offset is  base(alt) + bytes of lower rows of the same alternative, obtained per 32-row chunk
-// from __match_any_sync plus per-alternative running totals. Within a chunk decimal widths take at
-// most two values, so the in-chunk prefix is two popcounts.
-// Per-warp scratch: altw[Rq], altbase[Rq], running[Rq] (uint32).
+// k_emit_var: "{alt0,alt1,...}" and one "{ids}" per alternative for every owned variable symbol
+// (msa_transforms.cpp:297-317); SEDS ids are 1-based rows in ascending order.
+//  * wide (warp per symbol): a row's byte offset is base(alt) + bytes of lower rows of the same alternative,
+//    obtained per 32-row chunk from __match_any_sync plus per-alternative running totals. Within a chunk
+//    decimal widths take at most two values, so the in-chunk prefix is two popcounts.
+//    Scratch: altw[Rq], altbase[Rq], running[Rq] (uint32) + the stage of stage_symbol.
+//  * narrow (lane per single-column symbol, `nb` symbols per warp pass): the lane re-derives the residue
+//    order (cheaper than storing it), counts bytes per alternative, then places every id in a per-lane
+//    segment of shared memory; segments are copied out with 16-byte stores by the whole warp, so the SEDS
+//    (70 % of the output bytes) leaves the SM coalesced. The row number's digits are warp-uniform.
+//    Scratch (aliases the wide scratch): cnt[8][32], cur[8][32] (uint32), nb segments of seg_pitch bytes.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_emit_var(MsaGeom g, MsaBufs b, uint32_t Rq, uint32_t use_global) {
+struct EmitScratch {
+    uint32_t* altw;
+    uint32_t* altbase;
+    uint32_t* running;
+    uint8_t* stage;
+    uint16_t* cdesc;
+    uint32_t stage_bytes;
+};
+
+__device__ void emit_wide(const MsaGeom& g, const MsaBufs& b, const EmitScratch& sc, uint32_t k) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt = lanemask_lt();
+    uint32_t *altw = sc.altw, *altbase = sc.altbase, *running = sc.running;
+    const uint32_t e = b.sym[k];
+    const uint32_t s = e & kColMask, en = b.sym[k + 1] & kColMask;
+    const uint32_t slot0 = first_slot(b, s);
+    const uint32_t nalts = b.sym_nalts[k];
+    RowWalk w{b.vbits, b.refc, b.stash, g.Rp, sc.cdesc, sc.stage, s, false};
+    w.staged = stage_symbol(g, b, s, en, slot0, sc.cdesc, sc.stage, sc.stage_bytes);
+    uint8_t* eds = b.eds_out + b.eds_off[k];
+    uint8_t* seds = b.seds_out + b.seds_off[k];
+
+    // ---- EDS: '{' alt0 ',' alt1 ... '}' in leader-row order
+    unsigned long long run = 1;
+    uint32_t a_base = 0;
+    for (uint32_t r0 = 0; r0 < g.R; r0 += 32) {
+        const uint32_t r = r0 + lane;
+        const uint32_t mask = b.leadmask[(size_t)slot0 * (g.Rp >> 5) + (r0 >> 5)];
+        const bool isl = (mask >> lane) & 1u;
+        uint32_t n = 0;
+        if (isl) {
+            uint32_t c = s, slot = slot0;
+            while (next_char(w, r, c, en, slot) >= 0) ++n;
+        }
+        const unsigned long long contrib = isl ? (unsigned long long)n + 1ull : 0ull;
+        const unsigned long long inc = warp_inclusive_scan(contrib);
+        if (isl) {
+            const unsigned long long pos = run + inc - contrib;
+            const uint32_t a = a_base + (uint32_t)__popc(mask & lt);
+            eds[pos - 1] = a == 0 ? '{' : ',';
+            uint32_t c = s, slot = slot0;
+            unsigned long long at = pos;
+            int ch;
+            while ((ch = next_char(w, r, c, en, slot)) >= 0) eds[at++] = (uint8_t)ch;
+        }
+        run += __shfl_sync(0xffffffffu, inc, 31);
+        a_base += (uint32_t)__popc(mask);
+    }
+    if (lane == 0) eds[run - 1] = '}';
+
+    // ---- SEDS pass 1: bytes per alternative (each id costs separator + digits)
+    for (uint32_t i = lane; i < nalts; i += 32) {
+        altw[i] = 0;
+        running[i] = 0;
+    }
+    __syncwarp();
+    for (uint32_t r0 = 0; r0 < g.R; r0 += 32) {
+        const uint32_t r = r0 + lane;
+        const bool valid = r < g.R;
+        const uint32_t a = valid ? load_alt(g, b.altid, (size_t)slot0 * g.Rp + r) : kEmptySlot;
+        const uint32_t wd = decimal_width(r + 1u) + 1u;
+        const uint32_t wfirst = __shfl_sync(0xffffffffu, wd, 0);
+        const uint32_t mA = __ballot_sync(0xffffffffu, wd == wfirst);
+        const uint32_t peers = __match_any_sync(0xffffffffu, a);
+        if (valid && lane == (uint32_t)__ffs((int)peers) - 1u)
+            altw[a] += (uint32_t)__popc(peers & mA) * wfirst + (uint32_t)__popc(peers & ~mA) * (wfirst + 1u);
+        __syncwarp();
+    }
+    // exclusive scan over alternatives; every finished alternative adds its '}'
+    uint32_t carry = 0;
+    for (uint32_t i0 = 0; i0 < nalts; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const uint32_t v = i < nalts ? altw[i] + 1u : 0u;
+        const uint32_t inc = warp_inclusive_scan(v);
+        if (i < nalts) altbase[i] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    __syncwarp();
+    // ---- SEDS pass 2: place every id
+    for (uint32_t r0 = 0; r0 < g.R; r0 += 32) {
+        const uint32_t r = r0 + lane;
+        const bool valid = r < g.R;
+        const uint32_t a = valid ? load_alt(g, b.altid, (size_t)slot0 * g.Rp + r) : kEmptySlot;
+        const uint32_t wd = decimal_width(r + 1u) + 1u;
+        const uint32_t wfirst = __shfl_sync(0xffffffffu, wd, 0);
+        const uint32_t mA = __ballot_sync(0xffffffffu, wd == wfirst);
+        const uint32_t peers = __match_any_sync(0xffffffffu, a);
+        const uint32_t below = peers & lt;
+        const uint32_t pre = (uint32_t)__popc(below & mA) * wfirst + (uint32_t)__popc(below & ~mA) * (wfirst + 1u);
+        uint32_t done = 0;
+        if (valid) {
+            done = running[a] + pre;
+            uint8_t* dst = seds + altbase[a] + done;
+            dst[0] = done == 0 ? '{' : ',';
+            write_decimal(dst + 1, r + 1u, wd - 1u);
+            if (done + wd == altw[a]) dst[wd] = '}';
+        }
+        __syncwarp();
+        if (valid && lane == 31u - (uint32_t)__clz((int)peers)) running[a] = done + wd;
+        __syncwarp();
+    }
+    __syncwarp();
+}
+
+// warp-cooperative copy of n bytes from shared to global memory; (dst - src) is a multiple of 16
+__device__ __forceinline__ void warp_copy_out(uint8_t* dst, const uint8_t* src, uint32_t n) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t head = min(n, (uint32_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u));
+    if (lane < head) dst[lane] = src[lane];
+    const uint32_t body = (n - head) >> 4;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
+    uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+    for (uint32_t i = lane; i < body; i += 32) d4[i] = s4[i];
+    const uint32_t done = head + (body << 4);
+    if (done + lane < n) dst[done + lane] = src[done + lane];
+}
+
+// Narrow SEDS segment of one lane: alternative a occupies [start[a], start[a] + cnt[a]], '{' first and '}'
+// last. cnt[a * 32 + lane] holds the byte counts on entry; cur[] receives the write cursors (top bit = no id
+// placed yet). Returns the segment length.
+__device__ __forceinline__ uint32_t seg_layout(uint8_t* seg, const uint32_t* cnt, uint32_t* cur, uint32_t nalts) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t at = 0;
+    for (uint32_t a = 0; a < nalts; ++a) {
+        const uint32_t c = cnt[a * 32u + lane];
+        cur[a * 32u + lane] = at | 0x80000000u;
+        seg[at] = '{';
+        seg[at + c] = '}';
+        at += c + 1u;
+    }
+    return at;
+}
+
+__device__ __forceinline__ void seg_place(uint8_t* seg, uint32_t* cur, uint32_t a, uint32_t id) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t wd = decimal_width(id);
+    const uint32_t cv = cur[a * 32u + lane], pos = cv & 0x7fffffffu;
+    if (!(cv >> 31)) seg[pos] = ',';
+    write_decimal(seg + pos + 1u, id, wd);
+    cur[a * 32u + lane] = pos + wd + 1u;
+}
+
+// copy the finished segments out, one symbol at a time, whole warp per symbol
+__device__ __forceinline__ void segs_copy_out(const uint8_t* segs, uint32_t seg_pitch, uint32_t seg_bytes, uint32_t shift,
+                                              uint8_t* seds_dst) {
+    uint32_t ready = __ballot_sync(0xffffffffu, seg_bytes != 0u);
+    while (ready) {
+        const uint32_t bit = (uint32_t)__ffs((int)ready) - 1u;
+        ready &= ready - 1u;
+        const uint32_t n = __shfl_sync(0xffffffffu, seg_bytes, (int)bit);
+        const uint32_t sh = __shfl_sync(0xffffffffu, shift, (int)bit);
+        const unsigned long long dst =
+            __shfl_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(seds_dst), (int)bit);
+        warp_copy_out(reinterpret_cast<uint8_t*>((uintptr_t)dst), segs + (size_t)bit * seg_pitch + sh, n);
+    }
+}
+
+// k_emit_var: the single-column symbols (lane per symbol, nb symbols per warp pass).
+// idtab[r] = decimal digits of r + 1 packed in 24 bits (first digit lowest) | width << 24, built once per
+// block so the per-row decimal work is a table lookup (R <= 999 here: the host turns the narrow path off
+// for more rows).
+__global__ void k_emit_var(MsaGeom g, MsaBufs b, uint32_t per_warp_smem, uint32_t nb, uint32_t seg_pitch) {
+    const MsaStatus* st = b.status;
+    if (st->abort || st->halo_fail || nb == 0u) return;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    uint32_t* idtab = reinterpret_cast<uint32_t*>(EDSB_DYN_SMEM());
+    for (uint32_t r = threadIdx.x; r < g.R; r += blockDim.x) {
+        const uint32_t id = r + 1u, wd = decimal_width(id);
+        uint8_t d[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        write_decimal(d, id, wd);
+        idtab[r] = (uint32_t)d[0] | ((uint32_t)d[1] << 8) | ((uint32_t)d[2] << 16) | (wd << 24);
+    }
+    __syncthreads();
+    unsigned char* smem = EDSB_DYN_SMEM() + (((size_t)g.R * 4u + 15u) & ~(size_t)15u) + (size_t)warp * per_warp_smem;
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem);  // [8][32]
+    uint32_t* cur = cnt + 256;                           // [8][32]
+    uint8_t* segs = reinterpret_cast<uint8_t*>(cur + 256);
+    const uint32_t v_lo = st->v_lo, v_hi = st->v_hi;
+
+    for (uint32_t v0 = v_lo + (blockIdx.x * wpb + warp) * nb; v0 < v_hi; v0 += gridDim.x * wpb * nb) {
+        const uint32_t v = v0 + lane;
+        const bool have = lane < nb && v < v_hi;
+        const uint32_t k = have ? b.varsym[v] : 0u;
+        uint32_t s = 0, en = 0;
+        if (have) {
+            s = b.sym[k] & kColMask;
+            en = b.sym[k + 1] & kColMask;
+        }
+        uint32_t seg_bytes = 0, shift = 0;
+        uint8_t* seds_dst = nullptr;
+        if (have && en - s == 1u) {
+            const uint8_t* col = b.stash + (size_t)first_slot(b, s) * g.Rp;
+            // pass A: residue order + SEDS bytes per alternative (an id costs separator + digits)
+            Seen sn;
+            sn.lo = sn.hi = sn.n = 0;
+            for (uint32_t a = 0; a < 8u; ++a) cnt[a * 32u + lane] = 0;
+            bool ok = true;
+            for (uint32_t r0 = 0; r0 < g.R && ok; r0 += 4) {
+                uint32_t word = *reinterpret_cast<const uint32_t*>(col + r0);
+                const uint32_t lim = min(4u, g.R - r0);
+                for (uint32_t i = 0; i < lim; ++i) {
+                    const uint32_t ch = word & 0xffu;
+                    word >>= 8;
+                    const uint32_t a = ch ? seen_index(sn, ch) : 8u;
+                    if (a >= 8u) {
+                        ok = false;  // queued as wide by k_group
+                        break;
+                    }
+                    cnt[a * 32u + lane] += (idtab[r0 + i] >> 24) + 1u;
+                }
+            }
+            if (ok) {
+                // EDS text straight from the lane (a dozen bytes)
+                uint8_t* eds = b.eds_out + b.eds_off[k];
+                *eds++ = '{';
+                for (uint32_t a = 0; a < sn.n; ++a) {
+                    if (a) *eds++ = ',';
+                    const uint32_t ch = seen_byte(sn, a);
+                    if (ch != (uint32_t)'-') *eds++ = (uint8_t)ch;
+                }
+                *eds = '}';
+                seds_dst = b.seds_out + b.seds_off[k];
+                shift = ((uint32_t)(reinterpret_cast<uintptr_t>(seds_dst) & 15u) - ((lane * seg_pitch) & 15u)) & 15u;
+                uint8_t* seg = segs + (size_t)lane * seg_pitch + shift;
+                seg_bytes = seg_layout(seg, cnt, cur, sn.n);
+                // pass B: place every id
+                for (uint32_t r0 = 0; r0 < g.R; r0 += 4) {
+                    uint32_t word = *reinterpret_cast<const uint32_t*>(col + r0);
+                    const uint32_t lim = min(4u, g.R - r0);
+                    for (uint32_t i = 0; i < lim; ++i) {
+                        const uint32_t a = seen_index(sn, word & 0xffu);
+                        word >>= 8;
+                        const uint32_t t = idtab[r0 + i], wd = t >> 24;
+                        const uint32_t cv = cur[a * 32u + lane], pos = cv & 0x7fffffffu;
+                        if (!(cv >> 31)) seg[pos] = ',';
+                        seg[pos + 1u] = (uint8_t)t;
+                        if (wd > 1u) seg[pos + 2u] = (uint8_t)(t >> 8);
+                        if (wd > 2u) seg[pos + 3u] = (uint8_t)(t >> 16);
+                        cur[a * 32u + lane] = pos + wd + 1u;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        segs_copy_out(segs, seg_pitch, seg_bytes, shift, seds_dst);
+        __syncwarp();
+    }
+}
+
+// k_emit2: the queued symbols, warp per symbol.
+__global__ void k_emit2(MsaGeom g, MsaBufs b, uint32_t Rq, uint32_t use_global, uint32_t stage_bytes,
+                        uint32_t per_warp_smem) {
     const MsaStatus* st = b.status;
     if (st->abort || st->halo_fail) return;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const size_t per_warp = (size_t)Rq * 12u;
-    unsigned char* base = use_global ? b.group_ws + ((size_t)blockIdx.x * wpb + warp) * per_warp
-                                     : EDSB_DYN_SMEM() + (size_t)warp * per_warp;
-    uint32_t* altw = reinterpret_cast<uint32_t*>(base);
-    uint32_t* altbase = altw + Rq;
-    uint32_t* running = altbase + Rq;
-    const RowWalk w{b.vbits, b.refc, b.stash, g.Rp};
-    const uint32_t k_lo = st->k_lo, k_hi = st->k_hi;
-    const uint32_t lt = lanemask_lt();
-
-    for (uint32_t k = k_lo + blockIdx.x * wpb + warp; k < k_hi; k += gridDim.x * wpb) {
-        const uint32_t e = b.sym[k];
-        if (e & kCommonFlag) continue;  // warp-uniform
-        const uint32_t s = e & kColMask, en = b.sym[k + 1] & kColMask;
-        const uint32_t slot0 = first_slot(b, s);
-        const uint32_t nalts = b.sym_nalts[k];
-        uint8_t* eds = b.eds_out + b.eds_off[k];
-        uint8_t* seds = b.seds_out + b.seds_off[k];
-
-        // ---- EDS: '{' alt0 ',' alt1 ... '}' in leader-row order
-        unsigned long long run = 1;
-        uint32_t a_base = 0;
-        for (uint32_t r0 = 0; r0 < g.R; r0 += 32) {
-            const uint32_t r = r0 + lane;
-            const uint32_t mask = b.leadmask[(size_t)slot0 * (g.Rp >> 5) + (r0 >> 5)];
-            const bool isl = (mask >> lane) & 1u;
-            uint32_t n = 0;
-            if (isl) {
-                uint32_t c = s, slot = slot0;
-                while (next_char(w, r, c, en, slot) >= 0) ++n;
-            }
-            const unsigned long long contrib = isl ? (unsigned long long)n + 1ull : 0ull;
-            const unsigned long long inc = warp_inclusive_scan(contrib);
-            if (isl) {
-                const unsigned long long pos = run + inc - contrib;
-                const uint32_t a = a_base + (uint32_t)__popc(mask & lt);
-                eds[pos - 1] = a == 0 ? '{' : ',';
-                uint32_t c = s, slot = slot0;
-                unsigned long long at = pos;
-                int ch;
-                while ((ch = next_char(w, r, c, en, slot)) >= 0) eds[at++] = (uint8_t)ch;
-            }
-            run += __shfl_sync(0xffffffffu, inc, 31);
-            a_base += (uint32_t)__popc(mask);
-        }
-        if (lane == 0) eds[run - 1] = '}';
-
-        // ---- SEDS pass 1: bytes per alternative (each id costs separator + digits)
-        for (uint32_t i = lane; i < nalts; i += 32) {
-            altw[i] = 0;
-            running[i] = 0;
-        }
-        __syncwarp();
-        for (uint32_t r0 = 0; r0 < g.R; r0 += 32) {
-            const uint32_t r = r0 + lane;
-            const bool valid = r < g.R;
-            const uint32_t a = valid ? load_alt(g, b.altid, (size_t)slot0 * g.Rp + r) : kEmptySlot;
-            const uint32_t wd = decimal_width(r + 1u) + 1u;
-            const uint32_t wfirst = __shfl_sync(0xffffffffu, wd, 0);
-            const uint32_t mA = __ballot_sync(0xffffffffu, wd == wfirst);
-            const uint32_t peers = __match_any_sync(0xffffffffu, a);
-            if (valid && lane == (uint32_t)__ffs((int)peers) - 1u)
-                altw[a] += (uint32_t)__popc(peers & mA) * wfirst + (uint32_t)__popc(peers & ~mA) * (wfirst + 1u);
-            __syncwarp();
-        }
-        // exclusive scan over alternatives; every finished alternative adds its '}'
-        uint32_t carry = 0;
-        for (uint32_t i0 = 0; i0 < nalts; i0 += 32) {
-            const uint32_t i = i0 + lane;
-            const uint32_t v = i < nalts ? altw[i] + 1u : 0u;
-            const uint32_t inc = warp_inclusive_scan(v);
-            if (i < nalts) altbase[i] = carry + inc - v;
-            carry += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        __syncwarp();
-        // ---- SEDS pass 2: place every id
-        for (uint32_t r0 = 0; r0 < g.R; r0 += 32) {
-            const uint32_t r = r0 + lane;
-            const bool valid = r < g.R;
-            const uint32_t a = valid ? load_alt(g, b.altid, (size_t)slot0 * g.Rp + r) : kEmptySlot;
-            const uint32_t wd = decimal_width(r + 1u) + 1u;
-            const uint32_t wfirst = __shfl_sync(0xffffffffu, wd, 0);
-            const uint32_t mA = __ballot_sync(0xffffffffu, wd == wfirst);
-            const uint32_t peers = __match_any_sync(0xffffffffu, a);
-            const uint32_t below = peers & lt;
-            const uint32_t pre = (uint32_t)__popc(below & mA) * wfirst + (uint32_t)__popc(below & ~mA) * (wfirst + 1u);
-            uint32_t done = 0;
-            if (valid) {
-                done = running[a] + pre;
-                uint8_t* dst = seds + altbase[a] + done;
-                dst[0] = done == 0 ? '{' : ',';
-                write_decimal(dst + 1, r + 1u, wd - 1u);
-                if (done + wd == altw[a]) dst[wd] = '}';
-            }
-            __syncwarp();
-            if (valid && lane == 31u - (uint32_t)__clz((int)peers)) running[a] = done + wd;
-            __syncwarp();
-        }
-    }
+    const uint32_t warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    unsigned char* smem = EDSB_DYN_SMEM() + (size_t)warp * per_warp_smem;
+    unsigned char* base = use_global ? b.group_ws + ((size_t)blockIdx.x * wpb + warp) * ((size_t)Rq * 12u) : smem;
+    EmitScratch sc;
+    sc.altw = reinterpret_cast<uint32_t*>(base);
+    sc.altbase = sc.altw + Rq;
+    sc.running = sc.altbase + Rq;
+    sc.stage = reinterpret_cast<uint8_t*>(sc.running + Rq);
+    sc.cdesc = reinterpret_cast<uint16_t*>(sc.stage + stage_bytes);
+    sc.stage_bytes = use_global ? 0u : stage_bytes;
+    const uint32_t n_wide = st->n_wide;
+    for (uint32_t item = blockIdx.x * wpb + warp; item < n_wide; item += gridDim.x * wpb) emit_wide(g, b, sc, b.widelist[item]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -852,6 +1304,12 @@ __global__ void k_synth(uint8_t* text, const uint64_t* row_off, uint32_t R, uint
 // =============================================================================================
 // Host side
 // =============================================================================================
+
+#ifdef EDSB_EMU
+constexpr uint32_t kSymWarps = 2;  // fewer OS threads per emulated block
+#else
+constexpr uint32_t kSymWarps = 8;
+#endif
 
 static uint32_t pow2_ceil(uint32_t v) {
     uint32_t p = 1;
@@ -932,8 +1390,40 @@ void MsaPipeline::prepare(const eds_msa_view& v, uint32_t l, int leds) {
         if (v.row_start[r] + g.row_bytes > v.text_bytes) throw BadMsa("a row runs past the end of the buffer (rows of unequal length?)");
 
     cudaStream_t s = ctx_->stream;
-    d_rows_.reserve((size_t)v.n_rows * 8);
-    EDSB_CUDA(cudaMemcpyAsync(d_rows_.p, v.row_start, (size_t)v.n_rows * 8, cudaMemcpyHostToDevice, s));
+    // device copy of the row offsets, followed by the packed (vector address | byte shift) of the rows
+    // sorted by word shift: [row 0][class 0 rows][class 1]...[class 3]
+    h_rows_.resize((size_t)v.n_rows * 2);
+    long long dmin = 0, dmax = 0;
+    uint32_t count[4] = {0, 0, 0, 0};
+    bool all_aligned = true;
+    for (uint32_t r = 0; r < v.n_rows; ++r) {
+        const long long d = (long long)v.row_start[r] - (long long)g.a0;
+        const long long dv = d >> 4;
+        if (r == 0 || dv < dmin) dmin = dv;
+        if (r == 0 || dv > dmax) dmax = dv;
+        h_rows_[r] = v.row_start[r];
+        if (r > 0) {
+            ++count[(d & 15) >> 2];
+            all_aligned = all_aligned && (d & 15) == 0;
+        }
+    }
+    g.cls[0] = 1;
+    for (int c = 0; c < 4; ++c) g.cls[c + 1] = g.cls[c] + count[c];
+    g.all_aligned = all_aligned ? 1u : 0u;
+    {
+        uint32_t at[4] = {g.cls[0], g.cls[1], g.cls[2], g.cls[3]};
+        uint64_t* pack = h_rows_.data() + v.n_rows;
+        for (uint32_t r = 0; r < v.n_rows; ++r) {
+            const long long d = (long long)v.row_start[r] - (long long)g.a0;
+            const uint64_t e =
+                (uint64_t)(reinterpret_cast<uintptr_t>(v.text) + (unsigned long long)((d >> 4) * 16)) | (uint64_t)(d & 15);
+            pack[r == 0 ? 0 : at[(d & 15) >> 2]++] = e;
+        }
+    }
+    g.d_min_vec = dmin;
+    g.d_max_vec = dmax;
+    d_rows_.reserve((size_t)v.n_rows * 16);
+    EDSB_CUDA(cudaMemcpyAsync(d_rows_.p, h_rows_.data(), (size_t)v.n_rows * 16, cudaMemcpyHostToDevice, s));
     g.row_off = d_rows_.as<uint64_t>();
 
     const uint32_t P = partitions();
@@ -942,7 +1432,7 @@ void MsaPipeline::prepare(const eds_msa_view& v, uint32_t l, int leds) {
     d_tbits_.reserve((size_t)(g.n_words + 1) * 4);
     d_rank_.reserve((size_t)(g.n_words + 1) * 4);
     d_refc_.reserve((size_t)g.n_words * 32 + 32);
-    d_part_.reserve((size_t)P * (8 + 4 + 16));
+    d_part_.reserve((size_t)P * (8 + 8 + 16));
 }
 
 void MsaPipeline::bind(MsaBufs& b) {
@@ -957,11 +1447,11 @@ void MsaPipeline::bind(MsaBufs& b) {
     unsigned char* part = d_part_.as<unsigned char>();
     b.part_sz = reinterpret_cast<unsigned long long*>(part);
     b.part_cnt = reinterpret_cast<uint2*>(part + (size_t)P * 16);
-    b.part_sym = reinterpret_cast<uint32_t*>(part + (size_t)P * 24);
+    b.part_sym = reinterpret_cast<unsigned long long*>(part + (size_t)P * 24);
 
     d_varcol_.reserve((size_t)cap_var_ * 4);
     d_runs_.reserve((size_t)(cap_runs_ + 2) * 4);
-    d_sym_.reserve((size_t)(cap_runs_ + 2) * 4);
+    d_sym_.reserve((size_t)(cap_runs_ + 2) * 16);  // sym[], varsym[], multilist[], widelist[]
     d_stash_.reserve((size_t)cap_var_ * g.Rp);
     d_altid_.reserve((size_t)cap_var_ * g.Rp * (g.alt32 ? 4 : 2));
     d_leadmask_.reserve((size_t)cap_var_ * (g.Rp / 32) * 4);
@@ -971,6 +1461,9 @@ void MsaPipeline::bind(MsaBufs& b) {
     b.varcol = d_varcol_.as<uint32_t>();
     b.runs = d_runs_.as<uint32_t>();
     b.sym = d_sym_.as<uint32_t>();
+    b.varsym = b.sym + (size_t)cap_runs_ + 2;
+    b.multilist = b.varsym + (size_t)cap_runs_ + 2;
+    b.widelist = b.multilist + (size_t)cap_runs_ + 2;
     b.stash = d_stash_.as<uint8_t>();
     b.altid = d_altid_.p;
     b.leadmask = d_leadmask_.as<uint32_t>();
@@ -993,11 +1486,16 @@ void MsaPipeline::bind(MsaBufs& b) {
 void MsaPipeline::launch_scan(const MsaBufs& b) {
     const MsaGeom& g = geom_;
     cudaStream_t s = ctx_->stream;
-    const uint32_t per_sm = ctx_->scan_blocks_per_sm ? ctx_->scan_blocks_per_sm : 4u;
+    const uint32_t per_sm = ctx_->scan_blocks_per_sm ? ctx_->scan_blocks_per_sm : 16u;
     const uint32_t tiles = (g.n_chunks + 31) / 32;
     const uint32_t blocks = std::max(1u, std::min((tiles + 7) / 8, (uint32_t)ctx_->sm_count * per_sm));
     ctx_->clock.begin("k_scan");
-    EDSB_LAUNCH(k_scan, blocks, kScanThreads, 0, s, g, reinterpret_cast<uint16_t*>(b.mism), b.status);
+    const unsigned long long* pack = reinterpret_cast<const unsigned long long*>(g.row_off + g.R);
+    if (g.R <= (uint32_t)kRowCache) {
+        EDSB_LAUNCH(k_scan<true>, blocks, kScanThreads, 0, s, g, pack, reinterpret_cast<uint16_t*>(b.mism), b.status);
+    } else {
+        EDSB_LAUNCH(k_scan<false>, blocks, kScanThreads, 0, s, g, pack, reinterpret_cast<uint16_t*>(b.mism), b.status);
+    }
     ctx_->clock.end();
     ctx_->clock.begin("k_colbits");
     EDSB_LAUNCH(k_colbits, partitions(), kPartThreads, 0, s, g, b.mism, b.vbits, b.tbits, b.refc, b.part_cnt);
@@ -1016,9 +1514,8 @@ void MsaPipeline::run_once(MsaBufs& b) {
     EDSB_LAUNCH(k_compact, P, kPartThreads, 0, s, g, b);
     ctx_->clock.end();
 
-    const uint32_t stash_threads = g.R <= 128 ? 128u : 256u;
     ctx_->clock.begin("k_stash");
-    EDSB_LAUNCH(k_stash, sms * 16u, stash_threads, 0, s, g, b);
+    EDSB_LAUNCH(k_stash, sms * 8u, kStashThreads, 0, s, g, b);
     ctx_->clock.end();
 
     ctx_->clock.begin("k_sym_count");
@@ -1031,36 +1528,68 @@ void MsaPipeline::run_once(MsaBufs& b) {
     EDSB_LAUNCH(k_finalize, 1, 32, 0, s, g, b);
     ctx_->clock.end();
 
-    // per-warp scratch: shared memory while it fits, else a global workspace
+    // ---- variable symbols. Single-column ones (lane per symbol) are handled by k_group / k_emit_var; the
+    // rest is queued for k_group2 / k_emit2 (warp per symbol). Warp-path scratch lives in shared memory
+    // while it fits, else in a global workspace, plus a stage for the symbol's stash block (>= 2 variable
+    // columns; 2 KB when rows are few). k_emit_var needs nb segments of seg_pitch bytes per warp; nb == 0
+    // (too many rows for shared memory) turns the lane-per-symbol path off in k_group as well.
     const uint32_t Rq = std::max(32u, pow2_ceil(g.R));
     const uint32_t T = 2u * Rq;
     const size_t group_per_warp = (size_t)Rq * 16 + (size_t)T * 4;
     const size_t emit_per_warp = (size_t)Rq * 12;
+    const uint32_t stage_bytes = std::max<uint32_t>(2048u, 4u * g.Rp);
+    const size_t stage_per_warp = (size_t)stage_bytes + kStageCols * 2;
     const size_t smem_budget = std::min<size_t>(ctx_->smem_optin, 200 * 1024);
-    uint32_t gw = 8;  // warps per block
-    while (gw > 1 && gw * group_per_warp > smem_budget / 2) gw >>= 1;
+    // segments: 8 + sum of id widths + R bytes at most, pitch/4 odd (bank spread), room for the 16-byte shift
+    uint32_t seg_pitch = (uint32_t)((8 + g.sum_id_width + g.R + 16 + 3) & ~3ull);
+    if (((seg_pitch >> 2) & 1u) == 0) seg_pitch += 4;
+    uint32_t nb = 0, evw = kSymWarps;
+    if (!ctx_->narrow_off && g.R <= 999u) {
+        while (evw > 1 && evw * (2048 + 32 * (size_t)seg_pitch) > smem_budget / 2) evw >>= 1;
+        if (evw * (2048 + 32 * (size_t)seg_pitch) + 4 * (size_t)g.R + 16 <= smem_budget / 2) nb = 32;
+    }
+    const uint32_t narrow_ok = nb ? 1u : 0u;
+    const size_t ev_warp_smem = (2048 + (size_t)nb * seg_pitch + 15) & ~(size_t)15;
+    const size_t ev_smem = narrow_ok ? evw * ev_warp_smem + (((size_t)g.R * 4 + 15) & ~(size_t)15) : 0;
+
+    uint32_t gw = kSymWarps;  // warps per block
+    while (gw > 1 && gw * (group_per_warp + stage_per_warp) > smem_budget / 2) gw >>= 1;
     const bool group_global = gw * group_per_warp > smem_budget;
-    uint32_t ew = 8;
-    while (ew > 1 && ew * emit_per_warp > smem_budget / 2) ew >>= 1;
+    const uint32_t group_stage = (!group_global && gw * (group_per_warp + stage_per_warp) <= smem_budget) ? stage_bytes : 0u;
+    const size_t group_warp_smem = group_global ? 0 : ((group_per_warp + (group_stage ? stage_per_warp : 0) + 15) & ~(size_t)15);
+    uint32_t ew = kSymWarps;
+    while (ew > 1 && ew * (emit_per_warp + stage_per_warp) > smem_budget / 2) ew >>= 1;
     const bool emit_global = ew * emit_per_warp > smem_budget;
-    const uint32_t group_blocks = sms * (group_global ? 2u : std::max(1u, 32u / gw));
-    const uint32_t emit_blocks = sms * (emit_global ? 2u : std::max(1u, 32u / ew));
+    const uint32_t emit_stage = (!emit_global && ew * (emit_per_warp + stage_per_warp) <= smem_budget) ? stage_bytes : 0u;
+    const size_t emit_warp_smem = emit_global ? 0 : ((emit_per_warp + (emit_stage ? stage_per_warp : 0) + 15) & ~(size_t)15);
+    const size_t group_smem = gw * group_warp_smem, emit_smem = ew * emit_warp_smem;
+    int g1_occ = 4, g2_occ = 2, ev_occ = 2, e2_occ = 2;
+#ifndef EDSB_EMU
+    if (group_smem > 48 * 1024)
+        EDSB_CUDA(cudaFuncSetAttribute(k_group2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)group_smem));
+    if (emit_smem > 48 * 1024)
+        EDSB_CUDA(cudaFuncSetAttribute(k_emit2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
+    if (ev_smem > 48 * 1024)
+        EDSB_CUDA(cudaFuncSetAttribute(k_emit_var, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev_smem));
+    EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g1_occ, k_group, kPartThreads, 0));
+    EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g2_occ, k_group2, (int)(gw * 32u), group_smem));
+    EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ev_occ, k_emit_var, (int)(evw * 32u), ev_smem));
+    EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e2_occ, k_emit2, (int)(ew * 32u), emit_smem));
+#endif
+    const uint32_t g2_blocks = sms * (uint32_t)std::max(1, g2_occ);
+    const uint32_t e2_blocks = sms * (uint32_t)std::max(1, e2_occ);
     if (group_global || emit_global) {
-        const size_t need = std::max(group_global ? (size_t)group_blocks * gw * group_per_warp : 0,
-                                     emit_global ? (size_t)emit_blocks * ew * emit_per_warp : 0);
+        const size_t need = std::max(group_global ? (size_t)g2_blocks * gw * group_per_warp : 0,
+                                     emit_global ? (size_t)e2_blocks * ew * emit_per_warp : 0);
         d_ws_.reserve(need);
         b.group_ws = d_ws_.as<uint8_t>();
     }
-    const size_t group_smem = group_global ? 0 : gw * group_per_warp;
-    const size_t emit_smem = emit_global ? 0 : ew * emit_per_warp;
-#ifndef EDSB_EMU
-    if (group_smem > 48 * 1024)
-        EDSB_CUDA(cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)group_smem));
-    if (emit_smem > 48 * 1024)
-        EDSB_CUDA(cudaFuncSetAttribute(k_emit_var, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
-#endif
     ctx_->clock.begin("k_group");
-    EDSB_LAUNCH(k_group, group_blocks, gw * 32u, group_smem, s, g, b, Rq, T, group_global ? 1u : 0u);
+    EDSB_LAUNCH(k_group, sms * (uint32_t)std::max(1, g1_occ), kPartThreads, 0, s, g, b, narrow_ok);
+    ctx_->clock.end();
+    ctx_->clock.begin("k_group2");
+    EDSB_LAUNCH(k_group2, g2_blocks, gw * 32u, group_smem, s, g, b, Rq, T, group_global ? 1u : 0u, group_stage,
+                (uint32_t)group_warp_smem);
     ctx_->clock.end();
 
     ctx_->clock.begin("k_size_count");
@@ -1073,8 +1602,15 @@ void MsaPipeline::run_once(MsaBufs& b) {
     ctx_->clock.begin("k_emit_common");
     EDSB_LAUNCH(k_emit_common, sms * 8u, kPartThreads, 0, s, g, b);
     ctx_->clock.end();
-    ctx_->clock.begin("k_emit_var");
-    EDSB_LAUNCH(k_emit_var, emit_blocks, ew * 32u, emit_smem, s, g, b, Rq, emit_global ? 1u : 0u);
+    if (narrow_ok) {
+        ctx_->clock.begin("k_emit_var");
+        EDSB_LAUNCH(k_emit_var, sms * (uint32_t)std::max(1, ev_occ), evw * 32u, ev_smem, s, g, b, (uint32_t)ev_warp_smem, nb,
+                    seg_pitch);
+        ctx_->clock.end();
+    }
+    ctx_->clock.begin("k_emit2");
+    EDSB_LAUNCH(k_emit2, e2_blocks, ew * 32u, emit_smem, s, g, b, Rq, emit_global ? 1u : 0u, emit_stage,
+                (uint32_t)emit_warp_smem);
     ctx_->clock.end();
 
     EDSB_CUDA(cudaMemcpyAsync(h_status_, b.status, sizeof(MsaStatus), cudaMemcpyDeviceToHost, s));

@@ -21,6 +21,7 @@ struct MsaGeom {
     uint64_t row_bytes;  // bytes per held row segment (first..last held residue, newlines inside)
     uint64_t sum_id_width;  // sum of decimal_width(i), i = 1..R
     uint64_t hash_mask;     // all ones; tests narrow it to force hash collisions
+    long long d_min_vec, d_max_vec;  // min / max over rows of floor((row_off[r] - a0) / 16)
     uint32_t R;
     uint32_t Rp;  // R rounded up to a multiple of 32 (row pitch of the column stash)
     uint32_t lw;
@@ -33,6 +34,8 @@ struct MsaGeom {
     uint32_t l;
     uint32_t leds;   // 1: l-EDS boundaries (build_leds_boundaries), 0: plain EDS
     uint32_t alt32;  // alternative ids stored as uint32 (R > 65535) instead of uint16
+    uint32_t cls[5];       // k_scan: rows of word-shift class c are row_pack[cls[c]..cls[c+1])
+    uint32_t all_aligned;  // every row is 16-byte congruent with row 0
 };
 
 enum MsaAbort : uint32_t {
@@ -55,13 +58,15 @@ struct MsaStatus {
     uint32_t n_syms;  // symbols opening anywhere in the window
     uint32_t k_lo, k_hi;  // owned symbols are [k_lo, k_hi)
     uint32_t n_var_syms;  // owned variable symbols
+    uint32_t n_varsyms_window;  // variable symbols in the window
+    uint32_t v_lo, v_hi;        // owned slice of varsym[]
+    uint32_t n_multi, n_wide;   // entries of multilist / widelist
     uint32_t lead_lo, lead_hi;  // window columns of conserved text continuing a lower shard's symbol
     uint32_t lead_close;        // 1: that symbol's '}' belongs to this shard
     uint32_t tail_open;         // 1: the last owned symbol is conserved and is closed by a higher shard
     uint32_t abort;
     uint32_t bad_msa;
     uint32_t halo_fail;
-    uint32_t pad0;
     uint64_t need_var, need_runs, need_eds, need_seds;  // capacities wanted by the stage that aborted
     unsigned long long eds_total, seds_total, n_alts;
     uint64_t first_open_col;
@@ -74,11 +79,14 @@ struct MsaBufs {
     uint32_t* rankdir;   // variable columns before each 32-column word
     uint8_t* refc;       // row 0 in column space (no newlines), n_words * 32 bytes
     uint2* part_cnt;     // per partition {variable columns, run starts}
-    uint32_t* part_sym;  // per run partition: symbols opened
+    unsigned long long* part_sym;  // per run partition: symbols opened | variable symbols opened << 32
     unsigned long long* part_sz;  // per symbol partition: {eds bytes, seds bytes}
     uint32_t* varcol;    // window column of the k-th variable column
     uint32_t* runs;      // run k: start column | kCommonFlag; runs[n_runs] = ncols
     uint32_t* sym;       // symbol k: start column | kCommonFlag; sym[n_syms] = ncols
+    uint32_t* varsym;    // indices of the variable symbols, ascending
+    uint32_t* multilist; // variable symbols 2..15 columns wide (any order), queued by k_group
+    uint32_t* widelist;  // variable symbols for the warp-per-symbol path (any order)
     uint8_t* stash;      // stash[k * Rp + r] = residue of row r at the k-th variable column
     void* altid;         // altid[slot0 * Rp + r]: alternative index of row r in the symbol whose first variable column is slot0
     uint32_t* leadmask;  // leadmask[slot0 * Rp/32 + r/32]: rows that introduce an alternative

@@ -162,6 +162,31 @@ def check_hash_collision_fallback(lib, seed=11, n_cases=25):
         ctx.close()
 
 
+def check_wide_alphabet(ctx, seed=21, n_cases=8):
+    """More than 8 distinct residues in a column: the lane-per-symbol path must hand the symbol to the
+    warp-per-symbol path (its register list holds 8)."""
+    rng = np.random.default_rng(seed)
+    alphabet = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
+    for i in range(n_cases):
+        m = gen.random_alignment(rng, 40, int(rng.integers(5, 80)), p_var=0.2, p_sub=0.8, p_gap=0.05, alphabet=alphabet)
+        text = gen.to_fasta(m, 60)
+        l = int(rng.choice([0, 3]))
+        assert ctx.msa_transform_host(text, l)[:2] == oracle_lib.msa2eds(text, l), (seed, i, l, text)
+
+
+def check_narrow_off(lib, seed=12, n_cases=15):
+    """EDSB_DEBUG_NARROW_OFF=1: every variable symbol goes through the warp-per-symbol path."""
+    os.environ["EDSB_DEBUG_NARROW_OFF"] = "1"
+    try:
+        ctx = lib.context()
+    finally:
+        del os.environ["EDSB_DEBUG_NARROW_OFF"]
+    try:
+        check_random_against_oracle(ctx, seed, n_cases, max_rows=40, max_cols=100, ls=(0, 2, 10))
+    finally:
+        ctx.close()
+
+
 def shard_concat(ctx, dev, idx, cuts, halo, l):
     """Run every shard [cuts[i], cuts[i+1]) with `halo` columns on each side; concatenated outputs."""
     C = idx["n_cols"]

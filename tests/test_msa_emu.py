@@ -42,6 +42,14 @@ def test_hash_collision_fallback():
     msa_checks.check_hash_collision_fallback(emu_lib.lib(), n_cases=10)
 
 
+def test_wide_alphabet(ctx):
+    msa_checks.check_wide_alphabet(ctx, n_cases=5)
+
+
+def test_narrow_path_off():
+    msa_checks.check_narrow_off(emu_lib.lib(), n_cases=6)
+
+
 def test_shards(ctx):
     msa_checks.check_shards(ctx, on_gpu=False, seed=2, n_cases=12, max_cols=150)
 

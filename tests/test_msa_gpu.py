@@ -48,6 +48,14 @@ def test_hash_collision_fallback(lib):
     msa_checks.check_hash_collision_fallback(lib, n_cases=60)
 
 
+def test_wide_alphabet(ctx):
+    msa_checks.check_wide_alphabet(ctx, n_cases=30)
+
+
+def test_narrow_path_off(lib):
+    msa_checks.check_narrow_off(lib, n_cases=60)
+
+
 def test_shards(ctx):
     msa_checks.check_shards(ctx, on_gpu=True, seed=2, n_cases=80, max_cols=2000)
 
