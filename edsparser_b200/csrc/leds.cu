@@ -1,15 +1,913 @@
-// l-EDS merge on the GPU (placeholder until the kernels land).
+// l-EDS merge on the GPU: eds_to_leds_linear / eds_to_leds_cartesian
+// (draessld/EDSParser src/cpp/lib/transforms/eds_transforms.cpp:313-426) behind eds_leds_merge_host.
+//
+// Reference behaviour being reproduced byte for byte:
+//   EDS::parse + normalize_eds_format   formats/eds.cpp:39-155, 831-881   -> k_part_* with StripFn/DepthFn/EventFn
+//   EDS::parse_sources                  formats/eds.cpp:268-355           -> SetFn, RankFn, k_bits_fill, k_universal
+//   is_leds / select_independent_merge_pairs   eds_transforms.cpp:439-468 / 46-107  -> k_cand + RunFn (max-scan)
+//   merge_multiple_pairs / EDS::merge_adjacent eds_transforms.cpp:120-196, eds.cpp:1425-1695 -> k_kept, k_merge_write
+//   reconstruct_eds                     eds_transforms.cpp:207-296        -> k_rebuild (no text round trip)
+//   EDS::save / save_sources            formats/eds.cpp:600-659           -> k_expand, k_emit_eds, k_emit_seds
+//
+// Formulation (nothing is taken from the reference's code, which rebuilds the whole EDS object per pair):
+//  * every original string is a LEAF of an alternative pool {left, right, len, source bitset}; a merge round
+//    appends one pool entry per surviving (left alt, right alt) combination — a merge TREE, no string is
+//    copied until the final emit;
+//  * sources are dense bitsets (ids ranked by value, so ascending bit = ascending id). A set containing 0
+//    is the reference's universal marker: it is stored as ALL ONES, which makes the {0}-aware intersection
+//    of eds.cpp:1481-1500 a plain AND and "kept" a non-zero test;
+//  * the greedy left-to-right pair selection is "1st, 3rd, 5th ... candidate of every run of consecutive
+//    candidates": a max-scan for the run start plus a parity test;
+//  * CARTESIAN is the same machinery with zero-width bitsets (everything is kept).
 #include "leds.h"
 
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "scan.cuh"
+
 namespace edsb {
+
+namespace {
+
+constexpr uint32_t kNone = 0xffffffffu;
+constexpr uint32_t kMaxPathId = 1u << 26;  // presence bitmap of 8 MB
+constexpr uint32_t kBigLeaf = 96;          // leaves longer than this are copied by a whole block
+
+enum LedsErr : uint32_t {
+    kErrEdsSyntax = 1,
+    kErrSedsSyntax = 2,
+    kErrSedsBigId = 4,
+    kErrSedsOverflow = 8,
+};
+
+struct LedsStatus {
+    uint32_t err;
+    uint32_t empty_set;    // smallest set index with no ids (kNone if none)
+    uint32_t empty_merge;  // smallest left position of a selected pair that keeps nothing (kNone if none)
+    uint32_t n_big;        // entries of the big-copy list
+    uint32_t max_id;       // largest path id seen
+    uint32_t pad;
+    unsigned long long eds_total, seds_total;
+};
+
+__device__ __forceinline__ bool is_space(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13); }
+__device__ __forceinline__ bool is_digit(uint8_t c) { return c >= (uint8_t)'0' && c <= (uint8_t)'9'; }
+
+// ---- whitespace strip (eds.cpp:46, :272): stream compaction ---------------------------------------
+struct StripFn {
+    const uint8_t* in;
+    uint8_t* out;
+    __device__ unsigned long long value(unsigned long long i) const { return is_space(in[i]) ? 0ull : 1ull; }
+    __device__ void apply(unsigned long long i, unsigned long long prefix, unsigned long long v) const {
+        if (v) out[prefix] = in[i];
+    }
+};
+
+// ---- EDS text: brace depth -------------------------------------------------------------------------
+struct DepthFn {
+    const uint8_t* t;
+    uint8_t* depth;  // depth BEFORE the character: 0 outside a set, 1 inside
+    LedsStatus* st;
+    __device__ unsigned long long value(unsigned long long i) const {
+        return (t[i] == (uint8_t)'{' ? 1ull : 0ull) | (t[i] == (uint8_t)'}' ? 1ull << 32 : 0ull);
+    }
+    __device__ void apply(unsigned long long i, unsigned long long prefix, unsigned long long) const {
+        const long long d = (long long)(prefix & 0xffffffffull) - (long long)(prefix >> 32);
+        const uint8_t c = t[i];
+        if ((c == (uint8_t)'{' && d != 0) || (c == (uint8_t)'}' && d != 1) || d < 0 || d > 1) atomicOr(&st->err, (uint32_t)kErrEdsSyntax);
+        depth[i] = (uint8_t)(d == 1);
+    }
+};
+
+// ---- EDS text: strings and symbols ------------------------------------------------------------------
+// A string starts after '{' or ',' and at the first character of a run of bare text (compact format,
+// normalize_eds_format); a symbol starts at '{' and at the start of a bare run.
+struct EventFn {
+    const uint8_t* t;
+    const uint8_t* depth;
+    uint32_t* str_start;
+    uint32_t* str_end;
+    uint32_t* sym_first;
+    __device__ __forceinline__ void classify(unsigned long long i, bool& e0, bool& e1) const {
+        const uint8_t c = t[i];
+        e1 = c == (uint8_t)'{' || c == (uint8_t)',';
+        const bool bare = c != (uint8_t)'{' && c != (uint8_t)'}' && depth[i] == 0;
+        e0 = bare && (i == 0 || t[i - 1] == (uint8_t)'}');
+    }
+    __device__ unsigned long long value(unsigned long long i) const {
+        bool e0, e1;
+        classify(i, e0, e1);
+        const bool symstart = t[i] == (uint8_t)'{' || e0;
+        return (unsigned long long)(e0 + e1) | (symstart ? 1ull << 32 : 0ull);
+    }
+    __device__ void apply(unsigned long long i, unsigned long long prefix, unsigned long long) const {
+        bool e0, e1;
+        classify(i, e0, e1);
+        uint32_t j = (uint32_t)prefix;
+        const uint32_t si = (uint32_t)(prefix >> 32);
+        const uint8_t c = t[i];
+        if (c == (uint8_t)'{' || e0) sym_first[si] = j;
+        if (e0) {
+            str_start[j] = (uint32_t)i;
+            if (j > 0) str_end[j - 1] = (uint32_t)i - 1u;  // the previous string closed with the '}' before us
+            ++j;
+        }
+        if (e1) {
+            str_start[j] = (uint32_t)i + 1u;
+            if (j > 0) str_end[j - 1] = (c == (uint8_t)',') ? (uint32_t)i : (uint32_t)i - ((i > 0 && t[i - 1] == (uint8_t)'}') ? 1u : 0u);
+        }
+    }
+};
+
+__global__ void k_close_strings(const uint8_t* t, uint32_t n, uint32_t* str_end, uint32_t n_str, uint32_t* sym_first, uint32_t n_sym) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        if (n_str) str_end[n_str - 1] = n - ((n > 0 && t[n - 1] == (uint8_t)'}') ? 1u : 0u);
+        sym_first[n_sym] = n_str;
+    }
+}
+
+// ---- SEDS text ---------------------------------------------------------------------------------------
+// Local grammar checks are enough: '{' only at the start or after '}', '}' / ',' / digits only inside.
+struct SetFn {
+    const uint8_t* s;
+    unsigned long long n;
+    uint32_t* num_val;
+    uint32_t* num_set;
+    uint32_t* present;  // bitmap over id values
+    LedsStatus* st;
+    __device__ __forceinline__ bool numstart(unsigned long long i) const { return is_digit(s[i]) && (i == 0 || !is_digit(s[i - 1])); }
+    __device__ unsigned long long value(unsigned long long i) const {
+        return (s[i] == (uint8_t)'{' ? 1ull : 0ull) | (numstart(i) ? 1ull << 32 : 0ull);
+    }
+    __device__ void apply(unsigned long long i, unsigned long long prefix, unsigned long long) const {
+        const uint8_t c = s[i];
+        const uint8_t p = i ? s[i - 1] : (uint8_t)'}';
+        bool ok;
+        if (c == (uint8_t)'{')
+            ok = p == (uint8_t)'}';
+        else if (c == (uint8_t)'}' || c == (uint8_t)',' || is_digit(c))
+            ok = i > 0 && (p == (uint8_t)'{' || p == (uint8_t)',' || is_digit(p));
+        else
+            ok = false;
+        if (i + 1 == n && c != (uint8_t)'}') ok = false;
+        if (!ok) atomicOr(&st->err, (uint32_t)kErrSedsSyntax);
+        if (!numstart(i)) return;
+        const uint32_t q = (uint32_t)(prefix >> 32);
+        unsigned long long v = 0;
+        uint32_t digits = 0;
+        for (unsigned long long k = i; k < n && is_digit(s[k]); ++k) {
+            if (digits < 12) v = v * 10ull + (unsigned long long)(s[k] - (uint8_t)'0');
+            ++digits;
+        }
+        if (digits > 10 || v > 2147483647ull) {
+            atomicOr(&st->err, (uint32_t)kErrSedsOverflow);  // std::stoi -> std::out_of_range
+            v = 0;
+        } else if (v >= kMaxPathId) {
+            atomicOr(&st->err, (uint32_t)kErrSedsBigId);
+            v = 0;
+        }
+        num_val[q] = (uint32_t)v;
+        num_set[q] = (uint32_t)prefix - 1u;  // sets opened before this number, minus one
+        atomicOr(&present[v >> 5], 1u << (v & 31u));
+        atomicMax(&st->max_id, (uint32_t)v);
+    }
+};
+
+struct RankFn {
+    const uint32_t* present;
+    uint32_t* rank;
+    __device__ unsigned long long value(unsigned long long w) const { return (unsigned long long)__popc(present[w]); }
+    __device__ void apply(unsigned long long w, unsigned long long prefix, unsigned long long) const { rank[w] = (uint32_t)prefix; }
+};
+
+__global__ void k_id_table(const uint32_t* present, const uint32_t* rank, uint32_t n_words, uint32_t* id_of) {
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += gridDim.x * blockDim.x) {
+        uint32_t k = rank[w];
+        for (uint32_t bits = present[w]; bits; bits &= bits - 1) id_of[k++] = w * 32u + (uint32_t)__ffs((int)bits) - 1u;
+    }
+}
+
+__global__ void k_bits_fill(const uint32_t* num_val, const uint32_t* num_set, uint32_t n_num, const uint32_t* present,
+                            const uint32_t* rank, uint32_t* bits, uint32_t Wd, uint32_t n_sets) {
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_num; q += gridDim.x * blockDim.x) {
+        const uint32_t v = num_val[q], set = num_set[q];
+        if (set >= n_sets) continue;  // count mismatch: reported by the host
+        const uint32_t dense = rank[v >> 5] + (uint32_t)__popc(present[v >> 5] & low_bits(v & 31u));
+        atomicOr(&bits[(size_t)set * Wd + (dense >> 5)], 1u << (dense & 31u));
+    }
+}
+
+// A set that contains id 0 is universal (eds.cpp:1481-1487): store it as all ones. Sets with no id at
+// all are an error ("Empty path set at string k", eds.cpp:336-338).
+__global__ void k_universal(uint32_t* bits, uint32_t Wd, uint32_t n_sets, uint32_t P, uint32_t has_zero, LedsStatus* st) {
+    for (uint32_t set = blockIdx.x * blockDim.x + threadIdx.x; set < n_sets; set += gridDim.x * blockDim.x) {
+        uint32_t* b = bits + (size_t)set * Wd;
+        uint32_t any = 0;
+        for (uint32_t w = 0; w < Wd; ++w) any |= b[w];
+        if (!any) {
+            atomicMin(&st->empty_set, set);
+        } else if (has_zero && (b[0] & 1u)) {
+            for (uint32_t w = 0; w < Wd; ++w) b[w] = (w + 1 == Wd) ? low_bits(P - 32u * w) : 0xffffffffu;
+        }
+    }
+}
+
+// ---- the symbol table of a round and the alternative pool -------------------------------------------
+struct SymTab {
+    uint32_t* begin;  // first pool entry of the symbol's alternatives
+    uint32_t* count;  // number of alternatives
+};
+
+struct Pool {
+    uint32_t* left;   // kNone for a leaf
+    uint32_t* right;  // leaf: index of the original string
+    uint32_t* len;
+    uint32_t* bits;   // Wd words per entry
+};
+
+__global__ void k_init(const uint32_t* str_start, const uint32_t* str_end, const uint32_t* sym_first, uint32_t n_str,
+                       uint32_t n_sym, Pool pool, SymTab tab) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (uint32_t j = tid; j < n_str; j += nth) {
+        pool.left[j] = kNone;
+        pool.right[j] = j;
+        pool.len[j] = str_end[j] - str_start[j];
+    }
+    for (uint32_t i = tid; i < n_sym; i += nth) {
+        tab.begin[i] = sym_first[i];
+        tab.count[i] = sym_first[i + 1] - sym_first[i];
+    }
+}
+
+// short interior non-degenerate symbol (eds_transforms.cpp:75-97, 448-458)
+__device__ __forceinline__ bool short_solid(const SymTab& t, const Pool& pool, uint32_t i, uint32_t n, uint32_t l) {
+    return t.count[i] == 1u && i > 0 && i + 1 < n && pool.len[t.begin[i]] < l;
+}
+
+__global__ void k_cand(SymTab t, Pool pool, uint32_t n, uint32_t l, uint8_t* cand) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        bool c = false;
+        if (i + 1 < n)
+            c = short_solid(t, pool, i, n, l) || short_solid(t, pool, i + 1, n, l) || (t.count[i] > 1u && t.count[i + 1] > 1u);
+        cand[i] = c ? 1 : 0;
+    }
+}
+
+// Max-scan of "index after the last non-candidate": the exclusive prefix at a candidate is the start of
+// its run; the greedy scan of select_independent_merge_pairs keeps the 1st, 3rd, ... pair of each run.
+struct RunFn {
+    const uint8_t* cand;
+    uint8_t* sel;
+    __device__ unsigned long long value(unsigned long long i) const { return cand[i] ? 0ull : i + 1ull; }
+    __device__ void apply(unsigned long long i, unsigned long long prefix, unsigned long long) const {
+        sel[i] = (cand[i] && ((i - prefix) & 1ull) == 0ull) ? 1 : 0;
+    }
+};
+
+struct PairListFn {
+    const uint8_t* sel;
+    uint32_t* pairs_before;
+    uint32_t* pair_list;
+    __device__ unsigned long long value(unsigned long long i) const { return sel[i]; }
+    __device__ void apply(unsigned long long i, unsigned long long prefix, unsigned long long v) const {
+        pairs_before[i] = (uint32_t)prefix;
+        if (v) pair_list[prefix] = (uint32_t)i;
+    }
+};
+
+__device__ __forceinline__ bool meets(const uint32_t* a, const uint32_t* b, uint32_t Wd) {
+    for (uint32_t w = 0; w < Wd; ++w)
+        if (a[w] & b[w]) return true;
+    return Wd == 0;  // no sources: CARTESIAN keeps everything
+}
+
+// kept[q] = alternatives the merged symbol of pair q will have (warp per pair, lanes over combinations)
+__global__ void k_kept(SymTab t, Pool pool, const uint32_t* pair_list, uint32_t n_pairs, uint32_t Wd,
+                       unsigned long long* kept, LedsStatus* st) {
+    const uint32_t lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (uint32_t q = blockIdx.x * wpb + (threadIdx.x >> 5); q < n_pairs; q += gridDim.x * wpb) {
+        const uint32_t i = pair_list[q];
+        const uint32_t ab = t.begin[i], na = t.count[i], bb = t.begin[i + 1], nb = t.count[i + 1];
+        const unsigned long long combos = (unsigned long long)na * nb;
+        unsigned long long cnt = 0;
+        if (Wd == 0) {
+            cnt = combos;
+        } else {
+            for (unsigned long long c = lane; c < combos; c += 32) {
+                const uint32_t a = (uint32_t)(c / nb), bq = (uint32_t)(c % nb);
+                cnt += meets(pool.bits + (size_t)(ab + a) * Wd, pool.bits + (size_t)(bb + bq) * Wd, Wd) ? 1u : 0u;
+            }
+            cnt = warp_sum(cnt);
+        }
+        if (lane == 0) {
+            kept[q] = cnt;
+            if (cnt == 0) atomicMin(&st->empty_merge, i);
+        }
+    }
+}
+
+struct KeptFn {
+    const unsigned long long* kept;
+    unsigned long long* off;
+    __device__ unsigned long long value(unsigned long long q) const { return kept[q]; }
+    __device__ void apply(unsigned long long q, unsigned long long prefix, unsigned long long) const { off[q] = prefix; }
+};
+
+// New pool entries of every selected pair, i-major / j-minor (eds.cpp:1459-1468, 1640-1644).
+__global__ void k_merge_write(SymTab t, Pool pool, const uint32_t* pair_list, uint32_t n_pairs, uint32_t Wd,
+                              const unsigned long long* off, uint32_t pool_n) {
+    const uint32_t lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (uint32_t q = blockIdx.x * wpb + (threadIdx.x >> 5); q < n_pairs; q += gridDim.x * wpb) {
+        const uint32_t i = pair_list[q];
+        const uint32_t ab = t.begin[i], na = t.count[i], bb = t.begin[i + 1], nb = t.count[i + 1];
+        const unsigned long long combos = (unsigned long long)na * nb;
+        unsigned long long base = pool_n + off[q];
+        for (unsigned long long c0 = 0; c0 < combos; c0 += 32) {
+            const unsigned long long c = c0 + lane;
+            bool keep = false;
+            uint32_t a = 0, bq = 0;
+            if (c < combos) {
+                a = (uint32_t)(c / nb);
+                bq = (uint32_t)(c % nb);
+                keep = meets(pool.bits + (size_t)(ab + a) * Wd, pool.bits + (size_t)(bb + bq) * Wd, Wd);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const size_t e = (size_t)(base + (unsigned long long)__popc(m & lanemask_lt()));
+                pool.left[e] = ab + a;
+                pool.right[e] = bb + bq;
+                pool.len[e] = pool.len[ab + a] + pool.len[bb + bq];
+                for (uint32_t w = 0; w < Wd; ++w) pool.bits[e * Wd + w] = pool.bits[(size_t)(ab + a) * Wd + w] & pool.bits[(size_t)(bb + bq) * Wd + w];
+            }
+            base += (unsigned long long)__popc(m);
+        }
+    }
+}
+
+// reconstruct_eds without the text round trip: the next round's symbol table
+__global__ void k_rebuild(SymTab cur, SymTab next, const uint8_t* sel, const uint32_t* pairs_before, uint32_t n,
+                          const unsigned long long* kept, const unsigned long long* off, uint32_t pool_n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (i > 0 && sel[i - 1]) continue;  // right half of a merged pair
+        const uint32_t q = pairs_before[i], to = i - q;
+        if (sel[i]) {
+            next.begin[to] = pool_n + (uint32_t)off[q];
+            next.count[to] = (uint32_t)kept[q];
+        } else {
+            next.begin[to] = cur.begin[i];
+            next.count[to] = cur.count[i];
+        }
+    }
+}
+
+// ---- emit ---------------------------------------------------------------------------------------------
+constexpr uint32_t kFirst = 1u, kLast = 2u, kBraced = 4u;
+
+struct AltCountFn {
+    SymTab t;
+    unsigned long long* falt_off;
+    __device__ unsigned long long value(unsigned long long i) const { return t.count[i]; }
+    __device__ void apply(unsigned long long i, unsigned long long prefix, unsigned long long) const { falt_off[i] = prefix; }
+};
+
+// final alternative f -> (pool entry, position flags); warp per symbol, lanes over its alternatives
+__global__ void k_expand(SymTab t, uint32_t n, const unsigned long long* falt_off, uint32_t compact, uint32_t* falt_pool,
+                         uint8_t* falt_flags) {
+    const uint32_t lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (uint32_t i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+        const uint32_t cnt = t.count[i], b0 = t.begin[i];
+        const unsigned long long f0 = falt_off[i];
+        const uint32_t braced = (!compact || cnt > 1u) ? kBraced : 0u;
+        for (uint32_t a = lane; a < cnt; a += 32) {
+            falt_pool[f0 + a] = b0 + a;
+            falt_flags[f0 + a] = (uint8_t)((a == 0 ? kFirst : 0u) | (a + 1 == cnt ? kLast : 0u) | braced);
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t eds_cost(uint32_t len, uint32_t flags) {
+    // '{' with the first alternative, then the string, then ',' or (last) '}' when braced
+    return len + ((flags & kFirst) && (flags & kBraced) ? 1u : 0u) + ((flags & kLast) ? ((flags & kBraced) ? 1u : 0u) : 1u);
+}
+
+struct EdsOffFn {
+    const uint32_t* falt_pool;
+    const uint8_t* falt_flags;
+    const uint32_t* len;
+    unsigned long long* eds_off;
+    __device__ unsigned long long value(unsigned long long f) const { return eds_cost(len[falt_pool[f]], falt_flags[f]); }
+    __device__ void apply(unsigned long long f, unsigned long long prefix, unsigned long long) const { eds_off[f] = prefix; }
+};
+
+__device__ __forceinline__ bool is_universal(const uint32_t* b, uint32_t has_zero) { return has_zero && (b[0] & 1u); }
+
+// An alternative that was never merged prints the set it was given, verbatim (sorted, duplicates gone):
+// "{0,7}" stays "{0,7}". A merged one prints {0} when universal (eds.cpp:1481-1487), else its intersection.
+__device__ __forceinline__ const uint32_t* printable_bits(const Pool& pool, const uint32_t* raw_bits, uint32_t n_leaf,
+                                                          uint32_t e, uint32_t Wd, uint32_t has_zero, bool& universal) {
+    if (e < n_leaf) {
+        universal = false;
+        return raw_bits + (size_t)e * Wd;
+    }
+    const uint32_t* b = pool.bits + (size_t)e * Wd;
+    universal = is_universal(b, has_zero);
+    return b;
+}
+
+__global__ void k_seds_sizes(const uint32_t* falt_pool, unsigned long long n_falt, Pool pool, const uint32_t* raw_bits,
+                             uint32_t n_leaf, uint32_t Wd, uint32_t has_zero, const uint32_t* id_of, uint32_t* seds_sz) {
+    for (unsigned long long f = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; f < n_falt; f += (unsigned long long)gridDim.x * blockDim.x) {
+        bool universal;
+        const uint32_t* b = printable_bits(pool, raw_bits, n_leaf, falt_pool[f], Wd, has_zero, universal);
+        uint32_t sz = 3;  // "{0}"
+        if (!universal) {
+            sz = 1;  // '{', then per id: digits + (',' or '}')
+            for (uint32_t w = 0; w < Wd; ++w)
+                for (uint32_t bits = b[w]; bits; bits &= bits - 1) sz += decimal_width(id_of[w * 32u + (uint32_t)__ffs((int)bits) - 1u]) + 1u;
+        }
+        seds_sz[f] = sz;
+    }
+}
+
+struct SedsOffFn {
+    const uint32_t* seds_sz;
+    unsigned long long* seds_off;
+    __device__ unsigned long long value(unsigned long long f) const { return seds_sz[f]; }
+    __device__ void apply(unsigned long long f, unsigned long long prefix, unsigned long long) const { seds_off[f] = prefix; }
+};
+
+struct BigCopy {
+    unsigned long long dst;
+    uint32_t src, len;
+};
+
+// One thread per final alternative: iterative in-order walk of its merge tree, leaves copied from the
+// stripped input text. Long leaves are deferred to k_big_copy.
+__global__ void k_emit_eds(const uint32_t* falt_pool, const uint8_t* falt_flags, unsigned long long n_falt, Pool pool,
+                           const uint32_t* str_start, const uint8_t* text, const unsigned long long* eds_off, uint8_t* out,
+                           uint32_t* stack_ws, uint32_t stack_depth, BigCopy* big, uint32_t big_cap, LedsStatus* st) {
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t* stack = stack_ws + tid * stack_depth;
+    for (unsigned long long f = tid; f < n_falt; f += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t flags = falt_flags[f];
+        unsigned long long at = eds_off[f];
+        if ((flags & kFirst) && (flags & kBraced)) out[at++] = '{';
+        uint32_t sp = 0;
+        stack[sp++] = falt_pool[f];
+        while (sp) {
+            const uint32_t e = stack[--sp];
+            const uint32_t lft = pool.left[e];
+            if (lft == kNone) {
+                const uint32_t src = str_start[pool.right[e]], n = pool.len[e];
+                if (n > kBigLeaf) {
+                    const uint32_t slot = atomicAdd(&st->n_big, 1u);
+                    if (slot < big_cap) big[slot] = BigCopy{at, src, n};
+                } else {
+                    for (uint32_t k = 0; k < n; ++k) out[at + k] = text[src + k];
+                }
+                at += n;
+            } else {
+                stack[sp++] = pool.right[e];  // right is emitted after left
+                stack[sp++] = lft;
+            }
+        }
+        if (flags & kLast) {
+            if (flags & kBraced) out[at] = '}';
+        } else {
+            out[at] = ',';
+        }
+    }
+}
+
+__global__ void k_big_copy(const BigCopy* big, uint32_t n_big, const uint8_t* text, uint8_t* out) {
+    for (uint32_t q = blockIdx.x; q < n_big; q += gridDim.x) {
+        const BigCopy c = big[q];
+        for (uint32_t k = threadIdx.x; k < c.len; k += blockDim.x) out[c.dst + k] = text[c.src + k];
+    }
+}
+
+__global__ void k_emit_seds(const uint32_t* falt_pool, unsigned long long n_falt, Pool pool, const uint32_t* raw_bits,
+                            uint32_t n_leaf, uint32_t Wd, uint32_t has_zero, const uint32_t* id_of,
+                            const unsigned long long* seds_off, uint8_t* out) {
+    for (unsigned long long f = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; f < n_falt; f += (unsigned long long)gridDim.x * blockDim.x) {
+        bool universal;
+        const uint32_t* b = printable_bits(pool, raw_bits, n_leaf, falt_pool[f], Wd, has_zero, universal);
+        uint8_t* dst = out + seds_off[f];
+        if (universal) {
+            dst[0] = '{';
+            dst[1] = '0';
+            dst[2] = '}';
+            continue;
+        }
+        *dst++ = '{';
+        bool first = true;
+        for (uint32_t w = 0; w < Wd; ++w)
+            for (uint32_t bits = b[w]; bits; bits &= bits - 1) {
+                const uint32_t id = id_of[w * 32u + (uint32_t)__ffs((int)bits) - 1u], wd = decimal_width(id);
+                if (!first) *dst++ = ',';
+                first = false;
+                write_decimal(dst, id, wd);
+                dst += wd;
+            }
+        *dst = '}';
+    }
+}
+
+__global__ void k_newline(uint8_t* a, unsigned long long at_a, uint8_t* b, unsigned long long at_b) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        a[at_a] = '\n';
+        if (b) b[at_b] = '\n';
+    }
+}
+
+// ---- host-side error texts (error path only; formats/eds.cpp:80-82, 123-131, 278-349) ---------------
+std::string strip_host(const uint8_t* p, uint64_t n) {
+    std::string out;
+    out.reserve(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint8_t c = p[i];
+        if (!(c == ' ' || (c >= 9 && c <= 13))) out.push_back((char)c);
+    }
+    return out;
+}
+
+// what EDS::parse reports for a text the device found malformed
+std::string explain_eds_error(const std::string& t) {
+    std::string norm, bare;
+    int depth = 0;
+    for (char c : t) {
+        if (c == '{') {
+            if (!bare.empty() && depth == 0) {
+                norm += '{' + bare + '}';
+                bare.clear();
+            }
+            norm.push_back(c);
+            ++depth;
+        } else if (c == '}') {
+            norm.push_back(c);
+            --depth;
+        } else if (depth > 0) {
+            norm.push_back(c);
+        } else {
+            bare.push_back(c);
+        }
+    }
+    if (!bare.empty() && depth == 0) norm += '{' + bare + '}';
+    size_t p = 0;
+    while (p < norm.size()) {
+        if (norm[p] != '{') return "Expected '{' at position " + std::to_string(p);
+        ++p;
+        while (p < norm.size() && norm[p] != '}') ++p;
+        if (p >= norm.size()) return "Expected '}' at position " + std::to_string(p);
+        ++p;
+    }
+    return "malformed EDS text (nested braces are not supported)";
+}
+
+std::string explain_seds_error(const std::string& t, uint64_t n_strings, bool& out_of_range) {
+    out_of_range = false;
+    size_t p = 0;
+    uint64_t sets = 0;
+    while (p < t.size()) {
+        if (t[p] != '{') return "sEDS: Expected '{' at position " + std::to_string(p);
+        ++p;
+        bool any = false;
+        std::string num;
+        auto flush = [&]() -> bool {
+            if (num.empty()) return true;
+            any = true;
+            if (num.size() > 10 || std::stoull(num) > 2147483647ull) return false;
+            num.clear();
+            return true;
+        };
+        while (p < t.size() && t[p] != '}') {
+            if (t[p] == ',') {
+                if (!flush()) {
+                    out_of_range = true;
+                    return "stoi";
+                }
+            } else if (t[p] >= '0' && t[p] <= '9') {
+                num.push_back(t[p]);
+            } else {
+                return "sEDS: Invalid character '" + std::string(1, t[p]) + "' at position " + std::to_string(p);
+            }
+            ++p;
+        }
+        if (!flush()) {
+            out_of_range = true;
+            return "stoi";
+        }
+        if (p >= t.size()) return "sEDS: Expected '}' at position " + std::to_string(p);
+        ++p;
+        if (!any) return "sEDS: Empty path set at string " + std::to_string(sets);
+        ++sets;
+    }
+    if (sets != n_strings)
+        return "sEDS: Source count (" + std::to_string(sets) + ") does not match EDS cardinality (" + std::to_string(n_strings) + ")";
+    return "sEDS: path id too large for the device path (ids must be below 2^26)";
+}
+
+// grow-only device array that keeps its contents
+template <typename T>
+struct Keep {
+    T* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t n, size_t live, cudaStream_t s) {
+        if (n <= cap) return;
+        const size_t want = n + n / 2 + 64;
+        T* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, want * sizeof(T));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            throw BudgetError("the merged EDS does not fit in device memory (the CARTESIAN expansion has no bound in the reference either)");
+        }
+        if (p && live) EDSB_CUDA(cudaMemcpyAsync(q, p, live * sizeof(T), cudaMemcpyDeviceToDevice, s));
+        if (p) {
+            EDSB_CUDA(cudaStreamSynchronize(s));
+            cudaFree(p);
+        }
+        p = q;
+        cap = want;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+uint8_t* dup_host(const std::vector<uint8_t>& v) {
+    uint8_t* h = static_cast<uint8_t*>(malloc(v.size() ? v.size() : 1));
+    if (!h) throw std::bad_alloc();
+    if (!v.empty()) memcpy(h, v.data(), v.size());
+    return h;
+}
+
+}  // namespace
 
 LedsPipeline::LedsPipeline(eds_ctx* ctx) : ctx_(ctx) {}
 LedsPipeline::~LedsPipeline() {}
 
-void LedsPipeline::merge_host(const uint8_t*, uint64_t, const uint8_t*, uint64_t, uint32_t, bool, uint64_t, eds_buffer*,
-                              eds_buffer*, uint32_t*) {
-    (void)ctx_;
-    throw std::runtime_error("eds_leds_merge_host: not implemented yet");
+void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const uint8_t* seds_in, uint64_t seds_bytes,
+                              uint32_t l, bool compact, uint64_t max_output_bytes, eds_buffer* leds_out,
+                              eds_buffer* seds_out, uint32_t* rounds_out) {
+    if (l == 0) throw std::invalid_argument("context_length must be > 0 for l-EDS transformation");  // eds_transforms.cpp:322-324
+    if (eds_bytes >= 0xfffffff0ull || seds_bytes >= 0xfffffff0ull) throw std::invalid_argument("eds_leds_merge_host: inputs must be below 4 GiB (Length is uint32 in the reference too)");
+    const bool linear = seds_in != nullptr;
+    cudaStream_t s = ctx_->stream;
+    KernelClock& clk = ctx_->clock;
+    clk.reset();
+    const uint32_t sms = (uint32_t)ctx_->sm_count;
+    const unsigned P = std::max(1u, std::min(ctx_->partitions ? ctx_->partitions : sms * 4u, 4096u));
+#ifdef EDSB_EMU
+    const uint32_t G = 2u, B = kScanBlock;  // few OS threads per emulated launch
+#else
+    const uint32_t G = sms * 8u, B = kScanBlock;  // grid-stride launches
+#endif
+
+    DevBuf d_raw, d_text, d_depth, d_part, d_status, d_sraw, d_stext;
+    DevBuf d_str_start, d_str_end, d_sym_first, d_num_val, d_num_set, d_present, d_rank, d_idof, d_rawbits;
+    Keep<uint32_t> p_left, p_right, p_len, p_bits;
+    DevBuf d_tab[4], d_cand, d_sel, d_pairs_before, d_pair_list, d_kept, d_off;
+    DevBuf d_falt_off, d_falt_pool, d_falt_flags, d_eds_off, d_seds_sz, d_seds_off, d_out, d_sout, d_stack, d_big;
+    struct Cleanup {
+        std::vector<DevBuf*> bufs;
+        std::vector<Keep<uint32_t>*> keeps;
+        ~Cleanup() {
+            for (DevBuf* b : bufs) b->release();
+            for (auto* k : keeps) k->release();
+        }
+    } cleanup;
+    cleanup.bufs = {&d_raw, &d_text, &d_depth, &d_part, &d_status, &d_sraw, &d_stext, &d_str_start, &d_str_end, &d_sym_first,
+                    &d_num_val, &d_num_set, &d_present, &d_rank, &d_idof, &d_rawbits, &d_tab[0], &d_tab[1], &d_tab[2], &d_tab[3], &d_cand,
+                    &d_sel, &d_pairs_before, &d_pair_list, &d_kept, &d_off, &d_falt_off, &d_falt_pool, &d_falt_flags,
+                    &d_eds_off, &d_seds_sz, &d_seds_off, &d_out, &d_sout, &d_stack, &d_big};
+    cleanup.keeps = {&p_left, &p_right, &p_len, &p_bits};
+
+    d_part.reserve((size_t)(P + 1) * 8);
+    unsigned long long* part = d_part.as<unsigned long long>();
+    d_status.reserve(sizeof(LedsStatus));
+    LedsStatus* st = d_status.as<LedsStatus>();
+    LedsStatus hst;
+    memset(&hst, 0, sizeof(hst));
+    hst.empty_set = hst.empty_merge = kNone;
+    EDSB_CUDA(cudaMemcpyAsync(st, &hst, sizeof(hst), cudaMemcpyHostToDevice, s));
+
+    auto total_of = [&]() -> unsigned long long {
+        unsigned long long v = 0;
+        EDSB_CUDA(cudaMemcpyAsync(&v, part + P, 8, cudaMemcpyDeviceToHost, s));
+        EDSB_CUDA(cudaStreamSynchronize(s));
+        return v;
+    };
+    auto status_now = [&]() {
+        EDSB_CUDA(cudaMemcpyAsync(&hst, st, sizeof(hst), cudaMemcpyDeviceToHost, s));
+        EDSB_CUDA(cudaStreamSynchronize(s));
+        EDSB_CUDA(cudaGetLastError());
+    };
+#define LEDS_SCAN(name, Op, n, fn)                    \
+    do {                                              \
+        clk.begin(name);                              \
+        device_scan<Op>(s, P, (n), (fn), part);       \
+        clk.end();                                    \
+        ++clk.launches;                               \
+    } while (0)
+#define LEDS_LAUNCH(name, kernel, grid, block, ...)        \
+    do {                                                   \
+        clk.begin(name);                                   \
+        EDSB_LAUNCH(kernel, grid, block, 0, s, __VA_ARGS__); \
+        clk.end();                                         \
+    } while (0)
+
+    // ---- EDS text: strip, parse ----------------------------------------------------------------------
+    d_raw.reserve(eds_bytes + 16);
+    d_text.reserve(eds_bytes + 16);
+    if (eds_bytes) EDSB_CUDA(cudaMemcpyAsync(d_raw.p, eds_in, eds_bytes, cudaMemcpyHostToDevice, s));
+    uint8_t* text = d_text.as<uint8_t>();
+    LEDS_SCAN("strip_eds", OpSum64, eds_bytes, (StripFn{d_raw.as<uint8_t>(), text}));
+    const uint32_t n = (uint32_t)total_of();
+
+    uint32_t n_str = 0, n_sym = 0;
+    if (n) {
+        d_depth.reserve(n);
+        LEDS_SCAN("eds_depth", OpSum64, n, (DepthFn{text, d_depth.as<uint8_t>(), st}));
+        const unsigned long long oc = total_of();
+        status_now();
+        if ((hst.err & kErrEdsSyntax) || (uint32_t)oc != (uint32_t)(oc >> 32))
+            throw std::runtime_error(explain_eds_error(strip_host(eds_in, eds_bytes)));
+        d_str_start.reserve((size_t)(n + 2) * 4);
+        d_str_end.reserve((size_t)(n + 2) * 4);
+        d_sym_first.reserve((size_t)(n + 2) * 4);
+        const EventFn ev{text, d_depth.as<uint8_t>(), d_str_start.as<uint32_t>(), d_str_end.as<uint32_t>(), d_sym_first.as<uint32_t>()};
+        LEDS_SCAN("eds_events", OpSum64, n, ev);
+        const unsigned long long tot = total_of();
+        n_str = (uint32_t)tot;
+        n_sym = (uint32_t)(tot >> 32);
+        LEDS_LAUNCH("k_close_strings", k_close_strings, 1, 32, text, n, d_str_end.as<uint32_t>(), n_str, d_sym_first.as<uint32_t>(), n_sym);
+    }
+
+    // ---- SEDS text: sets -> dense bitsets --------------------------------------------------------------
+    uint32_t Wd = 0, n_paths = 0, has_zero = 0;
+    uint32_t* id_of = nullptr;
+    if (linear) {
+        d_sraw.reserve(seds_bytes + 16);
+        d_stext.reserve(seds_bytes + 16);
+        if (seds_bytes) EDSB_CUDA(cudaMemcpyAsync(d_sraw.p, seds_in, seds_bytes, cudaMemcpyHostToDevice, s));
+        uint8_t* stext = d_stext.as<uint8_t>();
+        LEDS_SCAN("strip_seds", OpSum64, seds_bytes, (StripFn{d_sraw.as<uint8_t>(), stext}));
+        const uint32_t ns = (uint32_t)total_of();
+        if (ns == 0) throw std::runtime_error("sEDS input is empty");
+        const uint32_t pw = kMaxPathId / 32;
+        d_present.reserve((size_t)pw * 4);
+        d_rank.reserve((size_t)pw * 4);
+        EDSB_CUDA(cudaMemsetAsync(d_present.p, 0, (size_t)pw * 4, s));
+        d_num_val.reserve((size_t)(ns / 2 + 2) * 4);
+        d_num_set.reserve((size_t)(ns / 2 + 2) * 4);
+        const SetFn sf{stext, ns, d_num_val.as<uint32_t>(), d_num_set.as<uint32_t>(), d_present.as<uint32_t>(), st};
+        LEDS_SCAN("seds_sets", OpSum64, ns, sf);
+        const unsigned long long tot = total_of();
+        const uint32_t n_sets = (uint32_t)tot, n_num = (uint32_t)(tot >> 32);
+        status_now();
+        bool oor = false;
+        if (hst.err & (kErrSedsSyntax | kErrSedsOverflow | kErrSedsBigId) || n_sets != n_str) {
+            const std::string msg = explain_seds_error(strip_host(seds_in, seds_bytes), n_str, oor);
+            if (oor) throw std::out_of_range(msg);
+            throw std::runtime_error(msg);
+        }
+        const uint32_t pw_used = hst.max_id / 32u + 1u;  // words of the presence bitmap that can be non-zero
+        LEDS_SCAN("id_rank", OpSum64, pw_used, (RankFn{d_present.as<uint32_t>(), d_rank.as<uint32_t>()}));
+        n_paths = (uint32_t)total_of();
+        Wd = (n_paths + 31) / 32;
+        d_idof.reserve((size_t)(n_paths + 1) * 4);
+        id_of = d_idof.as<uint32_t>();
+        LEDS_LAUNCH("k_id_table", k_id_table, G, B, d_present.as<uint32_t>(), d_rank.as<uint32_t>(), pw_used, id_of);
+        uint32_t w0 = 0;
+        EDSB_CUDA(cudaMemcpyAsync(&w0, d_present.p, 4, cudaMemcpyDeviceToHost, s));
+        EDSB_CUDA(cudaStreamSynchronize(s));
+        has_zero = w0 & 1u;
+        p_bits.ensure((size_t)std::max<uint32_t>(n_str, 1) * Wd, 0, s);
+        EDSB_CUDA(cudaMemsetAsync(p_bits.p, 0, (size_t)n_str * Wd * 4, s));
+        LEDS_LAUNCH("k_bits_fill", k_bits_fill, G, B, d_num_val.as<uint32_t>(), d_num_set.as<uint32_t>(), n_num,
+                    d_present.as<uint32_t>(), d_rank.as<uint32_t>(), p_bits.p, Wd, n_str);
+        d_rawbits.reserve((size_t)n_str * Wd * 4 + 16);  // the sets as given, for alternatives that are never merged
+        EDSB_CUDA(cudaMemcpyAsync(d_rawbits.p, p_bits.p, (size_t)n_str * Wd * 4, cudaMemcpyDeviceToDevice, s));
+        LEDS_LAUNCH("k_universal", k_universal, G, B, p_bits.p, Wd, n_str, n_paths, has_zero, st);
+        status_now();
+        if (hst.empty_set != kNone) throw std::runtime_error("sEDS: Empty path set at string " + std::to_string(hst.empty_set));
+    }
+
+    // ---- pool leaves, first symbol table ----------------------------------------------------------------
+    uint32_t pool_n = n_str;
+    p_left.ensure(std::max<size_t>(pool_n, 1), 0, s);
+    p_right.ensure(std::max<size_t>(pool_n, 1), 0, s);
+    p_len.ensure(std::max<size_t>(pool_n, 1), 0, s);
+    for (int i = 0; i < 4; ++i) d_tab[i].reserve((size_t)(n_sym + 2) * 4);
+    SymTab cur{d_tab[0].as<uint32_t>(), d_tab[1].as<uint32_t>()}, nxt{d_tab[2].as<uint32_t>(), d_tab[3].as<uint32_t>()};
+    Pool pool{p_left.p, p_right.p, p_len.p, p_bits.p};
+    if (n_str)
+        LEDS_LAUNCH("k_init", k_init, G, B, d_str_start.as<uint32_t>(), d_str_end.as<uint32_t>(), d_sym_first.as<uint32_t>(), n_str, n_sym, pool, cur);
+
+    // ---- merge rounds (eds_transforms.cpp:335-359) -------------------------------------------------------
+    d_cand.reserve((size_t)n_sym + 1);
+    d_sel.reserve((size_t)n_sym + 1);
+    d_pairs_before.reserve((size_t)(n_sym + 1) * 4);
+    d_pair_list.reserve((size_t)(n_sym + 1) * 4);
+    d_kept.reserve((size_t)(n_sym + 1) * 8);
+    d_off.reserve((size_t)(n_sym + 1) * 8);
+    uint32_t cur_n = n_sym, rounds = 0;
+    const uint32_t kMaxRounds = 10000;
+    while (cur_n >= 2) {
+        if (rounds >= kMaxRounds) throw std::runtime_error("Maximum iterations reached without convergence");
+        LEDS_LAUNCH("k_cand", k_cand, G, B, cur, pool, cur_n, l, d_cand.as<uint8_t>());
+        LEDS_SCAN("run_parity", OpMax64, cur_n, (RunFn{d_cand.as<uint8_t>(), d_sel.as<uint8_t>()}));
+        LEDS_SCAN("pair_list", OpSum64, cur_n, (PairListFn{d_sel.as<uint8_t>(), d_pairs_before.as<uint32_t>(), d_pair_list.as<uint32_t>()}));
+        const uint32_t n_pairs = (uint32_t)total_of();
+        if (n_pairs == 0) break;
+        LEDS_LAUNCH("k_kept", k_kept, G, B, cur, pool, d_pair_list.as<uint32_t>(), n_pairs, Wd, d_kept.as<unsigned long long>(), st);
+        LEDS_SCAN("kept_offsets", OpSum64, n_pairs, (KeptFn{d_kept.as<unsigned long long>(), d_off.as<unsigned long long>()}));
+        const unsigned long long added = total_of();
+        status_now();
+        if (hst.empty_merge != kNone)  // eds.cpp:1513-1519
+            throw std::runtime_error("Merging positions " + std::to_string(hst.empty_merge) + " and " +
+                                     std::to_string(hst.empty_merge + 1) + " results in empty set (no valid source intersections)");
+        if ((unsigned long long)pool_n + added >= 0xfffffff0ull || (max_output_bytes && added > max_output_bytes))
+            throw BudgetError("merged EDS exceeds the output budget (" + std::to_string(added) + " alternatives in one round)");
+        p_left.ensure((size_t)pool_n + added, pool_n, s);
+        p_right.ensure((size_t)pool_n + added, pool_n, s);
+        p_len.ensure((size_t)pool_n + added, pool_n, s);
+        if (Wd) p_bits.ensure(((size_t)pool_n + added) * Wd, (size_t)pool_n * Wd, s);
+        pool = Pool{p_left.p, p_right.p, p_len.p, p_bits.p};
+        LEDS_LAUNCH("k_merge_write", k_merge_write, G, B, cur, pool, d_pair_list.as<uint32_t>(), n_pairs, Wd, d_off.as<unsigned long long>(), pool_n);
+        LEDS_LAUNCH("k_rebuild", k_rebuild, G, B, cur, nxt, d_sel.as<uint8_t>(), d_pairs_before.as<uint32_t>(), cur_n,
+                    d_kept.as<unsigned long long>(), d_off.as<unsigned long long>(), pool_n);
+        std::swap(cur, nxt);
+        pool_n += (uint32_t)added;
+        cur_n -= n_pairs;
+        ++rounds;
+    }
+    if (rounds_out) *rounds_out = rounds;
+
+    // ---- emit (EDS::save / save_sources) -------------------------------------------------------------------
+    std::vector<uint8_t> h_eds, h_seds;
+    unsigned long long n_falt = 0, eds_total = 0, seds_total = 0;
+    if (cur_n) {
+        d_falt_off.reserve((size_t)(cur_n + 1) * 8);
+        LEDS_SCAN("alt_offsets", OpSum64, cur_n, (AltCountFn{cur, d_falt_off.as<unsigned long long>()}));
+        n_falt = total_of();
+        d_falt_pool.reserve((size_t)(n_falt + 1) * 4);
+        d_falt_flags.reserve((size_t)n_falt + 1);
+        d_eds_off.reserve((size_t)(n_falt + 1) * 8);
+        LEDS_LAUNCH("k_expand", k_expand, G, B, cur, cur_n, d_falt_off.as<unsigned long long>(), compact ? 1u : 0u,
+                    d_falt_pool.as<uint32_t>(), d_falt_flags.as<uint8_t>());
+        LEDS_SCAN("eds_offsets", OpSum64, n_falt, (EdsOffFn{d_falt_pool.as<uint32_t>(), d_falt_flags.as<uint8_t>(), pool.len, d_eds_off.as<unsigned long long>()}));
+        eds_total = total_of();
+        if (linear) {
+            d_seds_sz.reserve((size_t)(n_falt + 1) * 4);
+            d_seds_off.reserve((size_t)(n_falt + 1) * 8);
+            LEDS_LAUNCH("k_seds_sizes", k_seds_sizes, G, B, d_falt_pool.as<uint32_t>(), n_falt, pool, d_rawbits.as<uint32_t>(), n_str, Wd, has_zero, id_of,
+                        d_seds_sz.as<uint32_t>());
+            LEDS_SCAN("seds_offsets", OpSum64, n_falt, (SedsOffFn{d_seds_sz.as<uint32_t>(), d_seds_off.as<unsigned long long>()}));
+            seds_total = total_of();
+        }
+    }
+    if (max_output_bytes && eds_total + 1 + seds_total + 1 > max_output_bytes)
+        throw BudgetError("l-EDS output (" + std::to_string(eds_total + seds_total + 2) + " bytes) exceeds max_output_bytes");
+    d_out.reserve(eds_total + 16);
+    d_sout.reserve(seds_total + 16);
+    if (cur_n) {
+        const uint32_t threads_total = G * B, depth = rounds + 2;
+        d_stack.reserve((size_t)threads_total * depth * 4);
+        const uint32_t big_cap = (uint32_t)std::min<unsigned long long>(eds_total / kBigLeaf + 1, 0x7fffffffull);
+        d_big.reserve((size_t)big_cap * sizeof(BigCopy));
+        LEDS_LAUNCH("k_emit_eds", k_emit_eds, G, B, d_falt_pool.as<uint32_t>(), d_falt_flags.as<uint8_t>(), n_falt, pool,
+                    d_str_start.as<uint32_t>(), text, d_eds_off.as<unsigned long long>(), d_out.as<uint8_t>(), d_stack.as<uint32_t>(),
+                    depth, d_big.as<BigCopy>(), big_cap, st);
+        status_now();
+        if (hst.n_big > big_cap) throw std::runtime_error("edsparser_b200: big-copy list overflow");
+        if (hst.n_big) LEDS_LAUNCH("k_big_copy", k_big_copy, std::min<uint32_t>(hst.n_big, G), B, d_big.as<BigCopy>(), hst.n_big, text, d_out.as<uint8_t>());
+        if (linear)
+            LEDS_LAUNCH("k_emit_seds", k_emit_seds, G, B, d_falt_pool.as<uint32_t>(), n_falt, pool, d_rawbits.as<uint32_t>(), n_str, Wd, has_zero,
+                        id_of, d_seds_off.as<unsigned long long>(), d_sout.as<uint8_t>());
+    }
+    LEDS_LAUNCH("k_newline", k_newline, 1, 32, d_out.as<uint8_t>(), eds_total, linear ? d_sout.as<uint8_t>() : nullptr, seds_total);
+    h_eds.resize(eds_total + 1);
+    EDSB_CUDA(cudaMemcpyAsync(h_eds.data(), d_out.p, eds_total + 1, cudaMemcpyDeviceToHost, s));
+    if (linear) {
+        h_seds.resize(seds_total + 1);
+        EDSB_CUDA(cudaMemcpyAsync(h_seds.data(), d_sout.p, seds_total + 1, cudaMemcpyDeviceToHost, s));
+    }
+    EDSB_CUDA(cudaStreamSynchronize(s));
+    EDSB_CUDA(cudaGetLastError());
+    clk.resolve();
+    leds_out->data = dup_host(h_eds);
+    leds_out->bytes = h_eds.size();
+    seds_out->data = dup_host(h_seds);
+    seds_out->bytes = h_seds.size();
+#undef LEDS_SCAN
+#undef LEDS_LAUNCH
 }
 
 }  // namespace edsb

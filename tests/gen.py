@@ -53,3 +53,36 @@ def random_msa_text(rng, max_rows=9, max_cols=200, **kw):
     headers = [b">" + bytes(rng.integers(97, 123, int(rng.integers(0, 20))).astype(np.uint8)) for _ in range(n_rows)]
     text = to_fasta(m, wrap, headers, final_newline=bool(rng.integers(0, 2)))
     return text, m, wrap
+
+
+def random_eds(rng, n_sym=None, paths=4, p_deg=0.4, max_common=14, with_sources=True, universal_rate=0.1, compact_in=False):
+    """Random EDS text (+ SEDS text): degenerate symbols with 2-4 alternatives (some empty), commons of
+    random length. Sources: every alternative gets a non-empty subset of 1..paths (subsets of one symbol
+    cover all paths, may overlap), commons get {0}; a few sets carry the universal marker 0 next to ids."""
+    if n_sym is None:
+        n_sym = int(rng.integers(1, 30))
+    eds, seds = [], []
+    for _ in range(n_sym):
+        if rng.random() < p_deg:
+            k = int(rng.integers(2, 5))
+            alts = []
+            for _a in range(k):
+                ln = int(rng.choice([0, 1, 1, 2, 3, 6]))
+                alts.append(bytes(ALPHABET[rng.integers(0, 4, ln)]))
+            eds.append(b"{" + b",".join(alts) + b"}")
+            owner = rng.integers(0, k, paths)  # every path picks one alternative
+            for a in range(k):
+                ids = set(int(p) + 1 for p in np.nonzero(owner == a)[0])
+                if rng.random() < 0.3:
+                    ids.add(int(rng.integers(1, paths + 1)))  # overlap (heterozygous)
+                if not ids:
+                    ids.add(int(rng.integers(1, paths + 1)))
+                if rng.random() < universal_rate:
+                    ids.add(0)
+                seds.append(b"{" + b",".join(b"%d" % i for i in sorted(ids, key=lambda _x: rng.random())) + b"}")
+        else:
+            ln = int(rng.integers(0 if rng.random() < 0.05 else 1, max_common + 1))
+            s = bytes(ALPHABET[rng.integers(0, 4, ln)])
+            eds.append(s if (compact_in and ln > 0) else b"{" + s + b"}")
+            seds.append(b"{0}" if rng.random() > 0.1 else b"{%d}" % int(rng.integers(1, paths + 1)))
+    return b"".join(eds), (b"".join(seds) if with_sources else None)

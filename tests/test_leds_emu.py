@@ -1,0 +1,38 @@
+"""CPU tier: the l-EDS merge kernels' logic through the test-only CUDA emulator build."""
+import pytest
+
+import emu_lib
+import leds_checks
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = emu_lib.lib().context()
+    c.set_tuning(3, 1)
+    yield c
+    c.close()
+
+
+def test_golden_subset(ctx):
+    n, n_err = leds_checks.check_golden(ctx, stride=5)
+    assert n >= 95 and n_err >= 2
+
+
+def test_survey_vectors(ctx):
+    leds_checks.check_survey_vectors(ctx)
+
+
+def test_errors(ctx):
+    leds_checks.check_errors(ctx)
+
+
+def test_random(ctx):
+    leds_checks.check_random(ctx, seed=3, n_cases=40, max_sym=14)
+
+
+def test_long_strings_and_many_paths(ctx):
+    leds_checks.check_long_strings_and_many_paths(ctx)
+
+
+def test_msa_pipeline(ctx):
+    leds_checks.check_msa_pipeline(ctx, n_cases=2)
