@@ -398,7 +398,7 @@ static std::vector<int> meet(const std::vector<int>& a, const std::vector<int>& 
 // The reference re-serialises and re-parses after every round; on this model that is the
 // identity, so the round is applied in place. `first` = string index of each symbol's
 // first alternative (cum_set_sizes).
-static void apply_round(Eds& e, const std::vector<size_t>& pairs) {
+static void apply_round(Eds& e, const std::vector<size_t>& pairs, size_t max_out_bytes = 0) {
     std::vector<size_t> first(e.sym.size() + 1, 0);
     for (size_t i = 0; i < e.sym.size(); ++i) first[i + 1] = first[i] + e.sym[i].size();
     std::vector<std::vector<std::string>> nsym;
@@ -408,6 +408,7 @@ static void apply_round(Eds& e, const std::vector<size_t>& pairs) {
         if (next_pair < pairs.size() && pairs[next_pair] == i) {
             const auto& L = e.sym[i];
             const auto& Rr = e.sym[i + 1];
+            if (max_out_bytes && L.size() * Rr.size() > max_out_bytes) throw std::length_error("oracle: output budget exceeded");
             std::vector<std::string> merged;
             size_t kept_before = nsrc.size();
             for (size_t a = 0; a < L.size(); ++a)
@@ -449,7 +450,7 @@ static void eds_to_leds(const std::string& eds_in, const std::string* seds_in, u
         if (leds_holds(e, l)) break;
         std::vector<size_t> pairs = pick_pairs(e, l);
         if (pairs.empty()) break;
-        apply_round(e, pairs);
+        apply_round(e, pairs, max_out_bytes);
         if (max_out_bytes) {
             size_t bytes = 0;
             for (auto& s : e.sym)

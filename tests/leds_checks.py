@@ -40,10 +40,19 @@ def check_golden(ctx, stride=1):
     return n, n_err
 
 
+BUDGET = 1 << 22  # keeps a runaway cross product from exhausting host memory in the oracle
+
+
 def same_as_oracle(ctx, eds, seds, l, compact=True):
     try:
-        exp = oracle_lib.eds2leds(eds, seds, l, compact)
+        exp = oracle_lib.eds2leds(eds, seds, l, compact, max_out_bytes=BUDGET)
     except oracle_lib.OracleError as oe:
+        if oe.status == 4:  # the oracle's own size guard: ours must refuse or finish, never crash
+            try:
+                ctx.leds_merge_host(eds, seds, l, compact, max_output_bytes=BUDGET)
+            except capi.EdsError as e:
+                assert e.status == capi.EDS_ERR_BUDGET, e
+            return "budget"
         try:
             ctx.leds_merge_host(eds, seds, l, compact)
         except capi.EdsError as e:
