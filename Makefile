@@ -13,8 +13,8 @@ HDRS     := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/edsparser_b200.h
 OBJS     := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))
 EMUOBJS  := $(patsubst $(CSRC)/%.cu,build/emu_%.o,$(SRCS)) build/emu_runtime.o
 
-.PHONY: all lib emu oracle clean
-all: lib
+.PHONY: all lib emu oracle host clean
+all: lib host
 lib: edsparser_b200/libedsparser_b200.so
 
 build:
@@ -37,8 +37,21 @@ build/emu_runtime.o: tests/emu/cuda_emu.cpp tests/emu/cuda_emu.h | build
 tests/emu/libedsparser_emu.so: $(EMUOBJS)
 	$(CXX) -shared -pthread -o $@ $^
 
+# host layer: the reference's transforms API (C++17) + the msa2eds / eds2leds tools, over the C ABI
+HOST     := edsparser_b200/host
+HOSTINC  := -I$(HOST)/include -I$(HOST)/tools
+host: edsparser_b200/bin/msa2eds edsparser_b200/bin/eds2leds
+
+edsparser_b200/libedsparser_host.a: $(HOST)/src/host.cpp $(wildcard $(HOST)/include/edsparser/*.hpp $(HOST)/include/edsparser/*/*.hpp) include/edsparser_b200.h | build
+	$(CXX) -std=c++17 -O2 -fPIC -Wall $(HOSTINC) -c $(HOST)/src/host.cpp -o build/host.o
+	ar rcs $@ build/host.o
+
+edsparser_b200/bin/%: $(HOST)/tools/%.cpp $(HOST)/tools/cli_common.hpp edsparser_b200/libedsparser_host.a edsparser_b200/libedsparser_b200.so
+	mkdir -p edsparser_b200/bin
+	$(CXX) -std=c++17 -O2 -Wall $(HOSTINC) $< edsparser_b200/libedsparser_host.a -Ledsparser_b200 -ledsparser_b200 -Wl,-rpath,'$$ORIGIN/..' -o $@
+
 oracle:
 	$(MAKE) -C oracle all
 
 clean:
-	rm -rf build edsparser_b200/libedsparser_b200.so tests/emu/libedsparser_emu.so
+	rm -rf build edsparser_b200/libedsparser_b200.so edsparser_b200/libedsparser_host.a edsparser_b200/bin tests/emu/libedsparser_emu.so

@@ -24,7 +24,7 @@ EXPORTS = [
     "eds_last_error", "eds_version", "eds_ctx_create", "eds_ctx_destroy", "eds_ctx_synchronize",
     "eds_ctx_set_tuning", "eds_ctx_set_profiling", "eds_ctx_kernel_times", "eds_msa_index_host",
     "eds_msa_index_free", "eds_msa_transform_device", "eds_msa_transform_host", "eds_msa_conserved_bits",
-    "eds_msa_synth_device", "eds_msa_synth_free", "eds_buffer_to_host", "eds_buffer_free_host", "eds_leds_merge_host",
+    "eds_msa_synth_device", "eds_msa_synth_free", "eds_buffer_to_host", "eds_buffer_free_host", "eds_leds_merge_host", "eds_is_leds_host",
 ]
 
 
@@ -96,6 +96,7 @@ class Library:
         L.eds_buffer_free_host.argtypes = [P(Buffer)]
         L.eds_buffer_free_host.restype = None
         L.eds_leds_merge_host.argtypes = [vp, vp, u64, vp, u64, u32, i32, u64, P(Buffer), P(Buffer), P(u32)]
+        L.eds_is_leds_host.argtypes = [vp, vp, u64, u32, P(i32)]
         self.L = L
         _ = u8p
 
@@ -240,6 +241,14 @@ class Context:
         del k1, k2
         out, sout = _host_bytes(self.lib, o), _host_bytes(self.lib, so)
         return out, (sout if seds is not None else None), rounds.value
+
+
+    def is_leds(self, eds, l):
+        ea, en, keep = _as_pointer(eds)
+        out = ctypes.c_int()
+        self.lib.check(self.lib.L.eds_is_leds_host(self.handle, ea, en, l, ctypes.byref(out)))
+        del keep
+        return bool(out.value)
 
 
 _product = None

@@ -328,4 +328,14 @@ eds_status eds_leds_merge_host(eds_ctx* ctx, const uint8_t* eds_in, uint64_t eds
     return rc;
 }
 
+eds_status eds_is_leds_host(eds_ctx* ctx, const uint8_t* eds_in, uint64_t eds_bytes, uint32_t l, int* is_leds_out) {
+    return guarded([&] {
+        use_device(ctx);
+        if (!eds_in || !is_leds_out) throw std::invalid_argument("eds_is_leds_host: null argument");
+        *is_leds_out = 1;
+        if (l == 0) return;
+        ctx->leds->merge_host(eds_in, eds_bytes, nullptr, 0, l, true, 0, nullptr, nullptr, nullptr, is_leds_out);
+    });
+}
+
 }  // extern "C"

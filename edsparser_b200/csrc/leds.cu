@@ -654,7 +654,7 @@ LedsPipeline::~LedsPipeline() {}
 
 void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const uint8_t* seds_in, uint64_t seds_bytes,
                               uint32_t l, bool compact, uint64_t max_output_bytes, eds_buffer* leds_out,
-                              eds_buffer* seds_out, uint32_t* rounds_out) {
+                              eds_buffer* seds_out, uint32_t* rounds_out, int* check_only) {
     if (l == 0) throw std::invalid_argument("context_length must be > 0 for l-EDS transformation");  // eds_transforms.cpp:322-324
     if (eds_bytes >= 0xfffffff0ull || seds_bytes >= 0xfffffff0ull) throw std::invalid_argument("eds_leds_merge_host: inputs must be below 4 GiB (Length is uint32 in the reference too)");
     const bool linear = seds_in != nullptr;
@@ -825,6 +825,10 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
         LEDS_SCAN("run_parity", OpMax64, cur_n, (RunFn{d_cand.as<uint8_t>(), d_sel.as<uint8_t>()}));
         LEDS_SCAN("pair_list", OpSum64, cur_n, (PairListFn{d_sel.as<uint8_t>(), d_pairs_before.as<uint32_t>(), d_pair_list.as<uint32_t>()}));
         const uint32_t n_pairs = (uint32_t)total_of();
+        if (check_only) {
+            *check_only = n_pairs == 0 ? 1 : 0;
+            return;
+        }
         if (n_pairs == 0) break;
         LEDS_LAUNCH("k_kept", k_kept, G, B, cur, pool, d_pair_list.as<uint32_t>(), n_pairs, Wd, d_kept.as<unsigned long long>(), st);
         LEDS_SCAN("kept_offsets", OpSum64, n_pairs, (KeptFn{d_kept.as<unsigned long long>(), d_off.as<unsigned long long>()}));
@@ -849,6 +853,10 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
         ++rounds;
     }
     if (rounds_out) *rounds_out = rounds;
+    if (check_only) {  // fewer than two symbols: nothing can be merged
+        *check_only = 1;
+        return;
+    }
 
     // ---- emit (EDS::save / save_sources) -------------------------------------------------------------------
     std::vector<uint8_t> h_eds, h_seds;

@@ -20,7 +20,8 @@ class LedsPipeline {
     // Host text in, malloc'd host text out.
     void merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const uint8_t* seds_in, uint64_t seds_bytes, uint32_t l,
                     bool compact, uint64_t max_output_bytes, eds_buffer* leds_out, eds_buffer* seds_out,
-                    uint32_t* rounds_out);
+                    uint32_t* rounds_out, int* check_only = nullptr);
+    // check_only != nullptr: stop after the first round's pair selection; *check_only = 1 iff no pair exists
 
    private:
     eds_ctx* ctx_;

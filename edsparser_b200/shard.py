@@ -1,0 +1,43 @@
+"""Column sharding of msa2eds across ranks (one process per GPU): which columns a rank owns and holds, and
+the one exchange step of the path — an all-gather of the ranks' output byte counts, from which every rank
+gets the offsets of its slices in the single .eds / .seds pair. Plumbing only: the data
+path has no collective; torch.distributed (NCCL on GPUs, gloo in the CPU tests) moves 16 bytes per rank."""
+import os
+
+
+def plan(total_cols, world, rank, halo):
+    """(own_begin, own_end, win_begin, win_end) of `rank`: contiguous equal column ranges plus a halo."""
+    lo = total_cols * rank // world
+    hi = total_cols * (rank + 1) // world
+    return lo, hi, max(0, lo - halo), min(total_cols, hi + halo)
+
+
+def gather_offsets(dist, device, eds_bytes, seds_bytes, scratch=None):
+    """All-gather (eds_bytes, seds_bytes) of every rank; returns (eds_offset, seds_offset, eds_total, seds_total).
+    With world size 1 (or an uninitialised process group) nothing is exchanged."""
+    import torch
+
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return 0, 0, eds_bytes, seds_bytes
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if scratch is None:
+        scratch = (torch.zeros(2, dtype=torch.int64, device=device), torch.zeros(2 * world, dtype=torch.int64, device=device))
+    mine, everyone = scratch
+    mine[0], mine[1] = int(eds_bytes), int(seds_bytes)
+    dist.all_gather_into_tensor(everyone, mine)
+    counts = everyone.view(world, 2).cpu()
+    eds_off = int(counts[:rank, 0].sum())
+    seds_off = int(counts[:rank, 1].sum())
+    return eds_off, seds_off, int(counts[:, 0].sum()), int(counts[:, 1].sum())
+
+
+def write_slice(path, offset, data, total, rank):
+    """Every rank writes its slice of the one output file at its offset (rank 0 sizes the file first)."""
+    flags = os.O_WRONLY | os.O_CREAT
+    fd = os.open(path, flags, 0o644)
+    try:
+        if rank == 0:
+            os.ftruncate(fd, total)
+        os.pwrite(fd, data, offset)
+    finally:
+        os.close(fd)
