@@ -134,8 +134,10 @@ class Context:
     def __init__(self, lib, device=0, stream=None):
         self.lib = lib
         self.handle = ctypes.c_void_p()
-        lib.check(lib.L.eds_ctx_create(device, ctypes.c_void_p(stream) if stream else None,
-                                       ctypes.byref(self.handle)))
+        # stream None: the library makes its own stream. An integer is a cudaStream_t; torch reports the
+        # legacy default stream as 0, which the ABI spells cudaStreamLegacy (0x1) because NULL means "own".
+        arg = None if stream is None else ctypes.c_void_p(stream if stream else 1)
+        lib.check(lib.L.eds_ctx_create(device, arg, ctypes.byref(self.handle)))
 
     def close(self):
         if self.handle:
