@@ -104,6 +104,9 @@ eds_status eds_ctx_create(int device, void* stream, eds_ctx** out) {
             ctx->own_stream = true;
         }
         ctx->clock.stream = ctx->stream;
+        for (auto& a : ctx->aux) EDSB_CUDA(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+        for (auto& e : ctx->ev) EDSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        if (const char* se = getenv("EDSB_DEBUG_SERIAL")) ctx->serial = atoi(se) != 0;
         if (const char* hm = getenv("EDSB_DEBUG_HASH_MASK")) ctx->hash_mask = strtoull(hm, nullptr, 0);
         if (const char* no = getenv("EDSB_DEBUG_NARROW_OFF")) ctx->narrow_off = atoi(no) != 0;
         ctx->msa = new edsb::MsaPipeline(ctx);
@@ -121,6 +124,10 @@ void eds_ctx_destroy(eds_ctx* ctx) {
     ctx->synth_text.release();
     ctx->file_buf.release();
     ctx->clock.release();
+    for (auto& a : ctx->aux)
+        if (a) cudaStreamDestroy(a);
+    for (auto& e : ctx->ev)
+        if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

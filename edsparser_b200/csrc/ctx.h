@@ -25,8 +25,10 @@ struct KernelClock {
         ms.clear();
         launches = 0;
     }
-    void begin(const char* name) {
+    cudaStream_t cur = nullptr;  // stream of the launch being timed
+    void begin(const char* name, cudaStream_t on_stream = nullptr) {
         ++launches;
+        cur = on_stream ? on_stream : stream;
         if (!on) return;
         size_t i = names.size();
         names.push_back(name);
@@ -35,11 +37,11 @@ struct KernelClock {
             EDSB_CUDA(cudaEventCreate(&e));
             pool.push_back(e);
         }
-        EDSB_CUDA(cudaEventRecord(pool[2 * i], stream));
+        EDSB_CUDA(cudaEventRecord(pool[2 * i], cur));
     }
     void end() {
         if (!on) return;
-        EDSB_CUDA(cudaEventRecord(pool[2 * (names.size() - 1) + 1], stream));
+        EDSB_CUDA(cudaEventRecord(pool[2 * (names.size() - 1) + 1], cur));
     }
     void resolve() {
         ms.assign(names.size(), 0.f);
@@ -57,6 +59,10 @@ struct eds_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // side streams + events: independent kernels of one transform overlap (fork/join by events, no host sync)
+    cudaStream_t aux[2] = {nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool serial = false;  // EDSB_DEBUG_SERIAL=1: everything on the main stream
     int sm_count = 148;
     size_t smem_optin = 227 * 1024;
     uint32_t partitions = 0;          // 0 = default

@@ -1514,8 +1514,17 @@ void MsaPipeline::run_once(MsaBufs& b) {
     EDSB_LAUNCH(k_compact, P, kPartThreads, 0, s, g, b);
     ctx_->clock.end();
 
-    ctx_->clock.begin("k_stash");
-    EDSB_LAUNCH(k_stash, sms * 8u, kStashThreads, 0, s, g, b);
+    // fork: the stash gather (needs the variable-column list) runs beside the symbol-boundary kernels
+    // (need the run list); they join before the grouping kernels.
+    cudaStream_t s1 = ctx_->serial ? s : ctx_->aux[0], s2 = ctx_->serial ? s : ctx_->aux[1];
+    auto after = [&](cudaStream_t waiter, cudaStream_t producer, cudaEvent_t ev) {
+        if (waiter == producer) return;
+        EDSB_CUDA(cudaEventRecord(ev, producer));
+        EDSB_CUDA(cudaStreamWaitEvent(waiter, ev, 0));
+    };
+    after(s1, s, ctx_->ev[0]);
+    ctx_->clock.begin("k_stash", s1);
+    EDSB_LAUNCH(k_stash, sms * 8u, kStashThreads, 0, s1, g, b);
     ctx_->clock.end();
 
     ctx_->clock.begin("k_sym_count");
@@ -1584,6 +1593,7 @@ void MsaPipeline::run_once(MsaBufs& b) {
         d_ws_.reserve(need);
         b.group_ws = d_ws_.as<uint8_t>();
     }
+    after(s, s1, ctx_->ev[1]);  // join: stash ready
     ctx_->clock.begin("k_group");
     EDSB_LAUNCH(k_group, sms * (uint32_t)std::max(1, g1_occ), kPartThreads, 0, s, g, b, narrow_ok);
     ctx_->clock.end();
@@ -1599,8 +1609,11 @@ void MsaPipeline::run_once(MsaBufs& b) {
     EDSB_LAUNCH(k_size_scatter, P, kPartThreads, 0, s, g, b);
     ctx_->clock.end();
 
-    ctx_->clock.begin("k_emit_common");
-    EDSB_LAUNCH(k_emit_common, sms * 8u, kPartThreads, 0, s, g, b);
+    // fork: the three emit kernels write disjoint bytes of the outputs
+    after(s1, s, ctx_->ev[2]);
+    after(s2, s, ctx_->ev[3]);
+    ctx_->clock.begin("k_emit_common", s1);
+    EDSB_LAUNCH(k_emit_common, sms * 8u, kPartThreads, 0, s1, g, b);
     ctx_->clock.end();
     if (narrow_ok) {
         ctx_->clock.begin("k_emit_var");
@@ -1608,10 +1621,12 @@ void MsaPipeline::run_once(MsaBufs& b) {
                     seg_pitch);
         ctx_->clock.end();
     }
-    ctx_->clock.begin("k_emit2");
-    EDSB_LAUNCH(k_emit2, e2_blocks, ew * 32u, emit_smem, s, g, b, Rq, emit_global ? 1u : 0u, emit_stage,
+    ctx_->clock.begin("k_emit2", s2);
+    EDSB_LAUNCH(k_emit2, e2_blocks, ew * 32u, emit_smem, s2, g, b, Rq, emit_global ? 1u : 0u, emit_stage,
                 (uint32_t)emit_warp_smem);
     ctx_->clock.end();
+    after(s, s1, ctx_->ev[4]);  // join
+    after(s, s2, ctx_->ev[5]);
 
     EDSB_CUDA(cudaMemcpyAsync(h_status_, b.status, sizeof(MsaStatus), cudaMemcpyDeviceToHost, s));
     EDSB_CUDA(cudaStreamSynchronize(s));

@@ -338,6 +338,12 @@ inline cudaError_t cudaEventCreate(cudaEvent_t* e) {
     *e = new EmuEvent();
     return cudaSuccess;
 }
+enum { cudaEventDisableTiming = 2 };
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) {
+    *e = new EmuEvent();
+    return cudaSuccess;
+}
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) {
     delete e;
     return cudaSuccess;
