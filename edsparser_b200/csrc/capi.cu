@@ -107,8 +107,11 @@ eds_status eds_ctx_create(int device, void* stream, eds_ctx** out) {
         for (auto& a : ctx->aux) EDSB_CUDA(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
         for (auto& e : ctx->ev) EDSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         if (const char* se = getenv("EDSB_DEBUG_SERIAL")) ctx->serial = atoi(se) != 0;
+#ifndef EDSB_EMU
+        if (const char* fg = getenv("EDSB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg));
+#endif
         if (const char* hm = getenv("EDSB_DEBUG_HASH_MASK")) ctx->hash_mask = strtoull(hm, nullptr, 0);
-        if (const char* no = getenv("EDSB_DEBUG_NARROW_OFF")) ctx->narrow_off = atoi(no) != 0;
+        if (const char* no = getenv("EDSB_DEBUG_NARROW_OFF")) ctx->narrow_off = atoi(no);
         ctx->msa = new edsb::MsaPipeline(ctx);
         ctx->leds = new edsb::LedsPipeline(ctx);
         *out = ctx;

@@ -775,8 +775,59 @@ __device__ __forceinline__ void list_append(uint32_t* list, uint32_t* counter, b
     if (mine) list[base + (uint32_t)__popc(m & lanemask_lt())] = k;
 }
 
-// k_group: single-column symbols, lane per symbol (registers only); everything else is queued for k_group2
-// (two variable columns already give up to 25 alternatives, more than a lane's register list holds).
+// ---- single-column symbols when there are too many rows for the lane-per-symbol path: a WARP owns the
+// symbol, lanes run over rows, the residue list is warp-uniform. A chunk's unseen residues are appended in
+// lane (= row) order, which is the order of first rows.
+__device__ __forceinline__ uint32_t seen_lookup(const Seen& sn, uint32_t ch) {  // 8 = not in the list
+    const uint32_t sp = ch * 0x01010101u;
+    uint32_t x = sn.lo ^ sp;
+    uint32_t z = (x - 0x01010101u) & ~x & 0x80808080u;
+    if (z) return ((uint32_t)__ffs((int)z) - 1u) >> 3;
+    x = sn.hi ^ sp;
+    z = (x - 0x01010101u) & ~x & 0x80808080u;
+    if (z) return 4u + (((uint32_t)__ffs((int)z) - 1u) >> 3);
+    return 8u;
+}
+
+// class of this lane's residue (valid lanes), growing the warp-uniform list; false on overflow / NUL byte
+__device__ __forceinline__ bool warp_classify(Seen& sn, uint32_t ch, bool valid, uint32_t& cls) {
+    cls = valid ? seen_lookup(sn, ch) : 0u;
+    if (__any_sync(0xffffffffu, valid && ch == 0u)) return false;
+    uint32_t pending = __ballot_sync(0xffffffffu, valid && cls == 8u);
+    while (pending) {
+        const uint32_t leader = (uint32_t)__ffs((int)pending) - 1u;
+        const uint32_t nch = __shfl_sync(0xffffffffu, ch, (int)leader);
+        if (sn.n >= 8u) return false;
+        const uint32_t a = seen_index(sn, nch);  // appends: same in every lane
+        const bool mine = valid && cls == 8u && ch == nch;
+        if (mine) cls = a;
+        pending &= ~__ballot_sync(0xffffffffu, mine);
+    }
+    return true;
+}
+
+__device__ bool group_single_warp(const MsaGeom& g, const MsaBufs& b, uint32_t k, uint32_t s) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint8_t* col = b.stash + (size_t)first_slot(b, s) * g.Rp;
+    Seen sn;
+    sn.lo = sn.hi = sn.n = 0;
+    for (uint32_t r0 = 0; r0 < g.R; r0 += 32) {
+        const uint32_t r = r0 + lane;
+        uint32_t cls;
+        if (!warp_classify(sn, r < g.R ? col[r] : 0u, r < g.R, cls)) return false;
+    }
+    if (lane == 0) {
+        uint32_t chars = 0;
+        for (uint32_t a = 0; a < sn.n; ++a) chars += seen_byte(sn, a) != (uint32_t)'-';
+        b.sym_nalts[k] = sn.n;
+        b.sym_edsz[k] = 2ull + chars + (sn.n - 1u);
+    }
+    return true;
+}
+
+// k_group: single-column symbols — lane per symbol (registers only) when narrow_ok, else warp per symbol with
+// rows across lanes; everything else is queued for k_group2 (two variable columns already give up to 25
+// alternatives, more than the 8-entry residue list holds).
 __global__ void k_group(MsaGeom g, MsaBufs b, uint32_t narrow_ok) {
     MsaStatus* st = b.status;
     if (st->abort || st->halo_fail) return;
@@ -792,18 +843,31 @@ __global__ void k_group(MsaGeom g, MsaBufs b, uint32_t narrow_ok) {
             s = b.sym[k] & kColMask;
             en = b.sym[k + 1] & kColMask;
         }
-        uint32_t cls = !have ? 0u : ((narrow_ok && en - s == 1u) ? 1u : 3u);
-        if (cls == 1u) {
-            Seen sn;
-            if (narrow_scan(b.stash + (size_t)first_slot(b, s) * g.Rp, g.R, sn)) {
-                // alternative = the residue, or the empty string for '-'
-                uint32_t chars = 0;
-                for (uint32_t a = 0; a < sn.n; ++a) chars += seen_byte(sn, a) != (uint32_t)'-';
-                b.sym_nalts[k] = sn.n;
-                b.sym_edsz[k] = 2ull + chars + (sn.n - 1u);
-                alts_here += sn.n;
-            } else {
-                cls = 3u;
+        uint32_t cls = !have ? 0u : ((en - s == 1u && narrow_ok != 2u) ? 1u : 3u);  // narrow_ok 2: tests force the wide path
+        if (narrow_ok == 1u) {
+            if (cls == 1u) {
+                Seen sn;
+                if (narrow_scan(b.stash + (size_t)first_slot(b, s) * g.Rp, g.R, sn)) {
+                    // alternative = the residue, or the empty string for '-'
+                    uint32_t chars = 0;
+                    for (uint32_t a = 0; a < sn.n; ++a) chars += seen_byte(sn, a) != (uint32_t)'-';
+                    b.sym_nalts[k] = sn.n;
+                    b.sym_edsz[k] = 2ull + chars + (sn.n - 1u);
+                    alts_here += sn.n;
+                } else {
+                    cls = 3u;
+                }
+            }
+        } else {
+            uint32_t todo = __ballot_sync(0xffffffffu, cls == 1u);
+            while (todo) {
+                const uint32_t bit = (uint32_t)__ffs((int)todo) - 1u;
+                todo &= todo - 1u;
+                const uint32_t kw = __shfl_sync(0xffffffffu, k, (int)bit), sw = __shfl_sync(0xffffffffu, s, (int)bit);
+                const bool ok = group_single_warp(g, b, kw, sw);
+                if (lane == bit) {
+                    if (ok) alts_here += b.sym_nalts[kw]; else cls = 3u;
+                }
             }
         }
         list_append(b.widelist, &st->n_wide, cls == 3u, k);
@@ -1151,14 +1215,108 @@ __device__ __forceinline__ void segs_copy_out(const uint8_t* segs, uint32_t seg_
     }
 }
 
+// Single-column symbol, rows across lanes (any number of rows). Pass 1 grows the residue list and sums the
+// bytes of every alternative; pass 2 places the ids: per chunk and alternative one ballot gives the lanes of
+// that alternative, their in-chunk prefix is two popcounts (decimal widths take at most two values in a
+// chunk). All per-alternative state is warp-uniform and lives in registers (8 alternatives at most).
+__device__ bool emit_single_warp(const MsaGeom& g, const MsaBufs& b, uint32_t k, uint32_t s) {
+    const uint32_t lane = threadIdx.x & 31, lt = lanemask_lt();
+    const uint8_t* col = b.stash + (size_t)first_slot(b, s) * g.Rp;
+    Seen sn;
+    sn.lo = sn.hi = sn.n = 0;
+    uint32_t altw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint32_t r0 = 0; r0 < g.R; r0 += 32) {
+        const uint32_t r = r0 + lane;
+        const bool valid = r < g.R;
+        uint32_t cls;
+        if (!warp_classify(sn, valid ? col[r] : 0u, valid, cls)) return false;  // queued as wide by k_group
+        const uint32_t wd = decimal_width(r + 1u) + 1u;
+        const uint32_t wfirst = __shfl_sync(0xffffffffu, wd, 0);
+        const uint32_t mA = __ballot_sync(0xffffffffu, wd == wfirst);
+#pragma unroll
+        for (uint32_t a = 0; a < 8u; ++a) {
+            if (a < sn.n) {  // warp-uniform
+                const uint32_t m = __ballot_sync(0xffffffffu, valid && cls == a);
+                altw[a] += (uint32_t)__popc(m & mA) * wfirst + (uint32_t)__popc(m & ~mA) * (wfirst + 1u);
+            }
+        }
+    }
+    uint32_t base[8];
+    uint32_t at = 0;
+#pragma unroll
+    for (uint32_t a = 0; a < 8u; ++a) {
+        base[a] = at;
+        at += a < sn.n ? altw[a] + 1u : 0u;
+    }
+    uint8_t* seds = b.seds_out + b.seds_off[k];
+    if (lane == 0) {
+        uint8_t* eds = b.eds_out + b.eds_off[k];
+        *eds++ = '{';
+        for (uint32_t a = 0; a < sn.n; ++a) {
+            if (a) *eds++ = ',';
+            const uint32_t ch = seen_byte(sn, a);
+            if (ch != (uint32_t)'-') *eds++ = (uint8_t)ch;
+        }
+        *eds = '}';
+    }
+    if (lane < sn.n) {
+        // lane a closes alternative a; its '{' is written with the alternative's first id
+        uint32_t b0 = 0, w0 = 0;
+#pragma unroll
+        for (uint32_t a = 0; a < 8u; ++a)
+            if (a == lane) {
+                b0 = base[a];
+                w0 = altw[a];
+            }
+        seds[b0 + w0] = '}';
+    }
+    uint32_t running[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint32_t r0 = 0; r0 < g.R; r0 += 32) {
+        const uint32_t r = r0 + lane;
+        const bool valid = r < g.R;
+        const uint32_t cls = valid ? seen_lookup(sn, col[r]) : 8u;
+        const uint32_t wd = decimal_width(r + 1u) + 1u;
+        const uint32_t wfirst = __shfl_sync(0xffffffffu, wd, 0);
+        const uint32_t mA = __ballot_sync(0xffffffffu, wd == wfirst);
+        uint32_t pos = 0;
+#pragma unroll
+        for (uint32_t a = 0; a < 8u; ++a) {
+            if (a < sn.n) {  // warp-uniform
+                const uint32_t m = __ballot_sync(0xffffffffu, cls == a);
+                if (cls == a) pos = base[a] + running[a] + (uint32_t)__popc(m & lt & mA) * wfirst + (uint32_t)__popc(m & lt & ~mA) * (wfirst + 1u);
+                running[a] += (uint32_t)__popc(m & mA) * wfirst + (uint32_t)__popc(m & ~mA) * (wfirst + 1u);
+            }
+        }
+        if (valid) {
+            uint32_t b0 = 0;
+#pragma unroll
+            for (uint32_t a = 0; a < 8u; ++a)
+                if (a == cls) b0 = base[a];
+            seds[pos] = pos == b0 ? '{' : ',';
+            write_decimal(seds + pos + 1u, r + 1u, wd - 1u);
+        }
+    }
+    return true;
+}
+
 // k_emit_var: the single-column symbols (lane per symbol, nb symbols per warp pass).
 // idtab[r] = decimal digits of r + 1 packed in 24 bits (first digit lowest) | width << 24, built once per
 // block so the per-row decimal work is a table lookup (R <= 999 here: the host turns the narrow path off
 // for more rows).
 __global__ void k_emit_var(MsaGeom g, MsaBufs b, uint32_t per_warp_smem, uint32_t nb, uint32_t seg_pitch) {
     const MsaStatus* st = b.status;
-    if (st->abort || st->halo_fail || nb == 0u) return;
+    if (st->abort || st->halo_fail) return;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    if (nb == 0u) {
+        // too many rows for per-lane segments: warp per symbol, rows across lanes
+        const uint32_t v_lo = st->v_lo, v_hi = st->v_hi;
+        for (uint32_t v = v_lo + blockIdx.x * wpb + warp; v < v_hi; v += gridDim.x * wpb) {
+            const uint32_t k = b.varsym[v];
+            const uint32_t s = b.sym[k] & kColMask, en = b.sym[k + 1] & kColMask;
+            if (en - s == 1u) emit_single_warp(g, b, k, s);
+        }
+        return;
+    }
     uint32_t* idtab = reinterpret_cast<uint32_t*>(EDSB_DYN_SMEM());
     for (uint32_t r = threadIdx.x; r < g.R; r += blockDim.x) {
         const uint32_t id = r + 1u, wd = decimal_width(id);
@@ -1553,11 +1711,11 @@ void MsaPipeline::run_once(MsaBufs& b) {
     uint32_t seg_pitch = (uint32_t)((8 + g.sum_id_width + g.R + 16 + 3) & ~3ull);
     if (((seg_pitch >> 2) & 1u) == 0) seg_pitch += 4;
     uint32_t nb = 0, evw = kSymWarps;
-    if (!ctx_->narrow_off && g.R <= 999u) {
+    if (ctx_->narrow_off == 0 && g.R <= 160u) {  // beyond: rows-across-lanes path (per-lane segments would crowd shared memory)
         while (evw > 1 && evw * (2048 + 32 * (size_t)seg_pitch) > smem_budget / 2) evw >>= 1;
         if (evw * (2048 + 32 * (size_t)seg_pitch) + 4 * (size_t)g.R + 16 <= smem_budget / 2) nb = 32;
     }
-    const uint32_t narrow_ok = nb ? 1u : 0u;
+    const uint32_t narrow_ok = ctx_->narrow_off == 2 ? 2u : (nb ? 1u : 0u);  // 1 lane per symbol, 0 rows across lanes, 2 all wide
     const size_t ev_warp_smem = (2048 + (size_t)nb * seg_pitch + 15) & ~(size_t)15;
     const size_t ev_smem = narrow_ok ? evw * ev_warp_smem + (((size_t)g.R * 4 + 15) & ~(size_t)15) : 0;
 
@@ -1615,10 +1773,9 @@ void MsaPipeline::run_once(MsaBufs& b) {
     ctx_->clock.begin("k_emit_common", s1);
     EDSB_LAUNCH(k_emit_common, sms * 8u, kPartThreads, 0, s1, g, b);
     ctx_->clock.end();
-    if (narrow_ok) {
+    if (narrow_ok != 2u) {
         ctx_->clock.begin("k_emit_var");
-        EDSB_LAUNCH(k_emit_var, sms * (uint32_t)std::max(1, ev_occ), evw * 32u, ev_smem, s, g, b, (uint32_t)ev_warp_smem, nb,
-                    seg_pitch);
+        EDSB_LAUNCH(k_emit_var, sms * (uint32_t)std::max(1, ev_occ), evw * 32u, ev_smem, s, g, b, (uint32_t)ev_warp_smem, nb, seg_pitch);
         ctx_->clock.end();
     }
     ctx_->clock.begin("k_emit2", s2);

@@ -175,16 +175,19 @@ def check_wide_alphabet(ctx, seed=21, n_cases=8):
 
 
 def check_narrow_off(lib, seed=12, n_cases=15):
-    """EDSB_DEBUG_NARROW_OFF=1: every variable symbol goes through the warp-per-symbol path."""
-    os.environ["EDSB_DEBUG_NARROW_OFF"] = "1"
-    try:
-        ctx = lib.context()
-    finally:
-        del os.environ["EDSB_DEBUG_NARROW_OFF"]
-    try:
-        check_random_against_oracle(ctx, seed, n_cases, max_rows=40, max_cols=100, ls=(0, 2, 10))
-    finally:
-        ctx.close()
+    """EDSB_DEBUG_NARROW_OFF=1: single-column symbols take the rows-across-lanes path (what large R uses);
+    =2: every variable symbol goes through the hashed warp-per-symbol path."""
+    for mode in ("1", "2"):
+        os.environ["EDSB_DEBUG_NARROW_OFF"] = mode
+        try:
+            ctx = lib.context()
+        finally:
+            del os.environ["EDSB_DEBUG_NARROW_OFF"]
+        try:
+            check_random_against_oracle(ctx, seed, n_cases, max_rows=70, max_cols=100, ls=(0, 2, 10))
+            check_wide_alphabet(ctx, n_cases=3)
+        finally:
+            ctx.close()
 
 
 def shard_concat(ctx, dev, idx, cuts, halo, l):
