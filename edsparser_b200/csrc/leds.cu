@@ -649,8 +649,17 @@ uint8_t* dup_host(const std::vector<uint8_t>& v) {
 
 }  // namespace
 
-LedsPipeline::LedsPipeline(eds_ctx* ctx) : ctx_(ctx) {}
-LedsPipeline::~LedsPipeline() {}
+struct LedsPipeline::Bufs {
+    DevBuf d[36];
+    Keep<uint32_t> k[4];
+    ~Bufs() {
+        for (DevBuf& b : d) b.release();
+        for (auto& x : k) x.release();
+    }
+};
+
+LedsPipeline::LedsPipeline(eds_ctx* ctx) : ctx_(ctx), bufs_(new Bufs()) {}
+LedsPipeline::~LedsPipeline() { delete bufs_; }
 
 void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const uint8_t* seds_in, uint64_t seds_bytes,
                               uint32_t l, bool compact, uint64_t max_output_bytes, eds_buffer* leds_out,
@@ -669,24 +678,17 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
     const uint32_t G = sms * 8u, B = kScanBlock;  // grid-stride launches
 #endif
 
-    DevBuf d_raw, d_text, d_depth, d_part, d_status, d_sraw, d_stext;
-    DevBuf d_str_start, d_str_end, d_sym_first, d_num_val, d_num_set, d_present, d_rank, d_idof, d_rawbits;
-    Keep<uint32_t> p_left, p_right, p_len, p_bits;
-    DevBuf d_tab[4], d_cand, d_sel, d_pairs_before, d_pair_list, d_kept, d_off;
-    DevBuf d_falt_off, d_falt_pool, d_falt_flags, d_eds_off, d_seds_sz, d_seds_off, d_out, d_sout, d_stack, d_big;
-    struct Cleanup {
-        std::vector<DevBuf*> bufs;
-        std::vector<Keep<uint32_t>*> keeps;
-        ~Cleanup() {
-            for (DevBuf* b : bufs) b->release();
-            for (auto* k : keeps) k->release();
-        }
-    } cleanup;
-    cleanup.bufs = {&d_raw, &d_text, &d_depth, &d_part, &d_status, &d_sraw, &d_stext, &d_str_start, &d_str_end, &d_sym_first,
-                    &d_num_val, &d_num_set, &d_present, &d_rank, &d_idof, &d_rawbits, &d_tab[0], &d_tab[1], &d_tab[2], &d_tab[3], &d_cand,
-                    &d_sel, &d_pairs_before, &d_pair_list, &d_kept, &d_off, &d_falt_off, &d_falt_pool, &d_falt_flags,
-                    &d_eds_off, &d_seds_sz, &d_seds_off, &d_out, &d_sout, &d_stack, &d_big};
-    cleanup.keeps = {&p_left, &p_right, &p_len, &p_bits};
+    // grow-only device buffers owned by the pipeline: a second call of similar size allocates nothing
+    Bufs& B_ = *bufs_;
+    DevBuf &d_raw = B_.d[0], &d_text = B_.d[1], &d_depth = B_.d[2], &d_part = B_.d[3], &d_status = B_.d[4], &d_sraw = B_.d[5],
+           &d_stext = B_.d[6], &d_str_start = B_.d[7], &d_str_end = B_.d[8], &d_sym_first = B_.d[9], &d_num_val = B_.d[10],
+           &d_num_set = B_.d[11], &d_present = B_.d[12], &d_rank = B_.d[13], &d_idof = B_.d[14], &d_rawbits = B_.d[15],
+           &d_cand = B_.d[16], &d_sel = B_.d[17], &d_pairs_before = B_.d[18], &d_pair_list = B_.d[19], &d_kept = B_.d[20],
+           &d_off = B_.d[21], &d_falt_off = B_.d[22], &d_falt_pool = B_.d[23], &d_falt_flags = B_.d[24], &d_eds_off = B_.d[25],
+           &d_seds_sz = B_.d[26], &d_seds_off = B_.d[27], &d_out = B_.d[28], &d_sout = B_.d[29], &d_stack = B_.d[30],
+           &d_big = B_.d[31];
+    DevBuf* d_tab = &B_.d[32];  // 4 entries
+    Keep<uint32_t>&p_left = B_.k[0], &p_right = B_.k[1], &p_len = B_.k[2], &p_bits = B_.k[3];
 
     d_part.reserve((size_t)(P + 1) * 8);
     unsigned long long* part = d_part.as<unsigned long long>();
@@ -763,7 +765,8 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
         const uint32_t pw = kMaxPathId / 32;
         d_present.reserve((size_t)pw * 4);
         d_rank.reserve((size_t)pw * 4);
-        EDSB_CUDA(cudaMemsetAsync(d_present.p, 0, (size_t)pw * 4, s));
+        EDSB_CUDA(cudaMemsetAsync(d_present.p, 0, (size_t)std::min<uint32_t>(pw, present_dirty_words_) * 4, s));
+        present_dirty_words_ = pw;  // until this call's largest id is known
         d_num_val.reserve((size_t)(ns / 2 + 2) * 4);
         d_num_set.reserve((size_t)(ns / 2 + 2) * 4);
         const SetFn sf{stext, ns, d_num_val.as<uint32_t>(), d_num_set.as<uint32_t>(), d_present.as<uint32_t>(), st};
@@ -778,6 +781,7 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
             throw std::runtime_error(msg);
         }
         const uint32_t pw_used = hst.max_id / 32u + 1u;  // words of the presence bitmap that can be non-zero
+        present_dirty_words_ = pw_used;
         LEDS_SCAN("id_rank", OpSum64, pw_used, (RankFn{d_present.as<uint32_t>(), d_rank.as<uint32_t>()}));
         n_paths = (uint32_t)total_of();
         Wd = (n_paths + 31) / 32;

@@ -24,7 +24,10 @@ class LedsPipeline {
     // check_only != nullptr: stop after the first round's pair selection; *check_only = 1 iff no pair exists
 
    private:
+    struct Bufs;
     eds_ctx* ctx_;
+    Bufs* bufs_;
+    uint32_t present_dirty_words_ = 0xffffffffu;  // words of the id bitmap that may be non-zero
 };
 
 }  // namespace edsb
