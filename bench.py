@@ -265,12 +265,12 @@ def run_ours(args, rank, world):
         pinned.copy_(torch.frombuffer(bytearray(text), dtype=torch.uint8))
         ctx.msa_synth_free()
         e2e_steps = max(1, min(args.steps, 5))
-        for _ in range(2):
-            he, hs, _ = ctx.msa_transform_host(pinned, L)
+        he, hs, _ = ctx.msa_transform_host(pinned, L)  # warm-up, and the bytes for the size fields
+        ctx.msa_transform_host_raw(pinned.data_ptr(), len(text), L)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            he, hs, _ = ctx.msa_transform_host(pinned, L)
+            ctx.msa_transform_host_raw(pinned.data_ptr(), len(text), L)  # H2D + index + kernels + D2H into host strings
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         e2e = {"value": cells_step * e2e_steps / dt, "unit": "cells/s", "h2d_bytes_per_step": len(text),

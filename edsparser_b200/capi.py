@@ -194,6 +194,17 @@ class Context:
         del keep
         return _host_bytes(self.lib, e), _host_bytes(self.lib, s), st.as_dict()
 
+    def msa_transform_host_raw(self, addr, n, l, leds=True):
+        """The bare C call on (address, length) of host bytes; outputs are freed, only sizes and stats are
+        returned (bench.py's end-to-end timing: no Python-side copies inside the timed region)."""
+        e, s, st = Buffer(), Buffer(), MsaStats()
+        self.lib.check(self.lib.L.eds_msa_transform_host(self.handle, addr, n, l, 1 if leds else 0, ctypes.byref(e),
+                                                         ctypes.byref(s), ctypes.byref(st)))
+        sizes = (int(e.bytes), int(s.bytes))
+        self.lib.L.eds_buffer_free_host(ctypes.byref(e))
+        self.lib.L.eds_buffer_free_host(ctypes.byref(s))
+        return sizes, st.as_dict()
+
     def msa_transform_device(self, view, l=0, leds=None):
         """view: MsaView over device memory -> (eds Buffer, seds Buffer, stats dict); buffers stay on the device."""
         if leds is None:
