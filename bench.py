@@ -200,11 +200,13 @@ def run_ours(args, rank, world):
     view.own_begin, view.own_end = lo, hi
     counts = torch.zeros(2, dtype=torch.int64, device=dev)
     gathered = torch.zeros(2 * world, dtype=torch.int64, device=dev)
+    exchange = shard.OffsetExchange(dist if world > 1 else None, dev)
 
     def step():
         e, s, st = ctx.msa_transform_device(view, L)
-        # file offsets of this rank's slices: all-gather of the byte counts (no-op at N = 1)
-        shard.gather_offsets(dist if world > 1 else None, dev, int(e.bytes), int(s.bytes), (counts, gathered))
+        # file offsets of this rank's slices: all-gather of the byte counts, queued behind the transform on the
+        # same stream; the host reads them once, before it writes (exchange.offsets() after the loop)
+        exchange.post(int(e.bytes), int(s.bytes))
         return e, s, st
 
     def barrier():
@@ -228,6 +230,7 @@ def run_ours(args, rank, world):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
+    my_offsets = exchange.offsets()  # (eds offset, seds offset, eds total, seds total) of this rank's slices
     clocks = sampler.stop() if sampler else None
     cells_step = R * C_PER_GPU * world
     value = cells_step * args.steps / (ms_total / 1e3)

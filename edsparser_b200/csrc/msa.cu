@@ -1344,25 +1344,31 @@ __global__ void k_emit_var(MsaGeom g, MsaBufs b, uint32_t per_warp_smem, uint32_
         uint8_t* seds_dst = nullptr;
         if (have && en - s == 1u) {
             const uint8_t* col = b.stash + (size_t)first_slot(b, s) * g.Rp;
-            // pass A: residue order + SEDS bytes per alternative (an id costs separator + digits)
+            // pass A: residue order and rows per alternative, counted per id-width band (ids 1-9, 10-99, 100-999
+            // cost 2, 3, 4 bytes with their separator): eight 8-bit counters per band in one 64-bit register
+            // (R <= 160 here, so a band holds at most 90 rows). No shared memory in this loop.
             Seen sn;
             sn.lo = sn.hi = sn.n = 0;
-            for (uint32_t a = 0; a < 8u; ++a) cnt[a * 32u + lane] = 0;
+            unsigned long long rows1 = 0, rows2 = 0, rows3 = 0;
             bool ok = true;
-            for (uint32_t r0 = 0; r0 < g.R && ok; r0 += 4) {
-                uint32_t word = *reinterpret_cast<const uint32_t*>(col + r0);
-                const uint32_t lim = min(4u, g.R - r0);
-                for (uint32_t i = 0; i < lim; ++i) {
-                    const uint32_t ch = word & 0xffu;
-                    word >>= 8;
-                    const uint32_t a = ch ? seen_index(sn, ch) : 8u;
-                    if (a >= 8u) {
-                        ok = false;  // queued as wide by k_group
-                        break;
-                    }
-                    cnt[a * 32u + lane] += (idtab[r0 + i] >> 24) + 1u;
+            const uint32_t full = g.R & ~3u;
+            auto count_row = [&](uint32_t ch, uint32_t r) {
+                const uint32_t a = ch ? seen_index(sn, ch) : 8u;
+                if (a >= 8u) {
+                    ok = false;  // queued as wide by k_group
+                    return;
                 }
+                const unsigned long long one = 1ull << (8u * a);
+                if (r < 9u) rows1 += one; else if (r < 99u) rows2 += one; else rows3 += one;  // r is warp-uniform
+            };
+            for (uint32_t r0 = 0; r0 < full && ok; r0 += 4) {
+                const uint32_t word = *reinterpret_cast<const uint32_t*>(col + r0);
+                count_row(word & 0xffu, r0);
+                count_row((word >> 8) & 0xffu, r0 + 1u);
+                count_row((word >> 16) & 0xffu, r0 + 2u);
+                count_row(word >> 24, r0 + 3u);
             }
+            for (uint32_t r = full; r < g.R && ok; ++r) count_row(col[r], r);
             if (ok) {
                 // EDS text straight from the lane (a dozen bytes)
                 uint8_t* eds = b.eds_out + b.eds_off[k];
@@ -1371,28 +1377,34 @@ __global__ void k_emit_var(MsaGeom g, MsaBufs b, uint32_t per_warp_smem, uint32_
                     if (a) *eds++ = ',';
                     const uint32_t ch = seen_byte(sn, a);
                     if (ch != (uint32_t)'-') *eds++ = (uint8_t)ch;
+                    cnt[a * 32u + lane] = 2u * (uint32_t)((rows1 >> (8u * a)) & 0xffull) + 3u * (uint32_t)((rows2 >> (8u * a)) & 0xffull) +
+                                          4u * (uint32_t)((rows3 >> (8u * a)) & 0xffull);
                 }
                 *eds = '}';
                 seds_dst = b.seds_out + b.seds_off[k];
                 shift = ((uint32_t)(reinterpret_cast<uintptr_t>(seds_dst) & 15u) - ((lane * seg_pitch) & 15u)) & 15u;
                 uint8_t* seg = segs + (size_t)lane * seg_pitch + shift;
                 seg_bytes = seg_layout(seg, cnt, cur, sn.n);
-                // pass B: place every id
-                for (uint32_t r0 = 0; r0 < g.R; r0 += 4) {
-                    uint32_t word = *reinterpret_cast<const uint32_t*>(col + r0);
-                    const uint32_t lim = min(4u, g.R - r0);
-                    for (uint32_t i = 0; i < lim; ++i) {
-                        const uint32_t a = seen_index(sn, word & 0xffu);
-                        word >>= 8;
-                        const uint32_t t = idtab[r0 + i], wd = t >> 24;
-                        const uint32_t cv = cur[a * 32u + lane], pos = cv & 0x7fffffffu;
-                        if (!(cv >> 31)) seg[pos] = ',';
-                        seg[pos + 1u] = (uint8_t)t;
-                        if (wd > 1u) seg[pos + 2u] = (uint8_t)(t >> 8);
-                        if (wd > 2u) seg[pos + 3u] = (uint8_t)(t >> 16);
-                        cur[a * 32u + lane] = pos + wd + 1u;
-                    }
+                // pass B: place every id (digits and width of the row number come from the per-block table)
+                auto place_row = [&](uint32_t ch, uint32_t r) {
+                    const uint32_t a = seen_lookup(sn, ch);
+                    const uint32_t t = idtab[r], wd = t >> 24;
+                    uint32_t* cp = cur + a * 32u + lane;
+                    const uint32_t cv = *cp, pos = cv & 0x7fffffffu;
+                    if (!(cv >> 31)) seg[pos] = ',';
+                    seg[pos + 1u] = (uint8_t)t;
+                    if (wd > 1u) seg[pos + 2u] = (uint8_t)(t >> 8);  // wd is warp-uniform
+                    if (wd > 2u) seg[pos + 3u] = (uint8_t)(t >> 16);
+                    *cp = pos + wd + 1u;
+                };
+                for (uint32_t r0 = 0; r0 < full; r0 += 4) {
+                    const uint32_t word = *reinterpret_cast<const uint32_t*>(col + r0);
+                    place_row(word & 0xffu, r0);
+                    place_row((word >> 8) & 0xffu, r0 + 1u);
+                    place_row((word >> 16) & 0xffu, r0 + 2u);
+                    place_row(word >> 24, r0 + 3u);
                 }
+                for (uint32_t r = full; r < g.R; ++r) place_row(col[r], r);
             }
         }
         __syncwarp();
@@ -1712,8 +1724,20 @@ void MsaPipeline::run_once(MsaBufs& b) {
     if (((seg_pitch >> 2) & 1u) == 0) seg_pitch += 4;
     uint32_t nb = 0, evw = kSymWarps;
     if (ctx_->narrow_off == 0 && g.R <= 160u) {  // beyond: rows-across-lanes path (per-lane segments would crowd shared memory)
-        while (evw > 1 && evw * (2048 + 32 * (size_t)seg_pitch) > smem_budget / 2) evw >>= 1;
-        if (evw * (2048 + 32 * (size_t)seg_pitch) + 4 * (size_t)g.R + 16 <= smem_budget / 2) nb = 32;
+        // warps per block that put the most warps on an SM: a pass of the kernel is lane-serial, so what counts
+        // is covering all batches of 32 symbols in as few rounds as possible
+        const size_t per_warp = 2048 + 32 * (size_t)seg_pitch, fixed = 4 * (size_t)g.R + 16, room = ctx_->smem_optin;
+        uint32_t best = 0;
+        for (uint32_t w = kSymWarps; w >= 1; --w) {
+            const size_t blk = w * per_warp + fixed;
+            if (blk > room) continue;
+            const uint32_t resident = w * (uint32_t)std::min<size_t>(room / (blk + 1024), 32 / w ? 32 / w : 1);
+            if (resident > best) {
+                best = resident;
+                evw = w;
+            }
+        }
+        if (best) nb = 32;
     }
     const uint32_t narrow_ok = ctx_->narrow_off == 2 ? 2u : (nb ? 1u : 0u);  // 1 lane per symbol, 0 rows across lanes, 2 all wide
     const size_t ev_warp_smem = (2048 + (size_t)nb * seg_pitch + 15) & ~(size_t)15;

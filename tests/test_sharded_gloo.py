@@ -32,6 +32,9 @@ def _rank_main(rank, world, port, outdir):
         e, s, st = ctx.msa_transform_device(view, L)
         eds, seds = ctx.download(e), ctx.download(s)
         eo, so, et, stot = shard.gather_offsets(dist, torch.device("cpu"), len(eds), len(seds))
+        ex = shard.OffsetExchange(dist, torch.device("cpu"))  # the queued form used by bench.py gives the same offsets
+        ex.post(len(eds), len(seds))
+        assert ex.offsets() == (eo, so, et, stot)
         dist.barrier()
         shard.write_slice(os.path.join(outdir, "out.leds"), eo, eds, et, rank)
         shard.write_slice(os.path.join(outdir, "out.seds"), so, seds, stot, rank)
