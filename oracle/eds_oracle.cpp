@@ -6,7 +6,7 @@
 //
 // Parity status: PINNED. This restatement is checked byte-for-byte against
 //   * the reference's own golden strings (tests/cpp/test_msa.cpp:20-229,
-//     tests/cpp/test_merge.cpp:81-259,359-371, data/eds/*_l<N>.eds), and
+//     tests/cpp/test_merge.cpp:81-259,359-371, data/eds/*_l<N>.eds, data/vcf/*.{eds,seds}), and
 //   * outputs of the UNMODIFIED reference library built into oracle/_ref/
 //     (tests/golden/*.json, produced by tests/golden/make_golden.py),
 // see tests/test_oracle.py.
@@ -19,6 +19,7 @@
 // All file:line citations are relative to /root/reference/src/cpp/lib/.
 // ============================================================================
 #include <algorithm>
+#include <cctype>
 #include <climits>
 #include <cstdint>
 #include <cstdio>
@@ -464,6 +465,244 @@ static void eds_to_leds(const std::string& eds_in, const std::string* seds_in, u
     if (e.with_src) seds_out = seds_text(e);
 }
 
+
+// ---------------------------------------------------------------------------
+// VCF + FASTA -> EDS / l-EDS      (transforms/vcf_transforms.cpp)
+// ---------------------------------------------------------------------------
+
+struct VcfCounters {  // VCFStats, vcf_transforms.hpp:24-36
+    size_t total = 0, processed = 0, malformed = 0, unsupported_sv = 0, groups = 0;
+};
+
+// std::getline over an in-memory file: yields the bytes up to the next '\n'; fails only when nothing is left.
+struct LineReader {
+    const std::string& buf;
+    size_t at = 0;
+    bool eof_hit = false;  // eofbit: the last getline ran into the end without seeing '\n'
+    explicit LineReader(const std::string& b) : buf(b) {}
+    bool next(std::string& line) {
+        if (eof_hit || at >= buf.size()) { eof_hit = true; return false; }
+        size_t nl = buf.find('\n', at);
+        if (nl == std::string::npos) { line = buf.substr(at); at = buf.size(); eof_hit = true; }
+        else { line = buf.substr(at, nl - at); at = nl + 1; }
+        return true;
+    }
+};
+
+struct FastaIndex {  // FASTAMetadata :20-25
+    size_t n_bases = 0, wrap = 0, first_base_at = 0;
+};
+
+// parse_fasta_metadata :51-86
+static FastaIndex fasta_index(const std::string& fa) {
+    LineReader rd(fa);
+    std::string line;
+    if (!rd.next(line) || line.empty() || line[0] != '>')
+        throw std::runtime_error("Invalid FASTA format: expected header line starting with '>'");
+    FastaIndex ix;
+    // tellg() after a getline that hit EOF fails (sentry sets failbit) and so does the next getline (:72)
+    ix.first_base_at = rd.at;
+    if (!rd.next(line)) throw std::runtime_error("FASTA file is empty");
+    ix.wrap = line.size();
+    ix.n_bases = line.size();
+    while (rd.next(line)) {
+        if (line.empty()) continue;
+        if (line[0] == '>') break;
+        ix.n_bases += line.size();
+    }
+    return ix;
+}
+
+// read_fasta_region :98-129
+static std::string fasta_slice(const std::string& fa, const FastaIndex& ix, size_t from, size_t n) {
+    if (from >= ix.n_bases) return "";
+    if (from + n > ix.n_bases) n = ix.n_bases - from;
+    if (ix.wrap == 0) throw std::runtime_error("oracle: FASTA line width 0 (the reference divides by zero here)");
+    std::string out;
+    size_t p = ix.first_base_at + from + from / ix.wrap;
+    while (out.size() < n && p < fa.size()) {
+        char c = fa[p++];
+        if (c != '\n' && c != '\r') out.push_back(c);
+    }
+    return out;
+}
+
+struct VcfRecord {  // VCFVariant :27-33
+    std::string chrom, ref;
+    size_t pos = 0;
+    std::vector<std::string> alts;
+    std::vector<std::vector<int>> gts;
+};
+
+// std::getline(ss, tok, delim) tokenisation: a trailing empty piece is not produced
+static std::vector<std::string> split_on(const std::string& s, char delim) {
+    std::vector<std::string> out;
+    size_t at = 0;
+    while (at < s.size()) {
+        size_t d = s.find(delim, at);
+        if (d == std::string::npos) { out.push_back(s.substr(at)); break; }
+        out.push_back(s.substr(at, d - at));
+        at = d + 1;
+    }
+    return out;
+}
+static std::vector<std::string> split_space(const std::string& s) {  // operator>> tokens
+    std::vector<std::string> out;
+    size_t i = 0;
+    while (i < s.size()) {
+        while (i < s.size() && std::isspace(static_cast<unsigned char>(s[i]))) ++i;
+        size_t b = i;
+        while (i < s.size() && !std::isspace(static_cast<unsigned char>(s[i]))) ++i;
+        if (i > b) out.push_back(s.substr(b, i - b));
+    }
+    return out;
+}
+
+// parse_genotype :190-216
+static std::vector<int> gt_alleles(const std::string& gt) {
+    char d = gt.find('/') != std::string::npos ? '/' : '|';
+    std::vector<int> out;
+    for (const std::string& piece : split_on(gt, d)) {
+        if (piece == ".") continue;
+        try { out.push_back(std::stoi(piece)); } catch (...) {}
+    }
+    return out;
+}
+
+enum class LineKind { RECORD, HEADER, MALFORMED, SV };
+
+// parse_vcf_line :232-326 (+ parse_alt_field :142-176)
+static LineKind vcf_line(const std::string& line, VcfRecord& r, std::vector<std::string>* warnings) {
+    if (line.empty() || line[0] == '#') return LineKind::HEADER;  // n_samples from #CHROM is never used (:558)
+    std::vector<std::string> f;
+    for (std::string& t : split_on(line, '\t'))
+        if (!t.empty()) f.push_back(std::move(t));
+    if (f.size() < 5) f = split_space(line);
+    if (f.size() < 5) return LineKind::MALFORMED;
+    r.chrom = f[0];
+    try { r.pos = std::stoull(f[1]); } catch (...) { return LineKind::MALFORMED; }
+    r.ref = f[3];
+    for (const std::string& a : split_on(f[4], ',')) {
+        if (!a.empty() && a.front() == '<' && a.back() == '>') {
+            std::string kind = a.substr(1, a.size() - 2);
+            if (kind == "DEL") r.alts.push_back("");
+            else if (kind == "INS") r.alts.push_back(r.ref);
+            else {
+                if (warnings)
+                    warnings->push_back("Warning: Skipping variant at " + r.chrom + ":" + std::to_string(r.pos) +
+                                        " - Unsupported structural variant type: " + kind);
+                return LineKind::SV;
+            }
+        } else {
+            r.alts.push_back(a);  // an empty piece ("A,,C") reads as a plain empty allele
+        }
+    }
+    for (size_t i = 9; i < f.size(); ++i) r.gts.push_back(gt_alleles(f[i].substr(0, f[i].find(':'))));
+    return LineKind::RECORD;
+}
+
+// apply_variant_to_span :356-390
+static std::string with_allele(const std::string& span, size_t span_from, const VcfRecord& r, int allele) {
+    if (allele < 1 || allele > static_cast<int>(r.alts.size())) return span;
+    size_t off = (r.pos - 1) - span_from;
+    std::string out = span.substr(0, off);  // throws std::out_of_range when the span was cut short by the FASTA end
+    out += r.alts[allele - 1];
+    if (off + r.ref.size() < span.size()) out += span.substr(off + r.ref.size());
+    return out;
+}
+
+// parse_vcf_to_eds_streaming :677-729 = group_overlapping_variants :482-534 + merge_variant_group :396-476 +
+// generate_eds_from_variants :554-668
+static void vcf_to_eds(const std::string& vcf, const std::string& fa, std::string& eds, std::string& seds,
+                       VcfCounters& st, std::vector<std::string>* warnings) {
+    FastaIndex ix = fasta_index(fa);
+    std::vector<VcfRecord> recs;
+    {
+        LineReader rd(vcf);
+        std::string line;
+        while (rd.next(line)) {
+            VcfRecord r;
+            switch (vcf_line(line, r, warnings)) {
+                case LineKind::HEADER: break;
+                case LineKind::MALFORMED: ++st.total; ++st.malformed; break;
+                case LineKind::SV: ++st.total; ++st.unsupported_sv; break;
+                case LineKind::RECORD: ++st.total; ++st.processed; recs.push_back(std::move(r)); break;
+            }
+        }
+    }
+    // :715-718 — std::sort, unstable: the same call on the same sequence reproduces the reference's order of ties
+    std::sort(recs.begin(), recs.end(), [](const VcfRecord& a, const VcfRecord& b) { return a.pos < b.pos; });
+
+    size_t cursor = 0;
+    auto common = [&](size_t upto) {
+        std::string text = fasta_slice(fa, ix, cursor, upto - cursor);
+        if (!text.empty()) { eds += '{' + text + '}'; seds += "{0}"; }
+    };
+    size_t i = 0;
+    while (i < recs.size()) {
+        size_t from = recs[i].pos - 1, to = from + recs[i].ref.size(), j = i + 1;
+        while (j < recs.size() && recs[j].pos - 1 < to) { to = std::max(to, recs[j].pos - 1 + recs[j].ref.size()); ++j; }
+        ++st.groups;
+        std::string span = fasta_slice(fa, ix, from, to - from);
+        // haplotype list: the reference span, then every ALT of every record applied alone; equal strings once
+        std::vector<std::string> haps{span};
+        auto hap_id = [&](const std::string& h) -> int {
+            auto it = std::find(haps.begin(), haps.end(), h);
+            return it == haps.end() ? -1 : static_cast<int>(it - haps.begin());
+        };
+        for (size_t v = i; v < j; ++v)
+            for (size_t a = 0; a < recs[v].alts.size(); ++a) {
+                std::string h = with_allele(span, from, recs[v], static_cast<int>(a) + 1);
+                if (hap_id(h) < 0) haps.push_back(h);
+            }
+        size_t n_samples = recs[i].gts.size();
+        std::vector<std::set<int>> carriers(haps.size());
+        for (size_t s = 0; s < n_samples; ++s) {
+            std::set<int> mine;
+            for (size_t v = i; v < j; ++v) {
+                if (s >= recs[v].gts.size()) continue;
+                for (int a : recs[v].gts[s]) {
+                    int h = hap_id(with_allele(span, from, recs[v], a));
+                    if (h >= 0) mine.insert(h);
+                }
+            }
+            if (mine.empty()) mine.insert(0);
+            for (int h : mine) carriers[h].insert(static_cast<int>(s) + 1);
+        }
+        if (from > cursor) { common(from); cursor = from; }
+        eds += '{';
+        if (n_samples == 0) {  // :603-615
+            for (size_t h = 0; h < haps.size(); ++h) { if (h) eds += ','; eds += haps[h]; }
+            eds += '}';
+            seds += "{0}";
+        } else {
+            bool first = true;
+            for (size_t h = 0; h < haps.size(); ++h) {
+                if (carriers[h].empty()) continue;  // :619-624
+                if (!first) eds += ',';
+                first = false;
+                eds += haps[h];
+                seds += '{';
+                bool f1 = true;
+                for (int id : carriers[h]) { if (!f1) seds += ','; f1 = false; seds += std::to_string(id); }
+                seds += '}';
+            }
+            eds += '}';
+        }
+        cursor = from + span.size();  // group.end_pos :404
+        i = j;
+    }
+    if (cursor < ix.n_bases) common(ix.n_bases);
+}
+
+// parse_vcf_to_leds_streaming :735-755 — LINEAR merge, one thread, compact
+static void vcf_to_leds(const std::string& vcf, const std::string& fa, size_t l, std::string& eds, std::string& seds,
+                        VcfCounters& st, std::vector<std::string>* warnings) {
+    std::string e0, s0;
+    vcf_to_eds(vcf, fa, e0, s0, st, warnings);
+    eds_to_leds(e0, &s0, static_cast<uint32_t>(l), true, eds, seds, 0);
+}
+
 }  // namespace oracle
 
 // ---------------------------------------------------------------------------
@@ -533,6 +772,34 @@ int oracle_eds2leds(const char* eds, size_t n, const char* seds, size_t sn, unsi
     }
 }
 
+// stats: total, processed, malformed, unsupported_sv, groups. warnings (optional): '\n'-joined stderr lines.
+int oracle_vcf2eds(const char* vcf, size_t vn, const char* fa, size_t fn, size_t l, char** eds, size_t* eds_n,
+                   char** seds, size_t* seds_n, unsigned long long* stats, char** warnings, char* err, size_t errcap) {
+    try {
+        std::string e, s;
+        oracle::VcfCounters st;
+        std::vector<std::string> warn;
+        if (l) oracle::vcf_to_leds(std::string(vcf, vn), std::string(fa, fn), l, e, s, st, &warn);
+        else oracle::vcf_to_eds(std::string(vcf, vn), std::string(fa, fn), e, s, st, &warn);
+        *eds = dup_bytes(e);
+        *eds_n = e.size();
+        *seds = dup_bytes(s);
+        *seds_n = s.size();
+        if (stats) {
+            stats[0] = st.total; stats[1] = st.processed; stats[2] = st.malformed; stats[3] = st.unsupported_sv;
+            stats[4] = st.groups;
+        }
+        if (warnings) {
+            std::string w;
+            for (auto& x : warn) w += x + "\n";
+            *warnings = dup_bytes(w);
+        }
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail(ex, err, errcap);
+    }
+}
+
 void oracle_free(char* p) { std::free(p); }
 
 }  // extern "C"
@@ -540,6 +807,7 @@ void oracle_free(char* p) { std::free(p); }
 #ifdef EDS_ORACLE_MAIN
 // eds_oracle msa2eds <in.msa> <l> <out.eds> <out.seds>
 // eds_oracle eds2leds <in.eds> <in.seds|-> <l> <out.leds> <out.seds|-> <compact>
+// eds_oracle vcf2eds <in.vcf> <ref.fa> <l> <out.eds> <out.seds>
 static std::string slurp(const char* path) {
     std::ifstream f(path, std::ios::binary);
     if (!f) throw std::runtime_error(std::string("cannot open ") + path);
@@ -572,7 +840,21 @@ int main(int argc, char** argv) {
             if (linear && std::strcmp(argv[6], "-") != 0) spill(argv[6], s);
             return 0;
         }
-        std::cerr << "usage: eds_oracle msa2eds|eds2leds ...\n";
+        if (cmd == "vcf2eds" && argc == 7) {
+            size_t l = std::strtoull(argv[4], nullptr, 10);
+            std::string e, s;
+            oracle::VcfCounters st;
+            std::vector<std::string> warn;
+            if (l) oracle::vcf_to_leds(slurp(argv[2]), slurp(argv[3]), l, e, s, st, &warn);
+            else oracle::vcf_to_eds(slurp(argv[2]), slurp(argv[3]), e, s, st, &warn);
+            for (auto& w : warn) std::cerr << w << "\n";
+            spill(argv[5], e);
+            spill(argv[6], s);
+            std::cout << "stats total=" << st.total << " processed=" << st.processed << " malformed=" << st.malformed
+                      << " sv=" << st.unsupported_sv << " groups=" << st.groups << "\n";
+            return 0;
+        }
+        std::cerr << "usage: eds_oracle msa2eds|eds2leds|vcf2eds ...\n";
         return 2;
     } catch (const std::exception& ex) {
         std::cerr << "Error: " << ex.what() << "\n";

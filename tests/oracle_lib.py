@@ -33,6 +33,8 @@ def lib():
         L.oracle_msa_conserved.restype = ctypes.c_longlong
         L.oracle_eds2leds.argtypes = [cp, sz, cp, sz, ctypes.c_uint, ctypes.c_int, sz, pp, ps, pp, ps, cp, sz]
         L.oracle_eds2leds.restype = ctypes.c_int
+        L.oracle_vcf2eds.argtypes = [cp, sz, cp, sz, sz, pp, ps, pp, ps, ctypes.POINTER(ctypes.c_ulonglong), pp, cp, sz]
+        L.oracle_vcf2eds.restype = ctypes.c_int
         L.oracle_free.argtypes = [ctypes.c_void_p]
         _LIB = L
     return _LIB
@@ -81,3 +83,23 @@ def eds2leds(eds: bytes, seds, l: int, compact: bool = True, max_out_bytes: int 
         raise OracleError(rc, err.value.decode("latin-1"))
     out, sout = _take(L, e, en), _take(L, s, sn)
     return out, (sout if seds is not None else None)
+
+
+VCF_STAT_KEYS = ("total", "processed", "malformed", "sv", "groups")
+
+
+def vcf2eds(vcf: bytes, fasta: bytes, l: int = 0):
+    """Reference semantics of the vcf2eds CLI: l == 0 -> parse_vcf_to_eds_streaming, l > 0 -> ..._to_leds_...
+    Returns (eds, seds, stats dict, warning lines)."""
+    L = lib()
+    e, s, w = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    en, sn = ctypes.c_size_t(), ctypes.c_size_t()
+    st = (ctypes.c_ulonglong * 5)()
+    err = ctypes.create_string_buffer(512)
+    rc = L.oracle_vcf2eds(vcf, len(vcf), fasta, len(fasta), l, ctypes.byref(e), ctypes.byref(en), ctypes.byref(s),
+                          ctypes.byref(sn), st, ctypes.byref(w), err, 512)
+    if rc:
+        raise OracleError(rc, err.value.decode("latin-1"))
+    warn = ctypes.string_at(w.value).decode("latin-1").splitlines() if w.value else []
+    L.oracle_free(w)
+    return _take(L, e, en), _take(L, s, sn), dict(zip(VCF_STAT_KEYS, [int(x) for x in st])), warn

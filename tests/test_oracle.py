@@ -75,3 +75,36 @@ def test_reference_data_eds_pairs():
     # inputs/outputs are embedded in leds.json under "name".
     named = [c for c in _cases("leds.json") if c.get("name")]
     assert len(named) >= 20
+
+
+def _stats_line(st):
+    return "stats total=%d processed=%d malformed=%d sv=%d groups=%d" % tuple(st[k] for k in oracle_lib.VCF_STAT_KEYS)
+
+
+def test_vcf_golden_all():
+    # outputs of the unmodified reference (tests/golden/make_golden_vcf.py), incl. data/vcf/{small,test_overlaps,
+    # test_samepos} which the reference's own test_vcf.cpp reads
+    cases = _cases("vcf.json")
+    assert len(cases) > 300
+    n_err = 0
+    for c in cases:
+        vcf, fa = c["vcf"].encode("latin-1"), c["fa"].encode("latin-1")
+        if "error" in c:
+            n_err += 1
+            with pytest.raises(oracle_lib.OracleError) as ei:
+                oracle_lib.vcf2eds(vcf, fa, c["l"])
+            assert "Error: " + ei.value.message == c["error"], c["error"]
+            continue
+        eds, seds, st, _ = oracle_lib.vcf2eds(vcf, fa, c["l"])
+        assert eds == c["eds"].encode("latin-1"), (c.get("name"), c["l"])
+        assert seds == c["seds"].encode("latin-1"), (c.get("name"), c["l"])
+        assert _stats_line(st) == c["stats"]
+    assert n_err >= 10
+
+
+def test_vcf_reference_shipped_outputs():
+    # data/vcf/small.{eds,seds} and test_samepos as shipped by the reference
+    named = {(c["name"], c["l"]): c for c in _cases("vcf.json") if c.get("name")}
+    c = named[("test_samepos", 0)]
+    assert (c["eds"], c["seds"]) == ("{ACGT}{A,C,G}{CGTACGT}", "{0}{1,2}{1}{2}{0}")
+    assert named[("small", 0)]["eds"].startswith("{AGCT}{T,C}{AG}{C,G}{TAAGCTTACGA}{T}{CGATCG}")
