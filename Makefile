@@ -8,7 +8,7 @@ CXX      := $(firstword $(wildcard /usr/bin/g++) g++)
 ARCH     := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS  := -std=c++17 -O3 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
 CSRC     := edsparser_b200/csrc
-SRCS     := $(CSRC)/msa.cu $(CSRC)/leds.cu $(CSRC)/capi.cu
+SRCS     := $(CSRC)/msa.cu $(CSRC)/leds.cu $(CSRC)/vcf.cu $(CSRC)/capi.cu
 HDRS     := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/edsparser_b200.h
 OBJS     := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))
 EMUOBJS  := $(patsubst $(CSRC)/%.cu,build/emu_%.o,$(SRCS)) build/emu_runtime.o

@@ -19,12 +19,14 @@ EDS_ERR_CUDA = 4
 EDS_ERR_BAD_MSA = 5
 EDS_ERR_BUDGET = 6
 EDS_ERR_HALO = 7
+EDS_ERR_BAD_VCF = 8
 
 EXPORTS = [
     "eds_last_error", "eds_version", "eds_ctx_create", "eds_ctx_destroy", "eds_ctx_synchronize",
     "eds_ctx_set_tuning", "eds_ctx_set_profiling", "eds_ctx_kernel_times", "eds_msa_index_host",
     "eds_msa_index_free", "eds_msa_transform_device", "eds_msa_transform_host", "eds_msa_conserved_bits",
     "eds_msa_synth_device", "eds_msa_synth_free", "eds_buffer_to_host", "eds_buffer_free_host", "eds_leds_merge_host", "eds_is_leds_host",
+    "eds_vcf_transform_host", "eds_vcf_transform_device", "eds_device_upload", "eds_device_free",
 ]
 
 
@@ -62,6 +64,16 @@ class MsaStats(ctypes.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
+class VcfStats(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_uint64) for k in (
+        "total_variants", "processed_variants", "skipped_malformed", "skipped_unsupported_sv", "variant_groups",
+        "n_lines", "n_bases", "n_alleles", "n_haplotype_slots", "n_samples_max", "eds_bytes", "seds_bytes")] + [
+        (k, ctypes.c_uint32) for k in ("gpu_launches", "host_sorted", "retries", "leds_rounds")]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 class Library:
     """One loaded copy of the C ABI."""
 
@@ -97,6 +109,12 @@ class Library:
         L.eds_buffer_free_host.restype = None
         L.eds_leds_merge_host.argtypes = [vp, vp, u64, vp, u64, u32, i32, u64, P(Buffer), P(Buffer), P(u32)]
         L.eds_is_leds_host.argtypes = [vp, vp, u64, u32, P(i32)]
+        L.eds_vcf_transform_host.argtypes = [vp, vp, u64, vp, u64, u32, P(Buffer), P(Buffer), P(VcfStats),
+                                             P(P(ctypes.c_uint64)), P(u64)]
+        L.eds_vcf_transform_device.argtypes = [vp, vp, u64, vp, u64, P(Buffer), P(Buffer), P(VcfStats)]
+        L.eds_device_upload.argtypes = [vp, vp, u64, P(vp)]
+        L.eds_device_free.argtypes = [vp, vp]
+        L.eds_device_free.restype = None
         self.L = L
         _ = u8p
 
@@ -262,6 +280,39 @@ class Context:
         self.lib.check(self.lib.L.eds_is_leds_host(self.handle, ea, en, l, ctypes.byref(out)))
         del keep
         return bool(out.value)
+
+    # -- VCF front end --------------------------------------------------------------------------
+    def vcf_transform_host(self, vcf, fasta, l=0):
+        """bytes of a .vcf and a .fa -> (eds, seds, stats dict, offsets of the lines skipped as unsupported SVs)."""
+        va, vn, k1 = _as_pointer(vcf)
+        fa, fn, k2 = _as_pointer(fasta)
+        e, s, st = Buffer(), Buffer(), VcfStats()
+        sv, nsv = ctypes.POINTER(ctypes.c_uint64)(), ctypes.c_uint64()
+        self.lib.check(self.lib.L.eds_vcf_transform_host(self.handle, va, vn, fa, fn, l, ctypes.byref(e), ctypes.byref(s),
+                                                         ctypes.byref(st), ctypes.byref(sv), ctypes.byref(nsv)))
+        del k1, k2
+        lines = [int(sv[i]) for i in range(nsv.value)]
+        if nsv.value:
+            ctypes.CDLL(None).free(sv)
+        return _host_bytes(self.lib, e), _host_bytes(self.lib, s), st.as_dict(), lines
+
+    def upload(self, data):
+        """host bytes -> Buffer over fresh device memory (16-byte aligned and padded); free with device_free."""
+        a, n, keep = _as_pointer(data)
+        out = ctypes.c_void_p()
+        self.lib.check(self.lib.L.eds_device_upload(self.handle, a, n, ctypes.byref(out)))
+        del keep
+        return Buffer(out.value, n)
+
+    def device_free(self, buf):
+        self.lib.L.eds_device_free(self.handle, buf.data)
+
+    def vcf_transform_device(self, vcf_buf, fasta_buf):
+        """device Buffers in -> (eds Buffer, seds Buffer, stats dict), outputs stay on the device (l = 0 only)."""
+        e, s, st = Buffer(), Buffer(), VcfStats()
+        self.lib.check(self.lib.L.eds_vcf_transform_device(self.handle, vcf_buf.data, vcf_buf.bytes, fasta_buf.data,
+                                                           fasta_buf.bytes, ctypes.byref(e), ctypes.byref(s), ctypes.byref(st)))
+        return e, s, st.as_dict()
 
 
 _product = None

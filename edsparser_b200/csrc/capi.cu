@@ -12,6 +12,7 @@
 #include "ctx.h"
 #include "leds.h"
 #include "msa.h"
+#include "vcf.h"
 
 namespace {
 
@@ -25,6 +26,9 @@ eds_status guarded(F&& body) {
     } catch (const edsb::BadMsa& e) {
         g_last_error = e.what();
         return EDS_ERR_BAD_MSA;
+    } catch (const edsb::BadVcf& e) {
+        g_last_error = e.what();
+        return EDS_ERR_BAD_VCF;
     } catch (const edsb::HaloError& e) {
         g_last_error = e.what();
         return EDS_ERR_HALO;
@@ -116,6 +120,7 @@ eds_status eds_ctx_create(int device, void* stream, eds_ctx** out) {
         if (const char* no = getenv("EDSB_DEBUG_NARROW_OFF")) ctx->narrow_off = atoi(no);
         ctx->msa = new edsb::MsaPipeline(ctx);
         ctx->leds = new edsb::LedsPipeline(ctx);
+        ctx->vcf = new edsb::VcfPipeline(ctx);
         *out = ctx;
     });
 }
@@ -126,6 +131,9 @@ void eds_ctx_destroy(eds_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     delete ctx->msa;
     delete ctx->leds;
+    delete ctx->vcf;
+    for (auto& b : ctx->vcf_in) b.release();
+    for (auto& b : ctx->vcf_out) b.release();
     ctx->synth_text.release();
     ctx->file_buf.release();
     ctx->clock.release();
@@ -362,6 +370,91 @@ eds_status eds_is_leds_host(eds_ctx* ctx, const uint8_t* eds_in, uint64_t eds_by
         if (l == 0) return;
         ctx->leds->merge_host(eds_in, eds_bytes, nullptr, 0, l, true, 0, nullptr, nullptr, nullptr, is_leds_out);
     });
+}
+
+eds_status eds_vcf_transform_device(eds_ctx* ctx, const uint8_t* vcf, uint64_t vcf_bytes, const uint8_t* fasta,
+                                    uint64_t fasta_bytes, eds_buffer* eds_out, eds_buffer* seds_out,
+                                    eds_vcf_stats* stats) {
+    return guarded([&] {
+        use_device(ctx);
+        if (!vcf || !fasta || !eds_out || !seds_out) throw std::invalid_argument("eds_vcf_transform_device: null argument");
+        if (stats) memset(stats, 0, sizeof(*stats));
+        ctx->vcf->transform_device(vcf, vcf_bytes, fasta, fasta_bytes, eds_out, seds_out, stats, nullptr);
+    });
+}
+
+eds_status eds_vcf_transform_host(eds_ctx* ctx, const uint8_t* vcf, uint64_t vcf_bytes, const uint8_t* fasta,
+                                  uint64_t fasta_bytes, uint32_t l, eds_buffer* eds_out, eds_buffer* seds_out,
+                                  eds_vcf_stats* stats, uint64_t** sv_lines, uint64_t* n_sv_lines) {
+    if (sv_lines) *sv_lines = nullptr;
+    if (n_sv_lines) *n_sv_lines = 0;
+    eds_status rc = guarded([&] {
+        use_device(ctx);
+        if ((!vcf && vcf_bytes) || (!fasta && fasta_bytes) || !eds_out || !seds_out)
+            throw std::invalid_argument("eds_vcf_transform_host: null argument");
+        eds_out->data = seds_out->data = nullptr;
+        eds_out->bytes = seds_out->bytes = 0;
+        if (stats) memset(stats, 0, sizeof(*stats));
+        ctx->vcf_in[0].reserve(vcf_bytes + 16);
+        ctx->vcf_in[1].reserve(fasta_bytes + 16);
+        if (vcf_bytes) EDSB_CUDA(cudaMemcpyAsync(ctx->vcf_in[0].p, vcf, vcf_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        if (fasta_bytes) EDSB_CUDA(cudaMemcpyAsync(ctx->vcf_in[1].p, fasta, fasta_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        std::vector<uint64_t> sv;
+        eds_buffer d_eds{nullptr, 0}, d_seds{nullptr, 0};
+        ctx->vcf->transform_device(ctx->vcf_in[0].as<uint8_t>(), vcf_bytes, ctx->vcf_in[1].as<uint8_t>(), fasta_bytes, &d_eds,
+                                   &d_seds, stats, &sv);
+        if (sv_lines && n_sv_lines && !sv.empty()) {
+            *sv_lines = static_cast<uint64_t*>(malloc(sv.size() * sizeof(uint64_t)));
+            if (!*sv_lines) throw std::bad_alloc();
+            memcpy(*sv_lines, sv.data(), sv.size() * sizeof(uint64_t));
+            *n_sv_lines = sv.size();
+        }
+        if (l == 0) {
+            eds_out->data = to_host(ctx, d_eds);
+            eds_out->bytes = d_eds.bytes;
+            seds_out->data = to_host(ctx, d_seds);
+            seds_out->bytes = d_seds.bytes;
+        } else {
+            // parse_vcf_to_leds_streaming :750-752: LINEAR merge of the text just produced, still in HBM
+            uint32_t rounds = 0;
+            const uint32_t launches = ctx->clock.launches;
+            ctx->leds->merge_host(d_eds.data, d_eds.bytes, d_seds.data, d_seds.bytes, l, true, 0, eds_out, seds_out, &rounds,
+                                  nullptr, true);
+            if (stats) {
+                stats->leds_rounds = rounds;
+                stats->gpu_launches = launches + ctx->clock.launches;
+            }
+        }
+    });
+    if (rc != EDS_OK) {
+        if (eds_out) eds_buffer_free_host(eds_out);
+        if (seds_out) eds_buffer_free_host(seds_out);
+    }
+    return rc;
+}
+
+eds_status eds_device_upload(eds_ctx* ctx, const uint8_t* host, uint64_t bytes, uint8_t** device_out) {
+    return guarded([&] {
+        use_device(ctx);
+        if (!device_out || (!host && bytes)) throw std::invalid_argument("eds_device_upload: null argument");
+        void* p = nullptr;
+        EDSB_CUDA(cudaMalloc(&p, ((bytes + 16 + 255) / 256) * 256));
+        if (bytes) {
+            cudaError_t e = cudaMemcpyAsync(p, host, bytes, cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) {
+                cudaFree(p);
+                throw edsb::CudaError(std::string("host to device copy: ") + cudaGetErrorString(e));
+            }
+        }
+        *device_out = static_cast<uint8_t*>(p);
+    });
+}
+
+void eds_device_free(eds_ctx* ctx, uint8_t* device) {
+    if (!ctx || !device) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(device);
 }
 
 }  // extern "C"

@@ -10,6 +10,7 @@
 namespace edsb {
 class MsaPipeline;
 class LedsPipeline;
+class VcfPipeline;
 
 // One event pair per launch when profiling is on; resolved to milliseconds after the stream syncs.
 struct KernelClock {
@@ -72,6 +73,9 @@ struct eds_ctx {
     edsb::KernelClock clock;
     edsb::MsaPipeline* msa = nullptr;
     edsb::LedsPipeline* leds = nullptr;
+    edsb::VcfPipeline* vcf = nullptr;
+    edsb::DevBuf vcf_in[2];   // eds_vcf_transform_host: the .vcf and .fa bytes on the device
+    edsb::DevBuf vcf_out[2];  // EDS / SEDS text of the last VCF transform
     // synthetic alignment (eds_msa_synth_device)
     edsb::DevBuf synth_text;
     edsb::DevBuf file_buf;  // eds_msa_transform_host: the .msa bytes on the device

@@ -663,11 +663,20 @@ LedsPipeline::~LedsPipeline() { delete bufs_; }
 
 void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const uint8_t* seds_in, uint64_t seds_bytes,
                               uint32_t l, bool compact, uint64_t max_output_bytes, eds_buffer* leds_out,
-                              eds_buffer* seds_out, uint32_t* rounds_out, int* check_only) {
+                              eds_buffer* seds_out, uint32_t* rounds_out, int* check_only, bool input_on_device) {
     if (l == 0) throw std::invalid_argument("context_length must be > 0 for l-EDS transformation");  // eds_transforms.cpp:322-324
     if (eds_bytes >= 0xfffffff0ull || seds_bytes >= 0xfffffff0ull) throw std::invalid_argument("eds_leds_merge_host: inputs must be below 4 GiB (Length is uint32 in the reference too)");
     const bool linear = seds_in != nullptr;
     cudaStream_t s = ctx_->stream;
+    const cudaMemcpyKind in_kind = input_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    // the error explanations re-read the input on the host (rare path)
+    std::vector<uint8_t> h_in_copy;
+    auto host_view = [&](const uint8_t* p, uint64_t n) -> const uint8_t* {
+        if (!input_on_device) return p;
+        h_in_copy.resize(n ? n : 1);
+        if (n) EDSB_CUDA(cudaMemcpy(h_in_copy.data(), p, n, cudaMemcpyDeviceToHost));
+        return h_in_copy.data();
+    };
     KernelClock& clk = ctx_->clock;
     clk.reset();
     const uint32_t sms = (uint32_t)ctx_->sm_count;
@@ -727,7 +736,7 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
     // ---- EDS text: strip, parse ----------------------------------------------------------------------
     d_raw.reserve(eds_bytes + 16);
     d_text.reserve(eds_bytes + 16);
-    if (eds_bytes) EDSB_CUDA(cudaMemcpyAsync(d_raw.p, eds_in, eds_bytes, cudaMemcpyHostToDevice, s));
+    if (eds_bytes) EDSB_CUDA(cudaMemcpyAsync(d_raw.p, eds_in, eds_bytes, in_kind, s));
     uint8_t* text = d_text.as<uint8_t>();
     LEDS_SCAN("strip_eds", OpSum64, eds_bytes, (StripFn{d_raw.as<uint8_t>(), text}));
     const uint32_t n = (uint32_t)total_of();
@@ -739,7 +748,7 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
         const unsigned long long oc = total_of();
         status_now();
         if ((hst.err & kErrEdsSyntax) || (uint32_t)oc != (uint32_t)(oc >> 32))
-            throw std::runtime_error(explain_eds_error(strip_host(eds_in, eds_bytes)));
+            throw std::runtime_error(explain_eds_error(strip_host(host_view(eds_in, eds_bytes), eds_bytes)));
         d_str_start.reserve((size_t)(n + 2) * 4);
         d_str_end.reserve((size_t)(n + 2) * 4);
         d_sym_first.reserve((size_t)(n + 2) * 4);
@@ -757,7 +766,7 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
     if (linear) {
         d_sraw.reserve(seds_bytes + 16);
         d_stext.reserve(seds_bytes + 16);
-        if (seds_bytes) EDSB_CUDA(cudaMemcpyAsync(d_sraw.p, seds_in, seds_bytes, cudaMemcpyHostToDevice, s));
+        if (seds_bytes) EDSB_CUDA(cudaMemcpyAsync(d_sraw.p, seds_in, seds_bytes, in_kind, s));
         uint8_t* stext = d_stext.as<uint8_t>();
         LEDS_SCAN("strip_seds", OpSum64, seds_bytes, (StripFn{d_sraw.as<uint8_t>(), stext}));
         const uint32_t ns = (uint32_t)total_of();
@@ -776,7 +785,7 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
         status_now();
         bool oor = false;
         if (hst.err & (kErrSedsSyntax | kErrSedsOverflow | kErrSedsBigId) || n_sets != n_str) {
-            const std::string msg = explain_seds_error(strip_host(seds_in, seds_bytes), n_str, oor);
+            const std::string msg = explain_seds_error(strip_host(host_view(seds_in, seds_bytes), seds_bytes), n_str, oor);
             if (oor) throw std::out_of_range(msg);
             throw std::runtime_error(msg);
         }

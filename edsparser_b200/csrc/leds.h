@@ -20,8 +20,9 @@ class LedsPipeline {
     // Host text in, malloc'd host text out.
     void merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const uint8_t* seds_in, uint64_t seds_bytes, uint32_t l,
                     bool compact, uint64_t max_output_bytes, eds_buffer* leds_out, eds_buffer* seds_out,
-                    uint32_t* rounds_out, int* check_only = nullptr);
+                    uint32_t* rounds_out, int* check_only = nullptr, bool input_on_device = false);
     // check_only != nullptr: stop after the first round's pair selection; *check_only = 1 iff no pair exists
+    // input_on_device: eds_in / seds_in are device pointers (the VCF front end hands its output over in HBM)
 
    private:
     struct Bufs;

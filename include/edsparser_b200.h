@@ -30,7 +30,8 @@ typedef enum eds_status {
     EDS_ERR_CUDA = 4,             /* CUDA runtime failure or no device (no CPU fallback exists)        */
     EDS_ERR_BAD_MSA = 5,          /* input outside the reference's well-defined MSA domain (C.2)       */
     EDS_ERR_BUDGET = 6,           /* output larger than the caller's max_output_bytes                  */
-    EDS_ERR_HALO = 7              /* a symbol cannot be resolved inside the shard's window: widen it   */
+    EDS_ERR_HALO = 7,             /* a symbol cannot be resolved inside the shard's window: widen it   */
+    EDS_ERR_BAD_VCF = 8           /* VCF/FASTA input outside the reference's well-defined domain (C.4) */
 } eds_status;
 
 typedef struct eds_ctx eds_ctx; /* one per (device, stream); owns scratch + output buffers; not thread-safe */
@@ -164,6 +165,48 @@ eds_status eds_leds_merge_host(eds_ctx* ctx, const uint8_t* eds_in, uint64_t eds
 /* is_leds (eds_transforms.cpp:439-468): 1 iff no interior non-degenerate symbol is shorter than l and no
  * two degenerate symbols are adjacent (l = 0: always 1). Parsed and tested on the device. */
 eds_status eds_is_leds_host(eds_ctx* ctx, const uint8_t* eds_in, uint64_t eds_bytes, uint32_t l, int* is_leds_out);
+
+/* ------------------------------------------------------------------------------------------
+ * VCF front end: parse_vcf_to_eds_streaming (vcf_transforms.cpp:677-729) when l == 0,
+ * parse_vcf_to_leds_streaming (vcf_transforms.cpp:735-755: the same followed by the LINEAR merge,
+ * one thread, compact) when l > 0. One path id per sample column, 1-based (vcf_transforms.cpp:588).
+ * Only the first FASTA record is used and CHROM is ignored, as in the reference.
+ * Inputs the reference is undefined on return EDS_ERR_BAD_VCF instead of garbage: POS 0, a record
+ * that extends past the end of the FASTA sequence, FASTA lines of unequal width, '\r' in the FASTA.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct eds_vcf_stats {
+    /* VCFStats (vcf_transforms.hpp:24-36) */
+    uint64_t total_variants, processed_variants, skipped_malformed, skipped_unsupported_sv, variant_groups;
+    /* this implementation */
+    uint64_t n_lines;           /* lines of the VCF text, headers included                          */
+    uint64_t n_bases;           /* length of the first FASTA record                                 */
+    uint64_t n_alleles;         /* carrier bitsets built: one per (record, allele incl. REF)        */
+    uint64_t n_haplotype_slots; /* haplotype candidates over all groups before de-duplication       */
+    uint64_t n_samples_max;     /* widest sample matrix row                                         */
+    uint64_t eds_bytes, seds_bytes; /* size of the EDS / SEDS text before the optional l-EDS merge  */
+    uint32_t gpu_launches;      /* kernels launched by the front end                                */
+    uint32_t host_sorted;       /* 1: positions were not strictly increasing; the tie order of the
+                                   reference's unstable std::sort was reproduced on the host        */
+    uint32_t retries;           /* re-runs of the genotype kernel after the bitset width grew       */
+    uint32_t leds_rounds;       /* merge rounds (l > 0)                                             */
+} eds_vcf_stats;
+
+/* Host text in, malloc'd host text out (free with eds_buffer_free_host). sv_lines (optional):
+ * malloc'd byte offsets, in file order, of the records skipped for an unsupported symbolic ALT
+ * (vcf_transforms.cpp:299-305; the caller prints the reference's warning from them); free(). */
+eds_status eds_vcf_transform_host(eds_ctx* ctx, const uint8_t* vcf, uint64_t vcf_bytes, const uint8_t* fasta,
+                                  uint64_t fasta_bytes, uint32_t l, eds_buffer* eds_out, eds_buffer* seds_out,
+                                  eds_vcf_stats* stats, uint64_t** sv_lines, uint64_t* n_sv_lines);
+
+/* l == 0 only, everything in device memory: both inputs 16-byte aligned and readable up to the next
+ * 16-byte boundary (any cudaMalloc'd buffer is); outputs are owned by the ctx until its next VCF call. */
+eds_status eds_vcf_transform_device(eds_ctx* ctx, const uint8_t* vcf, uint64_t vcf_bytes, const uint8_t* fasta,
+                                    uint64_t fasta_bytes, eds_buffer* eds_out, eds_buffer* seds_out,
+                                    eds_vcf_stats* stats);
+
+/* Device memory for callers that stage inputs themselves (bench, tests): cudaMalloc / H2D copy / cudaFree. */
+eds_status eds_device_upload(eds_ctx* ctx, const uint8_t* host, uint64_t bytes, uint8_t** device_out);
+void eds_device_free(eds_ctx* ctx, uint8_t* device);
 
 #ifdef __cplusplus
 }

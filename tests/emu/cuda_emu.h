@@ -195,6 +195,18 @@ inline unsigned __match_any_sync(unsigned, T v) {
     return m;
 }
 
+// or-reduction over the lanes named by `mask` (every lane of the warp calls it, each with the mask of its own group)
+inline unsigned emu_reduce_or(unsigned mask, unsigned v) {
+    emu::WarpBox& w = emu::my_warp();
+    w.slot[emu::my_lane()] = v;
+    w.bar.wait();
+    unsigned r = 0;
+    for (unsigned i = 0; i < w.lanes; ++i)
+        if (mask & (1u << i)) r |= (unsigned)w.slot[i];
+    w.bar.wait();
+    return r;
+}
+
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
