@@ -40,7 +40,7 @@ tests/emu/libedsparser_emu.so: $(EMUOBJS)
 # host layer: the reference's transforms API (C++17) + the msa2eds / eds2leds tools, over the C ABI
 HOST     := edsparser_b200/host
 HOSTINC  := -I$(HOST)/include -I$(HOST)/tools
-host: edsparser_b200/bin/msa2eds edsparser_b200/bin/eds2leds
+host: edsparser_b200/bin/msa2eds edsparser_b200/bin/eds2leds edsparser_b200/bin/vcf2eds
 
 edsparser_b200/libedsparser_host.a: $(HOST)/src/host.cpp $(wildcard $(HOST)/include/edsparser/*.hpp $(HOST)/include/edsparser/*/*.hpp) include/edsparser_b200.h | build
 	$(CXX) -std=c++17 -O2 -fPIC -Wall $(HOSTINC) -c $(HOST)/src/host.cpp -o build/host.o

@@ -1,16 +1,22 @@
 // Host layer: the reference's transforms API on top of the C ABI (include/edsparser_b200.h). Status codes
 // are turned back into the exception classes the reference throws. No compute happens here.
+#include <cctype>
+#include <cstdlib>
 #include <fstream>
+#include <iostream>
 #include <iterator>
 #include <mutex>
 #include <sstream>
 #include <stdexcept>
+#include <string>
+#include <vector>
 
 #include "../../../include/edsparser_b200.h"
 #include "edsparser/common.hpp"
 #include "edsparser/formats/eds.hpp"
 #include "edsparser/transforms/eds_transforms.hpp"
 #include "edsparser/transforms/msa_transforms.hpp"
+#include "edsparser/transforms/vcf_transforms.hpp"
 
 namespace edsparser {
 
@@ -93,6 +99,70 @@ void merge(std::istream& input, std::ostream& output, Length l, std::istream* ph
     if (phasing_in && phasing_out) phasing_out->write(reinterpret_cast<const char*>(so.b.data), (std::streamsize)so.b.bytes);
 }
 
+// "Warning: Skipping variant at CHROM:POS - Unsupported structural variant type: X" (vcf_transforms.cpp:299-305) for a
+// record the device skipped; the fields are split the way parse_vcf_line does (:257-279).
+void warn_skipped_sv(const std::string& vcf, uint64_t line_at) {
+    size_t end = vcf.find('\n', line_at);
+    if (end == std::string::npos) end = vcf.size();
+    const std::string line = vcf.substr(line_at, end - line_at);
+    std::vector<std::string> f;
+    size_t at = 0;
+    while (at < line.size()) {
+        size_t d = line.find('\t', at);
+        if (d == std::string::npos) d = line.size();
+        if (d > at) f.push_back(line.substr(at, d - at));
+        at = d + 1;
+    }
+    if (f.size() < 5) {
+        f.clear();
+        std::istringstream ss(line);
+        std::string tok;
+        while (ss >> tok) f.push_back(tok);
+    }
+    if (f.size() < 5) return;
+    unsigned long long pos = 0;
+    try {
+        pos = std::stoull(f[1]);
+    } catch (...) {
+        return;
+    }
+    std::istringstream alts(f[4]);
+    std::string a;
+    while (std::getline(alts, a, ',')) {
+        if (a.size() >= 2 && a.front() == '<' && a.back() == '>') {
+            const std::string kind = a.substr(1, a.size() - 2);
+            if (kind != "DEL" && kind != "INS") {
+                std::cerr << "Warning: Skipping variant at " << f[0] << ":" << pos << " - Unsupported structural variant type: " << kind
+                          << std::endl;
+                return;
+            }
+        }
+    }
+}
+
+std::pair<std::string, std::string> vcf_transform(std::istream& vcf_stream, std::istream& fasta_stream, uint32_t l, VCFStats* stats) {
+    // the reference reads the FASTA first (vcf_transforms.cpp:683), so its errors win; both streams end up consumed
+    const std::string fasta = slurp(fasta_stream);
+    const std::string vcf = slurp(vcf_stream);
+    HostBuf e, s;
+    eds_vcf_stats st;
+    uint64_t* sv = nullptr;
+    uint64_t n_sv = 0;
+    const eds_status rc = eds_vcf_transform_host(t_session.get(), reinterpret_cast<const uint8_t*>(vcf.data()), vcf.size(),
+                                                 reinterpret_cast<const uint8_t*>(fasta.data()), fasta.size(), l, &e.b, &s.b, &st, &sv, &n_sv);
+    for (uint64_t i = 0; i < n_sv; ++i) warn_skipped_sv(vcf, sv[i]);
+    std::free(sv);
+    if (stats && (rc == EDS_OK || st.total_variants)) {  // the reference fills the counters before the merge can throw
+        stats->total_variants += st.total_variants;
+        stats->processed_variants += st.processed_variants;
+        stats->skipped_malformed += st.skipped_malformed;
+        stats->skipped_unsupported_sv += st.skipped_unsupported_sv;
+        stats->variant_groups = st.variant_groups;
+    }
+    if (rc != EDS_OK) rethrow(rc);
+    return {e.str(), s.str()};
+}
+
 }  // namespace
 
 namespace b200 {
@@ -115,6 +185,20 @@ void eds_to_leds_linear(std::istream& input, std::ostream& output, Length contex
 
 void eds_to_leds_cartesian(std::istream& input, std::ostream& output, Length context_length, size_t /*num_threads*/, bool compact) {
     merge(input, output, context_length, nullptr, nullptr, compact);
+}
+
+std::pair<std::string, std::string> parse_vcf_to_eds_streaming(std::istream& vcf_stream, std::istream& fasta_stream, VCFStats* stats) {
+    return vcf_transform(vcf_stream, fasta_stream, 0, stats);
+}
+
+std::pair<std::string, std::string> parse_vcf_to_leds_streaming(std::istream& vcf_stream, std::istream& fasta_stream,
+                                                                size_t context_length, VCFStats* stats) {
+    if (context_length == 0) {  // eds_to_leds_linear refuses l = 0 after the EDS has been built (vcf_transforms.cpp:742-752)
+        vcf_transform(vcf_stream, fasta_stream, 0, stats);
+        throw std::invalid_argument("context_length must be > 0 for l-EDS transformation");
+    }
+    if (context_length > 0xffffffffull) context_length = 0xffffffffull;
+    return vcf_transform(vcf_stream, fasta_stream, (uint32_t)context_length, stats);
 }
 
 EDS::EDS(std::istream& eds_stream) : text_(slurp(eds_stream)) {}

@@ -16,7 +16,8 @@ SMALL = (b">seq1\nAGTC--TCTATA\nAATAAATA----\n>seq2\nAGTCCCTATATA\nAATAAATAGGGG\
 
 @pytest.fixture(scope="module", autouse=True)
 def tools():
-    if not (os.path.exists(os.path.join(BIN, "msa2eds")) and os.path.exists(os.path.join(BIN, "eds2leds"))):
+    if not (os.path.exists(os.path.join(BIN, "msa2eds")) and os.path.exists(os.path.join(BIN, "eds2leds"))
+            and os.path.exists(os.path.join(BIN, "vcf2eds"))):
         subprocess.check_call(["make", "-C", ROOT, "lib", "host"], stdout=subprocess.DEVNULL)
 
 
@@ -42,6 +43,14 @@ def test_help_and_validation(tmp_path):
     assert rc == 1 and "the option '--input' is required but missing" in err
     rc, out, err = run("msa2eds", "-i", str(tmp_path / "missing.msa"))
     assert rc == 1 and "Failed to open input file" in err
+    rc, out, err = run("vcf2eds", "--help")
+    assert rc == 0 and out.startswith("vcf2eds - Transform VCF") and "[Performance] Runtime:" in err
+    rc, out, err = run("vcf2eds", "-i", str(tmp_path / "x.txt"), "-r", str(tmp_path / "r.fa"))
+    assert rc == 1 and err.startswith("Error: Input file must be a VCF file (.vcf)\nGot: ")
+    rc, out, err = run("vcf2eds", "-i", str(tmp_path / "x.vcf"), "-r", str(tmp_path / "r.fa"))
+    assert rc == 1 and err.startswith("Error: Reference FASTA file not found: ")
+    rc, out, err = run("vcf2eds", "-i", str(tmp_path / "x.vcf"))
+    assert rc == 1 and "the option '--reference' is required but missing" in err
 
 
 def test_fails_loudly_without_a_gpu(tmp_path):
@@ -84,6 +93,44 @@ def test_config1_through_the_tools(tmp_path):
     (tmp_path / "bad.seds").write_bytes(b"{0}{1}{2}{0}{3}{4}{0}")
     rc, out, err = run("eds2leds", "-i", str(tmp_path / "bad.eds"), "-s", str(tmp_path / "bad.seds"), "-l", "2")
     assert rc == 1 and err.startswith("Error: Merging positions 1 and 2 results in empty set (no valid source intersections)\n")
+
+
+@pytest.mark.gpu
+def test_vcf2eds_tool(tmp_path):
+    import vcf_checks
+
+    named = {(c["name"], c["l"]): c for c in vcf_checks.golden_cases() if c.get("name")}
+    c0 = named[("small", 0)]
+    (tmp_path / "small.vcf").write_bytes(c0["vcf"].encode("latin-1"))
+    (tmp_path / "small.fa").write_bytes(c0["fa"].encode("latin-1"))
+    rc, out, err = run("vcf2eds", "-i", str(tmp_path / "small.vcf"), "-r", str(tmp_path / "small.fa"))
+    assert rc == 0, err
+    assert out.startswith("VCF → EDS transformation\n  Input: \"%s\"\n  Reference: \"%s\"\nTransformation complete!\n"
+                          % (tmp_path / "small.vcf", tmp_path / "small.fa"))
+    assert ("Variant Processing Statistics:\n  Total variants read:        10\n  Successfully processed:     10\n"
+            "  Skipped (malformed):        0\n  Skipped (unsupported SV):   0\n  Total skipped:              0\n"
+            "  Variant groups created:     10\n  Success rate:               100.0%\n") in out
+    assert (tmp_path / "small.eds").read_bytes() == c0["eds"].encode("latin-1")
+    assert (tmp_path / "small.seds").read_bytes() == c0["seds"].encode("latin-1")
+    c3 = named[("small", 3)]
+    rc, out, err = run("vcf2eds", "-i", str(tmp_path / "small.vcf"), "-r", str(tmp_path / "small.fa"), "-l", "3")
+    assert rc == 0 and out.startswith("VCF → l-EDS transformation (l=3)\n  Using two-stage pipeline: VCF→EDS→l-EDS\n")
+    assert (tmp_path / "small_l3.leds").read_bytes() == c3["eds"].encode("latin-1")
+    assert (tmp_path / "small_l3.seds").read_bytes() == c3["seds"].encode("latin-1")
+    # unsupported symbolic allele: the reference's warning on stderr, the record counted and skipped
+    (tmp_path / "sv.vcf").write_bytes(vcf_checks.HDR + b"chr1\t5\t.\tA\tT,<DUP>\t.\t.\t.\tGT\t1|0\t0|0\t0|0\n"
+                                      b"chr1\t9\t.\tA\tT\t.\t.\t.\tGT\t1|0\t0|0\t0|0\n")
+    (tmp_path / "sv.fa").write_bytes(vcf_checks.FA)
+    rc, out, err = run("vcf2eds", "-i", str(tmp_path / "sv.vcf"), "-r", str(tmp_path / "sv.fa"), "-o", str(tmp_path / "o.eds"))
+    assert rc == 0 and err.startswith("Warning: Skipping variant at chr1:5 - Unsupported structural variant type: DUP\n")
+    assert "  Skipped (unsupported SV):   1\n" in out and "  Success rate:               50.0%\n" in out
+    exp = oracle_lib.vcf2eds((tmp_path / "sv.vcf").read_bytes(), vcf_checks.FA, 0)
+    assert ((tmp_path / "o.eds").read_bytes(), (tmp_path / "o.seds").read_bytes()) == exp[:2]
+    assert exp[3] == ["Warning: Skipping variant at chr1:5 - Unsupported structural variant type: DUP"]
+    # library errors: "Error: <what>", exit code 1
+    (tmp_path / "bad.fa").write_bytes(b"ACGT\n")
+    rc, out, err = run("vcf2eds", "-i", str(tmp_path / "sv.vcf"), "-r", str(tmp_path / "bad.fa"))
+    assert rc == 1 and err.startswith("Error: Invalid FASTA format: expected header line starting with '>'\n")
 
 
 @pytest.mark.gpu
