@@ -169,7 +169,12 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n):
+def workload_config(n, config=2):
+    if config == 4:
+        return {"workload": f"config 4: synthetic MSA {R} seq x {C_PER_GPU * n} columns, 1% variable columns, wrap {WRAP}, "
+                            f"msa2eds -l {L}, column-sharded over {n} GPU(s), halo {HALO}",
+                "rows": R, "cols_per_gpu": C_PER_GPU, "context_length": L, "seed": SEED,
+                "l2": "inputs larger than L2, no explicit flush", "parallelism": f"column-sharded x{n}"}
     return {"workload": f"config 2 per GPU: synthetic MSA {R} seq x {C_PER_GPU} columns, 1% variable columns, "
                         f"wrap {WRAP}, msa2eds -l {L}" + ("" if n == 1 else f"; {n} column shards of a {R} x {n * C_PER_GPU} alignment, halo {HALO}"),
             "rows": R, "cols_per_gpu": C_PER_GPU, "context_length": L, "seed": SEED,
@@ -261,9 +266,11 @@ def run_ours(args, rank, world):
                 "kernels_ms": {k: round(v, 4) for k, v in kern.items()}}
 
     # ---- end to end: .msa bytes in pinned host memory -> eds_msa_transform_host -> host strings
-    text = ctx.download(E.Buffer(view.text, view.text_bytes)) if world == 1 else None
+    text = ctx.download(E.Buffer(view.text, view.text_bytes)) if world == 1 and args.config == 2 else None
     e2e = None
-    if world == 1:
+    if args.config == 4:
+        pass  # device-resident scaling figure only (30 GB of pinned host text is not a bench default)
+    elif world == 1:
         pinned = torch.empty(len(text), dtype=torch.uint8).pin_memory()
         pinned.copy_(torch.frombuffer(bytearray(text), dtype=torch.uint8))
         ctx.msa_synth_free()
@@ -313,7 +320,7 @@ def run_ours(args, rank, world):
 
     # ---- CPU baseline: the reference library on a bounded sample (rank 0, N = 1 only)
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and args.config == 2:
         path, _ = write_sample_file(SAMPLE_COLS)
         with tempfile.TemporaryDirectory() as wd:
             reference_pass(path, wd)
@@ -333,8 +340,8 @@ def run_ours(args, rank, world):
         line = {
             "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(world), "gb_per_s": value / 1e9, "e2e": e2e, "roofline": roofline,
+            "scaling": "weak" if args.config == 2 else "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(world, args.config), "gb_per_s": value / 1e9, "e2e": e2e, "roofline": roofline,
             "cpu_baseline": cpu, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
             "output_bytes_per_step": out_bytes, "library": lib.version(),
         }
@@ -344,6 +351,14 @@ def run_ours(args, rank, world):
         dist.destroy_process_group()
 
 
+def use_config4(world):
+    """BASELINE config 4: 1000 sequences x 30 Mbp in total, column-sharded over the ranks (strong scaling)."""
+    global R, C_PER_GPU, SAMPLE_COLS
+    R = 1000
+    C_PER_GPU = 30_000_000 // world
+    SAMPLE_COLS = 200_000
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -351,6 +366,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4],
+                    help="2 (default, the metric's configuration): 100 x 10 Mbp per GPU, weak scaling; 4: BASELINE config 4, "
+                         "1000 x 30 Mbp column-sharded over the N GPUs (strong scaling, no e2e / cpu legs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -362,6 +380,8 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    if args.config == 4:
+        use_config4(max(world, 1))
     run_ours(args, rank, world)
 
 

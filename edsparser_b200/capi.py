@@ -130,7 +130,8 @@ class Library:
 
 
 def _host_bytes(lib, buf):
-    data = ctypes.string_at(buf.data, buf.bytes) if buf.data and buf.bytes else b""
+    # (ctypes.string_at takes a C int: outputs past 2 GiB go through an array view)
+    data = bytes((ctypes.c_ubyte * buf.bytes).from_address(buf.data)) if buf.data and buf.bytes else b""
     lib.L.eds_buffer_free_host(ctypes.byref(buf))
     return data
 

@@ -142,10 +142,21 @@ __global__ void k_fa_measure(const uint8_t* fa, VcfStatus* st) {
             if ((p - lo) % (lw + 1) != lw && p < bad) bad = p;
         }
     }
-    if (cnt) atomicAdd(&st->fa_nl, cnt);
-    if (last) atomicMax(&st->fa_last_base, last);
-    if (bad != kNone64) atomicMin(&st->fa_bad_nl, bad);
-    if (cr) atomicOr(&st->fa_err, (uint32_t)kFaCarriage);
+    // one set of atomics per warp
+    cnt = warp_sum(cnt);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const u64 l2 = __shfl_xor_sync(0xffffffffu, last, d), b2 = __shfl_xor_sync(0xffffffffu, bad, d);
+        last = l2 > last ? l2 : last;
+        bad = b2 < bad ? b2 : bad;
+        cr |= __shfl_xor_sync(0xffffffffu, cr, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (cnt) atomicAdd(&st->fa_nl, cnt);
+        if (last) atomicMax(&st->fa_last_base, last);
+        if (bad != kNone64) atomicMin(&st->fa_bad_nl, bad);
+        if (cr) atomicOr(&st->fa_err, (uint32_t)kFaCarriage);
+    }
 }
 
 struct Fasta {
@@ -157,24 +168,50 @@ struct Fasta {
 // ---------------------------------------------------------------------------------------------------------
 // VCF lines
 // ---------------------------------------------------------------------------------------------------------
-struct NlFn {  // scan over 16-byte vectors: line i + 1 starts after the i-th '\n'
-    const uint8_t* t;
-    u64 n;
-    u64* line_start;
-    __device__ __forceinline__ uint32_t mask(u64 c) const {
-        const uint32_t in = n - c * 16 >= 16 ? 0xffffu : low_bits((uint32_t)(n - c * 16));
-        return eq_bytes16(load16(t, c), 0x0a0a0a0au) & in;
-    }
-    __device__ u64 value(u64 c) const { return (u64)__popc(mask(c)); }
-    __device__ void apply(u64 c, u64 prefix, u64 v) const {
-        if (!v) return;
-        uint32_t m = mask(c);
+// Line index. Lines are long (one per site, thousands of sample columns), so newlines are rare: every warp streams a
+// contiguous run of 16-byte vectors, counts its newlines (k_nl_count), the host turns the per-warp counts into
+// starting line numbers (it needs the total anyway to size the index), and k_nl_write streams the same run again and
+// only falls into the prefix-sum path for the few tiles that do contain a newline. Line i + 1 starts after '\n' i.
+__device__ __forceinline__ uint32_t nl_mask(const uint8_t* t, u64 n, u64 c) {
+    const uint32_t in = n - c * 16 >= 16 ? 0xffffu : low_bits((uint32_t)(n - c * 16));
+    return eq_bytes16(load16(t, c), 0x0a0a0a0au) & in;
+}
+
+__device__ __forceinline__ void nl_run(u64 n_chunks, u64& lo, u64& hi) {
+    const u64 warp = gtid() >> 5, n_warps = gthreads() >> 5;
+    const u64 per = ((n_chunks + n_warps - 1) / n_warps + 31) / 32 * 32;
+    lo = warp * per < n_chunks ? warp * per : n_chunks;
+    hi = lo + per < n_chunks ? lo + per : n_chunks;
+}
+
+__global__ void k_nl_count(const uint8_t* t, u64 n, u64 n_chunks, u64* counts) {
+    u64 lo, hi;
+    nl_run(n_chunks, lo, hi);
+    const unsigned lane = threadIdx.x & 31;
+    uint32_t cnt = 0;
+    for (u64 c = lo + lane; c < hi; c += 32) cnt += (uint32_t)__popc(nl_mask(t, n, c));
+    cnt = warp_sum(cnt);
+    if (lane == 0) counts[gtid() >> 5] = cnt;
+}
+
+__global__ void k_nl_write(const uint8_t* t, u64 n, u64 n_chunks, const u64* first_line, u64* line_start) {
+    u64 lo, hi;
+    nl_run(n_chunks, lo, hi);
+    const unsigned lane = threadIdx.x & 31;
+    u64 line = first_line[gtid() >> 5];  // newlines before this run
+    for (u64 c0 = lo; c0 < hi; c0 += 32) {
+        const u64 c = c0 + lane;
+        uint32_t m = c < hi ? nl_mask(t, n, c) : 0u;
+        if (!__any_sync(0xffffffffu, m != 0)) continue;
+        const uint32_t cnt = (uint32_t)__popc(m), incl = warp_inclusive_scan(cnt);
+        u64 at = line + (incl - cnt);
         while (m) {
-            line_start[++prefix] = c * 16 + (u64)__ffs((int)m);
+            line_start[++at] = c * 16 + (u64)__ffs((int)m);
             m &= m - 1;
         }
+        line += __shfl_sync(0xffffffffu, incl, 31);
     }
-};
+}
 
 struct LineHead {
     u64 pos, ref_off, alt_off, gt_off;
@@ -377,15 +414,20 @@ __global__ void k_rec_check(const Rec* recs, u64 n_rec, u64* pos_out, VcfStatus*
 // One warp walks [from, le) in 512-byte tiles. tok(starts, base, first_index) runs per lane with the 16-bit mask of
 // fields that start in the lane's 16-byte vector and the index of the first of them; tile_end() is warp-uniform.
 template <typename Tok, typename TileEnd>
-__device__ __forceinline__ u64 warp_fields(const uint8_t* t, u64 from, u64 le, bool ws, Tok tok, TileEnd tile_end) {
+__device__ __forceinline__ u64 warp_fields(const uint8_t* t, u64 text_chunks, u64 from, u64 le, bool ws, Tok tok, TileEnd tile_end) {
     const unsigned lane = threadIdx.x & 31;
     u64 count = 0;
     uint32_t carry = 0;  // the byte before this tile belongs to a field
-    for (u64 c0 = from / 16; c0 * 16 < le; c0 += 32) {
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    u64 c0 = from / 16;
+    uint4 v = (c0 + lane) * 16 < le ? load16(t, c0 + lane) : zero;
+    for (; c0 * 16 < le; c0 += 32) {
         const u64 c = c0 + lane, base = c * 16;
+        // the vector after mine (fields that run past my 16 bytes) and my vector of the next tile, both in flight early
+        const uint4 vn = (base < le && c + 1 < text_chunks) ? load16(t, c + 1) : zero;
+        const uint4 v_next = (c + 32) * 16 < le ? load16(t, c + 32) : zero;
         uint32_t nd = 0;
         if (base < le) {
-            const uint4 v = load16(t, c);
             uint32_t dl = eq_bytes16(v, 0x09090909u);
             if (ws)
                 dl |= eq_bytes16(v, 0x20202020u) | eq_bytes16(v, 0x0b0b0b0bu) | eq_bytes16(v, 0x0c0c0c0cu) |
@@ -401,18 +443,20 @@ __device__ __forceinline__ u64 warp_fields(const uint8_t* t, u64 from, u64 le, b
         const uint32_t cnt = (uint32_t)__popc(starts);
         const uint32_t incl = warp_inclusive_scan(cnt);
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        tok(starts, base, count + (u64)(incl - cnt));
+        tok(starts, base, count + (u64)(incl - cnt), v, vn);
         tile_end();
         carry = __shfl_sync(0xffffffffu, nd, 31) >> 15;
         count += total;
+        v = v_next;
     }
     return count;
 }
 
-__global__ void k_first_fields(const uint8_t* t, const Rec* recs, VcfStatus* st) {
+__global__ void k_first_fields(const uint8_t* t, u64 text_chunks, const Rec* recs, VcfStatus* st) {
     const Rec r = recs[0];
     u64 n = 0;
-    if (r.gt_off) n = warp_fields(t, r.gt_off, r.line_end, r.mode != 0, [](uint32_t, u64, u64) {}, []() {});
+    if (r.gt_off)
+        n = warp_fields(t, text_chunks, r.gt_off, r.line_end, r.mode != 0, [](uint32_t, u64, u64, uint4, uint4) {}, []() {});
     if (threadIdx.x == 0) st->first_tokens = n;
 }
 
@@ -446,17 +490,104 @@ __device__ __forceinline__ void parse_gt(const uint8_t* t, u64 p, u64 le, bool w
     });
 }
 
+// bits |= v in the warp's shared-memory slice (no result needed: a reduction, not an atomic with return) or,
+// for records whose rows do not fit the slice, in global memory
+template <bool kShared>
+__device__ __forceinline__ void or_into(uint32_t* p, uint32_t v) {
 #ifdef EDSB_EMU
-__device__ __forceinline__ uint32_t group_or(uint32_t mask, uint32_t v) { return emu_reduce_or(mask, v); }
+    atomicOr(p, v);
 #else
-__device__ __forceinline__ uint32_t group_or(uint32_t mask, uint32_t v) { return __reduce_or_sync(mask, v); }
+    if (kShared)
+        asm volatile("red.shared.or.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+    else
+        atomicOr(p, v);
 #endif
+}
 
-// Warp per record: carriers of every allele of the record, bits[(row0 + a) * W + s / 32] bit s % 32.
-// The REF row is dense (most genotypes are 0|0): each lane merges its own fields (at most eight per 16 bytes, two
-// words), lanes that touch the same word are combined with match + or-reduce, one lane writes. ALT rows take
-// shared-memory atomics. Records whose rows do not fit the warp's shared-memory slice work in global memory.
-__global__ void k_gt(const uint8_t* t, Rec* recs, u64 n_rec, uint32_t W, uint32_t smem_words, uint32_t* bits, VcfStatus* st) {
+// The sample columns of one record: carriers of every allele, dst[a * W + s / 32] bit s % 32.
+template <bool kShared>
+__device__ __forceinline__ u64 gt_record(const uint8_t* t, u64 text_chunks, const Rec& r, uint32_t W, uint32_t* dst) {
+    const uint32_t cap = W * 32u;
+    const bool ws = r.mode != 0;
+    const uint32_t nalts = r.nalts;
+    const u64 le = r.line_end;
+    return warp_fields(
+        t, text_chunks, r.gt_off, le, ws,
+        [&](uint32_t starts, u64 base, u64 first, uint4 v, uint4 vn) {
+            if (!starts) return;
+            const uint32_t b0 = (uint32_t)(__ffs((int)starts) - 1);
+            // the usual vector: four diploid fields "d|d\t" (or "d/d\t") at one phase, checked a word at a time from
+            // registers; REF and first-ALT carriers leave as one 4-bit group each (two reductions when it straddles words)
+            if (!ws && starts == ((0x1111u << b0) & 0xffffu) && first + 3 < cap) {
+                const uint4 x = realign16(v, vn, b0);
+                const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+                bool regular = true;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t frame = xs[i] & 0xff00ff00u;
+                    regular = regular && (frame == 0x09007c00u || frame == 0x09002f00u) && (xs[i] & 0x00f000f0u) == 0x00300030u &&
+                              (((xs[i] & 0x000f000fu) + 0x00060006u) & 0x00100010u) == 0u;
+                }
+                if (regular) {
+                    uint32_t ref4 = 0, alt4 = 0, more = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint32_t d0 = xs[i] & 0xfu, d1 = (xs[i] >> 16) & 0xfu;
+                        d0 = d0 <= nalts ? d0 : 0u;
+                        d1 = d1 <= nalts ? d1 : 0u;
+                        ref4 |= (uint32_t)(d0 == 0u || d1 == 0u) << i;
+                        alt4 |= (uint32_t)(d0 == 1u || d1 == 1u) << i;
+                        more |= (d0 | d1) >> 1;
+                    }
+                    const uint32_t w = (uint32_t)(first >> 5), sh = (uint32_t)(first & 31);
+                    if (ref4) or_into<kShared>(&dst[w], ref4 << sh);
+                    if (alt4) or_into<kShared>(&dst[W + w], alt4 << sh);
+                    if (sh > 28u) {
+                        if (ref4 >> (32u - sh)) or_into<kShared>(&dst[w + 1], ref4 >> (32u - sh));
+                        if (alt4 >> (32u - sh)) or_into<kShared>(&dst[W + w + 1], alt4 >> (32u - sh));
+                    }
+                    if (more) {  // third and later alleles
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t d0 = xs[i] & 0xfu, d1 = (xs[i] >> 16) & 0xfu;
+                            const u64 smp = first + i;
+                            if (d0 >= 2u && d0 <= nalts) or_into<kShared>(&dst[(size_t)d0 * W + (smp >> 5)], 1u << (smp & 31));
+                            if (d1 >= 2u && d1 <= nalts) or_into<kShared>(&dst[(size_t)d1 * W + (smp >> 5)], 1u << (smp & 31));
+                        }
+                    }
+                    return;
+                }
+            }
+            u64 s = first;
+            while (starts) {
+                const uint32_t b = (uint32_t)(__ffs((int)starts) - 1);
+                const u64 p = base + b;
+                starts &= starts - 1;
+                if (s < cap) {
+                    const uint32_t w = (uint32_t)(s >> 5), bit = 1u << (s & 31);
+                    // one diploid field straight from registers; anything else byte by byte
+                    const uint32_t x = realign16(v, vn, b).x;
+                    const uint32_t d0 = (x & 0xffu) - (uint32_t)'0', sep = (x >> 8) & 0xffu;
+                    const uint32_t d1 = ((x >> 16) & 0xffu) - (uint32_t)'0', term = x >> 24;
+                    if (!ws && d0 <= 9u && d1 <= 9u && (sep == (uint32_t)'|' || sep == (uint32_t)'/') && p + 3 <= le &&
+                        (p + 3 == le || term == (uint32_t)'\t' || term == (uint32_t)':')) {
+                        const uint32_t a0 = d0 <= nalts ? d0 : 0u, a1 = d1 <= nalts ? d1 : 0u;
+                        or_into<kShared>(&dst[(size_t)a0 * W + w], bit);
+                        if (a1 != a0) or_into<kShared>(&dst[(size_t)a1 * W + w], bit);
+                    } else {
+                        parse_gt(t, p, le, ws, nalts, [&](uint32_t a) { or_into<kShared>(&dst[(size_t)a * W + w], bit); });
+                    }
+                }
+                ++s;
+            }
+        },
+        []() {});
+}
+
+// Warp per record: the carrier bitsets of the record's alleles are built in the warp's shared-memory slice with
+// reductions (red.shared.or) and stored once; records whose rows do not fit the slice work in global memory.
+__global__ void k_gt(const uint8_t* t, u64 text_chunks, Rec* recs, u64 n_rec, uint32_t W, uint32_t smem_words, uint32_t* bits,
+                     VcfStatus* st) {
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     uint32_t* slice = reinterpret_cast<uint32_t*>(EDSB_DYN_SMEM()) + (size_t)wid * smem_words;
     for (u64 k = (u64)blockIdx.x * wpb + wid; k < n_rec; k += (u64)gridDim.x * wpb) {
@@ -468,46 +599,7 @@ __global__ void k_gt(const uint8_t* t, Rec* recs, u64 n_rec, uint32_t W, uint32_
         for (u64 i = lane; i < need; i += 32) dst[i] = 0;
         __syncwarp();
         u64 n_fields = 0;
-        if (r.gt_off) {
-            const uint32_t cap = W * 32u;
-            const bool ws = r.mode != 0;
-            uint32_t lo_word = kNone32, lo_bits = 0, hi_bits = 0;
-            n_fields = warp_fields(
-                t, r.gt_off, r.line_end, ws,
-                [&](uint32_t starts, u64 base, u64 first) {
-                    lo_word = kNone32;
-                    lo_bits = hi_bits = 0;
-                    u64 s = first;
-                    while (starts) {
-                        const u64 p = base + (u64)(__ffs((int)starts) - 1);
-                        starts &= starts - 1;
-                        if (s < cap) {
-                            const uint32_t w = (uint32_t)(s >> 5), bit = 1u << (s & 31);
-                            parse_gt(t, p, r.line_end, ws, r.nalts, [&](uint32_t a) {
-                                if (a == 0) {
-                                    if (lo_word == kNone32) lo_word = w;
-                                    if (w == lo_word) lo_bits |= bit;
-                                    else hi_bits |= bit;
-                                } else {
-                                    atomicOr(&dst[(size_t)a * W + w], bit);
-                                }
-                            });
-                        }
-                        ++s;
-                    }
-                },
-                [&]() {
-                    uint32_t m = __match_any_sync(0xffffffffu, lo_word);
-                    uint32_t all = group_or(m, lo_bits);
-                    if (lo_word != kNone32 && lane == (unsigned)(__ffs((int)m) - 1)) dst[lo_word] |= all;
-                    __syncwarp();
-                    const uint32_t hi_word = hi_bits ? lo_word + 1 : kNone32;
-                    m = __match_any_sync(0xffffffffu, hi_word);
-                    all = group_or(m, hi_bits);
-                    if (hi_word != kNone32 && lane == (unsigned)(__ffs((int)m) - 1)) dst[hi_word] |= all;
-                    __syncwarp();
-                });
-        }
+        if (r.gt_off) n_fields = in_smem ? gt_record<true>(t, text_chunks, r, W, slice) : gt_record<false>(t, text_chunks, r, W, out);
         __syncwarp();
         if (in_smem)
             for (u64 i = lane; i < need; i += 32) out[i] = slice[i];
@@ -761,10 +853,11 @@ __global__ void k_emit_ref(Fasta fa, u64 n_bases, const u64* g_from, const u64* 
 // warp per entry: braces and "{0}" of the common text, then the group: {hap,hap,...} and {ids}{ids}...
 __global__ void k_emit_groups(const uint8_t* t, Fasta fa, GroupView gv, const uint32_t* g_first, uint32_t n_groups,
                               const u64* canon, const uint32_t* hap_len, const uint8_t* kept, const uint32_t* slot_bits,
-                              const uint32_t* slot_seds, uint32_t W, const u64* eds_off, const u64* seds_off, uint8_t* out,
-                              uint8_t* sout) {
+                              const uint32_t* slot_seds, uint32_t W, uint32_t stage_bytes, const u64* id_text,
+                              const u64* eds_off, const u64* seds_off, uint8_t* out, uint8_t* sout) {
     const unsigned lane = threadIdx.x & 31;
     const u64 warp = gtid() >> 5, n_warps = gthreads() >> 5;
+    uint8_t* const stage = EDSB_DYN_SMEM() + (size_t)(threadIdx.x >> 5) * stage_bytes;
     for (u64 g64 = warp; g64 <= n_groups; g64 += n_warps) {
         const uint32_t g = (uint32_t)g64;
         u64 eo = eds_off[g], so = seds_off[g];
@@ -807,30 +900,91 @@ __global__ void k_emit_groups(const uint8_t* t, Fasta fa, GroupView gv, const ui
                 eo += n;
                 const uint32_t sb = slot_seds[slot];
                 if (!sb) continue;
-                if (lane == 0) sout[so] = (uint8_t)'{';
+                // "{id,id,...}": 32 bitset words per round are rendered into the warp's shared-memory stage at the
+                // output's own 16-byte phase, then copied out with aligned 16-byte stores (bytes at the two ragged ends)
                 const u64 end = so + sb;
-                u64 at = so + 1;
+                u64 gpos = so;
                 for (uint32_t w0 = 0; w0 < W; w0 += 32) {
                     const uint32_t w = w0 + lane;
                     uint32_t v = w < W ? slot_bits[slot * W + w] : 0u;
                     const uint32_t mine = word_id_bytes(w, v);
                     const uint32_t incl = warp_inclusive_scan(mine);
-                    u64 p = at + (incl - mine);
-                    while (v) {
-                        const uint32_t id = w * 32u + (uint32_t)__ffs((int)v);
-                        v &= v - 1;
-                        const uint32_t dw = decimal_width(id);
-                        write_decimal(sout + p, id, dw);
-                        p += dw;
-                        sout[p] = p + 1 == end ? (uint8_t)'}' : (uint8_t)',';
-                        ++p;
+                    const uint32_t phase = (uint32_t)(gpos & 15u), open = w0 == 0 ? 1u : 0u;
+                    const uint32_t tile = open + __shfl_sync(0xffffffffu, incl, 31);
+                    if (open && lane == 0) stage[phase] = (uint8_t)'{';
+                    // lane = bit: the ids of one word are rendered side by side (neighbouring shared-memory banks);
+                    // digits come from the id table (L1-resident), offsets from a popcount when the word's ids share a width
+                    const uint32_t my_off = phase + open + (incl - mine);
+                    const uint32_t lo_id = w * 32u + 1u, wl = decimal_width(lo_id);
+                    const uint32_t my_dw = wl == decimal_width(lo_id + 31u) ? wl : 0u;
+                    const uint32_t end_q = (uint32_t)(end - gpos) + phase;
+                    const uint32_t live = __ballot_sync(0xffffffffu, v != 0);
+                    for (uint32_t rest = live; rest; rest &= rest - 1) {
+                        const int k = __ffs((int)rest) - 1;
+                        const uint32_t wk = __shfl_sync(0xffffffffu, v, k);
+                        const uint32_t base_k = __shfl_sync(0xffffffffu, my_off, k);
+                        const uint32_t dwk = __shfl_sync(0xffffffffu, my_dw, k);
+                        if ((wk >> lane) & 1u) {
+                            const uint32_t id = (w0 + (uint32_t)k) * 32u + lane + 1u;
+                            const uint32_t below = wk & lanemask_lt();
+                            uint32_t q = base_k + (dwk ? (uint32_t)__popc(below) * (dwk + 1u) : word_id_bytes(w0 + (uint32_t)k, below));
+                            const u64 e = __ldg(id_text + id);  // digits, then ','
+                            const uint32_t lo4 = (uint32_t)e, hi4 = (uint32_t)(e >> 32);
+                            uint8_t* const d = stage + q;
+                            switch ((uint32_t)(e >> 56)) {
+                                case 1: d[0] = (uint8_t)lo4; d[1] = (uint8_t)(lo4 >> 8); break;
+                                case 2: d[0] = (uint8_t)lo4; d[1] = (uint8_t)(lo4 >> 8); d[2] = (uint8_t)(lo4 >> 16); break;
+                                case 3: d[0] = (uint8_t)lo4; d[1] = (uint8_t)(lo4 >> 8); d[2] = (uint8_t)(lo4 >> 16); d[3] = (uint8_t)(lo4 >> 24); break;
+                                case 4: d[0] = (uint8_t)lo4; d[1] = (uint8_t)(lo4 >> 8); d[2] = (uint8_t)(lo4 >> 16); d[3] = (uint8_t)(lo4 >> 24);
+                                        d[4] = (uint8_t)hi4; break;
+                                case 5: d[0] = (uint8_t)lo4; d[1] = (uint8_t)(lo4 >> 8); d[2] = (uint8_t)(lo4 >> 16); d[3] = (uint8_t)(lo4 >> 24);
+                                        d[4] = (uint8_t)hi4; d[5] = (uint8_t)(hi4 >> 8); break;
+                                case 6: d[0] = (uint8_t)lo4; d[1] = (uint8_t)(lo4 >> 8); d[2] = (uint8_t)(lo4 >> 16); d[3] = (uint8_t)(lo4 >> 24);
+                                        d[4] = (uint8_t)hi4; d[5] = (uint8_t)(hi4 >> 8); d[6] = (uint8_t)(hi4 >> 16); break;
+                                default: {  // more than six digits: rendered here
+                                    const uint32_t dw = decimal_width(id);
+                                    write_decimal(d, id, dw);
+                                    d[dw] = (uint8_t)',';
+                                }
+                            }
+                        }
                     }
-                    at += __shfl_sync(0xffffffffu, incl, 31);
+                    if (tile && end_q <= phase + tile) {  // this round holds the end of the list: its last ',' is the '}'
+                        __syncwarp();
+                        if (lane == 0) stage[end_q - 1] = (uint8_t)'}';
+                    }
+                    __syncwarp();
+                    uint8_t* const dst = sout + (gpos - phase);  // 16-byte aligned
+                    const uint32_t hi = phase + tile;
+                    for (uint32_t j = lane * 16u; j < hi; j += 512u) {
+                        if (j >= phase && j + 16u <= hi) {
+                            *reinterpret_cast<uint4*>(dst + j) = *reinterpret_cast<const uint4*>(stage + j);
+                        } else {
+                            const uint32_t lo_b = j > phase ? j : phase, hi_b = j + 16u < hi ? j + 16u : hi;
+                            for (uint32_t i = lo_b; i < hi_b; ++i) dst[i] = stage[i];
+                        }
+                    }
+                    __syncwarp();
+                    gpos += tile;
                 }
                 so = end;
             }
         }
         if (lane == 0) out[eo] = (uint8_t)'}';
+    }
+}
+
+// id_text[id]: the decimal digits of id, first digit in the low byte, then ','; width in the top byte (0: more than six digits)
+__global__ void k_id_text(u64* id_text, u64 n) {
+    for (u64 id = gtid(); id < n; id += gthreads()) {
+        const uint32_t dw = id < 1000000ull ? decimal_width((uint32_t)id) : 0u;
+        u64 e = ((u64)dw << 56) | ((u64)(uint32_t)',' << (8 * dw));
+        uint32_t v = (uint32_t)id;
+        for (int j = (int)dw - 1; j >= 0; --j) {
+            e |= (u64)((uint32_t)'0' + v % 10u) << (8 * j);
+            v /= 10u;
+        }
+        id_text[id] = e;
     }
 }
 
@@ -842,7 +996,7 @@ __global__ void k_iota(uint32_t* p, u64 n) {
 
 // =============================================================================================================
 struct VcfPipeline::Bufs {
-    DevBuf d[28];
+    DevBuf d[30];
     ~Bufs() {
         for (DevBuf& b : d) b.release();
     }
@@ -872,7 +1026,7 @@ void VcfPipeline::transform_device(const uint8_t* vcf, uint64_t vcf_bytes, const
            &d_rec_of = B_.d[10], &d_incl = B_.d[11], &d_opens = B_.d[12], &d_gid = B_.d[13], &d_slot_base = B_.d[14],
            &d_gfirst = B_.d[15], &d_gfrom = B_.d[16], &d_gto = B_.d[17], &d_canon = B_.d[18], &d_hap_len = B_.d[19],
            &d_slot_bits = B_.d[20], &d_slot_seds = B_.d[21], &d_kept = B_.d[22], &d_geds = B_.d[23], &d_gseds = B_.d[24],
-           &d_eds_off = B_.d[25], &d_seds_off = B_.d[26];
+           &d_eds_off = B_.d[25], &d_seds_off = B_.d[26], &d_nl = B_.d[27], &d_id_text = B_.d[28];
     DevBuf& d_out = ctx_->vcf_out[0];
     DevBuf& d_sout = ctx_->vcf_out[1];
 
@@ -916,17 +1070,19 @@ void VcfPipeline::transform_device(const uint8_t* vcf, uint64_t vcf_bytes, const
     VCF_LAUNCH("k_fa_measure", k_fa_measure, G, B, 0, fasta, st);
 
     const u64 n_chunks = (vcf_bytes + 15) / 16;
-    const NlFn nlfn{vcf, (u64)vcf_bytes, nullptr};
-    {
-        auto reduce = k_part_reduce<OpSum64, NlFn>;
-        VCF_LAUNCH("line_count", reduce, P, kScanBlock, 0, n_chunks, nlfn, part);
-    }
-    // the reduce leaves per-partition totals; the grand total is their sum (P values, summed on the host)
-    std::vector<u64> h_part(P);
-    EDSB_CUDA(cudaMemcpyAsync(h_part.data(), part, (size_t)P * 8, cudaMemcpyDeviceToHost, s));
+    const uint32_t nl_blocks = std::max<uint32_t>(1u, (uint32_t)std::min<u64>((u64)G / 2u, (n_chunks + 32u * (B / 32u) - 1) / (32u * (B / 32u))));
+    const uint32_t nl_warps = nl_blocks * (B / 32u);
+    d_nl.reserve((size_t)nl_warps * 8);
+    VCF_LAUNCH("k_nl_count", k_nl_count, nl_blocks, B, 0, vcf, (u64)vcf_bytes, n_chunks, d_nl.as<u64>());
+    std::vector<u64> h_nl(nl_warps);
+    EDSB_CUDA(cudaMemcpyAsync(h_nl.data(), d_nl.p, (size_t)nl_warps * 8, cudaMemcpyDeviceToHost, s));
     EDSB_CUDA(cudaStreamSynchronize(s));
     u64 n_nl = 0;
-    for (u64 v : h_part) n_nl += v;
+    for (u64& v : h_nl) {
+        const u64 mine = v;
+        v = n_nl;
+        n_nl += mine;
+    }
     uint8_t last_byte = '\n';
     if (vcf_bytes) EDSB_CUDA(cudaMemcpyAsync(&last_byte, vcf + vcf_bytes - 1, 1, cudaMemcpyDeviceToHost, s));
     status_now();
@@ -950,10 +1106,8 @@ void VcfPipeline::transform_device(const uint8_t* vcf, uint64_t vcf_bytes, const
         const u64 zero = 0, tail = vcf_bytes + 1;
         EDSB_CUDA(cudaMemcpyAsync(line_start, &zero, 8, cudaMemcpyHostToDevice, s));
         if (open_tail) EDSB_CUDA(cudaMemcpyAsync(line_start + n_lines, &tail, 8, cudaMemcpyHostToDevice, s));
-        NlFn fn = nlfn;
-        fn.line_start = line_start;
-        auto apply = k_part_apply<OpSum64, NlFn>;
-        VCF_LAUNCH("line_starts", apply, P, kScanBlock, 0, n_chunks, fn, part);
+        EDSB_CUDA(cudaMemcpyAsync(d_nl.p, h_nl.data(), (size_t)nl_warps * 8, cudaMemcpyHostToDevice, s));
+        VCF_LAUNCH("k_nl_write", k_nl_write, nl_blocks, B, 0, vcf, (u64)vcf_bytes, n_chunks, d_nl.as<u64>(), line_start);
     }
 
     // ---- heads, records ----------------------------------------------------------------------------------------
@@ -972,7 +1126,7 @@ void VcfPipeline::transform_device(const uint8_t* vcf, uint64_t vcf_bytes, const
         VCF_SCAN("rows", OpSum64, n_rec, (RowFn{recs}));
         d_pos.reserve((size_t)n_rec * 8);
         VCF_LAUNCH("k_rec_check", k_rec_check, G, B, 0, recs, n_rec, d_pos.as<u64>(), st);
-        VCF_LAUNCH("k_first_fields", k_first_fields, 1, 32, 0, vcf, recs, st);
+        VCF_LAUNCH("k_first_fields", k_first_fields, 1, 32, 0, vcf, n_chunks, recs, st);
         n_rows = total_of();
     }
     status_now();
@@ -1017,11 +1171,13 @@ void VcfPipeline::transform_device(const uint8_t* vcf, uint64_t vcf_bytes, const
         auto run_gt = [&](const std::function<void()>& while_it_runs) {
             for (;;) {
                 d_bits.reserve((size_t)n_rows * W * 4 + 16);
-                const uint32_t wpb = 4;
-                uint32_t smem_words = std::max<uint32_t>(2u * W, 2048u);
-                while ((size_t)smem_words * wpb * 4 > 48u * 1024u) smem_words /= 2;
-                const uint32_t grid = (uint32_t)std::min<u64>((n_rec + wpb - 1) / wpb, (u64)sms * 16u);
-                VCF_LAUNCH("k_gt", k_gt, grid, wpb * 32, (size_t)smem_words * wpb * 4, vcf, recs, n_rec, W, smem_words,
+                // shared-memory slice per warp: room for REF + 3 ALT rows (wider records work in global memory)
+                const uint32_t wpb = 8;
+                uint32_t smem_words = std::max<uint32_t>(4u * W, 64u);
+                while ((size_t)smem_words * wpb * 4 > 40u * 1024u && smem_words > 2u * W) smem_words /= 2;
+                if ((size_t)smem_words * wpb * 4 > 40u * 1024u) smem_words = 8;  // everything in global memory
+                const uint32_t grid = (uint32_t)std::min<u64>((n_rec + wpb - 1) / wpb, (u64)sms * 32u);
+                VCF_LAUNCH("k_gt", k_gt, grid, wpb * 32, (size_t)smem_words * wpb * 4, vcf, n_chunks, recs, n_rec, W, smem_words,
                            d_bits.as<uint32_t>(), st);
                 while_it_runs();
                 status_now();
@@ -1102,9 +1258,23 @@ void VcfPipeline::transform_device(const uint8_t* vcf, uint64_t vcf_bytes, const
     d_sout.reserve(seds_total + 16);
     if (n_bases)
         VCF_LAUNCH("k_emit_ref", k_emit_ref, G, B, 0, fa, n_bases, g_from, g_to, n_groups, d_eds_off.as<u64>(), d_out.as<uint8_t>());
-    VCF_LAUNCH("k_emit_groups", k_emit_groups, G, B, 0, vcf, fa, gv, d_gfirst.as<uint32_t>(), n_groups, d_canon.as<u64>(),
-               d_hap_len.as<uint32_t>(), d_kept.as<uint8_t>(), d_slot_bits.as<uint32_t>(), d_slot_seds.as<uint32_t>(), W,
-               d_eds_off.as<u64>(), d_seds_off.as<u64>(), d_out.as<uint8_t>(), d_sout.as<uint8_t>());
+    {
+        // stage per warp: one round of 32 words = up to 1024 ids of (digits + 1) bytes, plus the phase and the '{'
+        uint32_t id_width = 1;
+        for (u64 top = (u64)W * 32u; top >= 10; top /= 10) ++id_width;
+        const uint32_t stage_bytes = ((1024u * (id_width + 1u) + 32u + 15u) / 16u) * 16u;
+        const uint32_t wpb = std::max<uint32_t>(1u, std::min<uint32_t>(B / 32u, (40u * 1024u) / stage_bytes));
+        const uint32_t grid = (uint32_t)std::min<u64>(((u64)n_groups + 1 + wpb - 1) / wpb, (u64)G * (B / 32u) / wpb);
+        if (id_text_n_ < (u64)W * 32u + 1) {
+            id_text_n_ = (u64)W * 32u + 1;
+            d_id_text.reserve((size_t)id_text_n_ * 8);
+            VCF_LAUNCH("k_id_text", k_id_text, G, B, 0, d_id_text.as<u64>(), id_text_n_);
+        }
+        VCF_LAUNCH("k_emit_groups", k_emit_groups, grid, wpb * 32, (size_t)stage_bytes * wpb, vcf, fa, gv, d_gfirst.as<uint32_t>(),
+                   n_groups, d_canon.as<u64>(), d_hap_len.as<uint32_t>(), d_kept.as<uint8_t>(), d_slot_bits.as<uint32_t>(),
+                   d_slot_seds.as<uint32_t>(), W, stage_bytes, d_id_text.as<u64>(), d_eds_off.as<u64>(), d_seds_off.as<u64>(),
+                   d_out.as<uint8_t>(), d_sout.as<uint8_t>());
+    }
     EDSB_CUDA(cudaStreamSynchronize(s));
     EDSB_CUDA(cudaGetLastError());
     clk.resolve();

@@ -32,6 +32,7 @@ class VcfPipeline {
     eds_ctx* ctx_;
     Bufs* bufs_;
     uint32_t words_hint_ = 0;  // sample-bitset width of the previous call
+    uint64_t id_text_n_ = 0;   // entries of the id -> decimal text table built so far
 };
 
 }  // namespace edsb
