@@ -182,7 +182,7 @@ class Context:
         self.lib.check(self.lib.L.eds_ctx_set_profiling(self.handle, 1 if on else 0))
 
     def kernel_times(self):
-        cap = 64
+        cap = 512
         names = (ctypes.c_char_p * cap)()
         ms = (ctypes.c_float * cap)()
         n = min(cap, self.lib.L.eds_ctx_kernel_times(self.handle, names, ms, cap))

@@ -172,8 +172,10 @@ struct SetFn {
         }
         num_val[q] = (uint32_t)v;
         num_set[q] = (uint32_t)prefix - 1u;  // sets opened before this number, minus one
-        atomicOr(&present[v >> 5], 1u << (v & 31u));
-        atomicMax(&st->max_id, (uint32_t)v);
+        // few distinct ids, millions of mentions: look before the atomic (a stale read only costs a redundant atomic)
+        const uint32_t bit = 1u << (v & 31u);
+        if (!(*reinterpret_cast<volatile uint32_t*>(&present[v >> 5]) & bit)) atomicOr(&present[v >> 5], bit);
+        if ((uint32_t)v > *reinterpret_cast<volatile uint32_t*>(&st->max_id)) atomicMax(&st->max_id, (uint32_t)v);
     }
 };
 
@@ -285,14 +287,34 @@ __device__ __forceinline__ bool meets(const uint32_t* a, const uint32_t* b, uint
     return Wd == 0;  // no sources: CARTESIAN keeps everything
 }
 
-// kept[q] = alternatives the merged symbol of pair q will have (warp per pair, lanes over combinations)
+// kept[q] = alternatives the merged symbol of pair q will have. Pairs with few combinations (a conserved symbol
+// against a variant site: the bulk of every round) take one thread each; the rest a warp, lanes over combinations.
+constexpr unsigned long long kSmallPair = 8;
+
 __global__ void k_kept(SymTab t, Pool pool, const uint32_t* pair_list, uint32_t n_pairs, uint32_t Wd,
                        unsigned long long* kept, LedsStatus* st) {
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_pairs; q += gridDim.x * blockDim.x) {
+        const uint32_t i = pair_list[q];
+        const uint32_t ab = t.begin[i], na = t.count[i], bb = t.begin[i + 1], nb = t.count[i + 1];
+        const unsigned long long combos = (unsigned long long)na * nb;
+        if (combos > kSmallPair) continue;
+        unsigned long long cnt = 0;
+        if (Wd == 0) {
+            cnt = combos;
+        } else {
+            for (uint32_t a = 0; a < na; ++a)
+                for (uint32_t b = 0; b < nb; ++b)
+                    cnt += meets(pool.bits + (size_t)(ab + a) * Wd, pool.bits + (size_t)(bb + b) * Wd, Wd) ? 1u : 0u;
+        }
+        kept[q] = cnt;
+        if (cnt == 0) atomicMin(&st->empty_merge, i);
+    }
     const uint32_t lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     for (uint32_t q = blockIdx.x * wpb + (threadIdx.x >> 5); q < n_pairs; q += gridDim.x * wpb) {
         const uint32_t i = pair_list[q];
         const uint32_t ab = t.begin[i], na = t.count[i], bb = t.begin[i + 1], nb = t.count[i + 1];
         const unsigned long long combos = (unsigned long long)na * nb;
+        if (combos <= kSmallPair) continue;
         unsigned long long cnt = 0;
         if (Wd == 0) {
             cnt = combos;
@@ -318,13 +340,30 @@ struct KeptFn {
 };
 
 // New pool entries of every selected pair, i-major / j-minor (eds.cpp:1459-1468, 1640-1644).
+__device__ __forceinline__ void write_entry(const Pool& pool, size_t e, uint32_t x, uint32_t y, uint32_t Wd) {
+    pool.left[e] = x;
+    pool.right[e] = y;
+    pool.len[e] = pool.len[x] + pool.len[y];
+    for (uint32_t w = 0; w < Wd; ++w) pool.bits[e * Wd + w] = pool.bits[(size_t)x * Wd + w] & pool.bits[(size_t)y * Wd + w];
+}
+
 __global__ void k_merge_write(SymTab t, Pool pool, const uint32_t* pair_list, uint32_t n_pairs, uint32_t Wd,
                               const unsigned long long* off, uint32_t pool_n) {
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_pairs; q += gridDim.x * blockDim.x) {  // thread per small pair
+        const uint32_t i = pair_list[q];
+        const uint32_t ab = t.begin[i], na = t.count[i], bb = t.begin[i + 1], nb = t.count[i + 1];
+        if ((unsigned long long)na * nb > kSmallPair) continue;
+        size_t e = (size_t)(pool_n + off[q]);
+        for (uint32_t a = 0; a < na; ++a)
+            for (uint32_t b = 0; b < nb; ++b)
+                if (meets(pool.bits + (size_t)(ab + a) * Wd, pool.bits + (size_t)(bb + b) * Wd, Wd)) write_entry(pool, e++, ab + a, bb + b, Wd);
+    }
     const uint32_t lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    for (uint32_t q = blockIdx.x * wpb + (threadIdx.x >> 5); q < n_pairs; q += gridDim.x * wpb) {
+    for (uint32_t q = blockIdx.x * wpb + (threadIdx.x >> 5); q < n_pairs; q += gridDim.x * wpb) {  // warp per large pair
         const uint32_t i = pair_list[q];
         const uint32_t ab = t.begin[i], na = t.count[i], bb = t.begin[i + 1], nb = t.count[i + 1];
         const unsigned long long combos = (unsigned long long)na * nb;
+        if (combos <= kSmallPair) continue;
         unsigned long long base = pool_n + off[q];
         for (unsigned long long c0 = 0; c0 < combos; c0 += 32) {
             const unsigned long long c = c0 + lane;
@@ -336,13 +375,7 @@ __global__ void k_merge_write(SymTab t, Pool pool, const uint32_t* pair_list, ui
                 keep = meets(pool.bits + (size_t)(ab + a) * Wd, pool.bits + (size_t)(bb + bq) * Wd, Wd);
             }
             const uint32_t m = __ballot_sync(0xffffffffu, keep);
-            if (keep) {
-                const size_t e = (size_t)(base + (unsigned long long)__popc(m & lanemask_lt()));
-                pool.left[e] = ab + a;
-                pool.right[e] = bb + bq;
-                pool.len[e] = pool.len[ab + a] + pool.len[bb + bq];
-                for (uint32_t w = 0; w < Wd; ++w) pool.bits[e * Wd + w] = pool.bits[(size_t)(ab + a) * Wd + w] & pool.bits[(size_t)(bb + bq) * Wd + w];
-            }
+            if (keep) write_entry(pool, (size_t)(base + (unsigned long long)__popc(m & lanemask_lt())), ab + a, bb + bq, Wd);
             base += (unsigned long long)__popc(m);
         }
     }

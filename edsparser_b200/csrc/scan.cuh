@@ -23,8 +23,10 @@ struct OpMax64 {
 
 #ifdef EDSB_EMU
 constexpr int kScanBlock = 64;
+constexpr int kScanItems = 2;
 #else
 constexpr int kScanBlock = 256;
+constexpr int kScanItems = 8;
 #endif
 
 template <typename Op>
@@ -82,6 +84,7 @@ __global__ void __launch_bounds__(kScanBlock) k_part_reduce(unsigned long long n
     if (threadIdx.x == 0) part[blockIdx.x] = tot;
 }
 
+// Each thread owns kScanItems consecutive elements of a batch: one block scan per kScanItems * blockDim.x elements.
 template <typename Op, typename Fn>
 __global__ void __launch_bounds__(kScanBlock) k_part_apply(unsigned long long n, Fn fn, typename Op::V* part) {
     typedef typename Op::V V;
@@ -91,12 +94,23 @@ __global__ void __launch_bounds__(kScanBlock) k_part_apply(unsigned long long n,
     V mine = Op::identity();
     for (unsigned q = threadIdx.x; q < blockIdx.x; q += blockDim.x) mine = Op::combine(mine, part[q]);
     V base = block_reduce<Op>(mine, s_scan);
-    for (unsigned long long i0 = lo; i0 < hi; i0 += blockDim.x) {
-        const unsigned long long i = i0 + threadIdx.x;
-        const V v = i < hi ? fn.value(i) : Op::identity();
+    const unsigned long long batch = (unsigned long long)blockDim.x * kScanItems;
+    for (unsigned long long i0 = lo; i0 < hi; i0 += batch) {
+        const unsigned long long first = i0 + (unsigned long long)threadIdx.x * kScanItems;
+        V vals[kScanItems];
+        V sum = Op::identity();
+#pragma unroll
+        for (int j = 0; j < kScanItems; ++j) {
+            vals[j] = first + j < hi ? fn.value(first + j) : Op::identity();
+            sum = Op::combine(sum, vals[j]);
+        }
         V total;
-        const V ex = block_scan_excl<Op>(v, s_scan, total);
-        if (i < hi) fn.apply(i, Op::combine(base, ex), v);
+        V run = Op::combine(base, block_scan_excl<Op>(sum, s_scan, total));
+#pragma unroll
+        for (int j = 0; j < kScanItems; ++j) {
+            if (first + j < hi) fn.apply(first + j, run, vals[j]);
+            run = Op::combine(run, vals[j]);
+        }
         base = Op::combine(base, total);
     }
     if (blockIdx.x == P - 1 && threadIdx.x == 0) part[P] = base;

@@ -919,32 +919,37 @@ __global__ void k_emit_groups(const uint8_t* t, Fasta fa, GroupView gv, const ui
                     const uint32_t my_dw = wl == decimal_width(lo_id + 31u) ? wl : 0u;
                     const uint32_t end_q = (uint32_t)(end - gpos) + phase;
                     const uint32_t live = __ballot_sync(0xffffffffu, v != 0);
+                    const uint32_t id0 = w0 * 32u + lane + 1u, lt = lanemask_lt();
                     for (uint32_t rest = live; rest; rest &= rest - 1) {
                         const int k = __ffs((int)rest) - 1;
                         const uint32_t wk = __shfl_sync(0xffffffffu, v, k);
                         const uint32_t base_k = __shfl_sync(0xffffffffu, my_off, k);
                         const uint32_t dwk = __shfl_sync(0xffffffffu, my_dw, k);
                         if ((wk >> lane) & 1u) {
-                            const uint32_t id = (w0 + (uint32_t)k) * 32u + lane + 1u;
-                            const uint32_t below = wk & lanemask_lt();
-                            uint32_t q = base_k + (dwk ? (uint32_t)__popc(below) * (dwk + 1u) : word_id_bytes(w0 + (uint32_t)k, below));
+                            const uint32_t id = id0 + (uint32_t)k * 32u;
+                            const uint32_t below = wk & lt;
+                            const uint32_t q = base_k + (dwk ? (uint32_t)__popc(below) * (dwk + 1u) : word_id_bytes(w0 + (uint32_t)k, below));
                             const u64 e = __ldg(id_text + id);  // digits, then ','
-                            const uint32_t lo4 = (uint32_t)e, hi4 = (uint32_t)(e >> 32);
+                            const uint32_t lo4 = (uint32_t)e, hi4 = (uint32_t)(e >> 32), dw = hi4 >> 24;
                             uint8_t* const d = stage + q;
-                            switch ((uint32_t)(e >> 56)) {
-                                case 1: d[0] = (uint8_t)lo4; d[1] = (uint8_t)(lo4 >> 8); break;
-                                case 2: d[0] = (uint8_t)lo4; d[1] = (uint8_t)(lo4 >> 8); d[2] = (uint8_t)(lo4 >> 16); break;
-                                case 3: d[0] = (uint8_t)lo4; d[1] = (uint8_t)(lo4 >> 8); d[2] = (uint8_t)(lo4 >> 16); d[3] = (uint8_t)(lo4 >> 24); break;
-                                case 4: d[0] = (uint8_t)lo4; d[1] = (uint8_t)(lo4 >> 8); d[2] = (uint8_t)(lo4 >> 16); d[3] = (uint8_t)(lo4 >> 24);
-                                        d[4] = (uint8_t)hi4; break;
-                                case 5: d[0] = (uint8_t)lo4; d[1] = (uint8_t)(lo4 >> 8); d[2] = (uint8_t)(lo4 >> 16); d[3] = (uint8_t)(lo4 >> 24);
-                                        d[4] = (uint8_t)hi4; d[5] = (uint8_t)(hi4 >> 8); break;
-                                case 6: d[0] = (uint8_t)lo4; d[1] = (uint8_t)(lo4 >> 8); d[2] = (uint8_t)(lo4 >> 16); d[3] = (uint8_t)(lo4 >> 24);
-                                        d[4] = (uint8_t)hi4; d[5] = (uint8_t)(hi4 >> 8); d[6] = (uint8_t)(hi4 >> 16); break;
-                                default: {  // more than six digits: rendered here
-                                    const uint32_t dw = decimal_width(id);
-                                    write_decimal(d, id, dw);
-                                    d[dw] = (uint8_t)',';
+                            if (dw == 4u) {
+                                d[0] = (uint8_t)lo4; d[1] = (uint8_t)(lo4 >> 8); d[2] = (uint8_t)(lo4 >> 16); d[3] = (uint8_t)(lo4 >> 24);
+                                d[4] = (uint8_t)hi4;
+                            } else if (dw == 3u) {
+                                d[0] = (uint8_t)lo4; d[1] = (uint8_t)(lo4 >> 8); d[2] = (uint8_t)(lo4 >> 16); d[3] = (uint8_t)(lo4 >> 24);
+                            } else if (dw == 0u) {  // more than six digits: rendered here
+                                const uint32_t w7 = decimal_width(id);
+                                write_decimal(d, id, w7);
+                                d[w7] = (uint8_t)',';
+                            } else {
+                                d[0] = (uint8_t)lo4;
+                                d[1] = (uint8_t)(lo4 >> 8);
+                                if (dw >= 2u) d[2] = (uint8_t)(lo4 >> 16);
+                                if (dw >= 5u) {
+                                    d[3] = (uint8_t)(lo4 >> 24);
+                                    d[4] = (uint8_t)hi4;
+                                    d[5] = (uint8_t)(hi4 >> 8);
+                                    if (dw == 6u) d[6] = (uint8_t)(hi4 >> 16);
                                 }
                             }
                         }
