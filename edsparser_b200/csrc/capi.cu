@@ -118,6 +118,7 @@ eds_status eds_ctx_create(int device, void* stream, eds_ctx** out) {
 #endif
         if (const char* hm = getenv("EDSB_DEBUG_HASH_MASK")) ctx->hash_mask = strtoull(hm, nullptr, 0);
         if (const char* no = getenv("EDSB_DEBUG_NARROW_OFF")) ctx->narrow_off = atoi(no);
+        if (const char* rs = getenv("EDSB_DEBUG_ROW_SLICES")) ctx->scan_row_slices = (uint32_t)atoi(rs);
         ctx->msa = new edsb::MsaPipeline(ctx);
         ctx->leds = new edsb::LedsPipeline(ctx);
         ctx->vcf = new edsb::VcfPipeline(ctx);

@@ -113,6 +113,14 @@ __device__ __forceinline__ void scan_aligned(const unsigned long long* pk, uint3
     }
 }
 
+// gridDim.y > 1 (few columns per device, many rows: a column shard of a deep alignment): the rows are split into
+// gridDim.y slices, every block scans one slice and ORs its 16 mismatch bits into the (pre-zeroed) word.
+__device__ __forceinline__ void row_slice(uint32_t lo, uint32_t hi, uint32_t& a, uint32_t& b) {
+    const uint32_t n = hi - lo;
+    a = lo + (uint32_t)((unsigned long long)n * blockIdx.y / gridDim.y);
+    b = lo + (uint32_t)((unsigned long long)n * (blockIdx.y + 1) / gridDim.y);
+}
+
 template <bool CACHED>
 __global__ void __launch_bounds__(kScanThreads, EDSB_SCAN_MINB) k_scan(MsaGeom g, const unsigned long long* row_pack, uint16_t* mism16,
                                                        MsaStatus* st) {
@@ -140,13 +148,19 @@ __global__ void __launch_bounds__(kScanThreads, EDSB_SCAN_MINB) k_scan(MsaGeom g
         uint4 ref, acc = make_uint4(0, 0, 0, 0);
         if (interior) {
             ref = ldg_nc(reinterpret_cast<const uint4*>(pk[0]) + jj);
+            uint32_t a, b;
             if (g.all_aligned) {
-                scan_aligned(pk + 1, g.R - 1, jj, ref, acc);
+                row_slice(1, g.R, a, b);
+                scan_aligned(pk + a, b - a, jj, ref, acc);
             } else {
-                scan_class<0>(pk + g.cls[0], g.cls[1] - g.cls[0], jj, ref, acc);
-                scan_class<1>(pk + g.cls[1], g.cls[2] - g.cls[1], jj, ref, acc);
-                scan_class<2>(pk + g.cls[2], g.cls[3] - g.cls[2], jj, ref, acc);
-                scan_class<3>(pk + g.cls[3], g.cls[4] - g.cls[3], jj, ref, acc);
+                row_slice(g.cls[0], g.cls[1], a, b);
+                scan_class<0>(pk + a, b - a, jj, ref, acc);
+                row_slice(g.cls[1], g.cls[2], a, b);
+                scan_class<1>(pk + a, b - a, jj, ref, acc);
+                row_slice(g.cls[2], g.cls[3], a, b);
+                scan_class<2>(pk + a, b - a, jj, ref, acc);
+                row_slice(g.cls[3], g.cls[4], a, b);
+                scan_class<3>(pk + a, b - a, jj, ref, acc);
             }
         } else {
             // edge tile: clamp every vector index into the buffer (bytes outside the row are masked below)
@@ -154,7 +168,9 @@ __global__ void __launch_bounds__(kScanThreads, EDSB_SCAN_MINB) k_scan(MsaGeom g
             long long v0 = jj + (d0 >> 4);
             v0 = v0 < 0 ? 0 : (v0 > vmax ? vmax : v0);
             ref = ldg_nc(vec + v0);
-            for (uint32_t r = 1; r < g.R; ++r) {
+            uint32_t r_lo, r_hi;
+            row_slice(1, g.R, r_lo, r_hi);
+            for (uint32_t r = r_lo; r < r_hi; ++r) {
                 const long long d = (long long)g.row_off[r] - (long long)g.a0;
                 const long long vi = jj + (d >> 4);
                 const uint32_t sh = (uint32_t)(d & 15);
@@ -189,7 +205,10 @@ __global__ void __launch_bounds__(kScanThreads, EDSB_SCAN_MINB) k_scan(MsaGeom g
         const uint32_t nl = eq_bytes16(ref, 0x0a0a0a0au);
         if (((nl ^ expect) | (nonzero_bytes16(acc) & expect)) & valid) bad = 1;
         mism &= valid & ~expect;
-        mism16[j] = (uint16_t)mism;
+        if (gridDim.y == 1)
+            mism16[j] = (uint16_t)mism;
+        else if (mism)
+            atomicOr(reinterpret_cast<uint32_t*>(mism16) + (j >> 1), mism << ((j & 1u) * 16u));
     }
     if (bad) atomicOr(&st->bad_msa, (uint32_t)kBadNewlineLayout);
 }
@@ -1659,12 +1678,19 @@ void MsaPipeline::launch_scan(const MsaBufs& b) {
     const uint32_t per_sm = ctx_->scan_blocks_per_sm ? ctx_->scan_blocks_per_sm : 16u;
     const uint32_t tiles = (g.n_chunks + 31) / 32;
     const uint32_t blocks = std::max(1u, std::min((tiles + 7) / 8, (uint32_t)ctx_->sm_count * per_sm));
+    // too few column blocks to fill the device and rows to spare: split the rows too (blocks x slices)
+    uint32_t slices = 1;
+    const uint32_t want = (uint32_t)ctx_->sm_count * per_sm * 2u;
+    if (blocks < want && g.R >= 128u) slices = std::min(std::min((want + blocks - 1) / blocks, g.R / 64u), 32u);
+    if (ctx_->scan_row_slices) slices = std::max(1u, std::min(ctx_->scan_row_slices, g.R > 1 ? g.R - 1 : 1u));
+    if (slices > 1) EDSB_CUDA(cudaMemsetAsync(b.mism, 0, ((size_t)g.n_chunks / 2 + 1) * 4, s));
     ctx_->clock.begin("k_scan");
     const unsigned long long* pack = reinterpret_cast<const unsigned long long*>(g.row_off + g.R);
+    const dim3 grid(blocks, slices);
     if (g.R <= (uint32_t)kRowCache) {
-        EDSB_LAUNCH(k_scan<true>, blocks, kScanThreads, 0, s, g, pack, reinterpret_cast<uint16_t*>(b.mism), b.status);
+        EDSB_LAUNCH(k_scan<true>, grid, kScanThreads, 0, s, g, pack, reinterpret_cast<uint16_t*>(b.mism), b.status);
     } else {
-        EDSB_LAUNCH(k_scan<false>, blocks, kScanThreads, 0, s, g, pack, reinterpret_cast<uint16_t*>(b.mism), b.status);
+        EDSB_LAUNCH(k_scan<false>, grid, kScanThreads, 0, s, g, pack, reinterpret_cast<uint16_t*>(b.mism), b.status);
     }
     ctx_->clock.end();
     ctx_->clock.begin("k_colbits");

@@ -33,8 +33,12 @@ def gather_offsets(dist, device, eds_bytes, seds_bytes, scratch=None):
 
 class OffsetExchange:
     """The same exchange without a host round trip per call: byte counts go to the device through a pinned
-    staging tensor, the all-gather is queued on the current stream, and the offsets are read back only when
-    the caller asks (`offsets()`), e.g. once before the file writes. Used by bench.py's timed loop."""
+    staging tensor, the all-gather is issued asynchronously behind the transform (the next transform on this rank
+    does not wait for the other ranks), and the offsets are read back only when the caller asks (`offsets()`),
+    e.g. once before the file writes. Two exchanges may be in flight (ring of two buffer sets). Used by bench.py's
+    timed loop."""
+
+    RING = 2
 
     def __init__(self, dist, device):
         import torch
@@ -42,22 +46,38 @@ class OffsetExchange:
         self.dist = dist
         self.world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
-        self.host = torch.zeros(2, dtype=torch.int64)
+        self.host = [torch.zeros(2, dtype=torch.int64) for _ in range(self.RING)]
         if device.type == "cuda":
-            self.host = self.host.pin_memory()
-        self.mine = torch.zeros(2, dtype=torch.int64, device=device)
-        self.everyone = torch.zeros(2 * self.world, dtype=torch.int64, device=device)
+            self.host = [h.pin_memory() for h in self.host]
+        self.mine = [torch.zeros(2, dtype=torch.int64, device=device) for _ in range(self.RING)]
+        self.everyone = [torch.zeros(2 * self.world, dtype=torch.int64, device=device) for _ in range(self.RING)]
+        self.work = [None] * self.RING
+        self.posted = 0
 
     def post(self, eds_bytes, seds_bytes):
-        self.host[0], self.host[1] = int(eds_bytes), int(seds_bytes)
-        self.mine.copy_(self.host, non_blocking=True)
+        k = self.posted % self.RING
+        if self.work[k] is not None:
+            self.work[k].wait()  # the exchange that used this buffer set two posts ago
+            self.work[k] = None
+        self.host[k][0], self.host[k][1] = int(eds_bytes), int(seds_bytes)
+        self.mine[k].copy_(self.host[k], non_blocking=True)
         if self.world > 1:
-            self.dist.all_gather_into_tensor(self.everyone, self.mine)
+            self.work[k] = self.dist.all_gather_into_tensor(self.everyone[k], self.mine[k], async_op=True)
         else:
-            self.everyone.copy_(self.mine)
+            self.everyone[k].copy_(self.mine[k])
+        self.posted += 1
+
+    def flush(self):
+        """Make the current stream wait for every exchange still in flight (no host synchronisation)."""
+        for w in self.work:
+            if w is not None:
+                w.wait()
+        self.work = [None] * self.RING
 
     def offsets(self):
-        counts = self.everyone.view(self.world, 2).cpu()
+        k = (self.posted - 1) % self.RING
+        self.flush()
+        counts = self.everyone[k].view(self.world, 2).cpu()
         return (int(counts[:self.rank, 0].sum()), int(counts[:self.rank, 1].sum()), int(counts[:, 0].sum()),
                 int(counts[:, 1].sum()))
 

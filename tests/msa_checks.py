@@ -190,6 +190,21 @@ def check_narrow_off(lib, seed=12, n_cases=15):
             ctx.close()
 
 
+def check_row_slices(lib, seed=14, n_cases=15):
+    """EDSB_DEBUG_ROW_SLICES=n: k_scan splits the rows into n slices that OR their mismatch bits together
+    (what a narrow column shard of a deep alignment uses)."""
+    for slices in ("2", "5"):
+        os.environ["EDSB_DEBUG_ROW_SLICES"] = slices
+        try:
+            ctx = lib.context()
+        finally:
+            del os.environ["EDSB_DEBUG_ROW_SLICES"]
+        try:
+            check_random_against_oracle(ctx, seed, n_cases, max_rows=40, max_cols=120, ls=(0, 3, 10))
+        finally:
+            ctx.close()
+
+
 def shard_concat(ctx, dev, idx, cuts, halo, l):
     """Run every shard [cuts[i], cuts[i+1]) with `halo` columns on each side; concatenated outputs."""
     C = idx["n_cols"]

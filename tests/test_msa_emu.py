@@ -50,6 +50,10 @@ def test_narrow_path_off():
     msa_checks.check_narrow_off(emu_lib.lib(), n_cases=6)
 
 
+def test_row_sliced_scan():
+    msa_checks.check_row_slices(emu_lib.lib(), n_cases=3)
+
+
 def test_shards(ctx):
     msa_checks.check_shards(ctx, on_gpu=False, seed=2, n_cases=12, max_cols=150)
 

@@ -56,6 +56,10 @@ def test_narrow_path_off(lib):
     msa_checks.check_narrow_off(lib, n_cases=60)
 
 
+def test_row_sliced_scan(lib):
+    msa_checks.check_row_slices(lib, n_cases=60)
+
+
 def test_shards(ctx):
     msa_checks.check_shards(ctx, on_gpu=True, seed=2, n_cases=80, max_cols=2000)
 
