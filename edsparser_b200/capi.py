@@ -138,9 +138,11 @@ def _host_bytes(lib, buf):
 
 def _as_pointer(data):
     """(address, length, keepalive) of bytes / bytearray / numpy / torch host data."""
-    if isinstance(data, (bytes, bytearray)):
-        arr = (ctypes.c_char * len(data)).from_buffer_copy(data) if isinstance(data, bytes) else (
-            ctypes.c_char * len(data)).from_buffer(data)
+    if isinstance(data, bytes):  # read-only input: the object's own buffer, no copy
+        ref = ctypes.c_char_p(data)
+        return ctypes.cast(ref, ctypes.c_void_p).value or 0, len(data), (ref, data)
+    if isinstance(data, bytearray):
+        arr = (ctypes.c_char * len(data)).from_buffer(data)
         return ctypes.addressof(arr), len(data), arr
     if hasattr(data, "data_ptr"):  # torch tensor (host, uint8)
         return data.data_ptr(), data.numel() * data.element_size(), data
@@ -296,6 +298,17 @@ class Context:
         if nsv.value:
             ctypes.CDLL(None).free(sv)
         return _host_bytes(self.lib, e), _host_bytes(self.lib, s), st.as_dict(), lines
+
+    def vcf_transform_host_raw(self, vcf_addr, vcf_n, fa_addr, fa_n, l=0):
+        """The bare C call on (address, length) pairs of host memory; outputs are freed, only sizes and stats are
+        returned (tools/bench_vcf.py's host-to-host timing: no Python-side copies inside the timed region)."""
+        e, s, st = Buffer(), Buffer(), VcfStats()
+        self.lib.check(self.lib.L.eds_vcf_transform_host(self.handle, vcf_addr, vcf_n, fa_addr, fa_n, l, ctypes.byref(e),
+                                                         ctypes.byref(s), ctypes.byref(st), None, None))
+        sizes = (int(e.bytes), int(s.bytes))
+        self.lib.L.eds_buffer_free_host(ctypes.byref(e))
+        self.lib.L.eds_buffer_free_host(ctypes.byref(s))
+        return sizes, st.as_dict()
 
     def upload(self, data):
         """host bytes -> Buffer over fresh device memory (16-byte aligned and padded); free with device_free."""
