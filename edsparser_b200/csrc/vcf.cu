@@ -530,14 +530,23 @@ __device__ __forceinline__ u64 gt_record(const uint8_t* t, u64 text_chunks, cons
                 }
                 if (regular) {
                     uint32_t ref4 = 0, alt4 = 0, more = 0;
+                    if (nalts == 1u) {  // biallelic site: a digit other than 1 is REF (0, or past the ALT list)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint32_t d0 = xs[i] & 0xfu, d1 = (xs[i] >> 16) & 0xfu;
-                        d0 = d0 <= nalts ? d0 : 0u;
-                        d1 = d1 <= nalts ? d1 : 0u;
-                        ref4 |= (uint32_t)(d0 == 0u || d1 == 0u) << i;
-                        alt4 |= (uint32_t)(d0 == 1u || d1 == 1u) << i;
-                        more |= (d0 | d1) >> 1;
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t dd = xs[i] & 0x000f000fu;
+                            ref4 |= (uint32_t)(dd != 0x00010001u) << i;
+                            alt4 |= (uint32_t)((dd & 0xffffu) == 1u || (dd >> 16) == 1u) << i;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            uint32_t d0 = xs[i] & 0xfu, d1 = (xs[i] >> 16) & 0xfu;
+                            d0 = d0 <= nalts ? d0 : 0u;
+                            d1 = d1 <= nalts ? d1 : 0u;
+                            ref4 |= (uint32_t)(d0 == 0u || d1 == 0u) << i;
+                            alt4 |= (uint32_t)(d0 == 1u || d1 == 1u) << i;
+                            more |= (d0 | d1) >> 1;
+                        }
                     }
                     const uint32_t w = (uint32_t)(first >> 5), sh = (uint32_t)(first & 31);
                     if (ref4) or_into<kShared>(&dst[w], ref4 << sh);
@@ -850,6 +859,26 @@ __global__ void k_emit_ref(Fasta fa, u64 n_bases, const u64* g_from, const u64* 
     }
 }
 
+// DW digits and the ',' of one id-text table entry into the stage at byte offset q: DW + 1 byte stores, no branches
+template <uint32_t DW>
+__device__ __forceinline__ void put_id(uint8_t* stage, uint32_t q, u64 e) {
+    const uint32_t lo4 = (uint32_t)e, hi4 = (uint32_t)(e >> 32);
+#ifdef EDSB_EMU
+    uint8_t* const d = stage + q;
+#pragma unroll
+    for (uint32_t j = 0; j <= DW; ++j) d[j] = (uint8_t)((j < 4u ? lo4 >> (8u * j) : hi4 >> (8u * (j - 4u))));
+#else
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(stage) + q;
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(lo4) : "memory");
+    asm volatile("st.shared.u8 [%0+1], %1;" ::"r"(a), "r"(lo4 >> 8) : "memory");
+    if (DW >= 2u) asm volatile("st.shared.u8 [%0+2], %1;" ::"r"(a), "r"(lo4 >> 16) : "memory");
+    if (DW >= 3u) asm volatile("st.shared.u8 [%0+3], %1;" ::"r"(a), "r"(lo4 >> 24) : "memory");
+    if (DW >= 4u) asm volatile("st.shared.u8 [%0+4], %1;" ::"r"(a), "r"(hi4) : "memory");
+    if (DW >= 5u) asm volatile("st.shared.u8 [%0+5], %1;" ::"r"(a), "r"(hi4 >> 8) : "memory");
+    if (DW >= 6u) asm volatile("st.shared.u8 [%0+6], %1;" ::"r"(a), "r"(hi4 >> 16) : "memory");
+#endif
+}
+
 // warp per entry: braces and "{0}" of the common text, then the group: {hap,hap,...} and {ids}{ids}...
 __global__ void k_emit_groups(const uint8_t* t, Fasta fa, GroupView gv, const uint32_t* g_first, uint32_t n_groups,
                               const u64* canon, const uint32_t* hap_len, const uint8_t* kept, const uint32_t* slot_bits,
@@ -916,10 +945,28 @@ __global__ void k_emit_groups(const uint8_t* t, Fasta fa, GroupView gv, const ui
                     // digits come from the id table (L1-resident), offsets from a popcount when the word's ids share a width
                     const uint32_t my_off = phase + open + (incl - mine);
                     const uint32_t lo_id = w * 32u + 1u, wl = decimal_width(lo_id);
-                    const uint32_t my_dw = wl == decimal_width(lo_id + 31u) ? wl : 0u;
+                    const uint32_t my_dw = (wl == decimal_width(lo_id + 31u) && wl <= 6u) ? wl : 0u;
                     const uint32_t end_q = (uint32_t)(end - gpos) + phase;
                     const uint32_t live = __ballot_sync(0xffffffffu, v != 0);
                     const uint32_t id0 = w0 * 32u + lane + 1u, lt = lanemask_lt();
+                    if (tile < 1536u) {
+                        // sparse round (rare-variant carriers): every lane renders the few ids of its own word
+                        uint32_t q = my_off;
+                        for (uint32_t bits = v; bits; bits &= bits - 1) {
+                            const uint32_t id = w * 32u + (uint32_t)__ffs((int)bits);
+                            const u64 e = __ldg(id_text + id);
+                            uint32_t dw = (uint32_t)(e >> 56);
+                            if (dw) {
+                                uint8_t* const d = stage + q;
+                                for (uint32_t j = 0; j <= dw; ++j) d[j] = (uint8_t)(e >> (8u * j));
+                            } else {
+                                dw = decimal_width(id);
+                                write_decimal(stage + q, id, dw);
+                                stage[q + dw] = (uint8_t)',';
+                            }
+                            q += dw + 1u;
+                        }
+                    } else
                     for (uint32_t rest = live; rest; rest &= rest - 1) {
                         const int k = __ffs((int)rest) - 1;
                         const uint32_t wk = __shfl_sync(0xffffffffu, v, k);
@@ -927,30 +974,19 @@ __global__ void k_emit_groups(const uint8_t* t, Fasta fa, GroupView gv, const ui
                         const uint32_t dwk = __shfl_sync(0xffffffffu, my_dw, k);
                         if ((wk >> lane) & 1u) {
                             const uint32_t id = id0 + (uint32_t)k * 32u;
-                            const uint32_t below = wk & lt;
-                            const uint32_t q = base_k + (dwk ? (uint32_t)__popc(below) * (dwk + 1u) : word_id_bytes(w0 + (uint32_t)k, below));
-                            const u64 e = __ldg(id_text + id);  // digits, then ','
-                            const uint32_t lo4 = (uint32_t)e, hi4 = (uint32_t)(e >> 32), dw = hi4 >> 24;
-                            uint8_t* const d = stage + q;
-                            if (dw == 4u) {
-                                d[0] = (uint8_t)lo4; d[1] = (uint8_t)(lo4 >> 8); d[2] = (uint8_t)(lo4 >> 16); d[3] = (uint8_t)(lo4 >> 24);
-                                d[4] = (uint8_t)hi4;
-                            } else if (dw == 3u) {
-                                d[0] = (uint8_t)lo4; d[1] = (uint8_t)(lo4 >> 8); d[2] = (uint8_t)(lo4 >> 16); d[3] = (uint8_t)(lo4 >> 24);
-                            } else if (dw == 0u) {  // more than six digits: rendered here
+                            const uint32_t below = (uint32_t)__popc(wk & lt);
+                            // dwk is warp-uniform; most ids of a wide matrix have four digits
+                            if (dwk == 4u) put_id<4>(stage, base_k + below * 5u, __ldg(id_text + id));
+                            else if (dwk == 3u) put_id<3>(stage, base_k + below * 4u, __ldg(id_text + id));
+                            else if (dwk == 5u) put_id<5>(stage, base_k + below * 6u, __ldg(id_text + id));
+                            else if (dwk == 2u) put_id<2>(stage, base_k + below * 3u, __ldg(id_text + id));
+                            else if (dwk == 6u) put_id<6>(stage, base_k + below * 7u, __ldg(id_text + id));
+                            else if (dwk == 1u) put_id<1>(stage, base_k + below * 2u, __ldg(id_text + id));
+                            else {  // the word straddles a power of ten, or more than six digits
+                                uint8_t* const d = stage + base_k + word_id_bytes(w0 + (uint32_t)k, wk & lt);
                                 const uint32_t w7 = decimal_width(id);
                                 write_decimal(d, id, w7);
                                 d[w7] = (uint8_t)',';
-                            } else {
-                                d[0] = (uint8_t)lo4;
-                                d[1] = (uint8_t)(lo4 >> 8);
-                                if (dw >= 2u) d[2] = (uint8_t)(lo4 >> 16);
-                                if (dw >= 5u) {
-                                    d[3] = (uint8_t)(lo4 >> 24);
-                                    d[4] = (uint8_t)hi4;
-                                    d[5] = (uint8_t)(hi4 >> 8);
-                                    if (dw == 6u) d[6] = (uint8_t)(hi4 >> 16);
-                                }
                             }
                         }
                     }
