@@ -39,7 +39,7 @@ def test_bad_inputs(ctx):
 
 
 def test_hash_collision_fallback():
-    msa_checks.check_hash_collision_fallback(emu_lib.lib(), n_cases=10)
+    msa_checks.check_hash_collision_fallback(emu_lib.lib(), n_cases=6)
 
 
 def test_wide_alphabet(ctx):
@@ -47,7 +47,7 @@ def test_wide_alphabet(ctx):
 
 
 def test_narrow_path_off():
-    msa_checks.check_narrow_off(emu_lib.lib(), n_cases=6)
+    msa_checks.check_narrow_off(emu_lib.lib(), n_cases=3)
 
 
 def test_row_sliced_scan():

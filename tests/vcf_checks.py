@@ -145,11 +145,12 @@ def check_wide(ctx, n_samples=300, n_sites=12, seed=5):
         check_case(ctx, vcf, fa, l, None)
 
 
-def synth_vcf(n_bases, n_sites, n_samples, seed=1, wrap=60, overlap_frac=0.01):
+def synth_vcf(n_bases, n_sites, n_samples, seed=1, wrap=60, overlap_frac=0.01, same_pos=True):
     """BASELINE config 5 shape at any size, numpy: random ACGT reference (FASTA wrap 60); sorted distinct
     sites, 80 % SNP / 10 % insertion (1-5 bp) / 10 % deletion (2-5 bp REF); a 1 % sub-population of same-position /
     adjacent companion records (grouping + the unstable sort); phased diploid genotypes, per-site ALT frequency
-    ~ Beta(0.3, 2.0). Returns (vcf bytes, fasta bytes)."""
+    ~ Beta(0.3, 2.0). same_pos=False keeps the companions at the next position only (no ties for the unstable sort).
+    Returns (vcf bytes, fasta bytes)."""
     import numpy as np
 
     rng = np.random.default_rng(seed)
@@ -175,7 +176,7 @@ def synth_vcf(n_bases, n_sites, n_samples, seed=1, wrap=60, overlap_frac=0.01):
             a = r[0]
         head.append("chr1\t%d\t.\t%s\t%s\t.\tPASS\t.\tGT" % (p, r, a))
         if rng.random() < overlap_frac:
-            q = p + int(rng.integers(0, 2))
+            q = p + (int(rng.integers(0, 2)) if same_pos else 1)
             r2 = refs[q - 1:q].decode()
             a2 = letters[(letters.index(r2) + 1) % 4] + ("" if rng.random() < 0.5 else "T")
             head.append("chr1\t%d\t.\t%s\t%s\t.\tPASS\t.\tGT" % (q, r2, a2))
@@ -198,3 +199,41 @@ def synth_vcf(n_bases, n_sites, n_samples, seed=1, wrap=60, overlap_frac=0.01):
             out.append(rows[i].tobytes())
             out.append(b"\n")
     return b"".join(out), fa
+
+
+def conserved_text(eds, seds):
+    """Concatenation of the symbols whose only source set is {0} (the common text between variant groups)."""
+    syms = eds[1:-1].split(b"}{") if eds else []
+    sets = seds[1:-1].split(b"}{") if seds else []
+    out, k = [], 0
+    for sym in syms:
+        n = sym.count(b",") + 1
+        if n == 1 and sets[k] == b"0":
+            out.append(sym)
+        k += n
+    assert k == len(sets)
+    return b"".join(out)
+
+
+def expected_conserved_text(vcf, fa):
+    """The reference outside the groups of overlapping records, from the record heads alone (sorted input)."""
+    ref = fa.split(b"\n", 1)[1].replace(b"\n", b"")
+    spans = []
+    for line in vcf.split(b"\n"):
+        if not line or line[:1] == b"#":
+            continue
+        f = line.split(b"\t", 5)
+        spans.append((int(f[1]) - 1, int(f[1]) - 1 + len(f[3])))
+    spans.sort(key=lambda t: t[0])
+    out, cursor, i = [], 0, 0
+    while i < len(spans):
+        lo, hi = spans[i]
+        j = i + 1
+        while j < len(spans) and spans[j][0] < hi:
+            hi = max(hi, spans[j][1])
+            j += 1
+        out.append(ref[cursor:lo])
+        cursor = hi
+        i = j
+    out.append(ref[cursor:])
+    return b"".join(out)
