@@ -117,6 +117,19 @@ def check_edges(ctx):
     run(b"chr1\t5\t.\tA\tT\t.\t.\t.\tGT\t0|1\t1|1\t0|0\nchr1\t5\t.\tA\tG\t.\t.\t.\tGT\t1|0\t0|0\t0|1\n", l=4)
     run(b"chr1\t5\t.\tA\tA\t.\t.\t.\tGT\t0|1\t1|1\t0|0\n")       # ALT equals the reference span
     run(b"chr1\t5\t.\tG\tT,T\t.\t.\t.\tGT\t0|1\t2|2\t0|0\n")     # REF field differs from the FASTA, duplicate ALTs
+    # degenerate VCF texts
+    check_case(ctx, b"", FA, 0, None)                              # empty file: the reference as one symbol
+    check_case(ctx, b"\n\n", FA, 0, None)
+    check_case(ctx, b"##only a header", FA, 0, None)
+    check_case(ctx, HDR, FA, 3, None)                             # no records, through the merge
+    # a later record with far more sample columns than the first one: the genotype kernel is re-run with wider bitsets
+    wide = b"\t".join(b"%d|%d" % (i % 2, (i // 2) % 2) for i in range(70))
+    run(b"chr1\t3\t.\tG\tT\t.\t.\t.\tGT\t0|1\t1|1\n" + b"chr1\t9\t.\tA\tC,G\t.\t.\t.\tGT\t" + wide + b"\n" +
+        b"chr1\t15\t.\tG\tT\t.\t.\t.\tGT\t1|1\n")
+    # a line exactly one 16-byte vector / one 512-byte tile long around the genotype columns
+    for pad in (0, 1, 15, 16, 17):
+        info = b"X" * (460 + pad)
+        run(b"chr1\t3\t.\tG\tT\t.\t.\t" + info + b"\tGT\t0|1\t1|1\t0|0\n")
     # FASTA edge cases
     run(b"chr1\t3\t.\tG\tT\t.\t.\t.\tGT\t0|1\t1|1\t0|0\n", fa=b">a\nACGTAC\n>b\nGGGGGG\n")  # second record ignored
     run(b"chr1\t3\t.\tG\tT\t.\t.\t.\tGT\t0|1\t1|1\t0|0\n", fa=b">a\nACGT\nAC\n\n\n")            # trailing blank lines
