@@ -26,7 +26,7 @@ EXPORTS = [
     "eds_ctx_set_tuning", "eds_ctx_set_profiling", "eds_ctx_kernel_times", "eds_msa_index_host",
     "eds_msa_index_free", "eds_msa_transform_device", "eds_msa_transform_host", "eds_msa_conserved_bits",
     "eds_msa_synth_device", "eds_msa_synth_free", "eds_buffer_to_host", "eds_buffer_free_host", "eds_leds_merge_host", "eds_is_leds_host",
-    "eds_vcf_transform_host", "eds_vcf_transform_device", "eds_device_upload", "eds_device_free",
+    "eds_vcf_transform_host", "eds_vcf_transform_host_view", "eds_vcf_transform_device", "eds_device_upload", "eds_device_free",
 ]
 
 
@@ -111,6 +111,7 @@ class Library:
         L.eds_is_leds_host.argtypes = [vp, vp, u64, u32, P(i32)]
         L.eds_vcf_transform_host.argtypes = [vp, vp, u64, vp, u64, u32, P(Buffer), P(Buffer), P(VcfStats),
                                              P(P(ctypes.c_uint64)), P(u64)]
+        L.eds_vcf_transform_host_view.argtypes = L.eds_vcf_transform_host.argtypes
         L.eds_vcf_transform_device.argtypes = [vp, vp, u64, vp, u64, P(Buffer), P(Buffer), P(VcfStats)]
         L.eds_device_upload.argtypes = [vp, vp, u64, P(vp)]
         L.eds_device_free.argtypes = [vp, vp]
@@ -298,6 +299,26 @@ class Context:
         if nsv.value:
             ctypes.CDLL(None).free(sv)
         return _host_bytes(self.lib, e), _host_bytes(self.lib, s), st.as_dict(), lines
+
+    def vcf_transform_host_view(self, vcf, fasta, l=0):
+        """Like vcf_transform_host, through eds_vcf_transform_host_view (results are views into pinned memory owned by
+        the context; copied into bytes here)."""
+        va, vn, k1 = _as_pointer(vcf)
+        fa, fn, k2 = _as_pointer(fasta)
+        e, s, st = Buffer(), Buffer(), VcfStats()
+        self.lib.check(self.lib.L.eds_vcf_transform_host_view(self.handle, va, vn, fa, fn, l, ctypes.byref(e), ctypes.byref(s),
+                                                              ctypes.byref(st), None, None))
+        del k1, k2
+        eds = bytes((ctypes.c_ubyte * e.bytes).from_address(e.data)) if e.bytes else b""
+        seds = bytes((ctypes.c_ubyte * s.bytes).from_address(s.data)) if s.bytes else b""
+        return eds, seds, st.as_dict()
+
+    def vcf_transform_host_view_raw(self, vcf_addr, vcf_n, fa_addr, fa_n, l=0):
+        """The bare C call of the view form: (eds bytes, seds bytes), stats; nothing to free."""
+        e, s, st = Buffer(), Buffer(), VcfStats()
+        self.lib.check(self.lib.L.eds_vcf_transform_host_view(self.handle, vcf_addr, vcf_n, fa_addr, fa_n, l, ctypes.byref(e),
+                                                              ctypes.byref(s), ctypes.byref(st), None, None))
+        return (int(e.bytes), int(s.bytes)), st.as_dict()
 
     def vcf_transform_host_raw(self, vcf_addr, vcf_n, fa_addr, fa_n, l=0):
         """The bare C call on (address, length) pairs of host memory; outputs are freed, only sizes and stats are

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <chrono>
+#include <functional>
 #include <new>
 #include <stdio.h>
 #include <string>
@@ -135,6 +136,8 @@ void eds_ctx_destroy(eds_ctx* ctx) {
     delete ctx->vcf;
     for (auto& b : ctx->vcf_in) b.release();
     for (auto& b : ctx->vcf_out) b.release();
+    for (void* h : ctx->host_out)
+        if (h) cudaFreeHost(h);
     ctx->synth_text.release();
     ctx->file_buf.release();
     ctx->clock.release();
@@ -384,9 +387,29 @@ eds_status eds_vcf_transform_device(eds_ctx* ctx, const uint8_t* vcf, uint64_t v
     });
 }
 
-eds_status eds_vcf_transform_host(eds_ctx* ctx, const uint8_t* vcf, uint64_t vcf_bytes, const uint8_t* fasta,
+}  // extern "C"
+
+namespace {
+// pinned, ctx-owned destination of a device buffer (grow-only)
+uint8_t* to_host_view(eds_ctx* ctx, int which, const eds_buffer& dev) {
+    if (ctx->host_out_cap[which] < dev.bytes + 1) {
+        if (ctx->host_out[which]) cudaFreeHost(ctx->host_out[which]);
+        ctx->host_out[which] = nullptr;
+        ctx->host_out_cap[which] = 0;
+        const size_t want = ((dev.bytes + dev.bytes / 8 + 4096) / 4096) * 4096;
+        EDSB_CUDA(cudaMallocHost(&ctx->host_out[which], want));
+        ctx->host_out_cap[which] = want;
+    }
+    if (dev.bytes) {
+        EDSB_CUDA(cudaMemcpyAsync(ctx->host_out[which], dev.data, dev.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        EDSB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return static_cast<uint8_t*>(ctx->host_out[which]);
+}
+
+eds_status vcf_transform_host_impl(eds_ctx* ctx, const uint8_t* vcf, uint64_t vcf_bytes, const uint8_t* fasta,
                                   uint64_t fasta_bytes, uint32_t l, eds_buffer* eds_out, eds_buffer* seds_out,
-                                  eds_vcf_stats* stats, uint64_t** sv_lines, uint64_t* n_sv_lines) {
+                                  eds_vcf_stats* stats, uint64_t** sv_lines, uint64_t* n_sv_lines, bool view) {
     if (sv_lines) *sv_lines = nullptr;
     if (n_sv_lines) *n_sv_lines = 0;
     eds_status rc = guarded([&] {
@@ -396,10 +419,20 @@ eds_status eds_vcf_transform_host(eds_ctx* ctx, const uint8_t* vcf, uint64_t vcf
         eds_out->data = seds_out->data = nullptr;
         eds_out->bytes = seds_out->bytes = 0;
         if (stats) memset(stats, 0, sizeof(*stats));
+        const bool trace = getenv("EDSB_TRACE_HOST") != nullptr;
+        auto t0 = std::chrono::steady_clock::now();
+        auto lap = [&](const char* what) {
+            if (!trace) return;
+            cudaStreamSynchronize(ctx->stream);
+            const auto t1 = std::chrono::steady_clock::now();
+            fprintf(stderr, "[edsb] %-22s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+            t0 = t1;
+        };
         ctx->vcf_in[0].reserve(vcf_bytes + 16);
         ctx->vcf_in[1].reserve(fasta_bytes + 16);
         if (vcf_bytes) EDSB_CUDA(cudaMemcpyAsync(ctx->vcf_in[0].p, vcf, vcf_bytes, cudaMemcpyHostToDevice, ctx->stream));
         if (fasta_bytes) EDSB_CUDA(cudaMemcpyAsync(ctx->vcf_in[1].p, fasta, fasta_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        lap("H2D");
         std::vector<uint64_t> sv;
         eds_buffer d_eds{nullptr, 0}, d_seds{nullptr, 0};
         ctx->vcf->transform_device(ctx->vcf_in[0].as<uint8_t>(), vcf_bytes, ctx->vcf_in[1].as<uint8_t>(), fasta_bytes, &d_eds,
@@ -410,17 +443,32 @@ eds_status eds_vcf_transform_host(eds_ctx* ctx, const uint8_t* vcf, uint64_t vcf
             memcpy(*sv_lines, sv.data(), sv.size() * sizeof(uint64_t));
             *n_sv_lines = sv.size();
         }
+        lap("front end");
         if (l == 0) {
-            eds_out->data = to_host(ctx, d_eds);
+            eds_out->data = view ? to_host_view(ctx, 0, d_eds) : to_host(ctx, d_eds);
             eds_out->bytes = d_eds.bytes;
-            seds_out->data = to_host(ctx, d_seds);
+            seds_out->data = view ? to_host_view(ctx, 1, d_seds) : to_host(ctx, d_seds);
             seds_out->bytes = d_seds.bytes;
+            lap("D2H");
         } else {
             // parse_vcf_to_leds_streaming :750-752: LINEAR merge of the text just produced, still in HBM
             uint32_t rounds = 0;
             const uint32_t launches = ctx->clock.launches;
+            std::function<uint8_t*(int, uint64_t)> sink;
+            if (view)
+                sink = [ctx](int which, uint64_t bytes) -> uint8_t* {
+                    if (ctx->host_out_cap[which] < bytes + 1) {
+                        if (ctx->host_out[which]) cudaFreeHost(ctx->host_out[which]);
+                        ctx->host_out[which] = nullptr;
+                        ctx->host_out_cap[which] = 0;
+                        const size_t want = ((bytes + bytes / 8 + 4096) / 4096) * 4096;
+                        EDSB_CUDA(cudaMallocHost(&ctx->host_out[which], want));
+                        ctx->host_out_cap[which] = want;
+                    }
+                    return static_cast<uint8_t*>(ctx->host_out[which]);
+                };
             ctx->leds->merge_host(d_eds.data, d_eds.bytes, d_seds.data, d_seds.bytes, l, true, 0, eds_out, seds_out, &rounds,
-                                  nullptr, true);
+                                  nullptr, true, sink);
             if (stats) {
                 stats->leds_rounds = rounds;
                 stats->gpu_launches = launches + ctx->clock.launches;
@@ -428,10 +476,30 @@ eds_status eds_vcf_transform_host(eds_ctx* ctx, const uint8_t* vcf, uint64_t vcf
         }
     });
     if (rc != EDS_OK) {
-        if (eds_out) eds_buffer_free_host(eds_out);
-        if (seds_out) eds_buffer_free_host(seds_out);
+        if (view) {
+            if (eds_out) *eds_out = eds_buffer{nullptr, 0};
+            if (seds_out) *seds_out = eds_buffer{nullptr, 0};
+        } else {
+            if (eds_out) eds_buffer_free_host(eds_out);
+            if (seds_out) eds_buffer_free_host(seds_out);
+        }
     }
     return rc;
+}
+}  // namespace
+
+extern "C" {
+
+eds_status eds_vcf_transform_host(eds_ctx* ctx, const uint8_t* vcf, uint64_t vcf_bytes, const uint8_t* fasta,
+                                  uint64_t fasta_bytes, uint32_t l, eds_buffer* eds_out, eds_buffer* seds_out,
+                                  eds_vcf_stats* stats, uint64_t** sv_lines, uint64_t* n_sv_lines) {
+    return vcf_transform_host_impl(ctx, vcf, vcf_bytes, fasta, fasta_bytes, l, eds_out, seds_out, stats, sv_lines, n_sv_lines, false);
+}
+
+eds_status eds_vcf_transform_host_view(eds_ctx* ctx, const uint8_t* vcf, uint64_t vcf_bytes, const uint8_t* fasta,
+                                       uint64_t fasta_bytes, uint32_t l, eds_buffer* eds_out, eds_buffer* seds_out,
+                                       eds_vcf_stats* stats, uint64_t** sv_lines, uint64_t* n_sv_lines) {
+    return vcf_transform_host_impl(ctx, vcf, vcf_bytes, fasta, fasta_bytes, l, eds_out, seds_out, stats, sv_lines, n_sv_lines, true);
 }
 
 eds_status eds_device_upload(eds_ctx* ctx, const uint8_t* host, uint64_t bytes, uint8_t** device_out) {

@@ -77,6 +77,8 @@ struct eds_ctx {
     edsb::VcfPipeline* vcf = nullptr;
     edsb::DevBuf vcf_in[2];   // eds_vcf_transform_host: the .vcf and .fa bytes on the device
     edsb::DevBuf vcf_out[2];  // EDS / SEDS text of the last VCF transform
+    void* host_out[2] = {nullptr, nullptr};  // pinned host copies of the last result (eds_vcf_transform_host_view), grow-only
+    size_t host_out_cap[2] = {0, 0};
     // synthetic alignment (eds_msa_synth_device)
     edsb::DevBuf synth_text;
     edsb::DevBuf file_buf;  // eds_msa_transform_host: the .msa bytes on the device

@@ -24,6 +24,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -673,13 +674,6 @@ struct Keep {
     }
 };
 
-uint8_t* dup_host(const std::vector<uint8_t>& v) {
-    uint8_t* h = static_cast<uint8_t*>(malloc(v.size() ? v.size() : 1));
-    if (!h) throw std::bad_alloc();
-    if (!v.empty()) memcpy(h, v.data(), v.size());
-    return h;
-}
-
 }  // namespace
 
 struct LedsPipeline::Bufs {
@@ -696,7 +690,8 @@ LedsPipeline::~LedsPipeline() { delete bufs_; }
 
 void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const uint8_t* seds_in, uint64_t seds_bytes,
                               uint32_t l, bool compact, uint64_t max_output_bytes, eds_buffer* leds_out,
-                              eds_buffer* seds_out, uint32_t* rounds_out, int* check_only, bool input_on_device) {
+                              eds_buffer* seds_out, uint32_t* rounds_out, int* check_only, bool input_on_device,
+                              const std::function<uint8_t*(int, uint64_t)>& sink) {
     if (l == 0) throw std::invalid_argument("context_length must be > 0 for l-EDS transformation");  // eds_transforms.cpp:322-324
     if (eds_bytes >= 0xfffffff0ull || seds_bytes >= 0xfffffff0ull) throw std::invalid_argument("eds_leds_merge_host: inputs must be below 4 GiB (Length is uint32 in the reference too)");
     const bool linear = seds_in != nullptr;
@@ -905,7 +900,6 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
     }
 
     // ---- emit (EDS::save / save_sources) -------------------------------------------------------------------
-    std::vector<uint8_t> h_eds, h_seds;
     unsigned long long n_falt = 0, eds_total = 0, seds_total = 0;
     if (cur_n) {
         d_falt_off.reserve((size_t)(cur_n + 1) * 8);
@@ -947,19 +941,34 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
                         id_of, d_seds_off.as<unsigned long long>(), d_sout.as<uint8_t>());
     }
     LEDS_LAUNCH("k_newline", k_newline, 1, 32, d_out.as<uint8_t>(), eds_total, linear ? d_sout.as<uint8_t>() : nullptr, seds_total);
-    h_eds.resize(eds_total + 1);
-    EDSB_CUDA(cudaMemcpyAsync(h_eds.data(), d_out.p, eds_total + 1, cudaMemcpyDeviceToHost, s));
-    if (linear) {
-        h_seds.resize(seds_total + 1);
-        EDSB_CUDA(cudaMemcpyAsync(h_seds.data(), d_sout.p, seds_total + 1, cudaMemcpyDeviceToHost, s));
+    // results straight into their final host buffers: malloc'd (the caller frees them), or wherever `sink` puts them
+    // (eds_vcf_transform_host_view: pinned memory kept by the context)
+    const uint64_t eds_bytes_out = eds_total + 1, seds_bytes_out = linear ? seds_total + 1 : 0;
+    auto place = [&](int which, uint64_t bytes) -> uint8_t* {
+        uint8_t* p = sink ? sink(which, bytes) : static_cast<uint8_t*>(malloc(bytes ? bytes : 1));
+        if (!p) throw std::bad_alloc();
+        return p;
+    };
+    uint8_t* h_eds_p = place(0, eds_bytes_out);
+    uint8_t* h_seds_p = nullptr;
+    try {
+        h_seds_p = place(1, seds_bytes_out);
+        EDSB_CUDA(cudaMemcpyAsync(h_eds_p, d_out.p, eds_bytes_out, cudaMemcpyDeviceToHost, s));
+        if (linear) EDSB_CUDA(cudaMemcpyAsync(h_seds_p, d_sout.p, seds_bytes_out, cudaMemcpyDeviceToHost, s));
+        EDSB_CUDA(cudaStreamSynchronize(s));
+        EDSB_CUDA(cudaGetLastError());
+    } catch (...) {
+        if (!sink) {
+            free(h_eds_p);
+            free(h_seds_p);
+        }
+        throw;
     }
-    EDSB_CUDA(cudaStreamSynchronize(s));
-    EDSB_CUDA(cudaGetLastError());
     clk.resolve();
-    leds_out->data = dup_host(h_eds);
-    leds_out->bytes = h_eds.size();
-    seds_out->data = dup_host(h_seds);
-    seds_out->bytes = h_seds.size();
+    leds_out->data = h_eds_p;
+    leds_out->bytes = eds_bytes_out;
+    seds_out->data = h_seds_p;
+    seds_out->bytes = seds_bytes_out;
 #undef LEDS_SCAN
 #undef LEDS_LAUNCH
 }

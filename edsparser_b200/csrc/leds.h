@@ -1,5 +1,6 @@
 // Host-side launcher of the l-EDS merge kernels (leds.cu): eds_to_leds_linear / eds_to_leds_cartesian.
 #pragma once
+#include <functional>
 #include <stdexcept>
 
 #include "ctx.h"
@@ -20,7 +21,9 @@ class LedsPipeline {
     // Host text in, malloc'd host text out.
     void merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const uint8_t* seds_in, uint64_t seds_bytes, uint32_t l,
                     bool compact, uint64_t max_output_bytes, eds_buffer* leds_out, eds_buffer* seds_out,
-                    uint32_t* rounds_out, int* check_only = nullptr, bool input_on_device = false);
+                    uint32_t* rounds_out, int* check_only = nullptr, bool input_on_device = false,
+                    const std::function<uint8_t*(int, uint64_t)>& sink = {});
+    // sink(which, bytes): where result `which` (0 l-EDS, 1 SEDS) goes instead of a fresh malloc'd buffer
     // check_only != nullptr: stop after the first round's pair selection; *check_only = 1 iff no pair exists
     // input_on_device: eds_in / seds_in are device pointers (the VCF front end hands its output over in HBM)
 

@@ -144,12 +144,12 @@ std::pair<std::string, std::string> vcf_transform(std::istream& vcf_stream, std:
     // the reference reads the FASTA first (vcf_transforms.cpp:683), so its errors win; both streams end up consumed
     const std::string fasta = slurp(fasta_stream);
     const std::string vcf = slurp(vcf_stream);
-    HostBuf e, s;
+    eds_buffer e{nullptr, 0}, s{nullptr, 0};  // views into pinned memory kept by the context: nothing to free
     eds_vcf_stats st;
     uint64_t* sv = nullptr;
     uint64_t n_sv = 0;
-    const eds_status rc = eds_vcf_transform_host(t_session.get(), reinterpret_cast<const uint8_t*>(vcf.data()), vcf.size(),
-                                                 reinterpret_cast<const uint8_t*>(fasta.data()), fasta.size(), l, &e.b, &s.b, &st, &sv, &n_sv);
+    const eds_status rc = eds_vcf_transform_host_view(t_session.get(), reinterpret_cast<const uint8_t*>(vcf.data()), vcf.size(),
+                                                      reinterpret_cast<const uint8_t*>(fasta.data()), fasta.size(), l, &e, &s, &st, &sv, &n_sv);
     for (uint64_t i = 0; i < n_sv; ++i) warn_skipped_sv(vcf, sv[i]);
     std::free(sv);
     if (stats && (rc == EDS_OK || st.total_variants)) {  // the reference fills the counters before the merge can throw
@@ -160,7 +160,7 @@ std::pair<std::string, std::string> vcf_transform(std::istream& vcf_stream, std:
         stats->variant_groups = st.variant_groups;
     }
     if (rc != EDS_OK) rethrow(rc);
-    return {e.str(), s.str()};
+    return {std::string(reinterpret_cast<const char*>(e.data), e.bytes), std::string(reinterpret_cast<const char*>(s.data), s.bytes)};
 }
 
 }  // namespace

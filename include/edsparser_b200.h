@@ -198,6 +198,14 @@ eds_status eds_vcf_transform_host(eds_ctx* ctx, const uint8_t* vcf, uint64_t vcf
                                   uint64_t fasta_bytes, uint32_t l, eds_buffer* eds_out, eds_buffer* seds_out,
                                   eds_vcf_stats* stats, uint64_t** sv_lines, uint64_t* n_sv_lines);
 
+/* Same call, but the results are VIEWS into pinned host memory owned by the ctx (grow-only, reused by every call):
+ * valid until the next eds_vcf_transform_host_view on this ctx, never to be freed by the caller. A fresh malloc'd
+ * gigabyte costs more in first-touch page faults and pageable copies than the whole device pipeline; a caller that
+ * streams the text on (writes the files, feeds a socket) should use this form. */
+eds_status eds_vcf_transform_host_view(eds_ctx* ctx, const uint8_t* vcf, uint64_t vcf_bytes, const uint8_t* fasta,
+                                       uint64_t fasta_bytes, uint32_t l, eds_buffer* eds_out, eds_buffer* seds_out,
+                                       eds_vcf_stats* stats, uint64_t** sv_lines, uint64_t* n_sv_lines);
+
 /* l == 0 only, everything in device memory: both inputs 16-byte aligned and readable up to the next
  * 16-byte boundary (any cudaMalloc'd buffer is); outputs are owned by the ctx until its next VCF call. */
 eds_status eds_vcf_transform_device(eds_ctx* ctx, const uint8_t* vcf, uint64_t vcf_bytes, const uint8_t* fasta,

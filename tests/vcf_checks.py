@@ -49,6 +49,7 @@ def check_case(ctx, vcf, fa, l, exp):
         assert "Error: " + ei.value.message == exp["error"], (ei.value.message, exp["error"])
         return "error"
     eds, seds, st, sv_lines = ctx.vcf_transform_host(vcf, fa, l)
+    assert ctx.vcf_transform_host_view(vcf, fa, l)[:2] == (eds, seds)  # pinned-view form of the same call
     assert eds == exp["eds"], (l, eds[:300], exp["eds"][:300])
     assert seds == exp["seds"], (l, seds[:300], exp["seds"][:300])
     assert stats_line(st) == exp["stats"]
