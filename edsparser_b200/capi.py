@@ -25,7 +25,7 @@ EXPORTS = [
     "eds_last_error", "eds_version", "eds_ctx_create", "eds_ctx_destroy", "eds_ctx_synchronize",
     "eds_ctx_set_tuning", "eds_ctx_set_profiling", "eds_ctx_kernel_times", "eds_msa_index_host",
     "eds_msa_index_free", "eds_msa_transform_device", "eds_msa_transform_host", "eds_msa_conserved_bits",
-    "eds_msa_synth_device", "eds_msa_synth_free", "eds_buffer_to_host", "eds_buffer_free_host", "eds_leds_merge_host", "eds_is_leds_host",
+    "eds_msa_synth_device", "eds_msa_synth_free", "eds_buffer_to_host", "eds_buffer_free_host", "eds_leds_merge_host", "eds_leds_merge_host_view", "eds_is_leds_host",
     "eds_vcf_transform_host", "eds_vcf_transform_host_view", "eds_vcf_transform_device", "eds_device_upload", "eds_device_free",
 ]
 
@@ -108,6 +108,7 @@ class Library:
         L.eds_buffer_free_host.argtypes = [P(Buffer)]
         L.eds_buffer_free_host.restype = None
         L.eds_leds_merge_host.argtypes = [vp, vp, u64, vp, u64, u32, i32, u64, P(Buffer), P(Buffer), P(u32)]
+        L.eds_leds_merge_host_view.argtypes = L.eds_leds_merge_host.argtypes
         L.eds_is_leds_host.argtypes = [vp, vp, u64, u32, P(i32)]
         L.eds_vcf_transform_host.argtypes = [vp, vp, u64, vp, u64, u32, P(Buffer), P(Buffer), P(VcfStats),
                                              P(P(ctypes.c_uint64)), P(u64)]
@@ -277,6 +278,27 @@ class Context:
         out, sout = _host_bytes(self.lib, o), _host_bytes(self.lib, so)
         return out, (sout if seds is not None else None), rounds.value
 
+
+    def leds_merge_host_view_raw(self, eds_addr, eds_n, seds_addr, seds_n, l, compact=True, max_output_bytes=0):
+        """The bare C call of the view form on (address, length) pairs: ((leds bytes, seds bytes), rounds)."""
+        o, so, rounds = Buffer(), Buffer(), ctypes.c_uint32()
+        self.lib.check(self.lib.L.eds_leds_merge_host_view(self.handle, eds_addr, eds_n, seds_addr, seds_n, l,
+                                                           1 if compact else 0, max_output_bytes, ctypes.byref(o),
+                                                           ctypes.byref(so), ctypes.byref(rounds)))
+        return (int(o.bytes), int(so.bytes)), rounds.value
+
+    def leds_merge_host_view(self, eds, seds, l, compact=True, max_output_bytes=0):
+        """Like leds_merge_host through eds_leds_merge_host_view (views into pinned memory, copied into bytes here)."""
+        ea, en, k1 = _as_pointer(eds)
+        sa, sn, k2 = _as_pointer(seds) if seds is not None else (None, 0, None)
+        o, so, rounds = Buffer(), Buffer(), ctypes.c_uint32()
+        self.lib.check(self.lib.L.eds_leds_merge_host_view(self.handle, ea, en, sa, sn, l, 1 if compact else 0,
+                                                           max_output_bytes, ctypes.byref(o), ctypes.byref(so),
+                                                           ctypes.byref(rounds)))
+        del k1, k2
+        out = bytes((ctypes.c_ubyte * o.bytes).from_address(o.data)) if o.bytes else b""
+        sout = bytes((ctypes.c_ubyte * so.bytes).from_address(so.data)) if so.bytes else b""
+        return out, (sout if seds is not None else None), rounds.value
 
     def is_leds(self, eds, l):
         ea, en, keep = _as_pointer(eds)

@@ -73,6 +73,19 @@ uint8_t* to_host(eds_ctx* ctx, const eds_buffer& dev) {
     return h;
 }
 
+// where a result goes under the *_view contract: pinned memory kept by the context, grown when needed
+uint8_t* view_slot(eds_ctx* ctx, int which, uint64_t bytes) {
+    if (ctx->host_out_cap[which] < bytes + 1) {
+        if (ctx->host_out[which]) cudaFreeHost(ctx->host_out[which]);
+        ctx->host_out[which] = nullptr;
+        ctx->host_out_cap[which] = 0;
+        const size_t want = ((bytes + bytes / 8 + 4096) / 4096) * 4096;
+        EDSB_CUDA(cudaMallocHost(&ctx->host_out[which], want));
+        ctx->host_out_cap[which] = want;
+    }
+    return static_cast<uint8_t*>(ctx->host_out[which]);
+}
+
 }  // namespace
 
 extern "C" {
@@ -366,6 +379,25 @@ eds_status eds_leds_merge_host(eds_ctx* ctx, const uint8_t* eds_in, uint64_t eds
     return rc;
 }
 
+eds_status eds_leds_merge_host_view(eds_ctx* ctx, const uint8_t* eds_in, uint64_t eds_bytes, const uint8_t* seds_in,
+                                    uint64_t seds_bytes, uint32_t l, int compact, uint64_t max_output_bytes,
+                                    eds_buffer* leds_out, eds_buffer* seds_out, uint32_t* rounds_out) {
+    eds_status rc = guarded([&] {
+        use_device(ctx);
+        if (!eds_in || !leds_out || !seds_out) throw std::invalid_argument("eds_leds_merge_host_view: null argument");
+        leds_out->data = seds_out->data = nullptr;
+        leds_out->bytes = seds_out->bytes = 0;
+        ctx->leds->merge_host(eds_in, eds_bytes, seds_in, seds_bytes, l, compact != 0, max_output_bytes, leds_out, seds_out,
+                              rounds_out, nullptr, false,
+                              [ctx](int which, uint64_t bytes) -> uint8_t* { return view_slot(ctx, which, bytes); });
+    });
+    if (rc != EDS_OK) {
+        if (leds_out) *leds_out = eds_buffer{nullptr, 0};
+        if (seds_out) *seds_out = eds_buffer{nullptr, 0};
+    }
+    return rc;
+}
+
 eds_status eds_is_leds_host(eds_ctx* ctx, const uint8_t* eds_in, uint64_t eds_bytes, uint32_t l, int* is_leds_out) {
     return guarded([&] {
         use_device(ctx);
@@ -392,14 +424,7 @@ eds_status eds_vcf_transform_device(eds_ctx* ctx, const uint8_t* vcf, uint64_t v
 namespace {
 // pinned, ctx-owned destination of a device buffer (grow-only)
 uint8_t* to_host_view(eds_ctx* ctx, int which, const eds_buffer& dev) {
-    if (ctx->host_out_cap[which] < dev.bytes + 1) {
-        if (ctx->host_out[which]) cudaFreeHost(ctx->host_out[which]);
-        ctx->host_out[which] = nullptr;
-        ctx->host_out_cap[which] = 0;
-        const size_t want = ((dev.bytes + dev.bytes / 8 + 4096) / 4096) * 4096;
-        EDSB_CUDA(cudaMallocHost(&ctx->host_out[which], want));
-        ctx->host_out_cap[which] = want;
-    }
+    view_slot(ctx, which, dev.bytes);
     if (dev.bytes) {
         EDSB_CUDA(cudaMemcpyAsync(ctx->host_out[which], dev.data, dev.bytes, cudaMemcpyDeviceToHost, ctx->stream));
         EDSB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -456,17 +481,7 @@ eds_status vcf_transform_host_impl(eds_ctx* ctx, const uint8_t* vcf, uint64_t vc
             const uint32_t launches = ctx->clock.launches;
             std::function<uint8_t*(int, uint64_t)> sink;
             if (view)
-                sink = [ctx](int which, uint64_t bytes) -> uint8_t* {
-                    if (ctx->host_out_cap[which] < bytes + 1) {
-                        if (ctx->host_out[which]) cudaFreeHost(ctx->host_out[which]);
-                        ctx->host_out[which] = nullptr;
-                        ctx->host_out_cap[which] = 0;
-                        const size_t want = ((bytes + bytes / 8 + 4096) / 4096) * 4096;
-                        EDSB_CUDA(cudaMallocHost(&ctx->host_out[which], want));
-                        ctx->host_out_cap[which] = want;
-                    }
-                    return static_cast<uint8_t*>(ctx->host_out[which]);
-                };
+                sink = [ctx](int which, uint64_t bytes) -> uint8_t* { return view_slot(ctx, which, bytes); };
             ctx->leds->merge_host(d_eds.data, d_eds.bytes, d_seds.data, d_seds.bytes, l, true, 0, eds_out, seds_out, &rounds,
                                   nullptr, true, sink);
             if (stats) {

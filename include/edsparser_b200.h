@@ -162,6 +162,12 @@ eds_status eds_leds_merge_host(eds_ctx* ctx, const uint8_t* eds_in, uint64_t eds
                                uint64_t seds_bytes, uint32_t l, int compact, uint64_t max_output_bytes,
                                eds_buffer* leds_out, eds_buffer* seds_out, uint32_t* rounds_out);
 
+/* Same merge; the results are VIEWS into pinned host memory owned by the ctx (shared with
+ * eds_vcf_transform_host_view): valid until the next *_view call on this ctx, never to be freed by the caller. */
+eds_status eds_leds_merge_host_view(eds_ctx* ctx, const uint8_t* eds_in, uint64_t eds_bytes, const uint8_t* seds_in,
+                                    uint64_t seds_bytes, uint32_t l, int compact, uint64_t max_output_bytes,
+                                    eds_buffer* leds_out, eds_buffer* seds_out, uint32_t* rounds_out);
+
 /* is_leds (eds_transforms.cpp:439-468): 1 iff no interior non-degenerate symbol is shorter than l and no
  * two degenerate symbols are adjacent (l = 0: always 1). Parsed and tested on the device. */
 eds_status eds_is_leds_host(eds_ctx* ctx, const uint8_t* eds_in, uint64_t eds_bytes, uint32_t l, int* is_leds_out);

@@ -34,6 +34,7 @@ def check_golden(ctx, stride=1):
                 raise AssertionError(("no error", c))
             continue
         out, sout, _ = ctx.leds_merge_host(eds, seds, c["l"], c["compact"])
+        assert ctx.leds_merge_host_view(eds, seds, c["l"], c["compact"])[:2] == (out, sout)  # pinned-view form
         assert out == c["eds"].encode("latin-1"), (c, out)
         if seds is not None:
             assert sout == c["seds"].encode("latin-1"), (c, sout)

@@ -167,9 +167,24 @@ def main():
             assert again[:2] == out[:2] and again[2] == 0
             parity = "is_leds holds and the merge is idempotent on its own output"
         alg = len(eds) + len(seds) + len(out[0]) + len(out[1])
+        # the C ABI alone: pinned input, results as pinned views (no Python copies inside the timed region)
+        import torch
+
+        pe = torch.empty(len(eds), dtype=torch.uint8).pin_memory()
+        pe.copy_(torch.frombuffer(bytearray(eds), dtype=torch.uint8))
+        ps = torch.empty(len(seds), dtype=torch.uint8).pin_memory()
+        ps.copy_(torch.frombuffer(bytearray(seds), dtype=torch.uint8))
+        assert ctx.leds_merge_host_view(eds, seds, L)[:2] == out[:2]
+        ctx.leds_merge_host_view_raw(pe.data_ptr(), len(eds), ps.data_ptr(), len(seds), L)
+        tv = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            ctx.leds_merge_host_view_raw(pe.data_ptr(), len(eds), ps.data_ptr(), len(seds), L)
+            tv.append(time.perf_counter() - t0)
+        del pe, ps
         line = {"workload": f"config 3 shape: genrandomeds-like {n} bp, 10% sites, 4 paths, eds2leds -l {L} LINEAR", "bp": n,
                 "in_bytes": len(eds) + len(seds), "out_bytes": len(out[0]) + len(out[1]), "rounds": out[2],
-                "gpu_host_to_host_ms": round(best * 1e3, 3), "bp_per_s": n / best, "algorithmic_GBps": alg / best / 1e9,
+                "gpu_host_to_host_ms": round(best * 1e3, 3), "c_abi_pinned_view_ms": round(min(tv) * 1e3, 3), "bp_per_s": n / best, "algorithmic_GBps": alg / best / 1e9,
                 "device_kernel_ms": round(dev_ms, 3), "device_algorithmic_GBps": round(alg / dev_ms / 1e6, 2),
                 "n_launches": n_launch, "top_kernels_ms": top, "parity": parity}
         if n <= 50_000:
