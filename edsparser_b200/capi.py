@@ -24,7 +24,8 @@ EDS_ERR_BAD_VCF = 8
 EXPORTS = [
     "eds_last_error", "eds_version", "eds_ctx_create", "eds_ctx_destroy", "eds_ctx_synchronize",
     "eds_ctx_set_tuning", "eds_ctx_set_profiling", "eds_ctx_kernel_times", "eds_msa_index_host",
-    "eds_msa_index_free", "eds_msa_transform_device", "eds_msa_transform_host", "eds_msa_conserved_bits",
+    "eds_msa_index_free", "eds_msa_transform_device", "eds_msa_transform_host", "eds_msa_transform_host_view",
+    "eds_msa_conserved_bits",
     "eds_msa_synth_device", "eds_msa_synth_free", "eds_buffer_to_host", "eds_buffer_free_host", "eds_leds_merge_host", "eds_leds_merge_host_view", "eds_is_leds_host",
     "eds_vcf_transform_host", "eds_vcf_transform_host_view", "eds_vcf_transform_device", "eds_device_upload", "eds_device_free",
 ]
@@ -100,6 +101,7 @@ class Library:
         L.eds_msa_index_free.restype = None
         L.eds_msa_transform_device.argtypes = [vp, P(MsaView), u32, i32, P(Buffer), P(Buffer), P(MsaStats)]
         L.eds_msa_transform_host.argtypes = [vp, vp, u64, u32, i32, P(Buffer), P(Buffer), P(MsaStats)]
+        L.eds_msa_transform_host_view.argtypes = L.eds_msa_transform_host.argtypes
         L.eds_msa_conserved_bits.argtypes = [vp, P(MsaView), vp, u64]
         L.eds_msa_synth_device.argtypes = [vp, u32, u64, u32, u64, u64, u64, u32, P(MsaView)]
         L.eds_msa_synth_free.argtypes = [vp]
@@ -216,6 +218,26 @@ class Context:
                                                          ctypes.byref(s), ctypes.byref(st)))
         del keep
         return _host_bytes(self.lib, e), _host_bytes(self.lib, s), st.as_dict()
+
+    def msa_transform_host_view_raw(self, addr, n, l, leds=True):
+        """The bare C call of the view form (results stay in pinned memory kept by the context): sizes and stats."""
+        e, s, st = Buffer(), Buffer(), MsaStats()
+        self.lib.check(self.lib.L.eds_msa_transform_host_view(self.handle, addr, n, l, 1 if leds else 0, ctypes.byref(e),
+                                                              ctypes.byref(s), ctypes.byref(st)))
+        return (int(e.bytes), int(s.bytes)), st.as_dict()
+
+    def msa_transform_host_view(self, text, l=0, leds=None):
+        """Like msa_transform_host through eds_msa_transform_host_view (views copied into bytes here)."""
+        if leds is None:
+            leds = l > 0
+        addr, n, keep = _as_pointer(text)
+        e, s, st = Buffer(), Buffer(), MsaStats()
+        self.lib.check(self.lib.L.eds_msa_transform_host_view(self.handle, addr, n, l, 1 if leds else 0, ctypes.byref(e),
+                                                              ctypes.byref(s), ctypes.byref(st)))
+        del keep
+        eds = bytes((ctypes.c_ubyte * e.bytes).from_address(e.data)) if e.bytes else b""
+        seds = bytes((ctypes.c_ubyte * s.bytes).from_address(s.data)) if s.bytes else b""
+        return eds, seds, st.as_dict()
 
     def msa_transform_host_raw(self, addr, n, l, leds=True):
         """The bare C call on (address, length) of host bytes; outputs are freed, only sizes and stats are

@@ -86,6 +86,16 @@ uint8_t* view_slot(eds_ctx* ctx, int which, uint64_t bytes) {
     return static_cast<uint8_t*>(ctx->host_out[which]);
 }
 
+// pinned, ctx-owned destination of a device buffer (grow-only)
+uint8_t* to_host_view(eds_ctx* ctx, int which, const eds_buffer& dev) {
+    view_slot(ctx, which, dev.bytes);
+    if (dev.bytes) {
+        EDSB_CUDA(cudaMemcpyAsync(ctx->host_out[which], dev.data, dev.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        EDSB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return static_cast<uint8_t*>(ctx->host_out[which]);
+}
+
 }  // namespace
 
 extern "C" {
@@ -266,8 +276,8 @@ eds_status eds_msa_transform_device(eds_ctx* ctx, const eds_msa_view* view, uint
     });
 }
 
-eds_status eds_msa_transform_host(eds_ctx* ctx, const uint8_t* file, uint64_t file_bytes, uint32_t l, int leds,
-                                  eds_buffer* eds_out, eds_buffer* seds_out, eds_msa_stats* stats) {
+static eds_status msa_transform_host_impl(eds_ctx* ctx, const uint8_t* file, uint64_t file_bytes, uint32_t l, int leds,
+                                          eds_buffer* eds_out, eds_buffer* seds_out, eds_msa_stats* stats, bool view) {
     eds_msa_index idx;
     memset(&idx, 0, sizeof(idx));
     eds_status rc = guarded([&] {
@@ -304,9 +314,9 @@ eds_status eds_msa_transform_host(eds_ctx* ctx, const uint8_t* file, uint64_t fi
         eds_buffer de, ds;
         ctx->msa->transform(v, l, leds, &de, &ds, stats);
         const double t3 = now();
-        eds_out->data = to_host(ctx, de);
+        eds_out->data = view ? to_host_view(ctx, 0, de) : to_host(ctx, de);
         eds_out->bytes = de.bytes;
-        seds_out->data = to_host(ctx, ds);
+        seds_out->data = view ? to_host_view(ctx, 1, ds) : to_host(ctx, ds);
         seds_out->bytes = ds.bytes;
         if (trace)
             fprintf(stderr, "[edsb trace] index (under the copy) %.3f ms, H2D %.3f ms (%.1f GB/s), transform %.3f ms, D2H %.3f ms\n", t1 - t0,
@@ -314,10 +324,25 @@ eds_status eds_msa_transform_host(eds_ctx* ctx, const uint8_t* file, uint64_t fi
     });
     eds_msa_index_free(&idx);
     if (rc != EDS_OK) {
-        if (eds_out) eds_buffer_free_host(eds_out);
-        if (seds_out) eds_buffer_free_host(seds_out);
+        if (view) {
+            if (eds_out) *eds_out = eds_buffer{nullptr, 0};
+            if (seds_out) *seds_out = eds_buffer{nullptr, 0};
+        } else {
+            if (eds_out) eds_buffer_free_host(eds_out);
+            if (seds_out) eds_buffer_free_host(seds_out);
+        }
     }
     return rc;
+}
+
+eds_status eds_msa_transform_host(eds_ctx* ctx, const uint8_t* file, uint64_t file_bytes, uint32_t l, int leds,
+                                  eds_buffer* eds_out, eds_buffer* seds_out, eds_msa_stats* stats) {
+    return msa_transform_host_impl(ctx, file, file_bytes, l, leds, eds_out, seds_out, stats, false);
+}
+
+eds_status eds_msa_transform_host_view(eds_ctx* ctx, const uint8_t* file, uint64_t file_bytes, uint32_t l, int leds,
+                                       eds_buffer* eds_out, eds_buffer* seds_out, eds_msa_stats* stats) {
+    return msa_transform_host_impl(ctx, file, file_bytes, l, leds, eds_out, seds_out, stats, true);
 }
 
 eds_status eds_msa_conserved_bits(eds_ctx* ctx, const eds_msa_view* view, uint8_t* out_bits, uint64_t out_bytes) {
@@ -422,16 +447,6 @@ eds_status eds_vcf_transform_device(eds_ctx* ctx, const uint8_t* vcf, uint64_t v
 }  // extern "C"
 
 namespace {
-// pinned, ctx-owned destination of a device buffer (grow-only)
-uint8_t* to_host_view(eds_ctx* ctx, int which, const eds_buffer& dev) {
-    view_slot(ctx, which, dev.bytes);
-    if (dev.bytes) {
-        EDSB_CUDA(cudaMemcpyAsync(ctx->host_out[which], dev.data, dev.bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        EDSB_CUDA(cudaStreamSynchronize(ctx->stream));
-    }
-    return static_cast<uint8_t*>(ctx->host_out[which]);
-}
-
 eds_status vcf_transform_host_impl(eds_ctx* ctx, const uint8_t* vcf, uint64_t vcf_bytes, const uint8_t* fasta,
                                   uint64_t fasta_bytes, uint32_t l, eds_buffer* eds_out, eds_buffer* seds_out,
                                   eds_vcf_stats* stats, uint64_t** sv_lines, uint64_t* n_sv_lines, bool view) {

@@ -69,19 +69,13 @@ thread_local Session t_session;
 
 std::string slurp(std::istream& in) { return std::string(std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>()); }
 
-struct HostBuf {
-    eds_buffer b{nullptr, 0};
-    ~HostBuf() { eds_buffer_free_host(&b); }
-    std::string str() const { return std::string(reinterpret_cast<const char*>(b.data), b.bytes); }
-};
-
 std::pair<std::string, std::string> msa_transform(std::istream& in, uint32_t l, int leds) {
     const std::string file = slurp(in);
-    HostBuf e, s;
-    const eds_status rc = eds_msa_transform_host(t_session.get(), reinterpret_cast<const uint8_t*>(file.data()), file.size(), l, leds,
-                                                 &e.b, &s.b, nullptr);
+    eds_buffer e{nullptr, 0}, s{nullptr, 0};  // views into pinned memory kept by the context: nothing to free
+    const eds_status rc = eds_msa_transform_host_view(t_session.get(), reinterpret_cast<const uint8_t*>(file.data()), file.size(), l, leds,
+                                                      &e, &s, nullptr);
     if (rc != EDS_OK) rethrow(rc);
-    return {e.str(), s.str()};
+    return {std::string(reinterpret_cast<const char*>(e.data), e.bytes), std::string(reinterpret_cast<const char*>(s.data), s.bytes)};
 }
 
 void merge(std::istream& input, std::ostream& output, Length l, std::istream* phasing_in, std::ostream* phasing_out, bool compact) {
@@ -89,14 +83,14 @@ void merge(std::istream& input, std::ostream& output, Length l, std::istream* ph
     const std::string eds = slurp(input);
     std::string seds;
     if (phasing_in) seds = slurp(*phasing_in);
-    HostBuf o, so;
+    eds_buffer o{nullptr, 0}, so{nullptr, 0};  // views into pinned memory kept by the context: nothing to free
     uint32_t rounds = 0;
-    const eds_status rc = eds_leds_merge_host(t_session.get(), reinterpret_cast<const uint8_t*>(eds.data()), eds.size(),
-                                              phasing_in ? reinterpret_cast<const uint8_t*>(seds.data()) : nullptr, seds.size(), l,
-                                              compact ? 1 : 0, g_budget, &o.b, &so.b, &rounds);
+    const eds_status rc = eds_leds_merge_host_view(t_session.get(), reinterpret_cast<const uint8_t*>(eds.data()), eds.size(),
+                                                   phasing_in ? reinterpret_cast<const uint8_t*>(seds.data()) : nullptr, seds.size(), l,
+                                                   compact ? 1 : 0, g_budget, &o, &so, &rounds);
     if (rc != EDS_OK) rethrow(rc);
-    output.write(reinterpret_cast<const char*>(o.b.data), (std::streamsize)o.b.bytes);
-    if (phasing_in && phasing_out) phasing_out->write(reinterpret_cast<const char*>(so.b.data), (std::streamsize)so.b.bytes);
+    output.write(reinterpret_cast<const char*>(o.data), (std::streamsize)o.bytes);
+    if (phasing_in && phasing_out) phasing_out->write(reinterpret_cast<const char*>(so.data), (std::streamsize)so.bytes);
 }
 
 // "Warning: Skipping variant at CHROM:POS - Unsupported structural variant type: X" (vcf_transforms.cpp:299-305) for a

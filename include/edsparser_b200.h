@@ -132,6 +132,11 @@ eds_status eds_msa_transform_device(eds_ctx* ctx, const eds_msa_view* view, uint
 eds_status eds_msa_transform_host(eds_ctx* ctx, const uint8_t* file, uint64_t file_bytes, uint32_t l, int leds,
                                   eds_buffer* eds_out, eds_buffer* seds_out, eds_msa_stats* stats);
 
+/* Same call; the results are VIEWS into pinned host memory owned by the ctx (valid until the next *_view call on this
+ * ctx, never to be freed by the caller): no allocation and no first-touch page faults per call. */
+eds_status eds_msa_transform_host_view(eds_ctx* ctx, const uint8_t* file, uint64_t file_bytes, uint32_t l, int leds,
+                                       eds_buffer* eds_out, eds_buffer* seds_out, eds_msa_stats* stats);
+
 /* Conserved-column bit vector B of msa_transforms.cpp:36-90 for the window: out_bits[c / 8] bit
  * (c % 8) = 1 iff window column c is conserved; out_bytes >= ceil(col_count / 8). For tests. */
 eds_status eds_msa_conserved_bits(eds_ctx* ctx, const eds_msa_view* view, uint8_t* out_bits, uint64_t out_bytes);

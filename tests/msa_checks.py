@@ -98,6 +98,8 @@ def check_random_against_oracle(ctx, seed, n_cases, max_rows=9, max_cols=200, ls
         l = int(rng.choice(ls))
         exp = oracle_lib.msa2eds(text, l)
         got = ctx.msa_transform_host(text, l)
+        if i % 4 == 0:
+            assert ctx.msa_transform_host_view(text, l)[:2] == got[:2]  # pinned-view form of the same call
         assert got[0] == exp[0], (seed, i, l, wrap, text)
         assert got[1] == exp[1], (seed, i, l, wrap, text)
 
