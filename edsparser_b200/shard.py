@@ -53,18 +53,22 @@ class OffsetExchange:
         self.everyone = [torch.zeros(2 * self.world, dtype=torch.int64, device=device) for _ in range(self.RING)]
         self.work = [None] * self.RING
         self.posted = 0
+        self.last = (0, 0)
+        # numpy views of the pinned staging tensors: a plain store instead of a tensor indexing op per value
+        self.host_np = [h.numpy() for h in self.host]
 
     def post(self, eds_bytes, seds_bytes):
+        self.last = (int(eds_bytes), int(seds_bytes))
+        if self.world == 1:  # nothing to exchange: the offsets are (0, 0) and the totals are this rank's counts
+            self.posted += 1
+            return
         k = self.posted % self.RING
         if self.work[k] is not None:
             self.work[k].wait()  # the exchange that used this buffer set two posts ago
             self.work[k] = None
-        self.host[k][0], self.host[k][1] = int(eds_bytes), int(seds_bytes)
+        self.host_np[k][0], self.host_np[k][1] = self.last
         self.mine[k].copy_(self.host[k], non_blocking=True)
-        if self.world > 1:
-            self.work[k] = self.dist.all_gather_into_tensor(self.everyone[k], self.mine[k], async_op=True)
-        else:
-            self.everyone[k].copy_(self.mine[k])
+        self.work[k] = self.dist.all_gather_into_tensor(self.everyone[k], self.mine[k], async_op=True)
         self.posted += 1
 
     def flush(self):
@@ -75,6 +79,8 @@ class OffsetExchange:
         self.work = [None] * self.RING
 
     def offsets(self):
+        if self.world == 1:
+            return 0, 0, self.last[0], self.last[1]
         k = (self.posted - 1) % self.RING
         self.flush()
         counts = self.everyone[k].view(self.world, 2).cpu()
