@@ -26,7 +26,7 @@ EXPORTS = [
     "eds_ctx_set_tuning", "eds_ctx_set_profiling", "eds_ctx_kernel_times", "eds_msa_index_host",
     "eds_msa_index_free", "eds_msa_transform_device", "eds_msa_transform_host", "eds_msa_transform_host_view",
     "eds_msa_conserved_bits",
-    "eds_msa_synth_device", "eds_msa_synth_free", "eds_buffer_to_host", "eds_buffer_free_host", "eds_leds_merge_host", "eds_leds_merge_host_view", "eds_is_leds_host",
+    "eds_msa_synth_device", "eds_msa_synth_free", "eds_buffer_to_host", "eds_buffer_to_host_view", "eds_buffer_free_host", "eds_leds_merge_host", "eds_leds_merge_host_view", "eds_is_leds_host",
     "eds_vcf_transform_host", "eds_vcf_transform_host_view", "eds_vcf_transform_device", "eds_device_upload", "eds_device_free",
 ]
 
@@ -107,6 +107,7 @@ class Library:
         L.eds_msa_synth_free.argtypes = [vp]
         L.eds_msa_synth_free.restype = None
         L.eds_buffer_to_host.argtypes = [vp, P(Buffer), P(Buffer)]
+        L.eds_buffer_to_host_view.argtypes = [vp, i32, P(Buffer), P(Buffer)]
         L.eds_buffer_free_host.argtypes = [P(Buffer)]
         L.eds_buffer_free_host.restype = None
         L.eds_leds_merge_host.argtypes = [vp, vp, u64, vp, u64, u32, i32, u64, P(Buffer), P(Buffer), P(u32)]
@@ -266,6 +267,12 @@ class Context:
         h = Buffer()
         self.lib.check(self.lib.L.eds_buffer_to_host(self.handle, ctypes.byref(device_buf), ctypes.byref(h)))
         return _host_bytes(self.lib, h)
+
+    def download_view(self, slot, device_buf):
+        """Copy a device-resident Buffer into the context's pinned slot (0 or 1); returns the host Buffer (a view)."""
+        h = Buffer()
+        self.lib.check(self.lib.L.eds_buffer_to_host_view(self.handle, slot, ctypes.byref(device_buf), ctypes.byref(h)))
+        return h
 
     def msa_conserved_bits(self, view):
         n = (view.col_count + 7) // 8

@@ -379,6 +379,15 @@ eds_status eds_buffer_to_host(eds_ctx* ctx, const eds_buffer* device_buf, eds_bu
     });
 }
 
+eds_status eds_buffer_to_host_view(eds_ctx* ctx, int slot, const eds_buffer* device_buf, eds_buffer* host_out) {
+    return guarded([&] {
+        use_device(ctx);
+        if (!device_buf || !host_out || slot < 0 || slot > 1) throw std::invalid_argument("eds_buffer_to_host_view: bad argument");
+        host_out->data = to_host_view(ctx, slot, *device_buf);
+        host_out->bytes = device_buf->bytes;
+    });
+}
+
 void eds_buffer_free_host(eds_buffer* buf) {
     if (!buf) return;
     free(buf->data);

@@ -156,6 +156,9 @@ void eds_msa_synth_free(eds_ctx* ctx);
 /* Copy a device-resident output (eds_msa_transform_device) into malloc'd host memory. */
 eds_status eds_buffer_to_host(eds_ctx* ctx, const eds_buffer* device_buf, eds_buffer* host_out);
 void eds_buffer_free_host(eds_buffer* buf);
+/* Same copy into pinned host memory kept by the ctx (slot 0 or 1, grow-only): host_out is a VIEW, valid until the
+ * next *_view call that uses the slot, never to be freed by the caller. */
+eds_status eds_buffer_to_host_view(eds_ctx* ctx, int slot, const eds_buffer* device_buf, eds_buffer* host_out);
 
 /* ------------------------------------------------------------------------------------------
  * l-EDS merge: eds_to_leds_linear (eds_transforms.cpp:313-373) when seds_in != NULL,
