@@ -356,6 +356,7 @@ def run_ours(args, rank, world):
             "output_bytes_per_step": out_bytes, "library": lib.version(),
         }
         print(json.dumps(line), flush=True)
+    barrier()  # every rank has finished its device work before any rank tears its context down
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
