@@ -1769,13 +1769,26 @@ void MsaPipeline::run_once(MsaBufs& b) {
     const size_t ev_warp_smem = (2048 + (size_t)nb * seg_pitch + 15) & ~(size_t)15;
     const size_t ev_smem = narrow_ok ? evw * ev_warp_smem + (((size_t)g.R * 4 + 15) & ~(size_t)15) : 0;
 
-    uint32_t gw = kSymWarps;  // warps per block
-    while (gw > 1 && gw * (group_per_warp + stage_per_warp) > smem_budget / 2) gw >>= 1;
+    // warps per block: the choice that keeps the most warps resident on an SM (the warp-per-symbol kernels are
+    // latency-bound: at R = 1000 a warp's scratch is 29 KB and 2-warp blocks fit 3 times = 6 warps, 1-warp blocks 7)
+    auto best_warps = [&](size_t per_warp) {
+        uint32_t best_w = 1, best_resident = 0;
+        for (uint32_t w = kSymWarps; w >= 1; w >>= 1) {
+            const size_t blk = w * per_warp + 1024;  // + the per-block reservation
+            if (blk > smem_budget) continue;
+            const uint32_t resident = w * (uint32_t)std::min<size_t>(ctx_->smem_optin / blk, 32);
+            if (resident > best_resident) {
+                best_resident = resident;
+                best_w = w;
+            }
+        }
+        return best_w;
+    };
+    uint32_t gw = best_warps(group_per_warp + stage_per_warp);
     const bool group_global = gw * group_per_warp > smem_budget;
     const uint32_t group_stage = (!group_global && gw * (group_per_warp + stage_per_warp) <= smem_budget) ? stage_bytes : 0u;
     const size_t group_warp_smem = group_global ? 0 : ((group_per_warp + (group_stage ? stage_per_warp : 0) + 15) & ~(size_t)15);
-    uint32_t ew = kSymWarps;
-    while (ew > 1 && ew * (emit_per_warp + stage_per_warp) > smem_budget / 2) ew >>= 1;
+    uint32_t ew = best_warps(emit_per_warp + stage_per_warp);
     const bool emit_global = ew * emit_per_warp > smem_budget;
     const uint32_t emit_stage = (!emit_global && ew * (emit_per_warp + stage_per_warp) <= smem_budget) ? stage_bytes : 0u;
     const size_t emit_warp_smem = emit_global ? 0 : ((emit_per_warp + (emit_stage ? stage_per_warp : 0) + 15) & ~(size_t)15);
