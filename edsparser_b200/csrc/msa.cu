@@ -19,6 +19,8 @@
 //   --k_size_*--> output offsets, --k_emit_*--> EDS and SEDS text.
 #include "msa.h"
 
+#include "idlist.cuh"
+
 #include <string.h>
 
 #include <algorithm>
@@ -827,13 +829,32 @@ __device__ __forceinline__ bool warp_classify(Seen& sn, uint32_t ch, bool valid,
 
 __device__ bool group_single_warp(const MsaGeom& g, const MsaBufs& b, uint32_t k, uint32_t s) {
     const uint32_t lane = threadIdx.x & 31;
-    const uint8_t* col = b.stash + (size_t)first_slot(b, s) * g.Rp;
+    const uint32_t slot0 = first_slot(b, s);
+    const uint8_t* col = b.stash + (size_t)slot0 * g.Rp;
+    const uint32_t Rw = g.Rp >> 5;
+    uint32_t* rowbits = b.rowbits ? b.rowbits + (size_t)slot0 * 8u * Rw : nullptr;
     Seen sn;
     sn.lo = sn.hi = sn.n = 0;
     for (uint32_t r0 = 0; r0 < g.R; r0 += 32) {
         const uint32_t r = r0 + lane;
         uint32_t cls;
-        if (!warp_classify(sn, r < g.R ? col[r] : 0u, r < g.R, cls)) return false;
+        if (!warp_classify(sn, r < g.R ? col[r] : 0u, r < g.R, cls)) {
+            if (b.seen && lane == 0) b.seen[(size_t)slot0 * 3u + 2u] = 0xffu;  // queued as wide: k_emit_var skips it
+            return false;
+        }
+        if (rowbits) {
+            // rows of every alternative in this chunk (a residue first seen in a later chunk has none here)
+#pragma unroll
+            for (uint32_t a = 0; a < 8u; ++a) {
+                const uint32_t m = __ballot_sync(0xffffffffu, r < g.R && cls == a);
+                if (lane == a) rowbits[a * Rw + (r0 >> 5)] = a < sn.n ? m : 0u;
+            }
+        }
+    }
+    if (b.seen && lane == 0) {
+        b.seen[(size_t)slot0 * 3u] = sn.lo;
+        b.seen[(size_t)slot0 * 3u + 1u] = sn.hi;
+        b.seen[(size_t)slot0 * 3u + 2u] = sn.n;
     }
     if (lane == 0) {
         uint32_t chars = 0;
@@ -1238,6 +1259,38 @@ __device__ __forceinline__ void segs_copy_out(const uint8_t* segs, uint32_t seg_
 // bytes of every alternative; pass 2 places the ids: per chunk and alternative one ballot gives the lanes of
 // that alternative, their in-chunk prefix is two popcounts (decimal widths take at most two values in a
 // chunk). All per-alternative state is warp-uniform and lives in registers (8 alternatives at most).
+// The same symbol from what k_group left behind (row bitsets + residue list): EDS text from the list, one staged
+// "{ids}" per alternative (idlist.cuh). No second classification of the 1000 rows.
+__device__ bool emit_single_from_bits(const MsaGeom& g, const MsaBufs& b, uint32_t k, uint32_t s, uint8_t* stage) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t slot0 = first_slot(b, s), Rw = g.Rp >> 5;
+    Seen sn;
+    sn.lo = b.seen[(size_t)slot0 * 3u];
+    sn.hi = b.seen[(size_t)slot0 * 3u + 1u];
+    sn.n = b.seen[(size_t)slot0 * 3u + 2u];
+    if (sn.n > 8u) return false;  // queued as wide by k_group
+    const uint32_t* rowbits = b.rowbits + (size_t)slot0 * 8u * Rw;
+    if (lane == 0) {
+        uint8_t* eds = b.eds_out + b.eds_off[k];
+        *eds++ = '{';
+        for (uint32_t a = 0; a < sn.n; ++a) {
+            if (a) *eds++ = ',';
+            const uint32_t ch = seen_byte(sn, a);
+            if (ch != (uint32_t)'-') *eds++ = (uint8_t)ch;
+        }
+        *eds = '}';
+    }
+    unsigned long long at = b.seds_off[k];
+    for (uint32_t a = 0; a < sn.n; ++a) {
+        uint32_t bytes = 0;
+        for (uint32_t w = lane; w < Rw; w += 32) bytes += word_id_bytes(w, rowbits[a * Rw + w]);
+        bytes = warp_sum(bytes) + 1u;  // '{' + "id," each, the last ',' is the '}'
+        warp_render_id_list(stage, rowbits + a * Rw, Rw, b.id_text, b.seds_out, at, bytes);
+        at += bytes;
+    }
+    return true;
+}
+
 __device__ bool emit_single_warp(const MsaGeom& g, const MsaBufs& b, uint32_t k, uint32_t s) {
     const uint32_t lane = threadIdx.x & 31, lt = lanemask_lt();
     const uint8_t* col = b.stash + (size_t)first_slot(b, s) * g.Rp;
@@ -1328,11 +1381,17 @@ __global__ void k_emit_var(MsaGeom g, MsaBufs b, uint32_t per_warp_smem, uint32_
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     if (nb == 0u) {
         // too many rows for per-lane segments: warp per symbol, rows across lanes
+        // per_warp_smem != 0: the id-list stage of this warp (idlist.cuh) and the bitsets k_group left in b.rowbits
+        uint8_t* stage = (per_warp_smem && b.rowbits) ? EDSB_DYN_SMEM() + (size_t)warp * per_warp_smem : nullptr;
         const uint32_t v_lo = st->v_lo, v_hi = st->v_hi;
         for (uint32_t v = v_lo + blockIdx.x * wpb + warp; v < v_hi; v += gridDim.x * wpb) {
             const uint32_t k = b.varsym[v];
             const uint32_t s = b.sym[k] & kColMask, en = b.sym[k + 1] & kColMask;
-            if (en - s == 1u) emit_single_warp(g, b, k, s);
+            if (en - s == 1u) {
+                if (stage) emit_single_from_bits(g, b, k, s, stage);
+                else emit_single_warp(g, b, k, s);
+                __syncwarp();
+            }
         }
         return;
     }
@@ -1524,7 +1583,8 @@ MsaPipeline::MsaPipeline(eds_ctx* ctx) : ctx_(ctx) {
 
 MsaPipeline::~MsaPipeline() {
     DevBuf* all[] = {&d_rows_, &d_mism_, &d_vbits_, &d_tbits_, &d_rank_, &d_refc_, &d_part_, &d_varcol_, &d_runs_,
-                     &d_sym_, &d_stash_, &d_altid_, &d_leadmask_, &d_symmeta_, &d_eds_, &d_seds_, &d_ws_, &d_status_};
+                     &d_sym_, &d_stash_, &d_altid_, &d_leadmask_, &d_symmeta_, &d_eds_, &d_seds_, &d_ws_, &d_status_,
+                     &d_rowbits_, &d_seen_, &d_id_text_};
     for (DevBuf* d : all) d->release();
     if (h_status_) cudaFreeHost(h_status_);
 }
@@ -1644,6 +1704,11 @@ void MsaPipeline::bind(MsaBufs& b) {
     d_stash_.reserve((size_t)cap_var_ * g.Rp);
     d_altid_.reserve((size_t)cap_var_ * g.Rp * (g.alt32 ? 4 : 2));
     d_leadmask_.reserve((size_t)cap_var_ * (g.Rp / 32) * 4);
+    const bool rows_across_lanes = ctx_->narrow_off != 0 || g.R > 160u;  // mirrors the choice of nb in enqueue
+    if (rows_across_lanes) {
+        d_rowbits_.reserve((size_t)cap_var_ * 8 * (g.Rp / 32) * 4);
+        d_seen_.reserve((size_t)cap_var_ * 3 * 4);
+    }
     d_symmeta_.reserve((size_t)(cap_runs_ + 2) * (4 + 8 + 8 + 8));
     d_eds_.reserve(cap_eds_);
     d_seds_.reserve(cap_seds_);
@@ -1656,6 +1721,9 @@ void MsaPipeline::bind(MsaBufs& b) {
     b.stash = d_stash_.as<uint8_t>();
     b.altid = d_altid_.p;
     b.leadmask = d_leadmask_.as<uint32_t>();
+    b.rowbits = rows_across_lanes ? d_rowbits_.as<uint32_t>() : nullptr;
+    b.seen = rows_across_lanes ? d_seen_.as<uint32_t>() : nullptr;
+    b.id_text = d_id_text_.as<unsigned long long>();
     unsigned char* meta = d_symmeta_.as<unsigned char>();
     const size_t n = (size_t)cap_runs_ + 2;
     b.sym_edsz = reinterpret_cast<unsigned long long*>(meta);
@@ -1766,8 +1834,22 @@ void MsaPipeline::run_once(MsaBufs& b) {
         if (best) nb = 32;
     }
     const uint32_t narrow_ok = ctx_->narrow_off == 2 ? 2u : (nb ? 1u : 0u);  // 1 lane per symbol, 0 rows across lanes, 2 all wide
-    const size_t ev_warp_smem = (2048 + (size_t)nb * seg_pitch + 15) & ~(size_t)15;
-    const size_t ev_smem = narrow_ok ? evw * ev_warp_smem + (((size_t)g.R * 4 + 15) & ~(size_t)15) : 0;
+    size_t ev_warp_smem = (2048 + (size_t)nb * seg_pitch + 15) & ~(size_t)15;
+    size_t ev_smem = narrow_ok ? evw * ev_warp_smem + (((size_t)g.R * 4 + 15) & ~(size_t)15) : 0;
+    if (narrow_ok == 0u && b.rowbits) {
+        // rows across lanes: one id-list stage per warp; the row bitsets come from k_group through global memory
+        const size_t per_warp = id_list_stage_bytes(g.R);
+        evw = kSymWarps;
+        while (evw > 1 && evw * per_warp > smem_budget / 2) evw >>= 1;
+        ev_warp_smem = evw * per_warp <= smem_budget ? per_warp : 0;
+        ev_smem = evw * ev_warp_smem;
+    }
+    if (id_text_n_ < (uint64_t)g.R + 1) {
+        id_text_n_ = (uint64_t)g.R + 1;
+        d_id_text_.reserve((size_t)id_text_n_ * 8);
+        b.id_text = d_id_text_.as<unsigned long long>();
+        EDSB_LAUNCH(k_id_text, 8, kPartThreads, 0, s, d_id_text_.as<unsigned long long>(), (unsigned long long)id_text_n_);
+    }
 
     // warps per block: the choice that keeps the most warps resident on an SM (the warp-per-symbol kernels are
     // latency-bound: at R = 1000 a warp's scratch is 29 KB and 2-warp blocks fit 3 times = 6 warps, 1-warp blocks 7)

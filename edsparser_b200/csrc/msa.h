@@ -38,7 +38,8 @@ class MsaPipeline {
     MsaStatus* h_status_ = nullptr;  // pinned
     std::vector<uint64_t> h_rows_;
     DevBuf d_rows_, d_mism_, d_vbits_, d_tbits_, d_rank_, d_refc_, d_part_, d_varcol_, d_runs_, d_sym_, d_stash_,
-        d_altid_, d_leadmask_, d_symmeta_, d_eds_, d_seds_, d_ws_, d_status_;
+        d_altid_, d_leadmask_, d_symmeta_, d_eds_, d_seds_, d_ws_, d_status_, d_rowbits_, d_seen_, d_id_text_;
+    uint64_t id_text_n_ = 0;  // entries of the id -> text table built so far
     uint32_t cap_var_ = 0, cap_runs_ = 0;
     uint64_t cap_eds_ = 0, cap_seds_ = 0;
 };

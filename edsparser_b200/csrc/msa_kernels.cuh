@@ -90,6 +90,12 @@ struct MsaBufs {
     uint8_t* stash;      // stash[k * Rp + r] = residue of row r at the k-th variable column
     void* altid;         // altid[slot0 * Rp + r]: alternative index of row r in the symbol whose first variable column is slot0
     uint32_t* leadmask;  // leadmask[slot0 * Rp/32 + r/32]: rows that introduce an alternative
+    // rows-across-lanes path (many rows): k_group leaves the rows of each of the (at most 8) alternatives of a
+    // single-column symbol as bitsets, rowbits[(slot0 * 8 + a) * Rp/32 + r/32], and the residue list, seen[slot0 * 3 ..]
+    // = {lo, hi, n}; k_emit_var renders them (idlist.cuh). Null when the lane-per-symbol path is in use.
+    uint32_t* rowbits;
+    uint32_t* seen;
+    const unsigned long long* id_text;  // id -> decimal text table, R + 1 entries
     uint32_t* sym_nalts;
     unsigned long long* sym_edsz;
     unsigned long long* eds_off;
