@@ -835,6 +835,10 @@ __device__ bool group_single_warp(const MsaGeom& g, const MsaBufs& b, uint32_t k
     uint32_t* rowbits = b.rowbits ? b.rowbits + (size_t)slot0 * 8u * Rw : nullptr;
     Seen sn;
     sn.lo = sn.hi = sn.n = 0;
+    if (rowbits) {
+        for (uint32_t i = lane; i < 8u * Rw; i += 32) rowbits[i] = 0u;
+        __syncwarp();
+    }
     for (uint32_t r0 = 0; r0 < g.R; r0 += 32) {
         const uint32_t r = r0 + lane;
         uint32_t cls;
@@ -843,12 +847,11 @@ __device__ bool group_single_warp(const MsaGeom& g, const MsaBufs& b, uint32_t k
             return false;
         }
         if (rowbits) {
-            // rows of every alternative in this chunk (a residue first seen in a later chunk has none here)
-#pragma unroll
-            for (uint32_t a = 0; a < 8u; ++a) {
-                const uint32_t m = __ballot_sync(0xffffffffu, r < g.R && cls == a);
-                if (lane == a) rowbits[a * Rw + (r0 >> 5)] = a < sn.n ? m : 0u;
-            }
+            // rows of every alternative in this chunk: one match groups the lanes by class, the first lane of each
+            // group stores the group's mask (the words of classes without rows here stay zero, see the fill above)
+            const uint32_t key = r < g.R ? cls : 0xffu;
+            const uint32_t peers = __match_any_sync(0xffffffffu, key);
+            if (key < 8u && lane == (uint32_t)__ffs((int)peers) - 1u) rowbits[key * Rw + (r0 >> 5)] = peers;
         }
     }
     if (b.seen && lane == 0) {
