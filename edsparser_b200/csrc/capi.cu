@@ -122,6 +122,10 @@ eds_status eds_ctx_create(int device, void* stream, eds_ctx** out) {
         if (device < 0 || device >= n) throw std::invalid_argument("eds_ctx_create: no such device");
         EDSB_CUDA(cudaSetDevice(device));
         eds_ctx* ctx = new eds_ctx();
+        struct Guard {  // a throw below must not leak the streams / events / pipelines created so far
+            eds_ctx* c;
+            ~Guard() { if (c) eds_ctx_destroy(c); }
+        } guard{ctx};
         ctx->device = device;
         cudaDeviceProp prop;
         EDSB_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -146,6 +150,7 @@ eds_status eds_ctx_create(int device, void* stream, eds_ctx** out) {
         ctx->msa = new edsb::MsaPipeline(ctx);
         ctx->leds = new edsb::LedsPipeline(ctx);
         ctx->vcf = new edsb::VcfPipeline(ctx);
+        guard.c = nullptr;
         *out = ctx;
     });
 }
@@ -280,11 +285,12 @@ static eds_status msa_transform_host_impl(eds_ctx* ctx, const uint8_t* file, uin
                                           eds_buffer* eds_out, eds_buffer* seds_out, eds_msa_stats* stats, bool view) {
     eds_msa_index idx;
     memset(&idx, 0, sizeof(idx));
+    // the caller's structs may be uninitialised: clear them before anything can fail (the error path frees them)
+    if (eds_out) *eds_out = eds_buffer{nullptr, 0};
+    if (seds_out) *seds_out = eds_buffer{nullptr, 0};
     eds_status rc = guarded([&] {
         use_device(ctx);
         if (!file || !eds_out || !seds_out) throw std::invalid_argument("eds_msa_transform_host: null argument");
-        eds_out->data = seds_out->data = nullptr;
-        eds_out->bytes = seds_out->bytes = 0;
         const bool trace = getenv("EDSB_TRACE") != nullptr;
         auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         // the copy is started first; rows are located on the host while the DMA engine runs
@@ -398,11 +404,11 @@ void eds_buffer_free_host(eds_buffer* buf) {
 eds_status eds_leds_merge_host(eds_ctx* ctx, const uint8_t* eds_in, uint64_t eds_bytes, const uint8_t* seds_in,
                                uint64_t seds_bytes, uint32_t l, int compact, uint64_t max_output_bytes,
                                eds_buffer* leds_out, eds_buffer* seds_out, uint32_t* rounds_out) {
+    if (leds_out) *leds_out = eds_buffer{nullptr, 0};
+    if (seds_out) *seds_out = eds_buffer{nullptr, 0};
     eds_status rc = guarded([&] {
         use_device(ctx);
         if (!eds_in || !leds_out || !seds_out) throw std::invalid_argument("eds_leds_merge_host: null argument");
-        leds_out->data = seds_out->data = nullptr;
-        leds_out->bytes = seds_out->bytes = 0;
         ctx->leds->merge_host(eds_in, eds_bytes, seds_in, seds_bytes, l, compact != 0, max_output_bytes, leds_out,
                               seds_out, rounds_out);
     });
@@ -416,11 +422,11 @@ eds_status eds_leds_merge_host(eds_ctx* ctx, const uint8_t* eds_in, uint64_t eds
 eds_status eds_leds_merge_host_view(eds_ctx* ctx, const uint8_t* eds_in, uint64_t eds_bytes, const uint8_t* seds_in,
                                     uint64_t seds_bytes, uint32_t l, int compact, uint64_t max_output_bytes,
                                     eds_buffer* leds_out, eds_buffer* seds_out, uint32_t* rounds_out) {
+    if (leds_out) *leds_out = eds_buffer{nullptr, 0};
+    if (seds_out) *seds_out = eds_buffer{nullptr, 0};
     eds_status rc = guarded([&] {
         use_device(ctx);
         if (!eds_in || !leds_out || !seds_out) throw std::invalid_argument("eds_leds_merge_host_view: null argument");
-        leds_out->data = seds_out->data = nullptr;
-        leds_out->bytes = seds_out->bytes = 0;
         ctx->leds->merge_host(eds_in, eds_bytes, seds_in, seds_bytes, l, compact != 0, max_output_bytes, leds_out, seds_out,
                               rounds_out, nullptr, false,
                               [ctx](int which, uint64_t bytes) -> uint8_t* { return view_slot(ctx, which, bytes); });
@@ -461,13 +467,13 @@ eds_status vcf_transform_host_impl(eds_ctx* ctx, const uint8_t* vcf, uint64_t vc
                                   eds_vcf_stats* stats, uint64_t** sv_lines, uint64_t* n_sv_lines, bool view) {
     if (sv_lines) *sv_lines = nullptr;
     if (n_sv_lines) *n_sv_lines = 0;
+    if (eds_out) *eds_out = eds_buffer{nullptr, 0};
+    if (seds_out) *seds_out = eds_buffer{nullptr, 0};
+    if (stats) memset(stats, 0, sizeof(*stats));
     eds_status rc = guarded([&] {
         use_device(ctx);
         if ((!vcf && vcf_bytes) || (!fasta && fasta_bytes) || !eds_out || !seds_out)
             throw std::invalid_argument("eds_vcf_transform_host: null argument");
-        eds_out->data = seds_out->data = nullptr;
-        eds_out->bytes = seds_out->bytes = 0;
-        if (stats) memset(stats, 0, sizeof(*stats));
         const bool trace = getenv("EDSB_TRACE_HOST") != nullptr;
         auto t0 = std::chrono::steady_clock::now();
         auto lap = [&](const char* what) {

@@ -136,13 +136,31 @@ __global__ void k_close_strings(const uint8_t* t, uint32_t n, uint32_t* str_end,
 struct SetFn {
     const uint8_t* s;
     unsigned long long n;
-    uint32_t* num_val;
-    uint32_t* num_set;
     uint32_t* present;  // bitmap over id values
     LedsStatus* st;
     __device__ __forceinline__ bool numstart(unsigned long long i) const { return is_digit(s[i]) && (i == 0 || !is_digit(s[i - 1])); }
     __device__ unsigned long long value(unsigned long long i) const {
         return (s[i] == (uint8_t)'{' ? 1ull : 0ull) | (numstart(i) ? 1ull << 32 : 0ull);
+    }
+    // the number that starts at i; false when std::stoi would throw or the id is beyond the device path's range
+    __device__ __forceinline__ bool parse(unsigned long long i, uint32_t& out, uint32_t& why) const {
+        unsigned long long v = 0;
+        uint32_t digits = 0;
+        for (unsigned long long k = i; k < n && is_digit(s[k]); ++k) {
+            if (digits < 12) v = v * 10ull + (unsigned long long)(s[k] - (uint8_t)'0');
+            ++digits;
+        }
+        out = 0;
+        if (digits > 10 || v > 2147483647ull) {
+            why = kErrSedsOverflow;  // std::stoi -> std::out_of_range
+            return false;
+        }
+        if (v >= kMaxPathId) {
+            why = kErrSedsBigId;
+            return false;
+        }
+        out = (uint32_t)v;
+        return true;
     }
     __device__ void apply(unsigned long long i, unsigned long long prefix, unsigned long long) const {
         const uint8_t c = s[i];
@@ -157,26 +175,32 @@ struct SetFn {
         if (i + 1 == n && c != (uint8_t)'}') ok = false;
         if (!ok) atomicOr(&st->err, (uint32_t)kErrSedsSyntax);
         if (!numstart(i)) return;
-        const uint32_t q = (uint32_t)(prefix >> 32);
-        unsigned long long v = 0;
-        uint32_t digits = 0;
-        for (unsigned long long k = i; k < n && is_digit(s[k]); ++k) {
-            if (digits < 12) v = v * 10ull + (unsigned long long)(s[k] - (uint8_t)'0');
-            ++digits;
-        }
-        if (digits > 10 || v > 2147483647ull) {
-            atomicOr(&st->err, (uint32_t)kErrSedsOverflow);  // std::stoi -> std::out_of_range
-            v = 0;
-        } else if (v >= kMaxPathId) {
-            atomicOr(&st->err, (uint32_t)kErrSedsBigId);
-            v = 0;
-        }
-        num_val[q] = (uint32_t)v;
-        num_set[q] = (uint32_t)prefix - 1u;  // sets opened before this number, minus one
+        uint32_t v, why = 0;
+        if (!parse(i, v, why)) atomicOr(&st->err, why);
         // few distinct ids, millions of mentions: look before the atomic (a stale read only costs a redundant atomic)
         const uint32_t bit = 1u << (v & 31u);
         if (!(*reinterpret_cast<volatile uint32_t*>(&present[v >> 5]) & bit)) atomicOr(&present[v >> 5], bit);
         if ((uint32_t)v > *reinterpret_cast<volatile uint32_t*>(&st->max_id)) atomicMax(&st->max_id, (uint32_t)v);
+    }
+};
+
+// Second pass over the same text once the ids are ranked: every number sets its bit in the dense bitset of its set
+// (the index of the set is the number of '{' before it, minus one). No per-number arrays: the text is the list.
+struct BitsFn {
+    SetFn f;
+    const uint32_t* rank;
+    uint32_t* bits;
+    uint32_t Wd, n_sets;
+    __device__ unsigned long long value(unsigned long long i) const { return f.value(i); }
+    __device__ void apply(unsigned long long i, unsigned long long prefix, unsigned long long) const {
+        if (!f.numstart(i)) return;
+        const uint32_t set = (uint32_t)prefix - 1u;
+        uint32_t v, why;
+        if (set >= n_sets || !f.parse(i, v, why)) return;  // reported after the first pass
+        const uint32_t dense = rank[v >> 5] + (uint32_t)__popc(f.present[v >> 5] & low_bits(v & 31u));
+        uint32_t* w = &bits[(size_t)set * Wd + (dense >> 5)];
+        const uint32_t bit = 1u << (dense & 31u);
+        if (!(*reinterpret_cast<volatile uint32_t*>(w) & bit)) atomicOr(w, bit);
     }
 };
 
@@ -191,16 +215,6 @@ __global__ void k_id_table(const uint32_t* present, const uint32_t* rank, uint32
     for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += gridDim.x * blockDim.x) {
         uint32_t k = rank[w];
         for (uint32_t bits = present[w]; bits; bits &= bits - 1) id_of[k++] = w * 32u + (uint32_t)__ffs((int)bits) - 1u;
-    }
-}
-
-__global__ void k_bits_fill(const uint32_t* num_val, const uint32_t* num_set, uint32_t n_num, const uint32_t* present,
-                            const uint32_t* rank, uint32_t* bits, uint32_t Wd, uint32_t n_sets) {
-    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_num; q += gridDim.x * blockDim.x) {
-        const uint32_t v = num_val[q], set = num_set[q];
-        if (set >= n_sets) continue;  // count mismatch: reported by the host
-        const uint32_t dense = rank[v >> 5] + (uint32_t)__popc(present[v >> 5] & low_bits(v & 31u));
-        atomicOr(&bits[(size_t)set * Wd + (dense >> 5)], 1u << (dense & 31u));
     }
 }
 
@@ -693,7 +707,9 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
                               eds_buffer* seds_out, uint32_t* rounds_out, int* check_only, bool input_on_device,
                               const std::function<uint8_t*(int, uint64_t)>& sink) {
     if (l == 0) throw std::invalid_argument("context_length must be > 0 for l-EDS transformation");  // eds_transforms.cpp:322-324
-    if (eds_bytes >= 0xfffffff0ull || seds_bytes >= 0xfffffff0ull) throw std::invalid_argument("eds_leds_merge_host: inputs must be below 4 GiB (Length is uint32 in the reference too)");
+    // string offsets into the EDS text are 32-bit (Length is uint32 in the reference too); the SEDS text has no such bound
+    // (config 5: 13 GB of source sets for 0.1 GB of EDS)
+    if (eds_bytes >= 0xfffffff0ull) throw std::invalid_argument("eds_leds_merge_host: the EDS text must be below 4 GiB (Length is uint32 in the reference too)");
     const bool linear = seds_in != nullptr;
     cudaStream_t s = ctx_->stream;
     const cudaMemcpyKind in_kind = input_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
@@ -718,8 +734,7 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
     // grow-only device buffers owned by the pipeline: a second call of similar size allocates nothing
     Bufs& B_ = *bufs_;
     DevBuf &d_raw = B_.d[0], &d_text = B_.d[1], &d_depth = B_.d[2], &d_part = B_.d[3], &d_status = B_.d[4], &d_sraw = B_.d[5],
-           &d_stext = B_.d[6], &d_str_start = B_.d[7], &d_str_end = B_.d[8], &d_sym_first = B_.d[9], &d_num_val = B_.d[10],
-           &d_num_set = B_.d[11], &d_present = B_.d[12], &d_rank = B_.d[13], &d_idof = B_.d[14], &d_rawbits = B_.d[15],
+           &d_stext = B_.d[6], &d_str_start = B_.d[7], &d_str_end = B_.d[8], &d_sym_first = B_.d[9], &d_present = B_.d[12], &d_rank = B_.d[13], &d_idof = B_.d[14], &d_rawbits = B_.d[15],
            &d_cand = B_.d[16], &d_sel = B_.d[17], &d_pairs_before = B_.d[18], &d_pair_list = B_.d[19], &d_kept = B_.d[20],
            &d_off = B_.d[21], &d_falt_off = B_.d[22], &d_falt_pool = B_.d[23], &d_falt_flags = B_.d[24], &d_eds_off = B_.d[25],
            &d_seds_sz = B_.d[26], &d_seds_off = B_.d[27], &d_out = B_.d[28], &d_sout = B_.d[29], &d_stack = B_.d[30],
@@ -762,11 +777,16 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
     } while (0)
 
     // ---- EDS text: strip, parse ----------------------------------------------------------------------
-    d_raw.reserve(eds_bytes + 16);
+    // input already in HBM (the VCF front end's output): read it where it is
+    const uint8_t* raw = eds_in;
+    if (!input_on_device) {
+        d_raw.reserve(eds_bytes + 16);
+        if (eds_bytes) EDSB_CUDA(cudaMemcpyAsync(d_raw.p, eds_in, eds_bytes, in_kind, s));
+        raw = d_raw.as<uint8_t>();
+    }
     d_text.reserve(eds_bytes + 16);
-    if (eds_bytes) EDSB_CUDA(cudaMemcpyAsync(d_raw.p, eds_in, eds_bytes, in_kind, s));
     uint8_t* text = d_text.as<uint8_t>();
-    LEDS_SCAN("strip_eds", OpSum64, eds_bytes, (StripFn{d_raw.as<uint8_t>(), text}));
+    LEDS_SCAN("strip_eds", OpSum64, eds_bytes, (StripFn{raw, text}));
     const uint32_t n = (uint32_t)total_of();
 
     uint32_t n_str = 0, n_sym = 0;
@@ -792,24 +812,26 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
     uint32_t Wd = 0, n_paths = 0, has_zero = 0;
     uint32_t* id_of = nullptr;
     if (linear) {
-        d_sraw.reserve(seds_bytes + 16);
+        const uint8_t* sraw = seds_in;
+        if (!input_on_device) {
+            d_sraw.reserve(seds_bytes + 16);
+            if (seds_bytes) EDSB_CUDA(cudaMemcpyAsync(d_sraw.p, seds_in, seds_bytes, in_kind, s));
+            sraw = d_sraw.as<uint8_t>();
+        }
         d_stext.reserve(seds_bytes + 16);
-        if (seds_bytes) EDSB_CUDA(cudaMemcpyAsync(d_sraw.p, seds_in, seds_bytes, in_kind, s));
         uint8_t* stext = d_stext.as<uint8_t>();
-        LEDS_SCAN("strip_seds", OpSum64, seds_bytes, (StripFn{d_sraw.as<uint8_t>(), stext}));
-        const uint32_t ns = (uint32_t)total_of();
+        LEDS_SCAN("strip_seds", OpSum64, seds_bytes, (StripFn{sraw, stext}));
+        const unsigned long long ns = total_of();
         if (ns == 0) throw std::runtime_error("sEDS input is empty");
         const uint32_t pw = kMaxPathId / 32;
         d_present.reserve((size_t)pw * 4);
         d_rank.reserve((size_t)pw * 4);
         EDSB_CUDA(cudaMemsetAsync(d_present.p, 0, (size_t)std::min<uint32_t>(pw, present_dirty_words_) * 4, s));
         present_dirty_words_ = pw;  // until this call's largest id is known
-        d_num_val.reserve((size_t)(ns / 2 + 2) * 4);
-        d_num_set.reserve((size_t)(ns / 2 + 2) * 4);
-        const SetFn sf{stext, ns, d_num_val.as<uint32_t>(), d_num_set.as<uint32_t>(), d_present.as<uint32_t>(), st};
+        const SetFn sf{stext, ns, d_present.as<uint32_t>(), st};
         LEDS_SCAN("seds_sets", OpSum64, ns, sf);
         const unsigned long long tot = total_of();
-        const uint32_t n_sets = (uint32_t)tot, n_num = (uint32_t)(tot >> 32);
+        const uint32_t n_sets = (uint32_t)tot;  // (the high half counts the ids, modulo 2^32: not used)
         status_now();
         bool oor = false;
         if (hst.err & (kErrSedsSyntax | kErrSedsOverflow | kErrSedsBigId) || n_sets != n_str) {
@@ -831,8 +853,7 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
         has_zero = w0 & 1u;
         p_bits.ensure((size_t)std::max<uint32_t>(n_str, 1) * Wd, 0, s);
         EDSB_CUDA(cudaMemsetAsync(p_bits.p, 0, (size_t)n_str * Wd * 4, s));
-        LEDS_LAUNCH("k_bits_fill", k_bits_fill, G, B, d_num_val.as<uint32_t>(), d_num_set.as<uint32_t>(), n_num,
-                    d_present.as<uint32_t>(), d_rank.as<uint32_t>(), p_bits.p, Wd, n_str);
+        LEDS_SCAN("seds_bits", OpSum64, ns, (BitsFn{sf, d_rank.as<uint32_t>(), p_bits.p, Wd, n_str}));
         d_rawbits.reserve((size_t)n_str * Wd * 4 + 16);  // the sets as given, for alternatives that are never merged
         EDSB_CUDA(cudaMemcpyAsync(d_rawbits.p, p_bits.p, (size_t)n_str * Wd * 4, cudaMemcpyDeviceToDevice, s));
         LEDS_LAUNCH("k_universal", k_universal, G, B, p_bits.p, Wd, n_str, n_paths, has_zero, st);

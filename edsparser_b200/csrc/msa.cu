@@ -827,7 +827,8 @@ __device__ __forceinline__ bool warp_classify(Seen& sn, uint32_t ch, bool valid,
     return true;
 }
 
-__device__ bool group_single_warp(const MsaGeom& g, const MsaBufs& b, uint32_t k, uint32_t s) {
+__device__ bool group_single_warp(const MsaGeom& g, const MsaBufs& b, uint32_t k, uint32_t s, uint32_t& nalts) {
+    nalts = 0;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t slot0 = first_slot(b, s);
     const uint8_t* col = b.stash + (size_t)slot0 * g.Rp;
@@ -865,6 +866,7 @@ __device__ bool group_single_warp(const MsaGeom& g, const MsaBufs& b, uint32_t k
         b.sym_nalts[k] = sn.n;
         b.sym_edsz[k] = 2ull + chars + (sn.n - 1u);
     }
+    nalts = sn.n;  // warp-uniform: the caller must not read sym_nalts back (no fence between lanes)
     return true;
 }
 
@@ -907,9 +909,10 @@ __global__ void k_group(MsaGeom g, MsaBufs b, uint32_t narrow_ok) {
                 const uint32_t bit = (uint32_t)__ffs((int)todo) - 1u;
                 todo &= todo - 1u;
                 const uint32_t kw = __shfl_sync(0xffffffffu, k, (int)bit), sw = __shfl_sync(0xffffffffu, s, (int)bit);
-                const bool ok = group_single_warp(g, b, kw, sw);
+                uint32_t na;
+                const bool ok = group_single_warp(g, b, kw, sw, na);
                 if (lane == bit) {
-                    if (ok) alts_here += b.sym_nalts[kw]; else cls = 3u;
+                    if (ok) alts_here += na; else cls = 3u;
                 }
             }
         }

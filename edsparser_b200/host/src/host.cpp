@@ -139,7 +139,7 @@ std::pair<std::string, std::string> vcf_transform(std::istream& vcf_stream, std:
     const std::string fasta = slurp(fasta_stream);
     const std::string vcf = slurp(vcf_stream);
     eds_buffer e{nullptr, 0}, s{nullptr, 0};  // views into pinned memory kept by the context: nothing to free
-    eds_vcf_stats st;
+    eds_vcf_stats st{};
     uint64_t* sv = nullptr;
     uint64_t n_sv = 0;
     const eds_status rc = eds_vcf_transform_host_view(t_session.get(), reinterpret_cast<const uint8_t*>(vcf.data()), vcf.size(),

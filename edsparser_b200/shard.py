@@ -95,6 +95,12 @@ def write_slice(path, offset, data, total, rank):
     try:
         if rank == 0:
             os.ftruncate(fd, total)
-        os.pwrite(fd, data, offset)
+        view = memoryview(data)
+        done = 0
+        while done < len(view):  # Linux caps one write at 0x7ffff000 bytes: loop until the slice is out
+            n = os.pwrite(fd, view[done:done + (1 << 30)], offset + done)
+            if n <= 0:
+                raise OSError("short write to %s at offset %d" % (path, offset + done))
+            done += n
     finally:
         os.close(fd)
