@@ -52,11 +52,12 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """dram read+write bytes per k_scan launch from the committed ncu capture, or None."""
+def ncu_traffic(kernel, rows, cols):
+    """dram read+write bytes per launch of `kernel` on a rows x cols window, from the committed ncu capture of that
+    very shape (profiles/ncu_traffic.json: {"<kernel>": {"<rows>x<cols>": bytes}}); None for any other shape."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            return json.load(f).get("k_scan_dram_bytes_per_launch")
+            return json.load(f).get(kernel, {}).get(f"{rows}x{cols}")
     except Exception:
         return None
 
@@ -160,7 +161,9 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": dict(workload_config(args.gpus), workload=workload_config(args.gpus)["workload"] +
+                       f" [this arm times a bounded sample per step: {R} seq x {cols} columns of the same generator; "
+                       "cells/s is size-independent for the reference, which is linear in the column count]"),
         "cpu_baseline": {"value": value, "unit": "cells/s", "cores": 1, "kind": kind, "sample": sample,
                          "host_cores": os.cpu_count()},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -182,6 +185,105 @@ def workload_config(n, config=2):
             "parallelism": f"column-sharded x{n}" if n > 1 else "single GPU"}
 
 
+def kernel_profile(ctx, view, steps):
+    """Per-kernel CUDA-event times of `steps` transforms (profiling adds an event pair per launch)."""
+    ctx.set_profiling(True)
+    acc = {}
+    for _ in range(steps):
+        ctx.msa_transform_device(view, L)
+        for name, t in ctx.kernel_times():
+            acc[name] = acc.get(name, 0.0) + t
+    ctx.set_profiling(False)
+    return {k: v / steps for k, v in acc.items()}
+
+
+def measure_device(lib, ctx, dist, dev, rank, world, rows, cols_per_gpu, steps, warmup, exchange):
+    """Device-resident leg: window [rank] of a rows x (world * cols_per_gpu) alignment generated in HBM, `steps`
+    transforms timed with CUDA events (max over ranks), then the per-kernel profile. Returns a dict (rank-local)."""
+    import torch
+
+    import edsparser_b200 as E
+    from edsparser_b200 import shard
+
+    total_cols = cols_per_gpu * world
+    halo = HALO
+    while True:
+        lo, hi, wb, we = shard.plan(total_cols, world, rank, halo)
+        view = ctx.msa_synth(rows, total_cols, WRAP, col_begin=wb, col_count=we - wb, seed=SEED, variable_ppm=PPM)
+        view.own_begin, view.own_end = lo, hi
+        try:
+            ctx.msa_transform_device(view, L)
+            break
+        except E.EdsError as err:  # EDS_ERR_HALO: a symbol does not close inside the window -> widen and retry
+            if err.status != E.EDS_ERR_HALO or halo > (1 << 24):
+                raise
+            halo *= 4
+
+    c_e, c_s, c_st = E.Buffer(), E.Buffer(), E.capi.MsaStats()
+    c_args = (ctx.handle, ctypes.byref(view), L, 1, ctypes.byref(c_e), ctypes.byref(c_s), ctypes.byref(c_st))
+    c_call = lib.L.eds_msa_transform_device
+
+    def step():
+        # the bare C call with preallocated argument structs: the transform returns after a device synchronisation, so
+        # every microsecond of Python between two calls is device idle time inside the timed region
+        rc = c_call(*c_args)
+        if rc:
+            lib.check(rc)
+        # file offsets of this rank's slices: all-gather of the byte counts, issued behind the transform; the host
+        # reads them once, before it writes (exchange.offsets() after the loop)
+        exchange.post(c_e.bytes, c_s.bytes)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    launches_per_step = int(c_st.gpu_launches)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        step()
+    exchange.flush()  # the last exchanges are inside the timed region
+    ev1.record()
+    barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    out_bytes = int(c_e.bytes) + int(c_s.bytes)
+    kern = kernel_profile(ctx, view, min(steps, 5))
+    row_bytes = (we - 1) + (we - 1) // WRAP - (wb + wb // WRAP) + 1
+    return {"view": view, "ms_total": ms_total, "out_bytes": out_bytes, "kern": kern, "lo": lo, "hi": hi, "wb": wb, "we": we,
+            "row_bytes": row_bytes, "launches_per_step": launches_per_step, "halo": halo}
+
+
+def roofline_of(m, rows, steps, world, serial_kern=None):
+    """roofline object of one measured leg: dominant kernel = the scan (fused with the column gather when it runs)."""
+    peak, peak_src = peaks()
+    kern = m["kern"]
+    name = "k_scan_fused" if "k_scan_fused" in kern else "k_scan"
+    scan_ms = kern.get(name, 0.0)
+    scan_bytes = rows * m["row_bytes"]  # every cell of the window read once (newlines ride along)
+    achieved = scan_bytes / (scan_ms / 1e3) / 1e9 if scan_ms > 0 else 0.0
+    # whole step, summed over ranks: cells of the owned ranges + output bytes of this rank x ranks (ranks are alike)
+    step_alg_bytes = (rows * (m["hi"] - m["lo"]) + m["out_bytes"]) * world
+    step_gbs = step_alg_bytes * steps / (m["ms_total"] / 1e3) / 1e9
+    out = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+           "traffic": ncu_traffic(name, rows, m["we"] - m["wb"]), "peak_source": peak_src, "kernel_ms": scan_ms,
+           "algorithmic_bytes_per_launch": scan_bytes,
+           "step": {"algorithmic_bytes": step_alg_bytes, "achieved_gbs": step_gbs, "frac": step_gbs / (peak * world),
+                    "peak_aggregate": peak * world},
+           "kernels_ms": {k: round(v, 4) for k, v in kern.items()},
+           "kernels_ms_note": "CUDA events around each launch while independent kernels overlap on side streams "
+                              "(overlapped ones read long); kernels_ms_serial = the same with everything on one stream"}
+    if serial_kern:
+        out["kernels_ms_serial"] = {k: round(v, 4) for k, v in serial_kern.items()}
+    return out
+
+
 def run_ours(args, rank, world):
     import torch
     import torch.distributed as dist
@@ -199,80 +301,38 @@ def run_ours(args, rank, world):
 
     from edsparser_b200 import shard
 
-    total_cols = C_PER_GPU * world
-    lo, hi, wb, we = shard.plan(total_cols, world, rank, HALO)
-    view = ctx.msa_synth(R, total_cols, WRAP, col_begin=wb, col_count=we - wb, seed=SEED, variable_ppm=PPM)
-    view.own_begin, view.own_end = lo, hi
     counts = torch.zeros(2, dtype=torch.int64, device=dev)
     gathered = torch.zeros(2 * world, dtype=torch.int64, device=dev)
     exchange = shard.OffsetExchange(dist if world > 1 else None, dev)
-
-    # the bare C call with preallocated argument structs: the transform returns after a device synchronisation, so
-    # every microsecond of Python between two calls is device idle time inside the timed region
-    c_e, c_s, c_st = E.Buffer(), E.Buffer(), E.capi.MsaStats()
-    c_args = (ctx.handle, ctypes.byref(view), L, 1, ctypes.byref(c_e), ctypes.byref(c_s), ctypes.byref(c_st))
-    c_call = lib.L.eds_msa_transform_device
-
-    def step():
-        rc = c_call(*c_args)
-        if rc:
-            lib.check(rc)
-        # file offsets of this rank's slices: all-gather of the byte counts, issued behind the transform; the host
-        # reads them once, before it writes (exchange.offsets() after the loop)
-        exchange.post(c_e.bytes, c_s.bytes)
-        return c_e, c_s, c_st
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        e, s, st = step()
-    launches_per_step = int(st.gpu_launches)
+    def serial_profile(view):
+        """the same transform on a context whose kernels all run on one stream: per-kernel times without overlap"""
+        os.environ["EDSB_DEBUG_SERIAL"] = "1"
+        try:
+            c2 = lib.context(local, stream)
+        finally:
+            del os.environ["EDSB_DEBUG_SERIAL"]
+        try:
+            c2.msa_transform_device(view, L)
+            return kernel_profile(c2, view, 3)
+        finally:
+            c2.close()
 
+    warmup = max(args.warmup, 3)
     sampler = ClockSampler(local) if rank == 0 else None
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        e, s, st = step()
-    exchange.flush()  # the last exchanges are inside the timed region
-    ev1.record()
-    barrier()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    m = measure_device(lib, ctx, dist, dev, rank, world, R, C_PER_GPU, args.steps, warmup, exchange)
     my_offsets = exchange.offsets()  # (eds offset, seds offset, eds total, seds total) of this rank's slices
     clocks = sampler.stop() if sampler else None
+    view, ms_total, out_bytes = m["view"], m["ms_total"], m["out_bytes"]
     cells_step = R * C_PER_GPU * world
     value = cells_step * args.steps / (ms_total / 1e3)
-    out_bytes = int(e.bytes) + int(s.bytes)
-
-    # ---- per-kernel times (CUDA events on the launch stream) for the roofline of the dominant kernel
-    ctx.set_profiling(True)
-    acc = {}
-    prof_steps = min(args.steps, 5)
-    for _ in range(prof_steps):
-        ctx.msa_transform_device(view, L)
-        for name, t in ctx.kernel_times():
-            acc[name] = acc.get(name, 0.0) + t
-    ctx.set_profiling(False)
-    kern = {k: v / prof_steps for k, v in acc.items()}
-    peak, peak_src = peaks()
-    scan_ms = kern.get("k_scan", 0.0)
-    row_bytes = (we - 1) + (we - 1) // WRAP - (wb + wb // WRAP) + 1
-    scan_bytes = R * row_bytes  # every cell of the window read once (newlines ride along)
-    achieved = scan_bytes / (scan_ms / 1e3) / 1e9 if scan_ms > 0 else 0.0
-    step_alg_bytes = R * (hi - lo) + out_bytes
-    roofline = {"bound": "hbm", "kernel": "k_scan", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
-                "kernel_ms": scan_ms, "algorithmic_bytes_per_launch": scan_bytes,
-                "step": {"algorithmic_bytes": step_alg_bytes,
-                         "achieved_gbs": step_alg_bytes * args.steps / (ms_total / 1e3) / 1e9,
-                         "frac": step_alg_bytes * args.steps / (ms_total / 1e3) / 1e9 / peak},
-                "kernels_ms": {k: round(v, 4) for k, v in kern.items()}}
+    roofline = roofline_of(m, R, args.steps, world, serial_profile(view))
+    launches_per_step = m["launches_per_step"]
 
     # ---- end to end: .msa bytes in pinned host memory -> eds_msa_transform_host -> host strings
     text = ctx.download(E.Buffer(view.text, view.text_bytes)) if world == 1 and args.config == 2 else None
@@ -296,6 +356,7 @@ def run_ours(args, rank, world):
         e2e = {"value": cells_step * e2e_steps / dt, "unit": "cells/s", "h2d_bytes_per_step": len(text),
                "d2h_bytes_per_step": len(he) + len(hs), "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
                "api": "eds_msa_transform_host_view (index + H2D + kernels + D2H into pinned host memory), pinned input"}
+        del pinned
     else:
         # per-rank shard from pinned host memory, same call; slowest rank decides
         shard_text = ctx.download(E.Buffer(view.text, view.text_bytes))
@@ -327,6 +388,27 @@ def run_ours(args, rank, world):
                "h2d_bytes_per_step": len(shard_text) * world, "d2h_bytes_per_step": nout * world,
                "ms_per_step": 1e3 * float(dt.item()) / e2e_steps, "steps": e2e_steps,
                "api": "per rank: pinned H2D + eds_msa_transform_device + D2H into pinned host memory + NCCL all-gather of offsets"}
+        del pinned, dtext
+    ctx.msa_synth_free()
+
+    # ---- BASELINE config 4 (1000 x 30 Mbp, strong-scaled over the ranks) rides in the same line: the configuration the
+    # north-star fraction is quoted on. Device-resident only.
+    config4 = None
+    if args.config == 2 and not args.no_config4:
+        try:
+            rows4, cols4 = 1000, 30_000_000 // world
+            steps4 = max(3, min(args.steps, 10))
+            m4 = measure_device(lib, ctx, dist, dev, rank, world, rows4, cols4, steps4, 3, exchange)
+            exchange.offsets()
+            r4 = roofline_of(m4, rows4, steps4, world, serial_profile(m4["view"]) if world == 1 else None)
+            ctx.msa_synth_free()
+            config4 = {"workload": f"config 4: synthetic MSA {rows4} seq x {cols4 * world} columns, 1% variable columns, wrap {WRAP}, "
+                                   f"msa2eds -l {L}, column-sharded over {world} GPU(s), halo {m4['halo']}",
+                       "scaling": "strong", "steps": steps4, "ms_per_step": m4["ms_total"] / steps4,
+                       "value": rows4 * cols4 * world * steps4 / (m4["ms_total"] / 1e3), "unit": "cells/s",
+                       "output_bytes_per_rank": m4["out_bytes"], "roofline": r4}
+        except Exception as err:  # the headline line must still be printed
+            config4 = {"error": str(err)[:300]}
 
     # ---- CPU baseline: the reference library on a bounded sample (rank 0, N = 1 only)
     cpu = None
@@ -349,11 +431,11 @@ def run_ours(args, rank, world):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak" if args.config == 2 else "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(world, args.config), "gb_per_s": value / 1e9, "e2e": e2e, "roofline": roofline,
             "cpu_baseline": cpu, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
-            "output_bytes_per_step": out_bytes, "library": lib.version(),
+            "output_bytes_per_step": out_bytes, "library": lib.version(), "config4": config4,
         }
         print(json.dumps(line), flush=True)
     barrier()  # every rank has finished its device work before any rank tears its context down
@@ -377,6 +459,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-config4", action="store_true", help="skip the config-4 (1000 x 30 Mbp) leg of the default run")
     ap.add_argument("--config", type=int, default=2, choices=[2, 4],
                     help="2 (default, the metric's configuration): 100 x 10 Mbp per GPU, weak scaling; 4: BASELINE config 4, "
                          "1000 x 30 Mbp column-sharded over the N GPUs (strong scaling, no e2e / cpu legs)")

@@ -144,6 +144,10 @@ eds_status eds_ctx_create(int device, void* stream, eds_ctx** out) {
 #ifndef EDSB_EMU
         if (const char* fg = getenv("EDSB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg));
 #endif
+        if (const char* fz = getenv("EDSB_FUSED")) ctx->fused = atoi(fz) != 0;
+        if (const char* fz = getenv("EDSB_FUSED_MIN_ROWS")) ctx->fused_min_rows = (uint32_t)atoi(fz);
+        if (const char* fz = getenv("EDSB_FUSED_NC")) ctx->fused_nc = (uint32_t)atoi(fz);
+        if (const char* fz = getenv("EDSB_FUSED_STAGES")) ctx->fused_stages = (uint32_t)atoi(fz);
         if (const char* hm = getenv("EDSB_DEBUG_HASH_MASK")) ctx->hash_mask = strtoull(hm, nullptr, 0);
         if (const char* no = getenv("EDSB_DEBUG_NARROW_OFF")) ctx->narrow_off = atoi(no);
         if (const char* rs = getenv("EDSB_DEBUG_ROW_SLICES")) ctx->scan_row_slices = (uint32_t)atoi(rs);

@@ -64,6 +64,11 @@ struct eds_ctx {
     cudaStream_t aux[2] = {nullptr, nullptr};
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool serial = false;  // EDSB_DEBUG_SERIAL=1: everything on the main stream
+    // k_scan_fused (scan + variable-column gather in one pass, scan_fused.cuh); EDSB_FUSED=0 selects k_scan + k_stash
+    bool fused = true;
+    uint32_t fused_min_rows = 32;  // shallower alignments: a tile is too small to pay for the staging
+    uint32_t fused_nc = 0;         // EDSB_FUSED_NC: force the cluster size (0 = by row count)
+    uint32_t fused_stages = 0;     // EDSB_FUSED_STAGES: cap the ring depth (0 = what fits)
     int sm_count = 148;
     size_t smem_optin = 227 * 1024;
     uint32_t partitions = 0;          // 0 = default

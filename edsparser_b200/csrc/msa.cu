@@ -215,6 +215,10 @@ __global__ void __launch_bounds__(kScanThreads, EDSB_SCAN_MINB) k_scan(MsaGeom g
     if (bad) atomicOr(&st->bad_msa, (uint32_t)kBadNewlineLayout);
 }
 
+}  // namespace edsb
+#include "scan_fused.cuh"
+namespace edsb {
+
 // ---------------------------------------------------------------------------------------------
 // k_colbits: p-space mismatch bits -> column-space V (variable) and T (run start) words, row 0 in
 // column space, per-partition counts. Thread per 32-column word.
@@ -1590,7 +1594,7 @@ MsaPipeline::MsaPipeline(eds_ctx* ctx) : ctx_(ctx) {
 MsaPipeline::~MsaPipeline() {
     DevBuf* all[] = {&d_rows_, &d_mism_, &d_vbits_, &d_tbits_, &d_rank_, &d_refc_, &d_part_, &d_varcol_, &d_runs_,
                      &d_sym_, &d_stash_, &d_altid_, &d_leadmask_, &d_symmeta_, &d_eds_, &d_seds_, &d_ws_, &d_status_,
-                     &d_rowbits_, &d_seen_, &d_id_text_};
+                     &d_rowbits_, &d_seen_, &d_id_text_, &d_fz_rows_, &d_fz_tmp_, &d_fz_col_, &d_fz_cnt_};
     for (DevBuf* d : all) d->release();
     if (h_status_) cudaFreeHost(h_status_);
 }
@@ -1688,6 +1692,140 @@ void MsaPipeline::prepare(const eds_msa_view& v, uint32_t l, int leds) {
     d_rank_.reserve((size_t)(g.n_words + 1) * 4);
     d_refc_.reserve((size_t)g.n_words * 32 + 32);
     d_part_.reserve((size_t)P * (8 + 8 + 16));
+    plan_fused();
+}
+
+// k_scan_fused geometry for the alignment of prepare(): cluster size (rows per CTA <= 128), stages that fit in shared
+// memory, the per-CTA row tables (slot 0 = row 0, then the CTA's rows sorted by word shift), co-resident clusters.
+void MsaPipeline::plan_fused() {
+    const MsaGeom& g = geom_;
+    fz_ = FzPlan();
+    if (!ctx_->fused || g.R < ctx_->fused_min_rows) return;
+    uint32_t NC = 1;
+    while (NC < kFzMaxNC && (g.R + NC - 1) / NC > kFzGroupRows) NC <<= 1;
+    if (ctx_->fused_nc) NC = ctx_->fused_nc;
+    if ((g.R + NC - 1) / NC > kFzGroupRows || NC > kFzMaxNC) return;  // too deep for one cluster: k_scan + k_stash
+#ifdef EDSB_EMU
+    if (NC > 1) return;  // clusters are not emulated
+#endif
+    const uint32_t RG = (((g.R + NC - 1) / NC) + 31u) & ~31u;
+    const uint32_t slot_pitch = 1u + RG;
+    uint32_t S = 0;
+    for (uint32_t s = 6; s >= 2; --s)
+        if (fz_smem_bytes(s, NC, RG, slot_pitch) + 1024 <= ctx_->smem_optin) {
+            S = s;
+            break;
+        }
+    if (ctx_->fused_stages && ctx_->fused_stages <= S) S = ctx_->fused_stages;
+    if (S < 2) return;
+    const uint32_t n_tiles = (g.n_chunks + kFzT - 1) / kFzT;
+    fz_.S = S;
+    fz_.NC = NC;
+    fz_.RG = RG;
+    fz_.slot_pitch = slot_pitch;
+    fz_.smem = fz_smem_bytes(S, NC, RG, slot_pitch);
+
+    // per-CTA tables, one upload: pack[NC][slot_pitch] u64 | meta[NC][8] u32 | info[NC][RG] u16
+    const size_t off_meta = (size_t)NC * slot_pitch * 8, off_info = off_meta + (size_t)NC * 32;
+    h_fz_.assign(off_info + (((size_t)NC * RG * 2 + 15) & ~(size_t)15), 0);
+    uint64_t* pack = reinterpret_cast<uint64_t*>(h_fz_.data());
+    uint32_t* meta = reinterpret_cast<uint32_t*>(h_fz_.data() + off_meta);
+    uint16_t* info = reinterpret_cast<uint16_t*>(h_fz_.data() + off_info);
+    const uint64_t* row_start = h_rows_.data();
+    auto packed = [&](uint32_t r) {
+        const long long d = (long long)row_start[r] - (long long)g.a0;
+        return (uint64_t)(reinterpret_cast<uintptr_t>(g.text) + (unsigned long long)((d >> 4) * 16)) | (uint64_t)(d & 15);
+    };
+    for (uint32_t c = 0; c < NC; ++c) {
+        const uint32_t lo = c * RG, hi = std::min(g.R, lo + RG);
+        uint32_t count[4] = {0, 0, 0, 0};
+        for (uint32_t r = std::max(lo, 1u); r < hi; ++r) ++count[(packed(r) & 15) >> 2];
+        uint32_t* m = meta + (size_t)c * 8;
+        m[1] = 1;
+        for (int k = 0; k < 4; ++k) m[2 + k] = m[1 + k] + count[k];
+        m[0] = m[5];
+        m[6] = lo;
+        m[7] = hi > lo ? hi - lo : 0;
+        uint32_t at[4] = {m[1], m[2], m[3], m[4]};
+        uint64_t* pk = pack + (size_t)c * slot_pitch;
+        pk[0] = packed(0);
+        for (uint32_t rl = 0; rl < RG; ++rl) {
+            const uint32_t r = lo + rl;
+            uint16_t v = 0xffffu;
+            if (r == 0) {
+                v = 0;
+            } else if (r < hi) {
+                const uint64_t e = packed(r);
+                const uint32_t slot = at[(e & 15) >> 2]++;
+                pk[slot] = e;
+                v = (uint16_t)((slot << 4) | (uint32_t)(e & 15));
+            }
+            info[(size_t)c * RG + rl] = v;
+        }
+    }
+    cudaStream_t s = ctx_->stream;
+    d_fz_rows_.reserve(h_fz_.size());
+    EDSB_CUDA(cudaMemcpyAsync(d_fz_rows_.p, h_fz_.data(), h_fz_.size(), cudaMemcpyHostToDevice, s));
+
+    // co-resident clusters (one CTA per SM at these shared-memory sizes): the grid is persistent
+    uint32_t regions = 0;
+#ifdef EDSB_EMU
+    regions = 3;
+#else
+    const uint32_t key = (NC << 24) ^ (S << 16) ^ slot_pitch;
+    if (fz_attr_smem_ < fz_.smem) {
+        EDSB_CUDA(cudaFuncSetAttribute(k_scan_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz_.smem));
+        fz_attr_smem_ = fz_.smem;
+    }
+    if (fz_occ_key_ != key) {
+        if (NC == 1) {
+            int per_sm = 0;
+            EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_fused, (kFzCW + 1) * 32, fz_.smem));
+            fz_occ_regions_ = (uint32_t)std::max(0, per_sm) * (uint32_t)ctx_->sm_count;
+        } else {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(NC * (uint32_t)ctx_->sm_count, 1, 1);
+            cfg.blockDim = dim3((kFzCW + 1) * 32, 1, 1);
+            cfg.dynamicSmemBytes = fz_.smem;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = NC;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            int n = 0;
+            EDSB_CUDA(cudaOccupancyMaxActiveClusters(&n, k_scan_fused, &cfg));
+            fz_occ_regions_ = (uint32_t)std::max(0, n);
+        }
+        fz_occ_key_ = key;
+    }
+    regions = fz_occ_regions_;
+#endif
+    regions = std::min(regions, n_tiles);
+    if (regions == 0) return;
+    fz_.regions = regions;
+    d_fz_cnt_.reserve((size_t)regions * 4);
+
+    FzParams& f = fzp_;
+    memset(&f, 0, sizeof(f));
+    f.pack = reinterpret_cast<const unsigned long long*>(d_fz_rows_.as<unsigned char>());
+    f.meta = reinterpret_cast<const uint32_t*>(d_fz_rows_.as<unsigned char>() + off_meta);
+    f.info = reinterpret_cast<const uint16_t*>(d_fz_rows_.as<unsigned char>() + off_info);
+    f.region_count = d_fz_cnt_.as<uint32_t>();
+    f.S = S;
+    f.NC = NC;
+    f.RG = RG;
+    f.slot_pitch = slot_pitch;
+    f.n_tiles = n_tiles;
+    f.all_aligned = g.all_aligned;
+    // tile t is fetched with bulk copies when vectors [32 t + dmin, 32 t + 32 + dmax] all lie inside the buffer
+    const long long T = (long long)kFzT, vmax = (long long)g.n_vec - 1;
+    f.tile_lo_ok = g.d_min_vec >= 0 ? 0 : (-g.d_min_vec + T - 1) / T;
+    const long long top = vmax - T - g.d_max_vec;
+    f.tile_hi_ok = top < 0 ? 0 : top / T + 1;
+    fz_.on = true;
 }
 
 void MsaPipeline::bind(MsaBufs& b) {
@@ -1718,6 +1856,16 @@ void MsaPipeline::bind(MsaBufs& b) {
     d_symmeta_.reserve((size_t)(cap_runs_ + 2) * (4 + 8 + 8 + 8));
     d_eds_.reserve(cap_eds_);
     d_seds_.reserve(cap_seds_);
+    if (fz_.on) {
+        // every cluster fills its own region of the temporary stash; 25 % + 64 slots of slack over an even split
+        fz_.capc = (uint32_t)(((uint64_t)cap_var_ + cap_var_ / 4) / fz_.regions + 64);
+        d_fz_tmp_.reserve((size_t)fz_.regions * fz_.capc * g.Rp);
+        d_fz_col_.reserve((size_t)fz_.regions * fz_.capc * 4);
+        fzp_.capc = fz_.capc;
+        fzp_.tmp_stash = d_fz_tmp_.as<uint8_t>();
+        fzp_.tmp_col = d_fz_col_.as<uint32_t>();
+        fzp_.mism16 = reinterpret_cast<uint16_t*>(d_mism_.p);
+    }
     b.varcol = d_varcol_.as<uint32_t>();
     b.runs = d_runs_.as<uint32_t>();
     b.sym = d_sym_.as<uint32_t>();
@@ -1746,9 +1894,36 @@ void MsaPipeline::bind(MsaBufs& b) {
     b.cap_seds = cap_seds_;
 }
 
-void MsaPipeline::launch_scan(const MsaBufs& b) {
+void MsaPipeline::launch_scan(const MsaBufs& b, bool allow_fused) {
     const MsaGeom& g = geom_;
     cudaStream_t s = ctx_->stream;
+    if (allow_fused && fz_.on) {
+        ctx_->clock.begin("k_scan_fused");
+        const uint32_t threads = (kFzCW + 1) * 32, blocks = fz_.regions * fz_.NC;
+#ifdef EDSB_EMU
+        EDSB_LAUNCH(k_scan_fused, blocks, threads, fz_.smem, s, g, fzp_, b.status);
+#else
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(blocks, 1, 1);
+        cfg.blockDim = dim3(threads, 1, 1);
+        cfg.dynamicSmemBytes = fz_.smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = fz_.NC;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = fz_.NC > 1 ? 1 : 0;
+        EDSB_CUDA(cudaLaunchKernelEx(&cfg, k_scan_fused, g, fzp_, b.status));
+#endif
+        ctx_->clock.end();
+        ctx_->clock.begin("k_colbits");
+        EDSB_LAUNCH(k_colbits, partitions(), kPartThreads, 0, s, g, b.mism, b.vbits, b.tbits, b.refc, b.part_cnt);
+        ctx_->clock.end();
+        return;
+    }
     const uint32_t per_sm = ctx_->scan_blocks_per_sm ? ctx_->scan_blocks_per_sm : 16u;
     const uint32_t tiles = (g.n_chunks + 31) / 32;
     const uint32_t blocks = std::max(1u, std::min((tiles + 7) / 8, (uint32_t)ctx_->sm_count * per_sm));
@@ -1778,7 +1953,7 @@ void MsaPipeline::run_once(MsaBufs& b) {
     const uint32_t P = partitions();
     const uint32_t sms = (uint32_t)ctx_->sm_count;
     EDSB_CUDA(cudaMemsetAsync(b.status, 0, sizeof(MsaStatus), s));
-    launch_scan(b);
+    launch_scan(b, true);
 
     ctx_->clock.begin("k_compact");
     EDSB_LAUNCH(k_compact, P, kPartThreads, 0, s, g, b);
@@ -1793,9 +1968,15 @@ void MsaPipeline::run_once(MsaBufs& b) {
         EDSB_CUDA(cudaStreamWaitEvent(waiter, ev, 0));
     };
     after(s1, s, ctx_->ev[0]);
-    ctx_->clock.begin("k_stash", s1);
-    EDSB_LAUNCH(k_stash, sms * 8u, kStashThreads, 0, s1, g, b);
-    ctx_->clock.end();
+    if (fz_.on) {
+        ctx_->clock.begin("k_restash", s1);
+        EDSB_LAUNCH(k_restash, sms * 8u, 256, 0, s1, g, b, fzp_, fz_.regions);
+        ctx_->clock.end();
+    } else {
+        ctx_->clock.begin("k_stash", s1);
+        EDSB_LAUNCH(k_stash, sms * 8u, kStashThreads, 0, s1, g, b);
+        ctx_->clock.end();
+    }
 
     ctx_->clock.begin("k_sym_count");
     EDSB_LAUNCH(k_sym_count, P, kPartThreads, 0, s, g, b);
@@ -1965,6 +2146,8 @@ void MsaPipeline::transform(const eds_msa_view& view, uint32_t l, int leds, eds_
         if (++retries > 8) throw std::runtime_error("edsparser_b200: buffer sizing did not converge");
         if (st.abort == kAbortVarCap || st.abort == kAbortRunsCap) {
             cap_var_ = std::max<uint32_t>(cap_var_, (uint32_t)std::min<uint64_t>(st.need_var + st.need_var / 16 + 64, 0x7fffffffu));
+            if (fz_.on && st.fz_need)  // a cluster's region of the temporary stash overflowed: size for the fullest one
+                cap_var_ = std::max<uint32_t>(cap_var_, (uint32_t)std::min<uint64_t>((uint64_t)st.fz_need * fz_.regions, 0x7fffffffu));
             cap_runs_ = std::max<uint32_t>(cap_runs_, (uint32_t)std::min<uint64_t>(st.need_runs + st.need_runs / 16 + 64, 0xfffffff0u));
         } else {
             cap_eds_ = std::max<uint64_t>(cap_eds_, st.need_eds + st.need_eds / 16 + 4096);
@@ -2008,7 +2191,7 @@ void MsaPipeline::conserved_bits(const eds_msa_view& view, uint8_t* out_bits, ui
     bind(b);
     cudaStream_t s = ctx_->stream;
     EDSB_CUDA(cudaMemsetAsync(b.status, 0, sizeof(MsaStatus), s));
-    launch_scan(b);
+    launch_scan(b, false);
     std::vector<uint32_t> words(g.n_words);
     EDSB_CUDA(cudaMemcpyAsync(words.data(), b.vbits, (size_t)g.n_words * 4, cudaMemcpyDeviceToHost, s));
     EDSB_CUDA(cudaMemcpyAsync(h_status_, b.status, sizeof(MsaStatus), cudaMemcpyDeviceToHost, s));

@@ -67,6 +67,7 @@ struct MsaStatus {
     uint32_t abort;
     uint32_t bad_msa;
     uint32_t halo_fail;
+    uint32_t fz_need;  // k_scan_fused: most variable columns any cluster found (its region of the temporary stash overflowed)
     uint64_t need_var, need_runs, need_eds, need_seds;  // capacities wanted by the stage that aborted
     unsigned long long eds_total, seds_total, n_alts;
     uint64_t first_open_col;

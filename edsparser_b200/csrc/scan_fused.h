@@ -1,0 +1,42 @@
+// Launch geometry of k_scan_fused (scan_fused.cuh), shared by the kernel and the host launcher.
+#pragma once
+#include "msa_kernels.cuh"
+#include "pipe.cuh"
+
+namespace edsb {
+
+constexpr uint32_t kFzT = 32;                    // 16-byte chunks per tile (lane = chunk)
+constexpr uint32_t kFzPitch = 16u * kFzT + 16u;  // bytes per staged row
+constexpr uint32_t kFzMaxNC = 8;                 // portable cluster size
+constexpr uint32_t kFzGroupRows = 128;           // most rows of one CTA (4 per lane in the gather)
+#ifdef EDSB_EMU
+constexpr int kFzCW = 2;
+#else
+constexpr int kFzCW = 8;
+#endif
+
+struct FzParams {
+    const unsigned long long* pack;  // [NC][slot_pitch]: (address of the vector holding p-space byte 0) | byte shift; slot 0 = row 0
+    const uint32_t* meta;            // [NC][8]: slots, class boundaries cls[0..4] (slot indices), first row, rows
+    const uint16_t* info;            // [NC][RG]: local row -> slot << 4 | shift (0xffff: no such row)
+    uint16_t* mism16;
+    uint8_t* tmp_stash;              // [regions * capc][Rp]
+    uint32_t* tmp_col;               // [regions * capc]: window column of the slot
+    uint32_t* region_count;          // [regions]
+    uint32_t S, NC, RG, slot_pitch, n_tiles, capc, all_aligned;
+    long long tile_lo_ok, tile_hi_ok;  // tiles [lo, hi) can be fetched with bulk copies (every vector inside the buffer)
+};
+
+inline size_t fz_smem_bytes(uint32_t S, uint32_t NC, uint32_t RG, uint32_t slot_pitch) {
+    size_t b = (size_t)S * slot_pitch * kFzPitch;  // stages
+    b += (size_t)kFzCW * 32 * 16;                  // red
+    b += (size_t)2 * NC * 32 * 4;                  // mask_in
+    b += (size_t)slot_pitch * 8;                   // s_pack
+    b += ((size_t)RG * 2 + 15) & ~(size_t)15;      // s_info
+    b += (size_t)16 * kFzT * 2;                    // s_vpos
+    b += 16;                                       // s_misc
+    b += (size_t)(2 * S + 3) * sizeof(Mbar) + 16;  // barriers
+    return b;
+}
+
+}  // namespace edsb

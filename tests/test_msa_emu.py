@@ -70,3 +70,23 @@ def test_partition_count_does_not_matter():
             msa_checks.check_random_against_oracle(c, seed=9, n_cases=5, max_cols=150)
     finally:
         c.close()
+
+
+def test_fused_scan_path():
+    """k_scan_fused (one CTA per tile under the emulator: clusters are GPU-only) against the oracle."""
+    import os
+
+    os.environ["EDSB_FUSED_MIN_ROWS"] = "2"
+    try:
+        c = emu_lib.lib().context()
+    finally:
+        del os.environ["EDSB_FUSED_MIN_ROWS"]
+    try:
+        c.set_tuning(3, 1)
+        c.set_profiling(True)
+        msa_checks.check_random_against_oracle(c, seed=3, n_cases=12, max_cols=700)
+        assert "k_scan_fused" in [n for n, _ in c.kernel_times()]
+        msa_checks.check_shards(c, on_gpu=False, seed=4, n_cases=4, max_cols=150)
+        msa_checks.check_synth(c, n_rows=40, n_cols=2500, wrap=80, l=10, variable_ppm=40000, shards=1)
+    finally:
+        c.close()

@@ -89,3 +89,31 @@ def test_synth_many_rows(ctx):
 def test_synth_wide_rows(ctx):
     # R > 4096: per-warp scratch moves to global memory; R > 65535 would switch ids to uint32
     msa_checks.check_synth(ctx, n_rows=5000, n_cols=3_000, wrap=70, l=5, variable_ppm=20000)
+
+
+def test_synth_cluster_sizes(ctx):
+    # k_scan_fused splits the rows of a tile over a thread-block cluster: 1 CTA up to 128 rows, then 2, 4, 8
+    for rows in (33, 128, 129, 200, 300, 520, 777, 1024):
+        st = msa_checks.check_synth(ctx, n_rows=rows, n_cols=40_000, wrap=80, l=10, variable_ppm=15000, shards=2)
+        assert st["n_variable_cols"] > 300
+
+
+def test_fused_scan_matches_two_pass(lib):
+    # the same alignments through k_scan + k_stash (EDSB_FUSED=0) and through k_scan_fused
+    import os
+
+    for env in ("0", "1"):
+        os.environ["EDSB_FUSED"] = env
+        try:
+            c = lib.context(0)
+        finally:
+            del os.environ["EDSB_FUSED"]
+        try:
+            c.set_profiling(True)
+            msa_checks.check_synth(c, n_rows=100, n_cols=150_000, wrap=80, l=10)
+            names = [n for n, _ in c.kernel_times()]
+            assert ("k_scan_fused" in names) == (env == "1") and ("k_stash" in names) == (env == "0")
+            c.set_profiling(False)
+            msa_checks.check_random_against_oracle(c, seed=5, n_cases=30, max_rows=150, max_cols=3000)
+        finally:
+            c.close()
