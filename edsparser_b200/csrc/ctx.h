@@ -69,6 +69,9 @@ struct eds_ctx {
     uint32_t fused_min_rows = 32;  // shallower alignments: a tile is too small to pay for the staging
     uint32_t fused_nc = 0;         // EDSB_FUSED_NC: force the cluster size (0 = by row count)
     uint32_t fused_stages = 0;     // EDSB_FUSED_STAGES: cap the ring depth (0 = what fits)
+    uint32_t fused_pw = 0;         // EDSB_FUSED_PW: producer warps (0 = default)
+    uint32_t fused_dw = 0;         // EDSB_FUSED_DW: duty warps (0 = default)
+    uint32_t fused_mode = 0;       // EDSB_FUSED_MODE: 0 = one bulk copy (TMA) per row (measured faster), 1 = 16-byte cp.async per lane
     int sm_count = 148;
     size_t smem_optin = 227 * 1024;
     uint32_t partitions = 0;          // 0 = default

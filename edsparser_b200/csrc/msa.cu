@@ -831,6 +831,29 @@ __device__ __forceinline__ bool warp_classify(Seen& sn, uint32_t ch, bool valid,
     return true;
 }
 
+// byte i (0..31) of the 32 bytes held in v[0..8)
+__device__ __forceinline__ uint32_t byte_of32(const uint32_t (&v)[8], uint32_t i) {
+    uint32_t w = v[0];
+#pragma unroll
+    for (uint32_t q = 1; q < 8u; ++q) w = (i >> 2) == q ? v[q] : w;
+    return (w >> ((i & 3u) * 8u)) & 0xffu;
+}
+
+// bit i = (byte i of the 32 bytes in v == ch)
+__device__ __forceinline__ uint32_t eq_mask32(const uint32_t (&v)[8], uint32_t ch) {
+    const uint32_t sp = ch * 0x01010101u;
+    uint32_t m = 0;
+#pragma unroll
+    for (uint32_t q = 0; q < 8u; ++q) m |= eq_bytes4(v[q], sp) << (4u * q);
+    return m;
+}
+
+// Single-column symbol, many rows: a LANE owns 32 consecutive rows — one word of every alternative's row bitset.
+// It peels its distinct residues off in order of first row (one SIMD byte compare over its 32 bytes per distinct
+// residue: the compare IS the bitset word), the warp merges the lanes' lists in lane order (= row order) into the
+// symbol's residue list, and every lane stores its words under the merged numbering: 128-byte coalesced stores.
+// ~600 warp instructions per 1024 rows instead of 32 dependent ballot rounds. False: more than 8 residues or a
+// NUL byte -> the symbol goes to the hashed warp path (k_group2).
 __device__ bool group_single_warp(const MsaGeom& g, const MsaBufs& b, uint32_t k, uint32_t s, uint32_t& nalts) {
     nalts = 0;
     const uint32_t lane = threadIdx.x & 31;
@@ -838,39 +861,97 @@ __device__ bool group_single_warp(const MsaGeom& g, const MsaBufs& b, uint32_t k
     const uint8_t* col = b.stash + (size_t)slot0 * g.Rp;
     const uint32_t Rw = g.Rp >> 5;
     uint32_t* rowbits = b.rowbits ? b.rowbits + (size_t)slot0 * 8u * Rw : nullptr;
-    Seen sn;
-    sn.lo = sn.hi = sn.n = 0;
-    if (rowbits) {
+    Seen G;
+    G.lo = G.hi = G.n = 0;
+    bool ok = true;
+    if (rowbits && Rw > 32u) {
+        // deeper than 1024 rows: a residue first seen in a later chunk has no words for the earlier chunks
         for (uint32_t i = lane; i < 8u * Rw; i += 32) rowbits[i] = 0u;
         __syncwarp();
     }
-    for (uint32_t r0 = 0; r0 < g.R; r0 += 32) {
-        const uint32_t r = r0 + lane;
-        uint32_t cls;
-        if (!warp_classify(sn, r < g.R ? col[r] : 0u, r < g.R, cls)) {
-            if (b.seen && lane == 0) b.seen[(size_t)slot0 * 3u + 2u] = 0xffu;  // queued as wide: k_emit_var skips it
-            return false;
+    for (uint32_t w0 = 0; w0 < Rw; w0 += 32) {
+        const uint32_t w = w0 + lane;
+        const bool have = w < Rw;
+        uint32_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (have) {
+            const uint4 a = *reinterpret_cast<const uint4*>(col + (size_t)w * 32u), c = *reinterpret_cast<const uint4*>(col + (size_t)w * 32u + 16u);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+            v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
         }
-        if (rowbits) {
-            // rows of every alternative in this chunk: one match groups the lanes by class, the first lane of each
-            // group stores the group's mask (the words of classes without rows here stay zero, see the fill above)
-            const uint32_t key = r < g.R ? cls : 0xffu;
-            const uint32_t peers = __match_any_sync(0xffffffffu, key);
-            if (key < 8u && lane == (uint32_t)__ffs((int)peers) - 1u) rowbits[key * Rw + (r0 >> 5)] = peers;
+        const uint32_t nrows = have ? min(32u, g.R - w * 32u) : 0u;
+        uint32_t remaining = low_bits(nrows);
+        Seen L;
+        L.lo = L.hi = L.n = 0;
+        uint32_t m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        bool lane_ok = true;
+#pragma unroll
+        for (uint32_t j = 0; j < 8u; ++j) {
+            if (remaining) {
+                const uint32_t ch = byte_of32(v, (uint32_t)__ffs((int)remaining) - 1u);
+                if (ch == 0u) lane_ok = false;
+                m[j] = eq_mask32(v, ch) & remaining;
+                remaining &= ~m[j];
+                if (j < 4u) L.lo |= ch << (8u * j); else L.hi |= ch << (8u * (j - 4u));
+                L.n = j + 1u;
+            }
+        }
+        if (remaining) lane_ok = false;  // a ninth residue
+        if (__any_sync(0xffffffffu, !lane_ok)) {
+            ok = false;
+            break;
+        }
+        // merge in lane order: the lowest lane that holds a residue the list does not know appends its news
+        for (;;) {
+            bool news = false;
+            for (uint32_t j = 0; j < L.n; ++j) news = news || seen_lookup(G, seen_byte(L, j)) == 8u;
+            const uint32_t pending = __ballot_sync(0xffffffffu, news);
+            if (!pending) break;
+            const int src = __ffs((int)pending) - 1;
+            const uint32_t slo = __shfl_sync(0xffffffffu, L.lo, src), shi = __shfl_sync(0xffffffffu, L.hi, src);
+            const uint32_t sn = __shfl_sync(0xffffffffu, L.n, src);
+            Seen src_list;
+            src_list.lo = slo;
+            src_list.hi = shi;
+            src_list.n = sn;
+            for (uint32_t j = 0; j < sn; ++j) {
+                const uint32_t ch = seen_byte(src_list, j);
+                if (seen_lookup(G, ch) == 8u) {
+                    if (G.n >= 8u) ok = false; else seen_index(G, ch);
+                }
+            }
+            if (!ok) break;
+        }
+        if (!ok) break;
+        if (rowbits && have) {
+            // words of this lane under the merged numbering
+#pragma unroll
+            for (uint32_t a = 0; a < 8u; ++a) {
+                if (a < G.n) {
+                    const uint32_t j = seen_lookup(L, seen_byte(G, a));
+                    uint32_t word = 0;
+#pragma unroll
+                    for (uint32_t q = 0; q < 8u; ++q) word = j == q ? m[q] : word;
+                    rowbits[a * Rw + w] = word;
+                }
+            }
         }
     }
+    if (!ok) {
+        if (b.seen && lane == 0) b.seen[(size_t)slot0 * 3u + 2u] = 0xffu;  // queued as wide: k_emit_var skips it
+        return false;
+    }
     if (b.seen && lane == 0) {
-        b.seen[(size_t)slot0 * 3u] = sn.lo;
-        b.seen[(size_t)slot0 * 3u + 1u] = sn.hi;
-        b.seen[(size_t)slot0 * 3u + 2u] = sn.n;
+        b.seen[(size_t)slot0 * 3u] = G.lo;
+        b.seen[(size_t)slot0 * 3u + 1u] = G.hi;
+        b.seen[(size_t)slot0 * 3u + 2u] = G.n;
     }
     if (lane == 0) {
         uint32_t chars = 0;
-        for (uint32_t a = 0; a < sn.n; ++a) chars += seen_byte(sn, a) != (uint32_t)'-';
-        b.sym_nalts[k] = sn.n;
-        b.sym_edsz[k] = 2ull + chars + (sn.n - 1u);
+        for (uint32_t a = 0; a < G.n; ++a) chars += seen_byte(G, a) != (uint32_t)'-';
+        b.sym_nalts[k] = G.n;
+        b.sym_edsz[k] = 2ull + chars + (G.n - 1u);
     }
-    nalts = sn.n;  // warp-uniform: the caller must not read sym_nalts back (no fence between lanes)
+    nalts = G.n;  // warp-uniform: the caller must not read sym_nalts back (no fence between lanes)
     return true;
 }
 
@@ -883,6 +964,23 @@ __global__ void k_group(MsaGeom g, MsaBufs b, uint32_t narrow_ok) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const uint32_t v_lo = st->v_lo, v_hi = st->v_hi;
     unsigned long long alts_here = 0;
+    if (narrow_ok != 1u) {
+        // many rows (or a test switch): a warp per symbol, symbols strided over all warps of the grid so that every
+        // warp has one dependent chain (symbol -> slot -> column) in flight instead of 32 in a row
+        for (uint32_t v = v_lo + blockIdx.x * wpb + warp; v < v_hi; v += gridDim.x * wpb) {
+            const uint32_t k = b.varsym[v];
+            const uint32_t s = b.sym[k] & kColMask, en = b.sym[k + 1] & kColMask;
+            bool wide = true;
+            if (en - s == 1u && narrow_ok != 2u) {  // narrow_ok 2: tests force the wide path
+                uint32_t na;
+                if (group_single_warp(g, b, k, s, na)) {
+                    wide = false;
+                    if (lane == 0) alts_here += na;
+                }
+            }
+            if (wide && lane == 0) b.widelist[atomicAdd(&st->n_wide, 1u)] = k;
+        }
+    } else
     for (uint32_t v0 = v_lo + (blockIdx.x * wpb + warp) * 32u; v0 < v_hi; v0 += gridDim.x * wpb * 32u) {
         const uint32_t v = v0 + lane;
         const bool have = v < v_hi;
@@ -892,32 +990,18 @@ __global__ void k_group(MsaGeom g, MsaBufs b, uint32_t narrow_ok) {
             s = b.sym[k] & kColMask;
             en = b.sym[k + 1] & kColMask;
         }
-        uint32_t cls = !have ? 0u : ((en - s == 1u && narrow_ok != 2u) ? 1u : 3u);  // narrow_ok 2: tests force the wide path
-        if (narrow_ok == 1u) {
-            if (cls == 1u) {
-                Seen sn;
-                if (narrow_scan(b.stash + (size_t)first_slot(b, s) * g.Rp, g.R, sn)) {
-                    // alternative = the residue, or the empty string for '-'
-                    uint32_t chars = 0;
-                    for (uint32_t a = 0; a < sn.n; ++a) chars += seen_byte(sn, a) != (uint32_t)'-';
-                    b.sym_nalts[k] = sn.n;
-                    b.sym_edsz[k] = 2ull + chars + (sn.n - 1u);
-                    alts_here += sn.n;
-                } else {
-                    cls = 3u;
-                }
-            }
-        } else {
-            uint32_t todo = __ballot_sync(0xffffffffu, cls == 1u);
-            while (todo) {
-                const uint32_t bit = (uint32_t)__ffs((int)todo) - 1u;
-                todo &= todo - 1u;
-                const uint32_t kw = __shfl_sync(0xffffffffu, k, (int)bit), sw = __shfl_sync(0xffffffffu, s, (int)bit);
-                uint32_t na;
-                const bool ok = group_single_warp(g, b, kw, sw, na);
-                if (lane == bit) {
-                    if (ok) alts_here += na; else cls = 3u;
-                }
+        uint32_t cls = !have ? 0u : (en - s == 1u ? 1u : 3u);
+        if (cls == 1u) {
+            Seen sn;
+            if (narrow_scan(b.stash + (size_t)first_slot(b, s) * g.Rp, g.R, sn)) {
+                // alternative = the residue, or the empty string for '-'
+                uint32_t chars = 0;
+                for (uint32_t a = 0; a < sn.n; ++a) chars += seen_byte(sn, a) != (uint32_t)'-';
+                b.sym_nalts[k] = sn.n;
+                b.sym_edsz[k] = 2ull + chars + (sn.n - 1u);
+                alts_here += sn.n;
+            } else {
+                cls = 3u;
             }
         }
         list_append(b.widelist, &st->n_wide, cls == 3u, k);
@@ -1709,21 +1793,37 @@ void MsaPipeline::plan_fused() {
     if (NC > 1) return;  // clusters are not emulated
 #endif
     const uint32_t RG = (((g.R + NC - 1) / NC) + 31u) & ~31u;
-    const uint32_t slot_pitch = 1u + RG;
+    uint32_t slot_pitch = 1;  // row 0 + the most rows any CTA of the cluster holds
+    for (uint32_t c = 0; c < NC; ++c) {
+        const uint32_t lo = std::max(c * RG, 1u), hi = std::min(g.R, (c + 1) * RG);
+        if (hi > lo) slot_pitch = std::max(slot_pitch, 1u + hi - lo);
+    }
+    uint32_t DW = std::max(1u, std::min(ctx_->fused_dw ? ctx_->fused_dw : 4u, kFzMaxDW));
+#ifdef EDSB_EMU
+    DW = std::min(DW, 2u);
+#endif
     uint32_t S = 0;
     for (uint32_t s = 6; s >= 2; --s)
-        if (fz_smem_bytes(s, NC, RG, slot_pitch) + 1024 <= ctx_->smem_optin) {
+        if (fz_smem_bytes(s, NC, RG, slot_pitch, DW) + 1024 <= ctx_->smem_optin) {
             S = s;
             break;
         }
     if (ctx_->fused_stages && ctx_->fused_stages <= S) S = ctx_->fused_stages;
     if (S < 2) return;
+    // a duty warp waits for phase q of a stage's barrier by parity, which is only sound while phase q - 1 is known
+    // to be complete: true when its previous tile (DW tiles back) is not older than the stage's previous use (S back)
+    DW = std::min(DW, S);
     const uint32_t n_tiles = (g.n_chunks + kFzT - 1) / kFzT;
+    fz_.PW = std::max(1u, std::min(ctx_->fused_pw ? ctx_->fused_pw : 4u, kFzMaxPW));
+#ifdef EDSB_EMU
+    fz_.PW = std::min(fz_.PW, 2u);
+#endif
     fz_.S = S;
+    fz_.DW = DW;
     fz_.NC = NC;
     fz_.RG = RG;
     fz_.slot_pitch = slot_pitch;
-    fz_.smem = fz_smem_bytes(S, NC, RG, slot_pitch);
+    fz_.smem = fz_smem_bytes(S, NC, RG, slot_pitch, DW);
 
     // per-CTA tables, one upload: pack[NC][slot_pitch] u64 | meta[NC][8] u32 | info[NC][RG] u16
     const size_t off_meta = (size_t)NC * slot_pitch * 8, off_info = off_meta + (size_t)NC * 32;
@@ -1772,7 +1872,7 @@ void MsaPipeline::plan_fused() {
 #ifdef EDSB_EMU
     regions = 3;
 #else
-    const uint32_t key = (NC << 24) ^ (S << 16) ^ slot_pitch;
+    const uint32_t key = (NC << 24) ^ (S << 16) ^ slot_pitch ^ (fz_.PW << 28) ^ (fz_.DW << 12);
     if (fz_attr_smem_ < fz_.smem) {
         EDSB_CUDA(cudaFuncSetAttribute(k_scan_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz_.smem));
         fz_attr_smem_ = fz_.smem;
@@ -1780,13 +1880,13 @@ void MsaPipeline::plan_fused() {
     if (fz_occ_key_ != key) {
         if (NC == 1) {
             int per_sm = 0;
-            EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_fused, (kFzCW + 1) * 32, fz_.smem));
+            EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_fused, (kFzCW + fz_.PW + fz_.DW) * 32, fz_.smem));
             fz_occ_regions_ = (uint32_t)std::max(0, per_sm) * (uint32_t)ctx_->sm_count;
         } else {
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof(cfg));
             cfg.gridDim = dim3(NC * (uint32_t)ctx_->sm_count, 1, 1);
-            cfg.blockDim = dim3((kFzCW + 1) * 32, 1, 1);
+            cfg.blockDim = dim3((kFzCW + fz_.PW + fz_.DW) * 32, 1, 1);
             cfg.dynamicSmemBytes = fz_.smem;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1806,7 +1906,7 @@ void MsaPipeline::plan_fused() {
     regions = std::min(regions, n_tiles);
     if (regions == 0) return;
     fz_.regions = regions;
-    d_fz_cnt_.reserve((size_t)regions * 4);
+    d_fz_cnt_.reserve((size_t)regions * DW * 4);
 
     FzParams& f = fzp_;
     memset(&f, 0, sizeof(f));
@@ -1820,6 +1920,9 @@ void MsaPipeline::plan_fused() {
     f.slot_pitch = slot_pitch;
     f.n_tiles = n_tiles;
     f.all_aligned = g.all_aligned;
+    f.PW = fz_.PW;
+    f.DW = fz_.DW;
+    f.mode = ctx_->fused_mode;
     // tile t is fetched with bulk copies when vectors [32 t + dmin, 32 t + 32 + dmax] all lie inside the buffer
     const long long T = (long long)kFzT, vmax = (long long)g.n_vec - 1;
     f.tile_lo_ok = g.d_min_vec >= 0 ? 0 : (-g.d_min_vec + T - 1) / T;
@@ -1858,12 +1961,15 @@ void MsaPipeline::bind(MsaBufs& b) {
     d_seds_.reserve(cap_seds_);
     if (fz_.on) {
         // every cluster fills its own region of the temporary stash; 25 % + 64 slots of slack over an even split
-        fz_.capc = (uint32_t)(((uint64_t)cap_var_ + cap_var_ / 4) / fz_.regions + 64);
-        d_fz_tmp_.reserve((size_t)fz_.regions * fz_.capc * g.Rp);
-        d_fz_col_.reserve((size_t)fz_.regions * fz_.capc * 4);
+        // every duty warp of every cluster fills its own region of the temporary stash (tiles reach the warps in
+        // rotation, so the regions fill evenly); 25 % + 64 slots of slack over an even split
+        const uint64_t n_regions = (uint64_t)fz_.regions * fz_.DW;
+        fz_.capc = (uint32_t)(((uint64_t)cap_var_ + cap_var_ / 4) / n_regions + 64);
+        d_fz_tmp_.reserve((size_t)n_regions * fz_.capc * g.Rp);
+        d_fz_col_.reserve((size_t)n_regions * fz_.capc * 8);
         fzp_.capc = fz_.capc;
         fzp_.tmp_stash = d_fz_tmp_.as<uint8_t>();
-        fzp_.tmp_col = d_fz_col_.as<uint32_t>();
+        fzp_.tmp_col = d_fz_col_.as<unsigned long long>();
         fzp_.mism16 = reinterpret_cast<uint16_t*>(d_mism_.p);
     }
     b.varcol = d_varcol_.as<uint32_t>();
@@ -1899,7 +2005,7 @@ void MsaPipeline::launch_scan(const MsaBufs& b, bool allow_fused) {
     cudaStream_t s = ctx_->stream;
     if (allow_fused && fz_.on) {
         ctx_->clock.begin("k_scan_fused");
-        const uint32_t threads = (kFzCW + 1) * 32, blocks = fz_.regions * fz_.NC;
+        const uint32_t threads = (kFzCW + fz_.PW + fz_.DW) * 32, blocks = fz_.regions * fz_.NC;
 #ifdef EDSB_EMU
         EDSB_LAUNCH(k_scan_fused, blocks, threads, fz_.smem, s, g, fzp_, b.status);
 #else
@@ -1970,7 +2076,7 @@ void MsaPipeline::run_once(MsaBufs& b) {
     after(s1, s, ctx_->ev[0]);
     if (fz_.on) {
         ctx_->clock.begin("k_restash", s1);
-        EDSB_LAUNCH(k_restash, sms * 8u, 256, 0, s1, g, b, fzp_, fz_.regions);
+        EDSB_LAUNCH(k_restash, sms * 8u, 256, 0, s1, g, b, fzp_, fz_.regions * fz_.DW);
         ctx_->clock.end();
     } else {
         ctx_->clock.begin("k_stash", s1);
@@ -2147,7 +2253,7 @@ void MsaPipeline::transform(const eds_msa_view& view, uint32_t l, int leds, eds_
         if (st.abort == kAbortVarCap || st.abort == kAbortRunsCap) {
             cap_var_ = std::max<uint32_t>(cap_var_, (uint32_t)std::min<uint64_t>(st.need_var + st.need_var / 16 + 64, 0x7fffffffu));
             if (fz_.on && st.fz_need)  // a cluster's region of the temporary stash overflowed: size for the fullest one
-                cap_var_ = std::max<uint32_t>(cap_var_, (uint32_t)std::min<uint64_t>((uint64_t)st.fz_need * fz_.regions, 0x7fffffffu));
+                cap_var_ = std::max<uint32_t>(cap_var_, (uint32_t)std::min<uint64_t>((uint64_t)st.fz_need * fz_.regions * fz_.DW, 0x7fffffffu));
             cap_runs_ = std::max<uint32_t>(cap_runs_, (uint32_t)std::min<uint64_t>(st.need_runs + st.need_runs / 16 + 64, 0xfffffff0u));
         } else {
             cap_eds_ = std::max<uint64_t>(cap_eds_, st.need_eds + st.need_eds / 16 + 4096);

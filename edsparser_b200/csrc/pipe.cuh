@@ -59,6 +59,10 @@ inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, Mbar* b) {
     b->tx -= bytes;
     mbar_check_(b);
 }
+inline void cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
+inline void cp_async16_at(uintptr_t dst, const void* src) { memcpy(reinterpret_cast<void*>(dst), src, 16); }
+inline uintptr_t smem_addr(void* p) { return reinterpret_cast<uintptr_t>(p); }
+inline void cp_async_arrive_noinc(Mbar* b) { mbar_arrive(b); }
 inline uint32_t cluster_rank() { return 0; }
 inline uint32_t cluster_id_x() { return blockIdx.x; }
 inline uint32_t cluster_count_x() { return gridDim.x; }
@@ -102,6 +106,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(b))
                  : "memory");
+}
+// 16 bytes global -> shared without a register round trip (LDGSTS, L1 bypassed); completion is reported to an mbarrier
+// by cp_async_arrive_noinc: "arrive once every cp.async this thread has issued so far has landed"
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// the same with the destination as a shared-window address (kept in a register and stepped by the caller)
+__device__ __forceinline__ void cp_async16_at(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ uint32_t smem_addr(void* p) { return smem_u32(p); }
+__device__ __forceinline__ void cp_async_arrive_noinc(Mbar* b) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_rank() {
     uint32_t r;

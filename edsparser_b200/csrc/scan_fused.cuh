@@ -29,29 +29,29 @@ template <int WS>
 __device__ __forceinline__ void fz_rows(const uint8_t* stg, const unsigned long long* s_pack, uint32_t first, uint32_t end,
                                         uint32_t lane, const uint4& ref, uint4& acc) {
     uint32_t slot = first;
-    for (; slot + 3u * kFzCW < end; slot += 4u * kFzCW) {
+    for (; slot + 4u <= end; slot += 4u) {
         uint4 lo[4], hi[4];
         uint32_t bs[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const uint8_t* row = stg + (size_t)(slot + u * kFzCW) * kFzPitch + 16u * lane;
+            const uint8_t* row = stg + (size_t)(slot + u) * kFzPitch + 16u * lane;
             lo[u] = *reinterpret_cast<const uint4*>(row);
             hi[u] = *reinterpret_cast<const uint4*>(row + 16);
-            bs[u] = ((uint32_t)s_pack[slot + u * kFzCW] & 3u) * 8u;
+            bs[u] = (reinterpret_cast<const uint32_t*>(s_pack)[2u * (slot + u)] & 3u) * 8u;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) xor_acc<WS>(lo[u], hi[u], bs[u], ref, acc);
     }
-    for (; slot < end; slot += kFzCW) {
+    for (; slot < end; ++slot) {
         const uint8_t* row = stg + (size_t)slot * kFzPitch + 16u * lane;
         const uint4 lo = *reinterpret_cast<const uint4*>(row), hi = *reinterpret_cast<const uint4*>(row + 16);
-        xor_acc<WS>(lo, hi, ((uint32_t)s_pack[slot] & 3u) * 8u, ref, acc);
+        xor_acc<WS>(lo, hi, (reinterpret_cast<const uint32_t*>(s_pack)[2u * slot] & 3u) * 8u, ref, acc);
     }
 }
 
 __device__ __forceinline__ void fz_rows_aligned(const uint8_t* stg, uint32_t first, uint32_t end, uint32_t lane, const uint4& ref,
                                                 uint4& acc) {
-    for (uint32_t slot = first; slot < end; slot += kFzCW) {
+    for (uint32_t slot = first; slot < end; ++slot) {
         const uint4 lo = *reinterpret_cast<const uint4*>(stg + (size_t)slot * kFzPitch + 16u * lane);
         acc.x |= lo.x ^ ref.x;
         acc.y |= lo.y ^ ref.y;
@@ -60,85 +60,60 @@ __device__ __forceinline__ void fz_rows_aligned(const uint8_t* stg, uint32_t fir
     }
 }
 
-__global__ void __launch_bounds__((kFzCW + 1) * 32, 1) k_scan_fused(MsaGeom g, FzParams f, MsaStatus* st) {
+// Warp roles of a CTA: [0, CW) consumers, [CW, CW + PW) producers, [CW + PW, CW + PW + DW) duty warps.
+//   producers -> full[s] -> consumers -> red_full[s] -> duty warp (tile % DW) -> empty[s]
+// Every arrow is an mbarrier. A duty warp turns the OR of the consumers' mismatch bits into the tile's final mask
+// (gaps of row 0, line breaks, window edges), stores it, lists the variable columns and copies them out of the
+// stage into its own region of the temporary stash. That is a few hundred dependent instructions per tile — more
+// than a tile's time budget — so DW warps take the tiles in rotation while the consumers stream on.
+__global__ void __launch_bounds__((kFzCW + kFzMaxPW + kFzMaxDW) * 32, 1) k_scan_fused(MsaGeom g, FzParams f, MsaStatus* st) {
     unsigned char* smem = EDSB_DYN_SMEM();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t S = f.S, NC = f.NC, RG = f.RG;
+    const uint32_t S = f.S, NC = f.NC, RG = f.RG, PW = f.PW, DW = f.DW;
     const uint32_t rank = NC > 1 ? cluster_rank() : 0u;
     const uint32_t cid = NC > 1 ? cluster_id_x() : blockIdx.x, ncl = NC > 1 ? cluster_count_x() : gridDim.x;
     const uint32_t stage_bytes = f.slot_pitch * kFzPitch;
 
     uint8_t* stages = smem;
-    uint4* red = reinterpret_cast<uint4*>(stages + (size_t)S * stage_bytes);
-    uint32_t* mask_in = reinterpret_cast<uint32_t*>(red + kFzCW * 32);
-    unsigned long long* s_pack = reinterpret_cast<unsigned long long*>(mask_in + 2u * NC * 32u);
+    uint32_t* red16 = reinterpret_cast<uint32_t*>(stages + (size_t)S * stage_bytes);  // [S][32]
+    uint32_t* mask_in = red16 + S * 32u;                                              // [2S][NC][32] (NC > 1)
+    unsigned long long* s_pack = reinterpret_cast<unsigned long long*>(mask_in + (NC > 1 ? 2u * S * NC * 32u : 0u));
     uint16_t* s_info = reinterpret_cast<uint16_t*>(s_pack + f.slot_pitch);
-    uint16_t* s_vpos = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s_info) + ((RG * 2u + 15u) & ~15u));
-    uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_vpos + 16u * kFzT);
-    Mbar* full = reinterpret_cast<Mbar*>(s_misc + 4);
+    uint32_t* s_off16 = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(s_info) + ((RG * 2u + 15u) & ~15u));  // [slot_pitch]
+    uint16_t* s_vpos = reinterpret_cast<uint16_t*>(s_off16 + ((f.slot_pitch + 3u) & ~3u));  // [DW][512]
+    Mbar* full = reinterpret_cast<Mbar*>(s_vpos + DW * 16u * kFzT);
     Mbar* empty = full + S;
-    Mbar* maskbar = empty + S;  // 2
-    Mbar* cbar = maskbar + 2;   // emulator: barrier of the consumer threads
+    Mbar* red_full = empty + S;    // [S]
+    Mbar* maskbar = red_full + S;  // [2S] cluster exchange of the partial masks
 
     const uint32_t* meta = f.meta + rank * 8u;
     const uint32_t nslots = meta[0];
     const uint32_t cls0 = meta[1], cls1 = meta[2], cls2 = meta[3], cls3 = meta[4], cls4 = meta[5];
-    for (uint32_t i = threadIdx.x; i < nslots; i += blockDim.x) s_pack[i] = f.pack[(size_t)rank * f.slot_pitch + i];
+    for (uint32_t i = threadIdx.x; i < nslots; i += blockDim.x) {
+        const unsigned long long e = f.pack[(size_t)rank * f.slot_pitch + i];
+        s_pack[i] = e;
+        s_off16[i] = (uint32_t)(((long long)((e & ~15ull) - (unsigned long long)(uintptr_t)g.text) >> 4) - g.d_min_vec);
+    }
     for (uint32_t i = threadIdx.x; i < RG; i += blockDim.x) s_info[i] = f.info[(size_t)rank * RG + i];
+    for (uint32_t i = threadIdx.x; i < S * 32u; i += blockDim.x) red16[i] = 0u;
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < S; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kFzCW);
+            mbar_init(&full[s], f.mode == 0 ? PW : PW * 32u);
+            mbar_init(&empty[s], kFzCW + 1);
+            mbar_init(&red_full[s], kFzCW);
+            mbar_init(&maskbar[2u * s], 1);
+            mbar_init(&maskbar[2u * s + 1u], 1);
         }
-        mbar_init(&maskbar[0], 1);
-        mbar_init(&maskbar[1], 1);
-        mbar_init(cbar, kFzCW * 32);
         mbar_fence_init();
     }
     __syncthreads();
     if (NC > 1) cluster_sync_all();  // peers complete transactions on our barriers: they must exist first
 
-    if (warp == (uint32_t)kFzCW) {
-        // ---------------------------------------------------------------- producer warp
-        const uint4* vec = reinterpret_cast<const uint4*>(g.text);
-        const long long vmax = (long long)g.n_vec - 1;
+    if (warp < (uint32_t)kFzCW) {
+        // ---------------------------------------------------------------- consumer warps: a contiguous share of the slots
+        const uint32_t n_rows = nslots - 1u;
+        const uint32_t my_lo = 1u + n_rows * warp / (uint32_t)kFzCW, my_hi = 1u + n_rows * (warp + 1u) / (uint32_t)kFzCW;
         uint32_t it = 0;
-        for (uint32_t tile = cid; tile < f.n_tiles; tile += ncl, ++it) {
-            const uint32_t s = it % S;
-            if (it >= S) mbar_wait(&empty[s], ((it / S) - 1u) & 1u);
-            uint8_t* dst = stages + (size_t)s * stage_bytes;
-            if ((long long)tile >= f.tile_lo_ok && (long long)tile < f.tile_hi_ok) {
-                if (lane == 0) mbar_arrive_expect_tx(&full[s], nslots * kFzPitch);
-                __syncwarp();
-                for (uint32_t slot = lane; slot < nslots; slot += 32)
-                    bulk_g2s(dst + (size_t)slot * kFzPitch,
-                             reinterpret_cast<const uint8_t*>((uintptr_t)(s_pack[slot] & ~15ull)) + (size_t)tile * (16u * kFzT), kFzPitch,
-                             &full[s]);
-            } else {
-                for (uint32_t idx = lane; idx < nslots * (kFzT + 1u); idx += 32) {
-                    const uint32_t slot = idx / (kFzT + 1u), k = idx % (kFzT + 1u);
-                    const long long d16 = (long long)((s_pack[slot] & ~15ull) - (unsigned long long)(uintptr_t)g.text) >> 4;
-                    long long vi = d16 + (long long)tile * kFzT + k;
-                    vi = vi < 0 ? 0 : (vi > vmax ? vmax : vi);
-                    reinterpret_cast<uint4*>(dst + (size_t)slot * kFzPitch)[k] = ldg_nc(vec + vi);
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full[s]);
-            }
-        }
-    } else {
-        // ---------------------------------------------------------------- consumer warps
-        uint32_t it = 0, local_cnt = 0, bad = 0, overflow = 0, cphase = 0;
-        auto consumer_sync = [&]() {
-#ifdef EDSB_EMU
-            mbar_arrive(cbar);
-            mbar_wait(cbar, cphase);
-            cphase ^= 1u;
-#else
-            asm volatile("bar.sync 1, %0;" ::"n"(kFzCW * 32) : "memory");
-#endif
-        };
-        (void)cphase;
         for (uint32_t tile = cid; tile < f.n_tiles; tile += ncl, ++it) {
             const uint32_t s = it % S;
             mbar_wait(&full[s], (it / S) & 1u);
@@ -146,98 +121,197 @@ __global__ void __launch_bounds__((kFzCW + 1) * 32, 1) k_scan_fused(MsaGeom g, F
             const uint4 ref = *reinterpret_cast<const uint4*>(stg + 16u * lane);  // slot 0 = row 0, shift 0
             uint4 acc = make_uint4(0, 0, 0, 0);
             if (f.all_aligned) {
-                fz_rows_aligned(stg, cls0 + warp, cls4, lane, ref, acc);
+                fz_rows_aligned(stg, my_lo, my_hi, lane, ref, acc);
             } else {
-                fz_rows<0>(stg, s_pack, cls0 + warp, cls1, lane, ref, acc);
-                fz_rows<1>(stg, s_pack, cls1 + warp, cls2, lane, ref, acc);
-                fz_rows<2>(stg, s_pack, cls2 + warp, cls3, lane, ref, acc);
-                fz_rows<3>(stg, s_pack, cls3 + warp, cls4, lane, ref, acc);
+                fz_rows<0>(stg, s_pack, max(my_lo, cls0), min(my_hi, cls1), lane, ref, acc);
+                fz_rows<1>(stg, s_pack, max(my_lo, cls1), min(my_hi, cls2), lane, ref, acc);
+                fz_rows<2>(stg, s_pack, max(my_lo, cls2), min(my_hi, cls3), lane, ref, acc);
+                fz_rows<3>(stg, s_pack, max(my_lo, cls3), min(my_hi, cls4), lane, ref, acc);
             }
-            red[warp * 32u + lane] = acc;
-            consumer_sync();
-            if (warp == 0) {
-                uint4 a = red[lane];
-                for (uint32_t w = 1; w < (uint32_t)kFzCW; ++w) {
-                    const uint4 o = red[w * 32u + lane];
-                    a.x |= o.x;
-                    a.y |= o.y;
-                    a.z |= o.z;
-                    a.w |= o.w;
+            // red16[s] is zero again by now: the duty warp of the tile that last used stage s cleared it before it let
+            // the stage go, and full[s] completed after that
+            const uint32_t nz = nonzero_bytes16(acc);
+            if (nz) atomicOr(&red16[s * 32u + lane], nz);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&red_full[s]);
+                mbar_arrive(&empty[s]);  // this warp is done with the stage
+            }
+        }
+    } else if (warp < (uint32_t)kFzCW + PW) {
+        // ---------------------------------------------------------------- producer warps
+        // mode 0: a lane issues one bulk copy per row it owns (UBLKCP takes uniform operands: the warp issues its
+        // lanes' copies one after the other, which is why the rows are spread over PW warps);
+        // mode 1: a warp copies a row with one 16-byte cp.async per lane, the 33rd vectors lane-per-row.
+        const uint32_t pw = warp - (uint32_t)kFzCW;
+        const uint4* vec = reinterpret_cast<const uint4*>(g.text);
+        const long long vmax = (long long)g.n_vec - 1;
+        const uint8_t* base0 = g.text + g.d_min_vec * 16;  // s_off16[slot] counts 16-byte vectors from here
+        uint32_t my_slots = 0;  // slots pw * 32 + lane + 32 * PW * m of all lanes together
+        for (uint32_t base = pw * 32u; base < nslots; base += 32u * PW) my_slots += min(32u, nslots - base);
+        uint32_t it = 0;
+        for (uint32_t tile = cid; tile < f.n_tiles; tile += ncl, ++it) {
+            const uint32_t s = it % S;
+            if (it >= S) mbar_wait(&empty[s], ((it / S) - 1u) & 1u);
+            uint8_t* dst = stages + (size_t)s * stage_bytes;
+            const size_t toff = (size_t)tile * (16u * kFzT);
+            if ((long long)tile >= f.tile_lo_ok && (long long)tile < f.tile_hi_ok) {
+                if (f.mode == 0) {
+                    if (lane == 0) mbar_arrive_expect_tx(&full[s], my_slots * kFzPitch);
+                    __syncwarp();
+                    for (uint32_t slot = pw * 32u + lane; slot < nslots; slot += 32u * PW)
+                        bulk_g2s(dst + (size_t)slot * kFzPitch, reinterpret_cast<const uint8_t*>((uintptr_t)(s_pack[slot] & ~15ull)) + toff,
+                                 kFzPitch, &full[s]);
+                } else {
+                    // lean issue loop: one shared-memory read (the row's offset in 16-byte units), one 64-bit multiply-add
+                    // and the copy per row; the destination steps by a constant
+                    const uint8_t* src0 = base0 + toff + 16u * lane;
+                    auto d = smem_addr(dst + (size_t)pw * kFzPitch + 16u * lane);
+#pragma unroll 4
+                    for (uint32_t slot = pw; slot < nslots; slot += PW) {
+                        cp_async16_at(d, src0 + (size_t)s_off16[slot] * 16u);
+                        d += PW * kFzPitch;
+                    }
+                    for (uint32_t slot = pw * 32u + lane; slot < nslots; slot += 32u * PW)
+                        cp_async16(dst + (size_t)slot * kFzPitch + 16u * kFzT,
+                                   reinterpret_cast<const uint8_t*>((uintptr_t)(s_pack[slot] & ~15ull)) + toff + 16u * kFzT);
+                    cp_async_arrive_noinc(&full[s]);
                 }
-                uint32_t nz = nonzero_bytes16(a);
-                if (NC > 1) {
-                    // partial mismatch bits of this CTA's rows -> every CTA of the cluster (distributed shared memory)
-                    const uint32_t par = it & 1u;
-                    uint32_t* mine = mask_in + (par * NC + rank) * 32u + lane;
-                    if (lane == 0) mbar_arrive_expect_tx(&maskbar[par], NC * 128u);
-                    for (uint32_t peer = 0; peer < NC; ++peer) st_async_u32(mine, nz, &maskbar[par], peer);
-                    mbar_wait(&maskbar[par], (it >> 1) & 1u);
-                    nz = 0;
-                    for (uint32_t p = 0; p < NC; ++p) nz |= mask_in[(par * NC + p) * 32u + lane];
+            } else {
+                for (uint32_t base = pw * 32u; base < nslots; base += 32u * PW) {
+                    const uint32_t hi_slot = min(nslots, base + 32u);
+                    for (uint32_t idx = lane; idx < (hi_slot - base) * (kFzT + 1u); idx += 32) {
+                        const uint32_t slot = base + idx / (kFzT + 1u), k = idx % (kFzT + 1u);
+                        const long long d16 = (long long)((s_pack[slot] & ~15ull) - (unsigned long long)(uintptr_t)g.text) >> 4;
+                        long long vi = d16 + (long long)tile * kFzT + k;
+                        vi = vi < 0 ? 0 : (vi > vmax ? vmax : vi);
+                        reinterpret_cast<uint4*>(dst + (size_t)slot * kFzPitch)[k] = ldg_nc(vec + vi);
+                    }
                 }
-                // bytes of this chunk that belong to the row segment; where line breaks must be: u % (lw + 1) == lw
-                const uint64_t j = (uint64_t)tile * kFzT + lane;
+                __syncwarp();
+                if (f.mode != 0 || lane == 0) mbar_arrive(&full[s]);
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- duty warps: lane = 16-byte chunk of the tile
+        const uint32_t dw = warp - (uint32_t)kFzCW - PW;
+        const uint32_t line = g.lw + 1u;
+        const uint64_t pend = (uint64_t)g.a0 + g.row_bytes;
+        const uint32_t region = cid * DW + dw;
+        uint16_t* vp = s_vpos + dw * (16u * kFzT);
+        uint32_t local_cnt = 0, bad = 0, overflow = 0;
+        // this lane's four rows of the gather: byte offset of the row inside a stage, and which of the four exist
+        uint32_t roff[4], rmask = 0;
+        const bool have_rows = 4u * lane < RG && rank * RG + 4u * lane < g.Rp;
+#pragma unroll
+        for (uint32_t k = 0; k < 4u; ++k) {
+            const uint32_t inf = have_rows ? s_info[4u * lane + k] : 0xffffu;
+            roff[k] = inf == 0xffffu ? 0u : (inf >> 4) * kFzPitch + (inf & 15u);
+            if (inf != 0xffffu) rmask |= 0xffu << (8u * k);
+        }
+        // position of this lane's chunk inside a text line, kept up to date by addition (no division per tile)
+        const uint32_t step = (uint32_t)(((uint64_t)DW * ncl * (16u * kFzT)) % line);
+        uint32_t rb;
+        {
+            const uint64_t t0 = (uint64_t)cid + (uint64_t)dw * ncl;
+            const uint64_t v = g.u_begin + t0 * (16u * kFzT) + 16u * lane + 16ull * line - g.a0;  // + 16 lines: never negative
+            rb = (uint32_t)(v % line);
+        }
+        uint32_t it = 0;
+        for (uint32_t tile = cid; tile < f.n_tiles; tile += ncl, ++it) {
+            if (it % DW != dw) continue;
+            const uint32_t s = it % S;
+            mbar_wait(&red_full[s], (it / S) & 1u);
+            uint32_t nz = red16[s * 32u + lane];
+            red16[s * 32u + lane] = 0u;
+            const uint8_t* stg = stages + (size_t)s * stage_bytes;  // the stage is held until this warp lets go
+            const uint4 ref = *reinterpret_cast<const uint4*>(stg + 16u * lane);
+            if (NC > 1) {
+                // partial mismatch bits of this CTA's rows -> every CTA of the cluster (distributed shared memory).
+                // 2S buffers: a peer's bits for tile it + 2S can only arrive after its duty for it + S, hence after OUR
+                // bits for it + S, hence after our stage of tile it was released, i.e. after this read.
+                const uint32_t mb = it % (2u * S);
+                uint32_t* mine = mask_in + (mb * NC + rank) * 32u + lane;
+                if (lane == 0) mbar_arrive_expect_tx(&maskbar[mb], NC * 128u);
+                for (uint32_t peer = 0; peer < NC; ++peer) st_async_u32(mine, nz, &maskbar[mb], peer);
+                mbar_wait(&maskbar[mb], (it / (2u * S)) & 1u);
+                nz = 0;
+                for (uint32_t p = 0; p < NC; ++p) nz |= mask_in[(mb * NC + p) * 32u + lane];
+            }
+            // bytes of this chunk that belong to the row segment; where line breaks must be: u % (lw + 1) == lw
+            const uint64_t j = (uint64_t)tile * kFzT + lane;
+            const uint64_t tp = (uint64_t)tile * (16u * kFzT);
+            uint32_t valid = 0xffffu, expect = 0;
+            if (tp >= g.a0 && tp + 16u * kFzT <= pend) {
+                // the whole tile lies inside the row segment (all but the first and the last tile of a window)
+                if (line > 16u) {  // at most one line break in 16 bytes
+                    const uint32_t i0 = g.lw - rb;
+                    if (i0 < 16u) expect = 1u << i0;
+                } else {
+                    uint32_t rem = rb;
+                    for (uint32_t i = 0; i < 16u; ++i) {
+                        if (rem == g.lw) expect |= 1u << i;
+                        rem = (rem == g.lw) ? 0u : rem + 1u;
+                    }
+                }
+            } else {
                 const uint64_t p0 = j * 16u;
-                const uint64_t pend = (uint64_t)g.a0 + g.row_bytes;
                 const uint32_t vlo = p0 >= g.a0 ? 0u : (uint32_t)(g.a0 - p0);
                 const uint32_t vhi = pend >= p0 + 16u ? 16u : (pend > p0 ? (uint32_t)(pend - p0) : 0u);
-                const uint32_t valid = low_bits(vhi) & ~low_bits(vlo);
-                uint32_t expect = 0;
+                valid = low_bits(vhi) & ~low_bits(vlo);
                 if (vlo < vhi) {
                     const uint64_t u_first = g.u_begin + (p0 + vlo - g.a0);
-                    uint32_t rem = (uint32_t)(u_first % (uint64_t)(g.lw + 1u));
+                    uint32_t rem = (uint32_t)(u_first % (uint64_t)line);
                     for (uint32_t i = vlo; i < vhi; ++i) {
                         if (rem == g.lw) expect |= 1u << i;
                         rem = (rem == g.lw) ? 0u : rem + 1u;
                     }
                 }
-                const uint32_t nl = eq_bytes16(ref, 0x0a0a0a0au);
-                if (((nl ^ expect) | (nz & expect)) & valid) bad |= (uint32_t)kBadNewlineLayout;
-                const uint32_t mism = (nz | eq_bytes16(ref, 0x2d2d2d2du)) & valid & ~expect;  // differs from row 0, or row 0 is '-'
-                if (rank == 0 && j < g.n_chunks) f.mism16[j] = (uint16_t)mism;
-                const uint32_t cnt = (uint32_t)__popc(mism);
-                const uint32_t incl = warp_inclusive_scan(cnt);
-                uint32_t at = incl - cnt;
-                for (uint32_t bits = mism; bits; bits &= bits - 1u) s_vpos[at++] = (uint16_t)(16u * lane + (uint32_t)__ffs((int)bits) - 1u);
-                if (lane == 31) s_misc[0] = incl;
             }
-            consumer_sync();
-            const uint32_t total = s_misc[0];
+            rb += step;
+            if (rb >= line) rb -= line;
+            const uint32_t nl = eq_bytes16(ref, 0x0a0a0a0au);
+            if (((nl ^ expect) | (nz & expect)) & valid) bad |= (uint32_t)kBadNewlineLayout;
+            const uint32_t mism = (nz | eq_bytes16(ref, 0x2d2d2d2du)) & valid & ~expect;  // differs from row 0, or row 0 is '-'
+            if (rank == 0 && j < g.n_chunks) f.mism16[j] = (uint16_t)mism;
+            const uint32_t cnt = (uint32_t)__popc(mism);
+            const uint32_t incl = warp_inclusive_scan(cnt);
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
             if (total) {
+                uint32_t at = incl - cnt;
+                for (uint32_t bits = mism; bits; bits &= bits - 1u) vp[at++] = (uint16_t)(16u * lane + (uint32_t)__ffs((int)bits) - 1u);
+                __syncwarp();
                 if (local_cnt + total <= f.capc) {
-                    for (uint32_t i = warp; i < total; i += (uint32_t)kFzCW) {
-                        const uint32_t vp = s_vpos[i];
-                        const size_t slotg = (size_t)cid * f.capc + local_cnt + i;
-                        for (uint32_t q = lane; q < RG / 4u; q += 32) {
-                            if (rank * RG + 4u * q >= g.Rp) break;
-                            uint32_t word = 0;
-#pragma unroll
-                            for (uint32_t k = 0; k < 4u; ++k) {
-                                const uint32_t inf = s_info[4u * q + k];
-                                if (inf != 0xffffu) {
-                                    const uint32_t ch = stg[(size_t)(inf >> 4) * kFzPitch + (inf & 15u) + vp];
-                                    word |= ch << (8u * k);
-                                    if (ch == (uint32_t)'\n') bad |= (uint32_t)kBadResidueByte;
-                                }
-                            }
-                            *reinterpret_cast<uint32_t*>(f.tmp_stash + slotg * g.Rp + rank * RG + 4u * q) = word;
-                        }
-                        if (rank == 0 && lane == 0) {
-                            const uint64_t u = g.u_begin + ((uint64_t)tile * (16u * kFzT) + vp - g.a0);
-                            f.tmp_col[slotg] = (uint32_t)(u - u / (uint64_t)(g.lw + 1u) - g.col_begin);
+                    // two columns per round: eight independent byte reads in flight per lane
+                    uint8_t* out = f.tmp_stash + ((size_t)region * f.capc + local_cnt) * g.Rp + rank * RG + 4u * lane;
+                    for (uint32_t i = 0; i < total; i += 2u) {
+                        const uint32_t v0 = vp[i], v1 = vp[min(i + 1u, total - 1u)];
+                        const uint8_t* c0 = stg + v0;
+                        const uint8_t* c1 = stg + v1;
+                        uint32_t w0 = (uint32_t)c0[roff[0]] | ((uint32_t)c0[roff[1]] << 8) | ((uint32_t)c0[roff[2]] << 16) | ((uint32_t)c0[roff[3]] << 24);
+                        uint32_t w1 = (uint32_t)c1[roff[0]] | ((uint32_t)c1[roff[1]] << 8) | ((uint32_t)c1[roff[2]] << 16) | ((uint32_t)c1[roff[3]] << 24);
+                        w0 &= rmask;
+                        w1 &= rmask;
+                        if (have_rows) {
+                            if (eq_bytes4(w0, 0x0a0a0a0au) | eq_bytes4(w1, 0x0a0a0a0au)) bad |= (uint32_t)kBadResidueByte;
+                            *reinterpret_cast<uint32_t*>(out + (size_t)i * g.Rp) = w0;
+                            if (i + 1u < total) *reinterpret_cast<uint32_t*>(out + (size_t)(i + 1u) * g.Rp) = w1;
                         }
                     }
+                    if (rank == 0)
+                        for (uint32_t i = lane; i < total; i += 32)
+                            f.tmp_col[(size_t)region * f.capc + local_cnt + i] = tp + vp[i];  // p-space position
                 } else {
                     overflow = 1;
                 }
                 local_cnt += total;
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with the stage
+            if (lane == 0) mbar_arrive(&empty[s]);
         }
         if (bad) atomicOr(&st->bad_msa, bad);
-        if (warp == 0 && lane == 0 && rank == 0) {
-            f.region_count[cid] = overflow ? 0u : local_cnt;
+        if (lane == 0 && rank == 0) {
+            f.region_count[region] = overflow ? 0u : local_cnt;
             if (overflow) {
                 atomicMax(&st->fz_need, local_cnt);
                 st->abort = kAbortVarCap;
@@ -257,7 +331,8 @@ __global__ void __launch_bounds__(256) k_restash(MsaGeom g, MsaBufs b, FzParams 
     for (uint64_t idx = (uint64_t)blockIdx.x * wpb + (threadIdx.x >> 5); idx < n; idx += (uint64_t)gridDim.x * wpb) {
         const uint32_t k = (uint32_t)(idx / f.capc), i = (uint32_t)(idx % f.capc);
         if (i >= f.region_count[k]) continue;
-        const uint32_t c = f.tmp_col[idx];
+        const uint64_t u = g.u_begin + (f.tmp_col[idx] - g.a0);  // position inside the wrapped row -> window column
+        const uint32_t c = (uint32_t)(u - u / (uint64_t)(g.lw + 1u) - g.col_begin);
         const uint32_t kg = b.rankdir[c >> 5] + (uint32_t)__popc(b.vbits[c >> 5] & low_bits(c & 31u));
         if (kg >= b.cap_var) continue;
         const uint4* src = reinterpret_cast<const uint4*>(f.tmp_stash + idx * g.Rp);
