@@ -77,6 +77,7 @@ struct eds_ctx {
     uint32_t partitions = 0;          // 0 = default
     uint32_t scan_blocks_per_sm = 0;  // 0 = default
     uint32_t scan_row_slices = 0;     // tests (EDSB_DEBUG_ROW_SLICES): force k_scan's row split; 0 = automatic
+    int tuple_off = 0;   // tests (EDSB_DEBUG_TUPLE_OFF): every multi-column symbol on the hashed row path
     int narrow_off = 0;  // tests (EDSB_DEBUG_NARROW_OFF): 1 = no lane-per-symbol path, 2 = every symbol on the hashed warp path
     uint64_t hash_mask = ~0ull;       // tests narrow it (EDSB_HASH_MASK) to exercise the exact-compare fallback
     edsb::KernelClock clock;

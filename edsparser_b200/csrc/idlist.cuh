@@ -61,9 +61,13 @@ inline uint32_t id_list_stage_bytes(unsigned long long n_ids) {
 
 // One warp: the list of the set bits of bits_in[0..W) as "{id,id,...}" = sb bytes at sout[so..so+sb) (sb = 1 + sum of
 // word_id_bytes; the caller has it from its size pass). sout must be 16-byte aligned; stage: id_list_stage_bytes().
+// lane_per_word_below: rounds of fewer bytes than this are rendered lane-per-word (each lane its own word's ids, one
+// after the other); larger ones lane-per-bit, word by word. vcf2eds (four-digit ids, thousands of samples) measured
+// the word-by-word form faster for crowded rounds; msa2eds renders every round lane-per-word (~100 warp
+// instructions per crowded word against ~10 per id).
 __device__ __forceinline__ void warp_render_id_list(uint8_t* stage, const uint32_t* bits_in, uint32_t W,
                                                     const unsigned long long* id_text, uint8_t* sout,
-                                                    unsigned long long so, uint32_t sb) {
+                                                    unsigned long long so, uint32_t sb, uint32_t lane_per_word_below = 1536u) {
     const unsigned lane = threadIdx.x & 31;
     // "{id,id,...}": 32 bitset words per round are rendered into the warp's shared-memory stage at the
     // output's own 16-byte phase, then copied out with aligned 16-byte stores (bytes at the two ragged ends)
@@ -85,7 +89,7 @@ __device__ __forceinline__ void warp_render_id_list(uint8_t* stage, const uint32
         const uint32_t end_q = (uint32_t)(end - gpos) + phase;
         const uint32_t live = __ballot_sync(0xffffffffu, v != 0);
         const uint32_t id0 = w0 * 32u + lane + 1u, lt = lanemask_lt();
-        if (tile < 1536u) {
+        if (tile < lane_per_word_below) {
             // sparse round (rare-variant carriers): every lane renders the few ids of its own word
             uint32_t q = my_off;
             for (uint32_t rem = v; rem; rem &= rem - 1) {

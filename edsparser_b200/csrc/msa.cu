@@ -1028,14 +1028,390 @@ __global__ void k_group2(MsaGeom g, MsaBufs b, uint32_t Rq, uint32_t T, uint32_t
     sc.cdesc = reinterpret_cast<uint16_t*>(sc.stage + stage_bytes);
     sc.T = T;
     sc.stage_bytes = use_global ? 0u : stage_bytes;
-    const uint32_t n_wide = st->n_wide;
+    const uint32_t n_wide = st->n_hard;
     unsigned long long alts_here = 0;
     for (uint32_t item = blockIdx.x * wpb + warp; item < n_wide; item += gridDim.x * wpb) {
-        const uint32_t kw = b.widelist[item];
+        const uint32_t kw = b.hardlist[item];
         group_wide(g, b, sc, kw);
         if (lane == 0) alts_here += b.sym_nalts[kw];
     }
     if (lane == 0 && alts_here) atomicAdd(&st->n_alts, alts_here);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Multi-column symbols, tuple formulation (k_group3 / k_emit3). The conserved columns inside a variable symbol are
+// the same in every row, so a row's string is a function of its residues at the symbol's nv VARIABLE columns only.
+//   1. key(row) = those nv bytes (nv <= 7: 56 bits), read as coalesced words from the stash: ~20 instructions a row
+//      instead of a walk over every column of the symbol;
+//   2. the distinct keys and the first row of each go through a 128-slot table in shared memory;
+//   3. only the distinct keys (a few dozen) are turned into gap-stripped strings, compared exactly (strings of up
+//      to 7 characters are their own 64-bit key; longer ones hash first and are verified) and numbered by first row;
+//   4. emit: rows -> per-alternative row bitsets in shared memory (one __match_any_sync per 32 rows), each rendered
+//      as "{ids}" through idlist.cuh into a staged, 16-byte aligned copy-out.
+// Scratch per warp is ~3.6 KB + R bytes (the hashed row path needs 28 KB at 1000 rows), so an SM holds 32 of these
+// warps instead of 6. Symbols outside the envelope (more than 7 variable or 64 total columns, more than 128
+// distinct keys) go to `hardlist` and take the hashed row path (k_group2 / k_emit2).
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kTS = 256;          // tuple table slots (open addressing, at most half full)
+constexpr uint32_t kTD = 128;          // most distinct tuples of a symbol
+constexpr uint32_t kTupleBitWords = 1024;  // k_emit3: row-bitset words per warp (alternatives x R/32 per batch)
+
+struct TupleScratch {
+    uint16_t* cdesc;            // [64]
+    unsigned long long* tkey;   // [kTS] 0 = empty
+    unsigned long long* thash;  // [kTS] string key of the tuple
+    uint32_t* trow;             // [kTS] first row
+    uint16_t* tlen;             // [kTS]
+    uint16_t* tlead;            // [kTS] slot of the tuple whose first row introduces this tuple's string
+    uint16_t* talt;             // [kTS]
+    uint8_t* dl;                // [kTS] occupied slots
+    uint32_t* ndist;            // distinct tuples so far
+    uint8_t* rslot;             // [R] slot of each row's tuple
+};
+
+inline size_t tuple_group_smem(uint32_t R) { return 128 + kTS * (8 + 8 + 4 + 2 + 2 + 2 + 1) + 16 + ((R + 15u) & ~15u) + 16; }
+
+__device__ __forceinline__ TupleScratch tuple_scratch(unsigned char* base) {
+    TupleScratch t;
+    t.cdesc = reinterpret_cast<uint16_t*>(base);
+    t.tkey = reinterpret_cast<unsigned long long*>(base + 128);
+    t.thash = t.tkey + kTS;
+    t.trow = reinterpret_cast<uint32_t*>(t.thash + kTS);
+    t.tlen = reinterpret_cast<uint16_t*>(t.trow + kTS);
+    t.tlead = t.tlen + kTS;
+    t.talt = t.tlead + kTS;
+    t.dl = reinterpret_cast<uint8_t*>(t.talt + kTS);
+    t.ndist = reinterpret_cast<uint32_t*>(t.dl + kTS);
+    t.rslot = reinterpret_cast<uint8_t*>(t.ndist + 4);
+    return t;
+}
+
+// columns [s, en) of a symbol: cdesc[i] = 0x100 | index of the variable column inside the symbol, or the conserved
+// character. Returns the number of variable columns (warp-uniform).
+__device__ __forceinline__ uint32_t describe_columns(const MsaBufs& b, uint32_t s, uint32_t en, uint16_t* cdesc) {
+    const uint32_t lane = threadIdx.x & 31, width = en - s;
+    uint32_t nv = 0;
+    for (uint32_t i0 = 0; i0 < width; i0 += 32) {
+        const uint32_t i = i0 + lane, c = s + i;
+        const bool in = i < width;
+        const uint32_t v = in ? (b.vbits[c >> 5] >> (c & 31u)) & 1u : 0u;
+        const uint32_t m = __ballot_sync(0xffffffffu, v);
+        if (in) cdesc[i] = v ? (uint16_t)(0x100u | (nv + (uint32_t)__popc(m & lanemask_lt()))) : (uint16_t)b.refc[c];
+        nv += (uint32_t)__popc(m);
+    }
+    __syncwarp();
+    return nv;
+}
+
+// gap-stripped string of a tuple: length, and its key (the string itself below 8 characters, else a tagged hash)
+__device__ __forceinline__ void tuple_string_key(const uint16_t* cdesc, uint32_t width, unsigned long long key, uint64_t hash_mask,
+                                                 unsigned long long& out, uint32_t& len) {
+    unsigned long long pk = 0, h = 14695981039346656037ull;
+    uint32_t n = 0;
+    for (uint32_t i = 0; i < width; ++i) {
+        const uint32_t d = cdesc[i];
+        const uint32_t ch = (d & 0x100u) ? (uint32_t)(key >> (8u * (d & 0xffu))) & 0xffu : d;
+        if (ch == (uint32_t)'-') continue;
+        if (n < 7u) pk |= (unsigned long long)ch << (8u * n);
+        h = (h ^ (unsigned long long)ch) * 1099511628211ull;
+        ++n;
+    }
+    len = n;
+    const bool exact = n <= 7u && hash_mask == ~0ull;
+    out = exact ? (pk | ((unsigned long long)n << 56)) : ((h & hash_mask) | (1ull << 63));
+}
+
+__device__ bool tuple_strings_equal(const uint16_t* cdesc, uint32_t width, unsigned long long ka, unsigned long long kb) {
+    uint32_t ia = 0, ib = 0;
+    for (;;) {
+        int ca = -1, cb = -1;
+        while (ia < width) {
+            const uint32_t d = cdesc[ia++];
+            const uint32_t ch = (d & 0x100u) ? (uint32_t)(ka >> (8u * (d & 0xffu))) & 0xffu : d;
+            if (ch != (uint32_t)'-') { ca = (int)ch; break; }
+        }
+        while (ib < width) {
+            const uint32_t d = cdesc[ib++];
+            const uint32_t ch = (d & 0x100u) ? (uint32_t)(kb >> (8u * (d & 0xffu))) & 0xffu : d;
+            if (ch != (uint32_t)'-') { cb = (int)ch; break; }
+        }
+        if (ca != cb) return false;
+        if (ca < 0) return true;
+    }
+}
+
+// One warp, one symbol. False (warp-uniform): outside the envelope, nothing was written.
+__device__ bool group_tuple(const MsaGeom& g, const MsaBufs& b, const TupleScratch& t, uint32_t k, uint32_t& nalts_out) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t s = b.sym[k] & kColMask, en = b.sym[k + 1] & kColMask, width = en - s;
+    if (width > kStageCols || (g.Rp >> 5) > kTupleBitWords || g.alt32) return false;
+    const uint32_t slot0 = first_slot(b, s);
+    const uint32_t nv = describe_columns(b, s, en, t.cdesc);
+    if (nv < 2u || nv > 7u) return false;  // (one variable column: the symbol owns a single stash / altid slot)
+    for (uint32_t i = lane; i < kTS; i += 32) {
+        t.tkey[i] = 0ull;
+        t.trow[i] = 0xffffffffu;
+    }
+    if (lane == 0) *t.ndist = 0u;
+    __syncwarp();
+    bool over = false;
+    const uint8_t* col0 = b.stash + (size_t)slot0 * g.Rp;
+    for (uint32_t r0 = 4u * lane; r0 < g.R; r0 += 128u) {
+        uint32_t w[7];
+#pragma unroll
+        for (uint32_t i = 0; i < 7u; ++i) w[i] = i < nv ? *reinterpret_cast<const uint32_t*>(col0 + (size_t)i * g.Rp + r0) : 0u;
+#pragma unroll
+        for (uint32_t q = 0; q < 4u; ++q) {
+            const uint32_t r = r0 + q;
+            if (r >= g.R) break;
+            unsigned long long key = 1ull << 63;
+#pragma unroll
+            for (uint32_t i = 0; i < 7u; ++i) key |= (unsigned long long)((w[i] >> (8u * q)) & 0xffu) << (8u * i);
+            uint32_t h = (uint32_t)((key ^ (key >> 29)) * 0x9e3779b1u >> 11) & (kTS - 1u);
+            uint32_t probes = 0;
+            for (;;) {
+                const unsigned long long old = atomicCAS(&t.tkey[h], 0ull, key);
+                if (old == key) break;
+                if (old == 0ull) {  // a new tuple: the table stays at most half full (short probe chains)
+                    if (atomicAdd(t.ndist, 1u) >= kTD) over = true;
+                    break;
+                }
+                h = (h + 1u) & (kTS - 1u);
+                if (++probes >= kTS) {
+                    over = true;
+                    break;
+                }
+            }
+            if (over) break;
+            atomicMin(&t.trow[h], r);
+            t.rslot[r] = (uint8_t)h;
+        }
+        if (*reinterpret_cast<volatile uint32_t*>(t.ndist) > kTD) over = true;  // some lane ran out of room: stop early
+    }
+    if (__any_sync(0xffffffffu, over)) return false;
+    __syncwarp();
+    // occupied slots
+    uint32_t D = 0;
+    for (uint32_t i0 = 0; i0 < kTS; i0 += 32) {
+        const bool occ = t.tkey[i0 + lane] != 0ull;
+        const uint32_t m = __ballot_sync(0xffffffffu, occ);
+        if (occ) t.dl[D + (uint32_t)__popc(m & lanemask_lt())] = (uint8_t)(i0 + lane);
+        D += (uint32_t)__popc(m);
+    }
+    __syncwarp();
+    for (uint32_t q = lane; q < D; q += 32) {
+        const uint32_t slot = t.dl[q];
+        unsigned long long sk;
+        uint32_t n;
+        tuple_string_key(t.cdesc, width, t.tkey[slot], g.hash_mask, sk, n);
+        t.thash[slot] = sk;
+        t.tlen[slot] = (uint16_t)n;
+    }
+    __syncwarp();
+    // the tuple with the smallest first row among those that spell the same string introduces the alternative
+    for (uint32_t q = lane; q < D; q += 32) {
+        const uint32_t slot = t.dl[q];
+        const unsigned long long mine = t.thash[slot], key = t.tkey[slot];
+        const uint32_t len = t.tlen[slot];
+        uint32_t best = t.trow[slot], best_slot = slot;
+        for (uint32_t u = 0; u < D; ++u) {
+            const uint32_t us = t.dl[u];
+            if (us == slot || t.thash[us] != mine || t.tlen[us] != len) continue;
+            if ((mine >> 63) && !tuple_strings_equal(t.cdesc, width, key, t.tkey[us])) continue;
+            if (t.trow[us] < best) {
+                best = t.trow[us];
+                best_slot = us;
+            }
+        }
+        t.tlead[slot] = (uint16_t)best_slot;
+    }
+    __syncwarp();
+    uint32_t nalts = 0, lensum = 0;
+    for (uint32_t q0 = 0; q0 < D; q0 += 32) {
+        const uint32_t q = q0 + lane;
+        const uint32_t slot = q < D ? t.dl[q] : 0u;
+        const bool leader = q < D && t.tlead[slot] == slot;
+        if (leader) {
+            uint32_t before = 0;
+            const uint32_t row = t.trow[slot];
+            for (uint32_t u = 0; u < D; ++u) {
+                const uint32_t us = t.dl[u];
+                before += (t.tlead[us] == us && t.trow[us] < row) ? 1u : 0u;
+            }
+            t.talt[slot] = (uint16_t)before;
+            lensum += t.tlen[slot];
+            store_alt(g, b.altid, (size_t)(slot0 + 1u) * g.Rp + before, row);  // first row of alternative `before`
+        }
+        nalts += (uint32_t)__popc(__ballot_sync(0xffffffffu, leader));
+    }
+    __syncwarp();
+    for (uint32_t q = lane; q < D; q += 32) {
+        const uint32_t slot = t.dl[q];
+        if (t.tlead[slot] != slot) t.talt[slot] = t.talt[t.tlead[slot]];
+    }
+    __syncwarp();
+    // rows that introduce an alternative (emit_wide reads them when rows are few): a row leads iff it is the first
+    // row of its tuple and that tuple leads its string
+    for (uint32_t r0 = 0; r0 < g.R; r0 += 32) {
+        const uint32_t r = r0 + lane;
+        uint32_t a = 0;
+        bool leads = false;
+        if (r < g.R) {
+            const uint32_t slot = t.rslot[r];
+            a = t.talt[slot];
+            leads = t.tlead[slot] == slot && t.trow[slot] == r;
+            store_alt(g, b.altid, (size_t)slot0 * g.Rp + r, a);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, leads);
+        if (lane == 0) b.leadmask[(size_t)slot0 * (g.Rp >> 5) + (r0 >> 5)] = m;
+    }
+    lensum = warp_sum(lensum);
+    if (lane == 0) {
+        b.sym_nalts[k] = nalts;
+        b.sym_edsz[k] = 2ull + lensum + (unsigned long long)(nalts - 1u);
+    }
+    nalts_out = nalts;
+    __syncwarp();
+    return true;
+}
+
+// k_group3: the queued multi-column symbols, warp per symbol; what the tuple formulation takes goes to easylist
+// (k_emit3), the rest to hardlist (k_group2 / k_emit2).
+__global__ void k_group3(MsaGeom g, MsaBufs b, uint32_t per_warp_smem, uint32_t force_hard, uint32_t emit_by_rows) {
+    MsaStatus* st = b.status;
+    if (st->abort || st->halo_fail) return;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const TupleScratch t = tuple_scratch(EDSB_DYN_SMEM() + (size_t)warp * per_warp_smem);
+    const uint32_t n_wide = st->n_wide;
+    unsigned long long alts_here = 0;
+    for (uint32_t item = blockIdx.x * wpb + warp; item < n_wide; item += gridDim.x * wpb) {
+        const uint32_t kw = b.widelist[item];
+        uint32_t na = 0;
+        const bool ok = !force_hard && group_tuple(g, b, t, kw, na);
+        if (lane == 0) {
+            if (ok) {
+                // emit_by_rows (few rows): emit_wide renders it from altid / leadmask, like the symbols of hardlist
+                if (emit_by_rows) b.emitlist[atomicAdd(&st->n_emit2, 1u)] = kw;
+                else b.easylist[atomicAdd(&st->n_easy, 1u)] = kw;
+                alts_here += na;
+            } else {
+                b.hardlist[atomicAdd(&st->n_hard, 1u)] = kw;
+                b.emitlist[atomicAdd(&st->n_emit2, 1u)] = kw;
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && alts_here) atomicAdd(&st->n_alts, alts_here);
+}
+
+// k_emit3: "{alt,...}" and "{ids}" per alternative for the symbols of easylist.
+// Scratch per warp: cdesc[64], row bitsets [kTupleBitWords], the id-list stage.
+__global__ void k_emit3(MsaGeom g, MsaBufs b, uint32_t per_warp_smem) {
+    const MsaStatus* st = b.status;
+    if (st->abort || st->halo_fail) return;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    unsigned char* base = EDSB_DYN_SMEM() + (size_t)warp * per_warp_smem;
+    uint16_t* cdesc = reinterpret_cast<uint16_t*>(base);
+    uint32_t* bits = reinterpret_cast<uint32_t*>(base + 128);
+    uint8_t* stage = base + 128 + kTupleBitWords * 4u;
+    const uint32_t Rw = g.Rp >> 5;
+    const uint32_t n_easy = st->n_easy;
+    for (uint32_t item = blockIdx.x * wpb + warp; item < n_easy; item += gridDim.x * wpb) {
+        const uint32_t k = b.easylist[item];
+        const uint32_t s = b.sym[k] & kColMask, en = b.sym[k + 1] & kColMask, width = en - s;
+        const uint32_t slot0 = first_slot(b, s);
+        const uint32_t A = b.sym_nalts[k];
+        describe_columns(b, s, en, cdesc);
+        const uint8_t* col0 = b.stash + (size_t)slot0 * g.Rp;
+        // ---- EDS text: the alternatives in order of first row
+        uint8_t* eds = b.eds_out + b.eds_off[k];
+        unsigned long long run = 1;
+        for (uint32_t a0 = 0; a0 < A; a0 += 32) {
+            const uint32_t a = a0 + lane;
+            const bool have = a < A;
+            const uint32_t row = have ? load_alt(g, b.altid, (size_t)(slot0 + 1u) * g.Rp + a) : 0u;
+            uint32_t n = 0;
+            if (have)
+                for (uint32_t i = 0; i < width; ++i) {
+                    const uint32_t d = cdesc[i];
+                    const uint32_t ch = (d & 0x100u) ? (uint32_t)col0[(size_t)(d & 0xffu) * g.Rp + row] : d;
+                    n += ch != (uint32_t)'-';
+                }
+            const unsigned long long contrib = have ? (unsigned long long)n + 1ull : 0ull;
+            const unsigned long long inc = warp_inclusive_scan(contrib);
+            if (have) {
+                unsigned long long at = run + inc - contrib;
+                eds[at - 1] = a == 0 ? '{' : ',';
+                for (uint32_t i = 0; i < width; ++i) {
+                    const uint32_t d = cdesc[i];
+                    const uint32_t ch = (d & 0x100u) ? (uint32_t)col0[(size_t)(d & 0xffu) * g.Rp + row] : d;
+                    if (ch != (uint32_t)'-') eds[at++] = (uint8_t)ch;
+                }
+            }
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) eds[run - 1] = '}';
+        // ---- SEDS: row bitsets of a batch of alternatives, then one rendered list each
+        unsigned long long at = b.seds_off[k];
+        const uint32_t batch = max(1u, min(A, kTupleBitWords / Rw));
+        for (uint32_t a_lo = 0; a_lo < A; a_lo += batch) {
+            const uint32_t nb = min(batch, A - a_lo);
+            for (uint32_t i = lane; i < nb * Rw; i += 32) bits[i] = 0u;
+            __syncwarp();
+            for (uint32_t r0 = 0; r0 < g.R; r0 += 32) {
+                const uint32_t r = r0 + lane;
+                const uint32_t a = r < g.R ? load_alt(g, b.altid, (size_t)slot0 * g.Rp + r) : kEmptySlot;
+                const bool inb = a >= a_lo && a < a_lo + nb;
+                const uint32_t peers = __match_any_sync(0xffffffffu, inb ? a : kEmptySlot);
+                if (inb && lane == (uint32_t)__ffs((int)peers) - 1u) bits[(a - a_lo) * Rw + (r0 >> 5)] = peers;
+            }
+            __syncwarp();
+            // sizes: a lane per alternative walks its words (ids, bytes); offsets by a warp scan.
+            // Then the alternatives with few rows (most of them, in a multi-column symbol) are written by their lane,
+            // the crowded ones one after the other by the whole warp through the staged renderer.
+            for (uint32_t j0 = 0; j0 < nb; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                uint32_t ids = 0, bytes = 0;
+                if (j < nb) {
+                    for (uint32_t w = 0; w < Rw; ++w) {
+                        const uint32_t v = bits[j * Rw + w];
+                        if (v) {
+                            ids += (uint32_t)__popc(v);
+                            bytes += word_id_bytes(w, v);
+                        }
+                    }
+                    bytes += 1u;  // '{' + "id," each, the last ',' is the '}'
+                }
+                const uint32_t incl = warp_inclusive_scan(bytes);
+                const unsigned long long mine = at + (incl - bytes);
+                const bool crowded = j < nb && ids > 24u;
+                if (j < nb && !crowded) {
+                    uint8_t* out = b.seds_out + mine;
+                    *out++ = '{';
+                    for (uint32_t w = 0; w < Rw; ++w)
+                        for (uint32_t v = bits[j * Rw + w]; v; v &= v - 1u) {
+                            const uint32_t id = w * 32u + (uint32_t)__ffs((int)v);
+                            const unsigned long long e = __ldg(b.id_text + id);  // digits, then ','; width in the top byte
+                            const uint32_t dw = (uint32_t)(e >> 56);             // (ids here are below 2^16: never 0)
+                            for (uint32_t q = 0; q <= dw; ++q) out[q] = (uint8_t)(e >> (8u * q));
+                            out += dw + 1u;
+                        }
+                    out[-1] = '}';
+                }
+                uint32_t todo = __ballot_sync(0xffffffffu, crowded);
+                while (todo) {
+                    const int src = __ffs((int)todo) - 1;
+                    todo &= todo - 1u;
+                    const unsigned long long so = __shfl_sync(0xffffffffu, mine, src);
+                    const uint32_t sb = __shfl_sync(0xffffffffu, bytes, src);
+                    warp_render_id_list(stage, bits + (j0 + (uint32_t)src) * Rw, Rw, b.id_text, b.seds_out, so, sb, 0xffffffffu);
+                }
+                at += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            __syncwarp();
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1355,6 +1731,34 @@ __device__ __forceinline__ void segs_copy_out(const uint8_t* segs, uint32_t seg_
 // chunk). All per-alternative state is warp-uniform and lives in registers (8 alternatives at most).
 // The same symbol from what k_group left behind (row bitsets + residue list): EDS text from the list, one staged
 // "{ids}" per alternative (idlist.cuh). No second classification of the 1000 rows.
+// bytes "id," of the ids of word w (id = 32 w + bit + 1) given the word's id widths: lo ids are wl wide, the rest wl + 1
+__device__ __forceinline__ uint32_t word_bytes_fast(uint32_t v, uint32_t lowmask, uint32_t wl) {
+    return (uint32_t)__popc(v) * (wl + 1u) + (uint32_t)__popc(v & ~lowmask);
+}
+
+// one id's text (digits + ',') into the stage: predicated byte stores, no branch on the width
+__device__ __forceinline__ void stage_id(uint8_t* stage, uint32_t q, unsigned long long e, uint32_t dw) {
+#ifdef EDSB_EMU
+    for (uint32_t j = 0; j <= dw; ++j) stage[q + j] = (uint8_t)(e >> (8u * j));
+#else
+    const uint32_t lo4 = (uint32_t)e, hi4 = (uint32_t)(e >> 32);
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(stage) + q;
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(lo4) : "memory");
+    asm volatile("st.shared.u8 [%0+1], %1;" ::"r"(a), "r"(lo4 >> 8) : "memory");
+    if (dw >= 2u) asm volatile("st.shared.u8 [%0+2], %1;" ::"r"(a), "r"(lo4 >> 16) : "memory");
+    if (dw >= 3u) asm volatile("st.shared.u8 [%0+3], %1;" ::"r"(a), "r"(lo4 >> 24) : "memory");
+    if (dw >= 4u) asm volatile("st.shared.u8 [%0+4], %1;" ::"r"(a), "r"(hi4) : "memory");
+    if (dw >= 5u) asm volatile("st.shared.u8 [%0+5], %1;" ::"r"(a), "r"(hi4 >> 8) : "memory");
+    if (dw >= 6u) asm volatile("st.shared.u8 [%0+6], %1;" ::"r"(a), "r"(hi4 >> 16) : "memory");
+#endif
+}
+
+// Single-column symbol from what k_group left behind (row bitsets + residue list): EDS text from the list; the SEDS
+// segment of the WHOLE symbol — every alternative's "{ids}" — is laid out in the warp's stage at the output's own
+// 16-byte phase and leaves with aligned 16-byte stores. A lane owns word w of every alternative, i.e. rows
+// 32 w .. 32 w + 31: every row is in exactly one alternative, so every lane renders exactly 32 ids — a balanced
+// ~400 warp instructions per 1024 rows, one scan per alternative, one copy-out per symbol. (stage: the symbol's
+// SEDS bytes + 32; alignments deeper than 1024 rows take one more round per 1024 rows.)
 __device__ bool emit_single_from_bits(const MsaGeom& g, const MsaBufs& b, uint32_t k, uint32_t s, uint8_t* stage) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t slot0 = first_slot(b, s), Rw = g.Rp >> 5;
@@ -1374,14 +1778,77 @@ __device__ bool emit_single_from_bits(const MsaGeom& g, const MsaBufs& b, uint32
         }
         *eds = '}';
     }
-    unsigned long long at = b.seds_off[k];
-    for (uint32_t a = 0; a < sn.n; ++a) {
-        uint32_t bytes = 0;
-        for (uint32_t w = lane; w < Rw; w += 32) bytes += word_id_bytes(w, rowbits[a * Rw + w]);
-        bytes = warp_sum(bytes) + 1u;  // '{' + "id," each, the last ',' is the '}'
-        warp_render_id_list(stage, rowbits + a * Rw, Rw, b.id_text, b.seds_out, at, bytes);
-        at += bytes;
+    const unsigned long long so = b.seds_off[k];
+    const uint32_t phase = (uint32_t)(so & 15u);
+    // bytes of every alternative (all words), hence where each starts in the stage
+    uint32_t start[8], fill[8];  // fill[a]: bytes of alternative a placed by the rounds so far
+    uint32_t run = phase;
+#pragma unroll
+    for (uint32_t a = 0; a < 8u; ++a) {
+        start[a] = fill[a] = 0;
+        if (a < sn.n) {
+            uint32_t bytes = 0;
+            for (uint32_t w = lane; w < Rw; w += 32) bytes += word_id_bytes(w, rowbits[a * Rw + w]);
+            bytes = warp_sum(bytes);
+            start[a] = run;
+            run += 1u + bytes;  // '{' + "id," each; the last ',' becomes '}'
+        }
     }
+    for (uint32_t w0 = 0; w0 < Rw; w0 += 32) {
+        const uint32_t w = w0 + lane;
+        // id widths of this lane's word: ids below `pow` are wl wide, the others wl + 1 (a word spans at most one power of ten)
+        const uint32_t lo_id = w * 32u + 1u, wl = decimal_width(lo_id);
+        uint32_t pow = 10;
+        for (uint32_t i = 1; i < wl; ++i) pow *= 10u;
+        const uint32_t lowmask = pow - lo_id >= 32u ? 0xffffffffu : low_bits(pow - lo_id);
+#pragma unroll
+        for (uint32_t a = 0; a < 8u; ++a) {
+            if (a < sn.n) {
+                const uint32_t v = w < Rw ? rowbits[a * Rw + w] : 0u;
+                const uint32_t mine = word_bytes_fast(v, lowmask, wl);
+                const uint32_t incl = warp_inclusive_scan(mine);
+                uint32_t q = start[a] + 1u + fill[a] + (incl - mine);
+                for (uint32_t rem = v; rem; rem &= rem - 1u) {
+                    const uint32_t id = w * 32u + (uint32_t)__ffs((int)rem);
+                    const unsigned long long e = __ldg(b.id_text + id);
+                    uint32_t dw = (uint32_t)(e >> 56);
+                    if (dw) {
+                        stage_id(stage, q, e, dw);
+                    } else {  // more than six digits
+                        dw = decimal_width(id);
+                        write_decimal(stage + q, id, dw);
+                        stage[q + dw] = (uint8_t)',';
+                    }
+                    q += dw + 1u;
+                }
+                fill[a] += __shfl_sync(0xffffffffu, incl, 31);
+            }
+        }
+    }
+    __syncwarp();
+    if (lane < sn.n) {
+        uint32_t st0 = 0, fl = 0;
+#pragma unroll
+        for (uint32_t a = 0; a < 8u; ++a)
+            if (a == lane) {
+                st0 = start[a];
+                fl = fill[a];
+            }
+        stage[st0] = (uint8_t)'{';
+        stage[st0 + fl] = (uint8_t)'}';
+    }
+    __syncwarp();
+    // copy out [phase, run): aligned 16-byte stores, bytes at the two ragged ends
+    uint8_t* const dst = b.seds_out + (so - phase);
+    for (uint32_t j = lane * 16u; j < run; j += 512u) {
+        if (j >= phase && j + 16u <= run) {
+            *reinterpret_cast<uint4*>(dst + j) = *reinterpret_cast<const uint4*>(stage + j);
+        } else {
+            const uint32_t lo_b = j > phase ? j : phase, hi_b = j + 16u < run ? j + 16u : run;
+            for (uint32_t i = lo_b; i < hi_b; ++i) dst[i] = stage[i];
+        }
+    }
+    __syncwarp();
     return true;
 }
 
@@ -1600,8 +2067,8 @@ __global__ void k_emit2(MsaGeom g, MsaBufs b, uint32_t Rq, uint32_t use_global, 
     sc.stage = reinterpret_cast<uint8_t*>(sc.running + Rq);
     sc.cdesc = reinterpret_cast<uint16_t*>(sc.stage + stage_bytes);
     sc.stage_bytes = use_global ? 0u : stage_bytes;
-    const uint32_t n_wide = st->n_wide;
-    for (uint32_t item = blockIdx.x * wpb + warp; item < n_wide; item += gridDim.x * wpb) emit_wide(g, b, sc, b.widelist[item]);
+    const uint32_t n_wide = st->n_emit2;
+    for (uint32_t item = blockIdx.x * wpb + warp; item < n_wide; item += gridDim.x * wpb) emit_wide(g, b, sc, b.emitlist[item]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1947,7 +2414,7 @@ void MsaPipeline::bind(MsaBufs& b) {
 
     d_varcol_.reserve((size_t)cap_var_ * 4);
     d_runs_.reserve((size_t)(cap_runs_ + 2) * 4);
-    d_sym_.reserve((size_t)(cap_runs_ + 2) * 16);  // sym[], varsym[], multilist[], widelist[]
+    d_sym_.reserve((size_t)(cap_runs_ + 2) * 24);  // sym[], varsym[], hardlist[], widelist[], easylist[], emitlist[]
     d_stash_.reserve((size_t)cap_var_ * g.Rp);
     d_altid_.reserve((size_t)cap_var_ * g.Rp * (g.alt32 ? 4 : 2));
     d_leadmask_.reserve((size_t)cap_var_ * (g.Rp / 32) * 4);
@@ -1976,8 +2443,10 @@ void MsaPipeline::bind(MsaBufs& b) {
     b.runs = d_runs_.as<uint32_t>();
     b.sym = d_sym_.as<uint32_t>();
     b.varsym = b.sym + (size_t)cap_runs_ + 2;
-    b.multilist = b.varsym + (size_t)cap_runs_ + 2;
-    b.widelist = b.multilist + (size_t)cap_runs_ + 2;
+    b.hardlist = b.varsym + (size_t)cap_runs_ + 2;
+    b.widelist = b.hardlist + (size_t)cap_runs_ + 2;
+    b.easylist = b.widelist + (size_t)cap_runs_ + 2;
+    b.emitlist = b.easylist + (size_t)cap_runs_ + 2;
     b.stash = d_stash_.as<uint8_t>();
     b.altid = d_altid_.p;
     b.leadmask = d_leadmask_.as<uint32_t>();
@@ -2131,7 +2600,7 @@ void MsaPipeline::run_once(MsaBufs& b) {
     size_t ev_smem = narrow_ok ? evw * ev_warp_smem + (((size_t)g.R * 4 + 15) & ~(size_t)15) : 0;
     if (narrow_ok == 0u && b.rowbits) {
         // rows across lanes: one id-list stage per warp; the row bitsets come from k_group through global memory
-        const size_t per_warp = id_list_stage_bytes(g.R);
+        const size_t per_warp = (size_t)((8 + g.sum_id_width + g.R + 32 + 15) & ~15ull);  // a symbol's whole SEDS segment + phase
         evw = kSymWarps;
         while (evw > 1 && evw * per_warp > smem_budget / 2) evw >>= 1;
         ev_warp_smem = evw * per_warp <= smem_budget ? per_warp : 0;
@@ -2168,19 +2637,43 @@ void MsaPipeline::run_once(MsaBufs& b) {
     const uint32_t emit_stage = (!emit_global && ew * (emit_per_warp + stage_per_warp) <= smem_budget) ? stage_bytes : 0u;
     const size_t emit_warp_smem = emit_global ? 0 : ((emit_per_warp + (emit_stage ? stage_per_warp : 0) + 15) & ~(size_t)15);
     const size_t group_smem = gw * group_warp_smem, emit_smem = ew * emit_warp_smem;
-    int g1_occ = 4, g2_occ = 2, ev_occ = 2, e2_occ = 2;
+    // tuple formulation of the multi-column symbols (k_group3 / k_emit3)
+    const size_t g3_warp_smem = (tuple_group_smem(g.R) + 15) & ~(size_t)15;
+    const size_t e3_warp_smem = (128 + (size_t)kTupleBitWords * 4 + id_list_stage_bytes(g.R) + 15) & ~(size_t)15;
+    const uint32_t g3w = kSymWarps, e3w = kSymWarps;
+    const size_t g3_smem = g3w * g3_warp_smem, e3_smem = e3w * e3_warp_smem;
+    // occupancy and shared-memory attributes depend on the row count and the test switches only: looked up once
+    const uint64_t plan_key = ((uint64_t)g.R << 8) ^ ((uint64_t)ctx_->narrow_off << 4) ^ (b.rowbits ? 1u : 0u) ^ ((uint64_t)nb << 40);
+    if (sym_plan_key_ != plan_key) {
+        sym_plan_key_ = plan_key;
+        int g1_occ = 4, g2_occ = 2, ev_occ = 2, e2_occ = 2, g3_occ = 2, e3_occ = 2;
 #ifndef EDSB_EMU
-    if (group_smem > 48 * 1024)
-        EDSB_CUDA(cudaFuncSetAttribute(k_group2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)group_smem));
-    if (emit_smem > 48 * 1024)
-        EDSB_CUDA(cudaFuncSetAttribute(k_emit2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
-    if (ev_smem > 48 * 1024)
-        EDSB_CUDA(cudaFuncSetAttribute(k_emit_var, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev_smem));
-    EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g1_occ, k_group, kPartThreads, 0));
-    EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g2_occ, k_group2, (int)(gw * 32u), group_smem));
-    EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ev_occ, k_emit_var, (int)(evw * 32u), ev_smem));
-    EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e2_occ, k_emit2, (int)(ew * 32u), emit_smem));
+        if (group_smem > 48 * 1024)
+            EDSB_CUDA(cudaFuncSetAttribute(k_group2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)group_smem));
+        if (emit_smem > 48 * 1024)
+            EDSB_CUDA(cudaFuncSetAttribute(k_emit2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
+        if (ev_smem > 48 * 1024)
+            EDSB_CUDA(cudaFuncSetAttribute(k_emit_var, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev_smem));
+        if (g3_smem > 48 * 1024)
+            EDSB_CUDA(cudaFuncSetAttribute(k_group3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g3_smem));
+        if (e3_smem > 48 * 1024)
+            EDSB_CUDA(cudaFuncSetAttribute(k_emit3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e3_smem));
+        EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g1_occ, k_group, kPartThreads, 0));
+        EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g2_occ, k_group2, (int)(gw * 32u), group_smem));
+        EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ev_occ, k_emit_var, (int)(evw * 32u), ev_smem));
+        EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e2_occ, k_emit2, (int)(ew * 32u), emit_smem));
+        EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g3_occ, k_group3, (int)(g3w * 32u), g3_smem));
+        EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e3_occ, k_emit3, (int)(e3w * 32u), e3_smem));
 #endif
+        sym_occ_[0] = std::max(1, g1_occ);
+        sym_occ_[1] = std::max(1, g2_occ);
+        sym_occ_[2] = std::max(1, ev_occ);
+        sym_occ_[3] = std::max(1, e2_occ);
+        sym_occ_[4] = std::max(1, g3_occ);
+        sym_occ_[5] = std::max(1, e3_occ);
+    }
+    const int g1_occ = sym_occ_[0], g2_occ = sym_occ_[1], ev_occ = sym_occ_[2], e2_occ = sym_occ_[3], g3_occ = sym_occ_[4],
+              e3_occ = sym_occ_[5];
     const uint32_t g2_blocks = sms * (uint32_t)std::max(1, g2_occ);
     const uint32_t e2_blocks = sms * (uint32_t)std::max(1, e2_occ);
     if (group_global || emit_global) {
@@ -2192,6 +2685,10 @@ void MsaPipeline::run_once(MsaBufs& b) {
     after(s, s1, ctx_->ev[1]);  // join: stash ready
     ctx_->clock.begin("k_group");
     EDSB_LAUNCH(k_group, sms * (uint32_t)std::max(1, g1_occ), kPartThreads, 0, s, g, b, narrow_ok);
+    ctx_->clock.end();
+    ctx_->clock.begin("k_group3");
+    EDSB_LAUNCH(k_group3, sms * (uint32_t)g3_occ, g3w * 32u, g3_smem, s, g, b, (uint32_t)g3_warp_smem,
+                (ctx_->narrow_off == 2 || ctx_->tuple_off) ? 1u : 0u, g.R <= 160u ? 1u : 0u);
     ctx_->clock.end();
     ctx_->clock.begin("k_group2");
     EDSB_LAUNCH(k_group2, g2_blocks, gw * 32u, group_smem, s, g, b, Rq, T, group_global ? 1u : 0u, group_stage,
@@ -2216,6 +2713,9 @@ void MsaPipeline::run_once(MsaBufs& b) {
         EDSB_LAUNCH(k_emit_var, sms * (uint32_t)std::max(1, ev_occ), evw * 32u, ev_smem, s, g, b, (uint32_t)ev_warp_smem, nb, seg_pitch);
         ctx_->clock.end();
     }
+    ctx_->clock.begin("k_emit3", s2);
+    EDSB_LAUNCH(k_emit3, sms * (uint32_t)e3_occ, e3w * 32u, e3_smem, s2, g, b, (uint32_t)e3_warp_smem);
+    ctx_->clock.end();
     ctx_->clock.begin("k_emit2", s2);
     EDSB_LAUNCH(k_emit2, e2_blocks, ew * 32u, emit_smem, s2, g, b, Rq, emit_global ? 1u : 0u, emit_stage,
                 (uint32_t)emit_warp_smem);

@@ -52,6 +52,8 @@ class MsaPipeline {
     DevBuf d_fz_rows_, d_fz_tmp_, d_fz_col_, d_fz_cnt_;
     size_t fz_attr_smem_ = 0;      // largest dynamic shared memory size set on k_scan_fused so far
     uint32_t fz_occ_key_ = 0, fz_occ_regions_ = 0;  // cached cluster occupancy (key = NC, S, slot_pitch)
+    uint64_t sym_plan_key_ = ~0ull;  // launch plan of the per-symbol kernels: occupancies looked up once per row count
+    int sym_occ_[6] = {1, 1, 1, 1, 1, 1};
     uint64_t id_text_n_ = 0;  // entries of the id -> text table built so far
     uint32_t cap_var_ = 0, cap_runs_ = 0;
     uint64_t cap_eds_ = 0, cap_seds_ = 0;

@@ -60,7 +60,9 @@ struct MsaStatus {
     uint32_t n_var_syms;  // owned variable symbols
     uint32_t n_varsyms_window;  // variable symbols in the window
     uint32_t v_lo, v_hi;        // owned slice of varsym[]
-    uint32_t n_multi, n_wide;   // entries of multilist / widelist
+    uint32_t n_hard, n_wide;    // entries of hardlist / widelist
+    uint32_t n_easy;            // entries of easylist
+    uint32_t n_emit2;           // entries of emitlist
     uint32_t lead_lo, lead_hi;  // window columns of conserved text continuing a lower shard's symbol
     uint32_t lead_close;        // 1: that symbol's '}' belongs to this shard
     uint32_t tail_open;         // 1: the last owned symbol is conserved and is closed by a higher shard
@@ -86,8 +88,10 @@ struct MsaBufs {
     uint32_t* runs;      // run k: start column | kCommonFlag; runs[n_runs] = ncols
     uint32_t* sym;       // symbol k: start column | kCommonFlag; sym[n_syms] = ncols
     uint32_t* varsym;    // indices of the variable symbols, ascending
-    uint32_t* multilist; // variable symbols 2..15 columns wide (any order), queued by k_group
-    uint32_t* widelist;  // variable symbols for the warp-per-symbol path (any order)
+    uint32_t* widelist;  // multi-column variable symbols (any order), queued by k_group
+    uint32_t* easylist;  // ... of which the tuple formulation takes (k_group3 / k_emit3)
+    uint32_t* hardlist;  // ... and the rest: hashed row path (k_group2)
+    uint32_t* emitlist;  // symbols k_emit2 renders row by row: hardlist, and with few rows easylist's too
     uint8_t* stash;      // stash[k * Rp + r] = residue of row r at the k-th variable column
     void* altid;         // altid[slot0 * Rp + r]: alternative index of row r in the symbol whose first variable column is slot0
     uint32_t* leadmask;  // leadmask[slot0 * Rp/32 + r/32]: rows that introduce an alternative
