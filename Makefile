@@ -8,7 +8,7 @@ CXX      := $(firstword $(wildcard /usr/bin/g++) g++)
 ARCH     := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS  := -std=c++17 -O3 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
 CSRC     := edsparser_b200/csrc
-SRCS     := $(CSRC)/msa.cu $(CSRC)/leds.cu $(CSRC)/vcf.cu $(CSRC)/capi.cu
+SRCS     := $(CSRC)/msa.cu $(CSRC)/leds.cu $(CSRC)/vcf.cu $(CSRC)/capi.cu $(CSRC)/shard.cu
 HDRS     := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/edsparser_b200.h
 OBJS     := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))
 EMUOBJS  := $(patsubst $(CSRC)/%.cu,build/emu_%.o,$(SRCS)) build/emu_runtime.o
@@ -24,7 +24,7 @@ build/%.o: $(CSRC)/%.cu $(HDRS) | build
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
 
 edsparser_b200/libedsparser_b200.so: $(OBJS)
-	$(NVCC) -shared $(ARCH) -o $@ $^
+	$(NVCC) -shared $(ARCH) -o $@ $^ -ldl
 
 emu: tests/emu/libedsparser_emu.so
 
@@ -35,7 +35,7 @@ build/emu_runtime.o: tests/emu/cuda_emu.cpp tests/emu/cuda_emu.h | build
 	$(CXX) -std=c++17 -O1 -g -fPIC -Wall -Itests/emu -c $< -o $@
 
 tests/emu/libedsparser_emu.so: $(EMUOBJS)
-	$(CXX) -shared -pthread -o $@ $^
+	$(CXX) -shared -pthread -o $@ $^ -ldl
 
 # host layer: the reference's transforms API (C++17) + the msa2eds / eds2leds tools, over the C ABI
 HOST     := edsparser_b200/host

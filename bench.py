@@ -299,11 +299,12 @@ def run_ours(args, rank, world):
     stream = torch.cuda.current_stream().cuda_stream
     ctx = lib.context(local, stream)
 
-    from edsparser_b200 import shard
-
-    counts = torch.zeros(2, dtype=torch.int64, device=dev)
-    gathered = torch.zeros(2 * world, dtype=torch.int64, device=dev)
-    exchange = shard.OffsetExchange(dist if world > 1 else None, dev)
+    # the path's one exchange — an all-gather of the ranks' output byte counts — is posted by the LIBRARY (NCCL called
+    # from C++, include/edsparser_b200.h eds_comm_*); torch.distributed only ships the 128-byte NCCL id and the barriers
+    uid = [lib.nccl_unique_id() if (rank == 0 and world > 1) else None]
+    if world > 1:
+        dist.broadcast_object_list(uid, src=0)
+    exchange = E.Comm(ctx, uid[0], rank, world)
 
     def barrier():
         if world > 1:
@@ -371,9 +372,9 @@ def run_ours(args, rank, world):
         def e2e_step():
             dtext[: len(shard_text)].copy_(pinned, non_blocking=True)
             ee, ss, _ = ctx.msa_transform_device(hview, L)
+            exchange.post(int(ee.bytes), int(ss.bytes))
             a, b = ctx.download_view(0, ee), ctx.download_view(1, ss)  # D2H into pinned host memory kept by the context
-            counts[0], counts[1] = int(a.bytes), int(b.bytes)
-            dist.all_gather_into_tensor(gathered, counts)
+            exchange.offsets()  # where this rank's slices go in the one file pair
             return int(a.bytes) + int(b.bytes)
 
         e2e_step()
@@ -387,7 +388,7 @@ def run_ours(args, rank, world):
         e2e = {"value": cells_step * e2e_steps / float(dt.item()), "unit": "cells/s",
                "h2d_bytes_per_step": len(shard_text) * world, "d2h_bytes_per_step": nout * world,
                "ms_per_step": 1e3 * float(dt.item()) / e2e_steps, "steps": e2e_steps,
-               "api": "per rank: pinned H2D + eds_msa_transform_device + D2H into pinned host memory + NCCL all-gather of offsets"}
+               "api": "per rank: pinned H2D + eds_msa_transform_device + D2H into pinned host memory + eds_comm_post / eds_comm_offsets (NCCL all-gather of the byte counts, issued by the library)"}
         del pinned, dtext
     ctx.msa_synth_free()
 
@@ -439,6 +440,7 @@ def run_ours(args, rank, world):
         }
         print(json.dumps(line), flush=True)
     barrier()  # every rank has finished its device work before any rank tears its context down
+    exchange.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -6,4 +6,4 @@ ctypes plumbing used by tests/, bench.py and __graft_entry__.py.
 """
 from .capi import (EDS_ERR_BAD_MSA, EDS_ERR_BUDGET, EDS_ERR_CUDA, EDS_ERR_HALO, EDS_ERR_INVALID_ARGUMENT,  # noqa: F401
                    EDS_ERR_OUT_OF_RANGE, EDS_ERR_RUNTIME, EDS_OK, EXPORTS, PRODUCT_SO, Buffer, Context, EdsError,
-                   Library, MsaStats, MsaView, load)
+                   Comm, Group, Library, MsaStats, MsaView, load)

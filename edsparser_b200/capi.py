@@ -28,6 +28,9 @@ EXPORTS = [
     "eds_msa_conserved_bits",
     "eds_msa_synth_device", "eds_msa_synth_free", "eds_buffer_to_host", "eds_buffer_to_host_view", "eds_buffer_free_host", "eds_leds_merge_host", "eds_leds_merge_host_view", "eds_is_leds_host",
     "eds_vcf_transform_host", "eds_vcf_transform_host_view", "eds_vcf_transform_device", "eds_device_upload", "eds_device_free",
+    "eds_group_create", "eds_group_destroy", "eds_group_size", "eds_group_ctx", "eds_group_msa_transform_host",
+    "eds_group_msa_transform_fd", "eds_nccl_unique_id", "eds_comm_create", "eds_comm_destroy", "eds_comm_post",
+    "eds_comm_offsets", "eds_comm_flush",
 ]
 
 
@@ -120,6 +123,21 @@ class Library:
         L.eds_device_upload.argtypes = [vp, vp, u64, P(vp)]
         L.eds_device_free.argtypes = [vp, vp]
         L.eds_device_free.restype = None
+        L.eds_group_create.argtypes = [P(i32), i32, P(vp)]
+        L.eds_group_destroy.argtypes = [vp]
+        L.eds_group_destroy.restype = None
+        L.eds_group_size.argtypes = [vp]
+        L.eds_group_ctx.argtypes = [vp, i32]
+        L.eds_group_ctx.restype = vp
+        L.eds_group_msa_transform_host.argtypes = [vp, vp, u64, u32, i32, u64, P(Buffer), P(Buffer), P(MsaStats)]
+        L.eds_group_msa_transform_fd.argtypes = [vp, vp, u64, u32, i32, u64, i32, i32, P(u64), P(MsaStats)]
+        L.eds_nccl_unique_id.argtypes = [vp]
+        L.eds_comm_create.argtypes = [vp, vp, i32, i32, P(vp)]
+        L.eds_comm_destroy.argtypes = [vp]
+        L.eds_comm_destroy.restype = None
+        L.eds_comm_post.argtypes = [vp, u64, u64]
+        L.eds_comm_offsets.argtypes = [vp, P(u64)]
+        L.eds_comm_flush.argtypes = [vp]
         self.L = L
         _ = u8p
 
@@ -132,6 +150,82 @@ class Library:
 
     def context(self, device=0, stream=None):
         return Context(self, device, stream)
+
+    def group(self, devices):
+        return Group(self, devices)
+
+    def nccl_unique_id(self):
+        buf = ctypes.create_string_buffer(128)
+        self.check(self.L.eds_nccl_unique_id(buf))
+        return buf.raw
+
+
+class Group:
+    """eds_group: one process, N devices, column-sharded msa2eds with the NCCL exchange inside the library."""
+
+    def __init__(self, lib, devices):
+        self.lib = lib
+        devices = list(devices)
+        arr = (ctypes.c_int * len(devices))(*devices)
+        h = ctypes.c_void_p()
+        lib.check(lib.L.eds_group_create(arr, len(devices), ctypes.byref(h)))
+        self.handle, self.n = h, len(devices)
+
+    def close(self):
+        if self.handle:
+            self.lib.L.eds_group_destroy(self.handle)
+            self.handle = None
+
+    def msa_transform_host(self, file_bytes, l, leds=None, halo=0):
+        leds = (1 if l > 0 else 0) if leds is None else leds
+        e, s = Buffer(), Buffer()
+        st = (MsaStats * self.n)()
+        src = ctypes.c_char_p(bytes(file_bytes))
+        self.lib.check(self.lib.L.eds_group_msa_transform_host(self.handle, src, len(file_bytes), l, leds, halo, ctypes.byref(e),
+                                                               ctypes.byref(s), st))
+        return _host_bytes(self.lib, e), _host_bytes(self.lib, s), [x.as_dict() for x in st]  # (_host_bytes frees)
+
+    def msa_transform_files(self, file_bytes, l, eds_path, seds_path, leds=None, halo=0):
+        leds = (1 if l > 0 else 0) if leds is None else leds
+        fe = os.open(eds_path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+        fs = os.open(seds_path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+        try:
+            tot = (ctypes.c_uint64 * 2)()
+            src = ctypes.c_char_p(bytes(file_bytes))
+            self.lib.check(self.lib.L.eds_group_msa_transform_fd(self.handle, src, len(file_bytes), l, leds, halo, fe, fs, tot, None))
+            return int(tot[0]), int(tot[1])
+        finally:
+            os.close(fe)
+            os.close(fs)
+
+
+class Comm:
+    """eds_comm: one process per GPU; the byte-count all-gather behind each transform, NCCL called from the library."""
+
+    def __init__(self, ctx, unique_id, rank, world):
+        self.lib = ctx.lib
+        h = ctypes.c_void_p()
+        idbuf = ctypes.create_string_buffer(bytes(unique_id), 128) if unique_id is not None else None
+        self.lib.check(self.lib.L.eds_comm_create(ctx.handle, idbuf, rank, world, ctypes.byref(h)))
+        self.handle = h
+        self._out = (ctypes.c_uint64 * 4)()
+
+    def post(self, eds_bytes, seds_bytes):
+        rc = self.lib.L.eds_comm_post(self.handle, eds_bytes, seds_bytes)
+        if rc:
+            self.lib.check(rc)
+
+    def flush(self):
+        self.lib.check(self.lib.L.eds_comm_flush(self.handle))
+
+    def offsets(self):
+        self.lib.check(self.lib.L.eds_comm_offsets(self.handle, self._out))
+        return tuple(int(x) for x in self._out)
+
+    def close(self):
+        if self.handle:
+            self.lib.L.eds_comm_destroy(self.handle)
+            self.handle = None
 
 
 def _host_bytes(lib, buf):

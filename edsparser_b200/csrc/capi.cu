@@ -98,6 +98,10 @@ uint8_t* to_host_view(eds_ctx* ctx, int which, const eds_buffer& dev) {
 
 }  // namespace
 
+namespace edsb {
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace edsb
+
 extern "C" {
 
 const char* eds_last_error(void) { return g_last_error.c_str(); }

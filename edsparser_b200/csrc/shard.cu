@@ -1,0 +1,608 @@
+// Multi-GPU msa2eds behind the C ABI: the alignment's columns shard across the GPUs of one node.
+//
+//   eds_group  — ONE process drives N devices: a context and a host thread per device, an in-process NCCL
+//                communicator (ncclCommInitAll). eds_group_msa_transform_host / _fd: every device receives its
+//                column window of the .msa bytes (+ halo, widened and retried on EDS_ERR_HALO), transforms it,
+//                the devices all-gather their (eds, seds) byte counts over NCCL, and each copies its slice to its
+//                offset of the one output pair (host buffers, or pwrite into the two files).
+//   eds_comm   — one process PER GPU (torchrun / mpirun): the caller ships the 128-byte NCCL id from rank 0,
+//                every rank builds the communicator here (ncclCommInitRank) and posts its counts behind each
+//                transform; offsets are read when the caller is about to write.
+// The data path itself has no collective: 16 bytes per rank and step are all that crosses NVLink.
+// NCCL is loaded with dlopen("libnccl.so.2") on first use, so single-GPU users do not need it installed.
+// Under EDSB_EMU (CPU test tier) the devices are played one after the other and the counts are summed on the host.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#ifndef EDSB_EMU
+#include <dlfcn.h>
+#endif
+
+#include "ctx.h"
+#include "msa.h"
+
+namespace edsb {
+void set_last_error(const std::string& msg);  // capi.cu
+}
+
+namespace {
+
+// ---- the slice of NCCL this file uses, resolved at run time ---------------------------------------------------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct {
+    char internal[128];
+} ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclUint64 = 5 };
+
+struct Nccl {
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string why;
+    bool ok = false;
+};
+
+Nccl& nccl() {
+    static Nccl n;
+    static std::once_flag once;
+    std::call_once(once, [] {
+#ifdef EDSB_EMU
+        n.why = "NCCL is not part of the emulated build";
+#else
+        void* h = nullptr;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (h) break;
+        }
+        if (!h) {
+            n.why = std::string("NCCL not found (dlopen libnccl.so.2): ") + dlerror();
+            return;
+        }
+        auto sym = [&](const char* s) { return dlsym(h, s); };
+        n.GetUniqueId = reinterpret_cast<decltype(n.GetUniqueId)>(sym("ncclGetUniqueId"));
+        n.CommInitRank = reinterpret_cast<decltype(n.CommInitRank)>(sym("ncclCommInitRank"));
+        n.CommInitAll = reinterpret_cast<decltype(n.CommInitAll)>(sym("ncclCommInitAll"));
+        n.CommDestroy = reinterpret_cast<decltype(n.CommDestroy)>(sym("ncclCommDestroy"));
+        n.AllGather = reinterpret_cast<decltype(n.AllGather)>(sym("ncclAllGather"));
+        n.GroupStart = reinterpret_cast<decltype(n.GroupStart)>(sym("ncclGroupStart"));
+        n.GroupEnd = reinterpret_cast<decltype(n.GroupEnd)>(sym("ncclGroupEnd"));
+        n.GetErrorString = reinterpret_cast<decltype(n.GetErrorString)>(sym("ncclGetErrorString"));
+        n.ok = n.GetUniqueId && n.CommInitRank && n.CommInitAll && n.CommDestroy && n.AllGather && n.GroupStart && n.GroupEnd;
+        if (!n.ok) n.why = "libnccl.so.2 lacks an expected symbol";
+#endif
+    });
+    return n;
+}
+
+void nccl_check(int rc, const char* what) {
+    if (rc == ncclSuccess) return;
+    Nccl& n = nccl();
+    throw edsb::CudaError(std::string(what) + ": " + (n.GetErrorString ? n.GetErrorString(rc) : "NCCL error"));
+}
+
+struct Barrier {
+    std::mutex m;
+    std::condition_variable cv;
+    unsigned n = 1, count = 0, gen = 0;
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        const unsigned g = gen;
+        if (++count == n) {
+            count = 0;
+            ++gen;
+            cv.notify_all();
+        } else {
+            cv.wait(lk, [&] { return gen != g; });
+        }
+    }
+};
+
+// columns [lo, hi) owned by shard k of n, held window [wb, we)
+void shard_plan(uint64_t total, uint32_t n, uint32_t k, uint64_t halo, uint64_t& lo, uint64_t& hi, uint64_t& wb, uint64_t& we) {
+    lo = (uint64_t)((unsigned __int128)total * k / n);
+    hi = (uint64_t)((unsigned __int128)total * (k + 1) / n);
+    wb = lo > halo ? lo - halo : 0;
+    we = std::min(total, hi + halo);
+}
+
+template <typename F>
+eds_status guarded_shard(F&& body) {
+    try {
+        body();
+        return EDS_OK;
+    } catch (const edsb::BadMsa& e) {
+        edsb::set_last_error(e.what());
+        return EDS_ERR_BAD_MSA;
+    } catch (const edsb::HaloError& e) {
+        edsb::set_last_error(e.what());
+        return EDS_ERR_HALO;
+    } catch (const edsb::CudaError& e) {
+        edsb::set_last_error(e.what());
+        return EDS_ERR_CUDA;
+    } catch (const std::invalid_argument& e) {
+        edsb::set_last_error(e.what());
+        return EDS_ERR_INVALID_ARGUMENT;
+    } catch (const std::bad_alloc&) {
+        edsb::set_last_error("out of host memory");
+        return EDS_ERR_RUNTIME;
+    } catch (const std::exception& e) {
+        edsb::set_last_error(e.what());
+        return EDS_ERR_RUNTIME;
+    }
+}
+
+}  // namespace
+
+// =====================================================================================================================
+struct eds_comm {
+    eds_ctx* ctx = nullptr;
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    static constexpr int kRing = 2;
+    uint64_t* h_mine[kRing] = {nullptr, nullptr};  // pinned: this rank's (eds, seds) bytes
+    uint64_t* h_all[kRing] = {nullptr, nullptr};   // pinned: everyone's, as gathered
+    uint64_t* d_mine = nullptr;                    // device: kRing x 2
+    uint64_t* d_all = nullptr;                     // device: kRing x 2 x world
+    cudaEvent_t done[kRing] = {nullptr, nullptr};
+    uint64_t posted = 0;
+};
+
+struct eds_group {
+    std::vector<eds_ctx*> ctx;
+    std::vector<int> devices;
+    std::vector<ncclComm_t> comm;       // empty: single device, or the emulated build
+    std::vector<edsb::DevBuf> window;   // per device: the window's rows, 16-byte aligned pitch
+    std::vector<uint64_t*> d_counts;    // per device: 2 + 2 n
+    std::vector<uint64_t*> h_counts;    // per device, pinned: 2 + 2 n
+};
+
+extern "C" {
+
+// ---- one process per GPU ---------------------------------------------------------------------------------------------
+eds_status eds_nccl_unique_id(uint8_t out[128]) {
+    return guarded_shard([&] {
+        if (!out) throw std::invalid_argument("eds_nccl_unique_id: null argument");
+        Nccl& n = nccl();
+        if (!n.ok) throw edsb::CudaError(n.why);
+        ncclUniqueId id;
+        nccl_check(n.GetUniqueId(&id), "ncclGetUniqueId");
+        memcpy(out, id.internal, 128);
+    });
+}
+
+eds_status eds_comm_create(eds_ctx* ctx, const uint8_t id[128], int rank, int world, eds_comm** out) {
+    return guarded_shard([&] {
+        if (!ctx || !out || world < 1 || rank < 0 || rank >= world) throw std::invalid_argument("eds_comm_create: bad argument");
+        *out = nullptr;
+        EDSB_CUDA(cudaSetDevice(ctx->device));
+        eds_comm* c = new eds_comm();
+        c->ctx = ctx;
+        c->rank = rank;
+        c->world = world;
+        try {
+            if (world > 1) {
+                if (!id) throw std::invalid_argument("eds_comm_create: null id");
+                Nccl& n = nccl();
+                if (!n.ok) throw edsb::CudaError(n.why);
+                ncclUniqueId uid;
+                memcpy(uid.internal, id, 128);
+                nccl_check(n.CommInitRank(&c->comm, world, uid, rank), "ncclCommInitRank");
+            }
+            for (int i = 0; i < eds_comm::kRing; ++i) {
+                EDSB_CUDA(cudaMallocHost(&c->h_mine[i], 16));
+                EDSB_CUDA(cudaMallocHost(&c->h_all[i], (size_t)world * 16));
+                EDSB_CUDA(cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming));
+            }
+            EDSB_CUDA(cudaMalloc(&c->d_mine, eds_comm::kRing * 16));
+            EDSB_CUDA(cudaMalloc(&c->d_all, (size_t)eds_comm::kRing * world * 16));
+        } catch (...) {
+            eds_comm_destroy(c);
+            throw;
+        }
+        *out = c;
+    });
+}
+
+void eds_comm_destroy(eds_comm* c) {
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    cudaStreamSynchronize(c->ctx->stream);
+    if (c->comm) nccl().CommDestroy(c->comm);
+    for (int i = 0; i < eds_comm::kRing; ++i) {
+        if (c->h_mine[i]) cudaFreeHost(c->h_mine[i]);
+        if (c->h_all[i]) cudaFreeHost(c->h_all[i]);
+        if (c->done[i]) cudaEventDestroy(c->done[i]);
+    }
+    if (c->d_mine) cudaFree(c->d_mine);
+    if (c->d_all) cudaFree(c->d_all);
+    delete c;
+}
+
+// Enqueue, behind whatever the context's stream holds: counts -> device, all-gather, gathered counts -> pinned host.
+// No host synchronisation; two posts may be in flight.
+eds_status eds_comm_post(eds_comm* c, uint64_t eds_bytes, uint64_t seds_bytes) {
+    return guarded_shard([&] {
+        if (!c) throw std::invalid_argument("eds_comm_post: null comm");
+        EDSB_CUDA(cudaSetDevice(c->ctx->device));
+        const int k = (int)(c->posted % eds_comm::kRing);
+        cudaStream_t s = c->ctx->stream;
+        if (c->posted >= (uint64_t)eds_comm::kRing) EDSB_CUDA(cudaEventSynchronize(c->done[k]));  // the post that used this slot
+        c->h_mine[k][0] = eds_bytes;
+        c->h_mine[k][1] = seds_bytes;
+        if (c->world == 1) {
+            c->h_all[k][0] = eds_bytes;
+            c->h_all[k][1] = seds_bytes;
+        } else {
+            uint64_t* dm = c->d_mine + (size_t)k * 2;
+            uint64_t* da = c->d_all + (size_t)k * 2 * c->world;
+            EDSB_CUDA(cudaMemcpyAsync(dm, c->h_mine[k], 16, cudaMemcpyHostToDevice, s));
+            nccl_check(nccl().AllGather(dm, da, 2, ncclUint64, c->comm, s), "ncclAllGather");
+            EDSB_CUDA(cudaMemcpyAsync(c->h_all[k], da, (size_t)c->world * 16, cudaMemcpyDeviceToHost, s));
+        }
+        EDSB_CUDA(cudaEventRecord(c->done[k], s));
+        ++c->posted;
+    });
+}
+
+// Offsets of this rank's slices from the LAST post: {eds offset, seds offset, eds total, seds total}. Waits for it.
+eds_status eds_comm_offsets(eds_comm* c, uint64_t out[4]) {
+    return guarded_shard([&] {
+        if (!c || !out) throw std::invalid_argument("eds_comm_offsets: null argument");
+        if (c->posted == 0) throw std::invalid_argument("eds_comm_offsets: nothing was posted");
+        EDSB_CUDA(cudaSetDevice(c->ctx->device));
+        const int k = (int)((c->posted - 1) % eds_comm::kRing);
+        EDSB_CUDA(cudaEventSynchronize(c->done[k]));
+        out[0] = out[1] = out[2] = out[3] = 0;
+        for (int r = 0; r < c->world; ++r) {
+            if (r < c->rank) {
+                out[0] += c->h_all[k][2 * r];
+                out[1] += c->h_all[k][2 * r + 1];
+            }
+            out[2] += c->h_all[k][2 * r];
+            out[3] += c->h_all[k][2 * r + 1];
+        }
+    });
+}
+
+// Make the context's stream wait for every post still in flight (inside a timed region: no host synchronisation).
+eds_status eds_comm_flush(eds_comm* c) {
+    return guarded_shard([&] {
+        if (!c) throw std::invalid_argument("eds_comm_flush: null comm");
+        // the posts were enqueued on the context's own stream: they are ordered before anything enqueued from now on
+    });
+}
+
+// ---- one process, N devices ------------------------------------------------------------------------------------------
+eds_status eds_group_create(const int* devices, int n_devices, eds_group** out) {
+    return guarded_shard([&] {
+        if (!out || n_devices < 1 || n_devices > 64) throw std::invalid_argument("eds_group_create: bad argument");
+        *out = nullptr;
+        eds_group* g = new eds_group();
+        try {
+            for (int i = 0; i < n_devices; ++i) {
+                const int dev = devices ? devices[i] : i;
+                eds_ctx* c = nullptr;
+#ifdef EDSB_EMU
+                const eds_status rc = eds_ctx_create(0, nullptr, &c);  // the emulator has one device: played in turn
+#else
+                const eds_status rc = eds_ctx_create(dev, nullptr, &c);
+#endif
+                if (rc != EDS_OK) throw edsb::CudaError(eds_last_error());
+                g->ctx.push_back(c);
+                g->devices.push_back(dev);
+            }
+            g->window.resize(n_devices);
+            g->d_counts.assign(n_devices, nullptr);
+            g->h_counts.assign(n_devices, nullptr);
+            for (int i = 0; i < n_devices; ++i) {
+                EDSB_CUDA(cudaSetDevice(g->ctx[i]->device));
+                EDSB_CUDA(cudaMalloc(&g->d_counts[i], (size_t)(2 + 2 * n_devices) * 8));
+                EDSB_CUDA(cudaMallocHost(&g->h_counts[i], (size_t)(2 + 2 * n_devices) * 8));
+            }
+#ifndef EDSB_EMU
+            if (n_devices > 1) {
+                Nccl& n = nccl();
+                if (!n.ok) throw edsb::CudaError(n.why);
+                g->comm.assign(n_devices, nullptr);
+                nccl_check(n.CommInitAll(g->comm.data(), n_devices, g->devices.data()), "ncclCommInitAll");
+            }
+#endif
+        } catch (...) {
+            eds_group_destroy(g);
+            throw;
+        }
+        *out = g;
+    });
+}
+
+void eds_group_destroy(eds_group* g) {
+    if (!g) return;
+    for (size_t i = 0; i < g->ctx.size(); ++i) {
+        cudaSetDevice(g->ctx[i]->device);
+        if (i < g->comm.size() && g->comm[i]) nccl().CommDestroy(g->comm[i]);
+        if (i < g->window.size()) g->window[i].release();
+        if (i < g->d_counts.size() && g->d_counts[i]) cudaFree(g->d_counts[i]);
+        if (i < g->h_counts.size() && g->h_counts[i]) cudaFreeHost(g->h_counts[i]);
+        eds_ctx_destroy(g->ctx[i]);
+    }
+    delete g;
+}
+
+int eds_group_size(const eds_group* g) { return g ? (int)g->ctx.size() : 0; }
+eds_ctx* eds_group_ctx(eds_group* g, int i) { return (g && i >= 0 && i < (int)g->ctx.size()) ? g->ctx[i] : nullptr; }
+
+}  // extern "C"
+
+namespace {
+
+// What the device threads share during one sharded transform.
+struct ShardRun {
+    eds_group* g;
+    const uint8_t* file;
+    uint64_t file_bytes;
+    uint32_t l;
+    int leds;
+    uint64_t halo;
+    eds_msa_index idx;
+    int eds_fd = -1, seds_fd = -1;  // >= 0: pwrite the slices; else into the host buffers below
+    uint8_t* h_eds = nullptr;
+    uint8_t* h_seds = nullptr;
+    uint64_t eds_total = 0, seds_total = 0;
+    eds_msa_stats* stats = nullptr;
+    Barrier bar;
+    std::vector<std::string> error;  // per device
+    std::vector<eds_status> status;
+    std::vector<uint64_t> counts;    // emulated build: 2 per device
+};
+
+void pwrite_all(int fd, const uint8_t* p, uint64_t n, uint64_t off) {
+    while (n) {
+        const ssize_t w = pwrite(fd, p, (size_t)std::min<uint64_t>(n, 1u << 30), (off_t)off);
+        if (w <= 0) throw std::runtime_error("pwrite failed while writing an output slice");
+        p += w;
+        n -= (uint64_t)w;
+        off += (uint64_t)w;
+    }
+}
+
+// One device's part. Every path reaches the barriers the same number of times (an error is recorded and the thread
+// keeps stepping), so no thread is left waiting.
+void shard_worker(ShardRun& run, uint32_t k) {
+    eds_group* g = run.g;
+    const uint32_t n = (uint32_t)g->ctx.size();
+    eds_ctx* ctx = g->ctx[k];
+    const eds_msa_index& idx = run.idx;
+    eds_buffer de{nullptr, 0}, ds{nullptr, 0};
+    eds_msa_stats st;
+    memset(&st, 0, sizeof(st));
+    auto fail = [&](eds_status rc, const std::string& msg) {
+        if (run.status[k] == EDS_OK) {
+            run.status[k] = rc;
+            run.error[k] = msg;
+        }
+    };
+    try {
+        EDSB_CUDA(cudaSetDevice(ctx->device));
+        cudaStream_t s = ctx->stream;
+        uint64_t halo = std::max<uint64_t>(run.halo, (uint64_t)run.l + 2);
+        for (int attempt = 0;; ++attempt) {
+            uint64_t lo, hi, wb, we;
+            shard_plan(idx.n_cols, n, k, halo, lo, hi, wb, we);
+            // the window's bytes of every row, rows at a 16-byte aligned pitch (k_scan's one-load-per-row path)
+            const uint64_t lw = idx.line_width;
+            const uint64_t u_begin = wb + wb / lw, last = we - 1;
+            const uint64_t row_bytes = last + last / lw - u_begin + 1;
+            const uint64_t pitch = ((row_bytes + 15) & ~15ull) + 16;
+            g->window[k].reserve((size_t)(pitch * idx.n_rows + 64));
+            uint8_t* dwin = g->window[k].as<uint8_t>();
+            std::vector<uint64_t> rows(idx.n_rows);
+            for (uint32_t r = 0; r < idx.n_rows; ++r) {
+                rows[r] = (uint64_t)r * pitch;
+                EDSB_CUDA(cudaMemcpyAsync(dwin + rows[r], run.file + idx.row_start[r] + u_begin, (size_t)row_bytes, cudaMemcpyHostToDevice, s));
+            }
+            eds_msa_view v;
+            memset(&v, 0, sizeof(v));
+            v.text = dwin;
+            v.text_bytes = pitch * idx.n_rows;
+            v.row_start = rows.data();
+            v.n_rows = idx.n_rows;
+            v.line_width = idx.line_width;
+            v.total_cols = idx.n_cols;
+            v.col_begin = wb;
+            v.col_count = we - wb;
+            v.own_begin = lo;
+            v.own_end = hi;
+            try {
+                ctx->msa->transform(v, run.l, run.leds, &de, &ds, &st);
+                break;
+            } catch (const edsb::HaloError&) {
+                // a symbol of the owned range does not close inside the window: widen and go again
+                if (we - wb >= idx.n_cols || attempt > 24) throw;
+                halo *= 4;
+            }
+        }
+    } catch (const edsb::BadMsa& e) {
+        fail(EDS_ERR_BAD_MSA, e.what());
+    } catch (const edsb::HaloError& e) {
+        fail(EDS_ERR_HALO, e.what());
+    } catch (const edsb::CudaError& e) {
+        fail(EDS_ERR_CUDA, e.what());
+    } catch (const std::invalid_argument& e) {
+        fail(EDS_ERR_INVALID_ARGUMENT, e.what());
+    } catch (const std::exception& e) {
+        fail(EDS_ERR_RUNTIME, e.what());
+    }
+    const bool bad = run.status[k] != EDS_OK;
+    if (run.stats) run.stats[k] = st;
+
+    // ---- the exchange: every device learns every device's byte counts (a failed device reports ~0: all abort)
+    uint64_t mine[2] = {bad ? ~0ull : de.bytes, bad ? ~0ull : ds.bytes};
+    std::vector<uint64_t> all(2 * (size_t)n, 0);
+    try {
+        if (g->comm.empty()) {
+            run.counts[2 * k] = mine[0];
+            run.counts[2 * k + 1] = mine[1];
+            run.bar.wait();
+            all = run.counts;
+        } else {
+            cudaStream_t s = ctx->stream;
+            uint64_t* h = g->h_counts[k];
+            uint64_t* d = g->d_counts[k];
+            h[0] = mine[0];
+            h[1] = mine[1];
+            EDSB_CUDA(cudaMemcpyAsync(d, h, 16, cudaMemcpyHostToDevice, s));
+            nccl_check(nccl().AllGather(d, d + 2, 2, ncclUint64, g->comm[k], s), "ncclAllGather");
+            EDSB_CUDA(cudaMemcpyAsync(h + 2, d + 2, (size_t)n * 16, cudaMemcpyDeviceToHost, s));
+            EDSB_CUDA(cudaStreamSynchronize(s));
+            for (uint32_t i = 0; i < 2 * n; ++i) all[i] = h[2 + i];
+            run.bar.wait();
+        }
+    } catch (const std::exception& e) {
+        fail(EDS_ERR_CUDA, e.what());
+        run.bar.wait();
+        for (uint32_t i = 0; i < 2 * n; ++i) all[i] = ~0ull;
+    }
+    bool any_bad = false;
+    uint64_t eoff = 0, soff = 0, etot = 0, stot = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (all[2 * i] == ~0ull) any_bad = true;
+        if (i < k) {
+            eoff += all[2 * i];
+            soff += all[2 * i + 1];
+        }
+        etot += all[2 * i];
+        stot += all[2 * i + 1];
+    }
+    if (k == 0 && !any_bad) {
+        run.eds_total = etot;
+        run.seds_total = stot;
+        if (run.eds_fd < 0) {
+            run.h_eds = static_cast<uint8_t*>(malloc(etot ? etot : 1));
+            run.h_seds = static_cast<uint8_t*>(malloc(stot ? stot : 1));
+            if (!run.h_eds || !run.h_seds) fail(EDS_ERR_RUNTIME, "out of host memory");
+        } else {
+            if (ftruncate(run.eds_fd, (off_t)etot) != 0 || ftruncate(run.seds_fd, (off_t)stot) != 0)
+                fail(EDS_ERR_RUNTIME, "ftruncate failed on an output file");
+        }
+    }
+    run.bar.wait();  // the destination exists
+    if (any_bad || run.status[0] != EDS_OK) return;
+    try {
+        cudaStream_t s = ctx->stream;
+        if (run.eds_fd < 0) {
+            if (de.bytes) EDSB_CUDA(cudaMemcpyAsync(run.h_eds + eoff, de.data, de.bytes, cudaMemcpyDeviceToHost, s));
+            if (ds.bytes) EDSB_CUDA(cudaMemcpyAsync(run.h_seds + soff, ds.data, ds.bytes, cudaMemcpyDeviceToHost, s));
+            EDSB_CUDA(cudaStreamSynchronize(s));
+        } else {
+            // through the context's pinned result buffers, then pwrite at this device's offsets
+            std::vector<uint8_t> tmp;
+            for (int which = 0; which < 2; ++which) {
+                const eds_buffer& d = which ? ds : de;
+                tmp.resize(d.bytes ? d.bytes : 1);
+                if (d.bytes) {
+                    EDSB_CUDA(cudaMemcpyAsync(tmp.data(), d.data, d.bytes, cudaMemcpyDeviceToHost, s));
+                    EDSB_CUDA(cudaStreamSynchronize(s));
+                }
+                pwrite_all(which ? run.seds_fd : run.eds_fd, tmp.data(), d.bytes, which ? soff : eoff);
+            }
+        }
+    } catch (const std::exception& e) {
+        fail(EDS_ERR_RUNTIME, e.what());
+    }
+}
+
+eds_status group_transform(eds_group* g, const uint8_t* file, uint64_t file_bytes, uint32_t l, int leds, uint64_t halo, int eds_fd,
+                           int seds_fd, eds_buffer* eds_out, eds_buffer* seds_out, uint64_t* totals, eds_msa_stats* stats) {
+    if (eds_out) *eds_out = eds_buffer{nullptr, 0};
+    if (seds_out) *seds_out = eds_buffer{nullptr, 0};
+    return guarded_shard([&] {
+        if (!g || !file) throw std::invalid_argument("eds_group_msa_transform: null argument");
+        if (eds_fd < 0 && (!eds_out || !seds_out)) throw std::invalid_argument("eds_group_msa_transform: no destination");
+        const uint32_t n = (uint32_t)g->ctx.size();
+        ShardRun run;
+        run.g = g;
+        run.file = file;
+        run.file_bytes = file_bytes;
+        run.l = l;
+        run.leds = leds;
+        run.halo = halo ? halo : 4096;
+        run.eds_fd = eds_fd;
+        run.seds_fd = seds_fd;
+        run.stats = stats;
+        run.bar.n = n;
+        run.error.assign(n, "");
+        run.status.assign(n, EDS_OK);
+        run.counts.assign(2 * (size_t)n, 0);
+        memset(&run.idx, 0, sizeof(run.idx));
+        if (eds_msa_index_host(file, file_bytes, &run.idx) != EDS_OK) throw edsb::BadMsa(eds_last_error());
+        if (run.idx.n_cols < n) {
+            eds_msa_index_free(&run.idx);
+            throw std::invalid_argument("eds_group_msa_transform: fewer columns than devices");
+        }
+#ifdef EDSB_EMU
+        // the emulator runs one kernel at a time: play the devices on threads all the same (the barrier needs them)
+#endif
+        std::vector<std::thread> th;
+        for (uint32_t k = 0; k < n; ++k) th.emplace_back([&run, k] { shard_worker(run, k); });
+        for (auto& t : th) t.join();
+        eds_msa_index_free(&run.idx);
+        for (uint32_t k = 0; k < n; ++k)
+            if (run.status[k] != EDS_OK) {
+                free(run.h_eds);
+                free(run.h_seds);
+                const std::string msg = run.error[k];
+                switch (run.status[k]) {
+                    case EDS_ERR_BAD_MSA: throw edsb::BadMsa(msg);
+                    case EDS_ERR_HALO: throw edsb::HaloError(msg);
+                    case EDS_ERR_CUDA: throw edsb::CudaError(msg);
+                    case EDS_ERR_INVALID_ARGUMENT: throw std::invalid_argument(msg);
+                    default: throw std::runtime_error(msg);
+                }
+            }
+        if (eds_fd < 0) {
+            eds_out->data = run.h_eds;
+            eds_out->bytes = run.eds_total;
+            seds_out->data = run.h_seds;
+            seds_out->bytes = run.seds_total;
+        }
+        if (totals) {
+            totals[0] = run.eds_total;
+            totals[1] = run.seds_total;
+        }
+    });
+}
+
+}  // namespace
+
+extern "C" {
+
+eds_status eds_group_msa_transform_host(eds_group* g, const uint8_t* file, uint64_t file_bytes, uint32_t l, int leds, uint64_t halo,
+                                        eds_buffer* eds_out, eds_buffer* seds_out, eds_msa_stats* per_device_stats) {
+    return group_transform(g, file, file_bytes, l, leds, halo, -1, -1, eds_out, seds_out, nullptr, per_device_stats);
+}
+
+eds_status eds_group_msa_transform_fd(eds_group* g, const uint8_t* file, uint64_t file_bytes, uint32_t l, int leds, uint64_t halo,
+                                      int eds_fd, int seds_fd, uint64_t totals[2], eds_msa_stats* per_device_stats) {
+    if (eds_fd < 0 || seds_fd < 0) {
+        edsb::set_last_error("eds_group_msa_transform_fd: bad file descriptor");
+        return EDS_ERR_INVALID_ARGUMENT;
+    }
+    return group_transform(g, file, file_bytes, l, leds, halo, eds_fd, seds_fd, nullptr, nullptr, totals, per_device_stats);
+}
+
+}  // extern "C"

@@ -5,6 +5,7 @@
 #define EDSPARSER_TRANSFORMS_EDS_TRANSFORMS_HPP
 
 #include <iostream>
+#include <vector>
 
 #include "../common.hpp"
 #include "../formats/eds.hpp"
@@ -24,6 +25,8 @@ bool is_leds(const EDS& eds, Length context_length);
 // which has no bound in the reference. 0 = unlimited.
 namespace b200 {
 void set_device(int device);
+// msa2eds column-sharded over these devices of one node (one entry: the same as set_device)
+void set_devices(const std::vector<int>& devices);
 void set_max_output_bytes(uint64_t bytes);
 }  // namespace b200
 

@@ -39,6 +39,7 @@ namespace {
 
 int g_device = 0;
 uint64_t g_budget = 0;
+std::vector<int> g_devices;  // more than one entry: msa2eds is column-sharded over these devices (eds_group)
 
 [[noreturn]] void rethrow(eds_status rc) {
     const std::string what = eds_last_error();
@@ -69,8 +70,39 @@ thread_local Session t_session;
 
 std::string slurp(std::istream& in) { return std::string(std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>()); }
 
+// one group per thread and device list, like the per-thread context
+struct GroupSession {
+    eds_group* group = nullptr;
+    std::vector<int> devices;
+    ~GroupSession() { eds_group_destroy(group); }
+    eds_group* get() {
+        if (!group || devices != g_devices) {
+            eds_group_destroy(group);
+            group = nullptr;
+            const eds_status rc = eds_group_create(g_devices.data(), (int)g_devices.size(), &group);
+            if (rc != EDS_OK) rethrow(rc);
+            devices = g_devices;
+        }
+        return group;
+    }
+};
+thread_local GroupSession t_group;
+
 std::pair<std::string, std::string> msa_transform(std::istream& in, uint32_t l, int leds) {
     const std::string file = slurp(in);
+    if (g_devices.size() > 1) {
+        // column-sharded over the devices: every device transforms its column range (+ halo), the byte counts are
+        // all-gathered over NCCL inside the library and every device writes its slice of the one result
+        eds_buffer e{nullptr, 0}, s{nullptr, 0};
+        const eds_status rc = eds_group_msa_transform_host(t_group.get(), reinterpret_cast<const uint8_t*>(file.data()), file.size(), l, leds,
+                                                           0, &e, &s, nullptr);
+        if (rc != EDS_OK) rethrow(rc);
+        std::pair<std::string, std::string> out{std::string(reinterpret_cast<const char*>(e.data), e.bytes),
+                                                std::string(reinterpret_cast<const char*>(s.data), s.bytes)};
+        eds_buffer_free_host(&e);
+        eds_buffer_free_host(&s);
+        return out;
+    }
     eds_buffer e{nullptr, 0}, s{nullptr, 0};  // views into pinned memory kept by the context: nothing to free
     const eds_status rc = eds_msa_transform_host_view(t_session.get(), reinterpret_cast<const uint8_t*>(file.data()), file.size(), l, leds,
                                                       &e, &s, nullptr);
@@ -161,6 +193,10 @@ std::pair<std::string, std::string> vcf_transform(std::istream& vcf_stream, std:
 
 namespace b200 {
 void set_device(int device) { g_device = device; }
+void set_devices(const std::vector<int>& devices) {
+    g_devices = devices;
+    if (!devices.empty()) g_device = devices[0];
+}
 void set_max_output_bytes(uint64_t bytes) { g_budget = bytes; }
 }  // namespace b200
 

@@ -18,7 +18,9 @@ static void usage() {
                  "  -o [ --output ] arg               Output EDS file (default: <input>.eds)\n"
                  "  -s [ --sources ] arg              Output source file (default: <output>.seds)\n"
                  "  -l [ --context-length ] arg (=0)  Create l-EDS with minimum context length (0 = regular EDS)\n"
-                 "  --device arg (=0)                 CUDA device to run on (B200 build)\n\n"
+                 "  --device arg (=0)                 CUDA device to run on (B200 build)\n"
+                 "  --gpus arg (=1)                   Shard the alignment's columns over this many GPUs of the node,\n"
+                 "                                    starting at --device (NCCL exchange of the output offsets)\n\n"
                  "OUTPUT:\n"
                  "  Regular EDS:     <input_base>.eds, <input_base>.seds\n"
                  "  l-EDS (with -l): <input_base>_l<N>.leds, <input_base>_l<N>.seds\n\n";
@@ -29,7 +31,7 @@ int main(int argc, char** argv) {
     timer.start();
     try {
         const cli::Args args(argc, argv, {{"help", 'h', false}, {"input", 'i', true}, {"output", 'o', true},
-                                         {"sources", 's', true}, {"context-length", 'l', true}, {"device", 0, true}});
+                                         {"sources", 's', true}, {"context-length", 'l', true}, {"device", 0, true}, {"gpus", 0, true}});
         if (args.has("help")) {
             usage();
             cli::print_performance(timer);
@@ -42,7 +44,15 @@ int main(int argc, char** argv) {
         const unsigned long l_arg = args.has("context-length") ? args.to_uint("context-length") : 0;
         if (l_arg > 0xfffffffful) throw std::invalid_argument("the argument for option '--context-length' is invalid");
         const Length context_length = (Length)l_arg;
-        if (args.has("device")) b200::set_device((int)args.to_uint("device"));
+        const int first_device = args.has("device") ? (int)args.to_uint("device") : 0;
+        b200::set_device(first_device);
+        if (args.has("gpus")) {
+            const unsigned long n = args.to_uint("gpus");
+            if (n < 1 || n > 64) throw std::invalid_argument("the argument for option '--gpus' is invalid");
+            std::vector<int> devices;
+            for (unsigned long i = 0; i < n; ++i) devices.push_back(first_device + (int)i);
+            b200::set_devices(devices);
+        }
 
         if (input_file.extension() != ".msa") {
             std::cerr << "Error: Input file must be an MSA file (.msa)\n";

@@ -226,6 +226,47 @@ eds_status eds_vcf_transform_device(eds_ctx* ctx, const uint8_t* vcf, uint64_t v
                                     uint64_t fasta_bytes, eds_buffer* eds_out, eds_buffer* seds_out,
                                     eds_vcf_stats* stats);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU msa2eds: the alignment's columns shard across the GPUs of one node (SURVEY.md §8e,
+ * BASELINE config 4). Every device transforms a contiguous column range plus a halo (widened and
+ * retried on EDS_ERR_HALO); the ONE exchange is an NCCL all-gather of the shards' (eds, seds) byte
+ * counts, from which every shard gets the offsets of its slices of the single output pair. NCCL is
+ * called from this library (dlopen of libnccl.so.2 on first use), not from the caller.
+ *
+ * eds_group: ONE process drives N devices (what `msa2eds --gpus N` uses): one context and one host
+ * thread per device, an in-process communicator. Stands behind parse_msa_to_eds_streaming /
+ * parse_msa_to_leds_streaming (msa_transforms.cpp:334-365) like the single-device entry points.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct eds_group eds_group;
+/* devices = NULL: devices 0 .. n_devices - 1 */
+eds_status eds_group_create(const int* devices, int n_devices, eds_group** out);
+void eds_group_destroy(eds_group* group);
+int eds_group_size(const eds_group* group);
+eds_ctx* eds_group_ctx(eds_group* group, int i); /* e.g. for eds_ctx_set_profiling / eds_ctx_kernel_times */
+/* .msa bytes in host memory -> malloc'd host strings (free with eds_buffer_free_host). halo = 0: default (4096
+ * columns, never less than l + 2). per_device_stats: NULL or eds_group_size() entries. */
+eds_status eds_group_msa_transform_host(eds_group* group, const uint8_t* file, uint64_t file_bytes, uint32_t l, int leds,
+                                        uint64_t halo, eds_buffer* eds_out, eds_buffer* seds_out,
+                                        eds_msa_stats* per_device_stats);
+/* Same, every device pwrite()s its slices into the two open files at its offsets (device 0 sizes them);
+ * totals[0..1] = bytes of the .eds / .seds. */
+eds_status eds_group_msa_transform_fd(eds_group* group, const uint8_t* file, uint64_t file_bytes, uint32_t l, int leds,
+                                      uint64_t halo, int eds_fd, int seds_fd, uint64_t totals[2],
+                                      eds_msa_stats* per_device_stats);
+
+/* eds_comm: one process PER GPU (torchrun, mpirun): rank 0 makes the 128-byte NCCL id, the launcher ships it to
+ * every rank, each rank builds the communicator for its context. After every eds_msa_transform_device the rank
+ * posts its byte counts (enqueued behind the transform, no host synchronisation, two posts may be in flight);
+ * eds_comm_offsets waits for the last post and returns {eds offset, seds offset, eds total, seds total}. */
+typedef struct eds_comm eds_comm;
+eds_status eds_nccl_unique_id(uint8_t out[128]);
+eds_status eds_comm_create(eds_ctx* ctx, const uint8_t id[128], int rank, int world, eds_comm** out);
+void eds_comm_destroy(eds_comm* comm);
+eds_status eds_comm_post(eds_comm* comm, uint64_t eds_bytes, uint64_t seds_bytes);
+eds_status eds_comm_offsets(eds_comm* comm, uint64_t out[4]);
+eds_status eds_comm_flush(eds_comm* comm);
+
 /* Device memory for callers that stage inputs themselves (bench, tests): cudaMalloc / H2D copy / cudaFree. */
 eds_status eds_device_upload(eds_ctx* ctx, const uint8_t* host, uint64_t bytes, uint8_t** device_out);
 void eds_device_free(eds_ctx* ctx, uint8_t* device);

@@ -146,3 +146,24 @@ def test_is_leds():
         assert ctx.is_leds(b"{A,C}{G,T}", 0) and ctx.is_leds(b"{AC}", 5) and ctx.is_leds(b"{A}{C,G}", 9)
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+def test_msa2eds_gpus_option(tmp_path):
+    """msa2eds --gpus N: one .eds/.seds pair written from N column shards == the oracle (N = the box's devices, at most 4;
+    on a one-GPU box the option still goes through the group entry point with one device)."""
+    import torch
+    from edsparser_b200 import synth
+
+    text = synth.fasta_window(60, 50_000, 70, seed=3, variable_ppm=20_000)
+    src = tmp_path / "shape.msa"
+    src.write_bytes(text)
+    exp = oracle_lib.msa2eds(text, 10)
+    for n in sorted({1, min(2, torch.cuda.device_count()), min(4, torch.cuda.device_count())}):
+        out = tmp_path / f"o{n}.leds"
+        rc, so, err = run("msa2eds", "-i", str(src), "-l", "10", "-o", str(out), "--gpus", str(n))
+        assert rc == 0, err
+        assert out.read_bytes() == exp[0]
+        assert (tmp_path / "shape_l10.seds").read_bytes() == exp[1]
+    rc, so, err = run("msa2eds", "-i", str(src), "--gpus", "0")
+    assert rc == 1 and "--gpus" in err
