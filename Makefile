@@ -55,3 +55,27 @@ oracle:
 
 clean:
 	rm -rf build edsparser_b200/libedsparser_b200.so edsparser_b200/libedsparser_host.a edsparser_b200/bin tests/emu/libedsparser_emu.so
+
+# The reference's own C++ tests, UNMODIFIED (sources stay under /root/reference; only binaries are produced, into the
+# git-ignored tests/_refbin/ which travels to the GPU box): compiled with -Dmain=reference_main next to
+# tests/refwrap/run_each.cpp (runs the test functions one by one), linked against this repo's host layer + the product
+# library (*_gpu), against the emulator build (*_emu, CPU tier) and against the unmodified reference library (*_ref:
+# which of the reference's asserts hold against the reference itself -> tests/golden/ref_cpp_tests.json).
+REF      ?= /root/reference
+REFTESTS := test_msa test_merge test_sources test_stats
+REFFLAGS := -std=c++17 -O1 -rdynamic -Wno-unused-variable -Wno-unused-result
+REFMAIN  := -Dmain=reference_main -c
+REFOURS  := $(HOSTINC) -I$(HOST)/include/edsparser
+reftests: $(patsubst %,tests/_refbin/%_gpu,$(REFTESTS)) $(patsubst %,tests/_refbin/%_emu,$(REFTESTS)) $(patsubst %,tests/_refbin/%_ref,$(REFTESTS))
+tests/_refbin/%_gpu: $(REF)/tests/cpp/%.cpp tests/refwrap/run_each.cpp edsparser_b200/libedsparser_host.a edsparser_b200/libedsparser_b200.so
+	mkdir -p tests/_refbin
+	$(CXX) $(REFFLAGS) $(REFOURS) $(REFMAIN) $< -o $@.o
+	$(CXX) $(REFFLAGS) $@.o tests/refwrap/run_each.cpp edsparser_b200/libedsparser_host.a -Ledsparser_b200 -ledsparser_b200 -ldl -Wl,-rpath,'$$ORIGIN/../../edsparser_b200' -o $@ && rm -f $@.o
+tests/_refbin/%_emu: $(REF)/tests/cpp/%.cpp tests/refwrap/run_each.cpp edsparser_b200/libedsparser_host.a tests/emu/libedsparser_emu.so
+	mkdir -p tests/_refbin
+	$(CXX) $(REFFLAGS) $(REFOURS) $(REFMAIN) $< -o $@.o
+	$(CXX) $(REFFLAGS) $@.o tests/refwrap/run_each.cpp edsparser_b200/libedsparser_host.a -Ltests/emu -ledsparser_emu -ldl -Wl,-rpath,'$$ORIGIN/../emu' -o $@ && rm -f $@.o
+tests/_refbin/%_ref: $(REF)/tests/cpp/%.cpp tests/refwrap/run_each.cpp oracle/_ref/libedsparser_ref.a
+	mkdir -p tests/_refbin
+	$(CXX) $(REFFLAGS) -Ioracle/sdsl_standin -I$(REF)/src/cpp/lib $(REFMAIN) $< -o $@.o
+	$(CXX) $(REFFLAGS) -fopenmp $@.o tests/refwrap/run_each.cpp oracle/_ref/libedsparser_ref.a -ldl -o $@ && rm -f $@.o

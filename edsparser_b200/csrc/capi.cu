@@ -450,6 +450,47 @@ eds_status eds_leds_merge_host_view(eds_ctx* ctx, const uint8_t* eds_in, uint64_
     return rc;
 }
 
+eds_status eds_parse_host(eds_ctx* ctx, const uint8_t* eds, uint64_t eds_bytes, const uint8_t* seds, uint64_t seds_bytes,
+                          eds_parsed* out) {
+    if (out) memset(out, 0, sizeof(*out));
+    return guarded([&] {
+        use_device(ctx);
+        if ((!eds && eds_bytes) || !out) throw std::invalid_argument("eds_parse_host: null argument");
+        static const uint8_t nothing = 0;
+        ctx->leds->merge_host(eds ? eds : &nothing, eds_bytes, seds, seds_bytes, 0, false, 0, nullptr, nullptr, nullptr, nullptr, false,
+                              {}, out);
+    });
+}
+
+void eds_parsed_free(eds_parsed* p) {
+    if (!p) return;
+    free(p->text);
+    free(p->str_start);
+    free(p->str_end);
+    free(p->sym_first);
+    free(p->src_off);
+    free(p->src_ids);
+    memset(p, 0, sizeof(*p));
+}
+
+eds_status eds_merge_adjacent_host(eds_ctx* ctx, const uint8_t* eds, uint64_t eds_bytes, const uint8_t* seds, uint64_t seds_bytes,
+                                   uint64_t pos1, eds_buffer* eds_out, eds_buffer* seds_out) {
+    if (eds_out) *eds_out = eds_buffer{nullptr, 0};
+    if (seds_out) *seds_out = eds_buffer{nullptr, 0};
+    eds_status rc = guarded([&] {
+        use_device(ctx);
+        if (!eds || !eds_out || !seds_out) throw std::invalid_argument("eds_merge_adjacent_host: null argument");
+        if (pos1 >= 0xfffffffeull) throw std::out_of_range("eds_merge_adjacent_host: position out of range");
+        ctx->leds->merge_host(eds, eds_bytes, seds, seds_bytes, 0, false, 0, eds_out, seds_out, nullptr, nullptr, false, {}, nullptr,
+                              &pos1);
+    });
+    if (rc != EDS_OK) {
+        if (eds_out) eds_buffer_free_host(eds_out);
+        if (seds_out) eds_buffer_free_host(seds_out);
+    }
+    return rc;
+}
+
 eds_status eds_is_leds_host(eds_ctx* ctx, const uint8_t* eds_in, uint64_t eds_bytes, uint32_t l, int* is_leds_out) {
     return guarded([&] {
         use_device(ctx);

@@ -412,6 +412,77 @@ __global__ void k_rebuild(SymTab cur, SymTab next, const uint8_t* sel, const uin
     }
 }
 
+
+// ---- EDS::Statistics (eds.cpp:361-505) as one reduction over the symbols, and the sources as id lists ------------
+struct EdsStatsDev {
+    unsigned long long total_chars, num_degenerate, num_common_chars, total_change_size, num_empty_strings, sum_ctx,
+        num_ctx_blocks, max_paths_per_string, total_paths;
+    uint32_t min_ctx, max_ctx;
+};
+
+__global__ void k_eds_stats(SymTab t, Pool pool, uint32_t n_sym, EdsStatsDev* out) {
+    unsigned long long chars = 0, ndeg = 0, common = 0, change = 0, empty = 0, sctx = 0, nctx = 0;
+    uint32_t mn = 0xffffffffu, mx = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_sym; i += gridDim.x * blockDim.x) {
+        const uint32_t b0 = t.begin[i], cnt = t.count[i];
+        if (cnt > 1u) {
+            ++ndeg;
+            change += cnt - 1u;
+        } else {
+            const uint32_t len = pool.len[b0];
+            mn = min(mn, len);
+            mx = max(mx, len);
+            sctx += len;
+            ++nctx;
+            common += len;
+        }
+        for (uint32_t a = 0; a < cnt; ++a) {
+            const uint32_t len = pool.len[b0 + a];
+            chars += len;
+            empty += len == 0u;
+        }
+    }
+    // few partial results per thread: one atomic each (a statistics call, not the hot path)
+    atomicAdd(&out->total_chars, chars);
+    atomicAdd(&out->num_degenerate, ndeg);
+    atomicAdd(&out->num_common_chars, common);
+    atomicAdd(&out->total_change_size, change);
+    atomicAdd(&out->num_empty_strings, empty);
+    atomicAdd(&out->sum_ctx, sctx);
+    atomicAdd(&out->num_ctx_blocks, nctx);
+    atomicMin(&out->min_ctx, mn);
+    atomicMax(&out->max_ctx, mx);
+}
+
+struct SrcCountFn {
+    const uint32_t* bits;
+    uint32_t Wd;
+    unsigned long long* off;
+    EdsStatsDev* st;
+    __device__ unsigned long long value(unsigned long long j) const {
+        unsigned long long c = 0;
+        for (uint32_t w = 0; w < Wd; ++w) c += (unsigned long long)__popc(bits[j * Wd + w]);
+        return c;
+    }
+    __device__ void apply(unsigned long long j, unsigned long long prefix, unsigned long long v) const {
+        off[j] = prefix;
+        atomicMax(&st->max_paths_per_string, v);
+    }
+};
+
+__global__ void k_src_ids(const uint32_t* bits, uint32_t Wd, uint32_t n_str, const unsigned long long* off, const uint32_t* id_of,
+                          int32_t* ids) {
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_str; j += gridDim.x * blockDim.x) {
+        unsigned long long at = off[j];
+        for (uint32_t w = 0; w < Wd; ++w)
+            for (uint32_t b = bits[(size_t)j * Wd + w]; b; b &= b - 1) ids[at++] = (int32_t)id_of[w * 32u + (uint32_t)__ffs((int)b) - 1u];
+    }
+}
+
+__global__ void k_select_one(uint8_t* sel, uint32_t n, uint32_t pos) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) sel[i] = i == pos ? 1 : 0;
+}
+
 // ---- emit ---------------------------------------------------------------------------------------------
 constexpr uint32_t kFirst = 1u, kLast = 2u, kBraced = 4u;
 
@@ -705,8 +776,10 @@ LedsPipeline::~LedsPipeline() { delete bufs_; }
 void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const uint8_t* seds_in, uint64_t seds_bytes,
                               uint32_t l, bool compact, uint64_t max_output_bytes, eds_buffer* leds_out,
                               eds_buffer* seds_out, uint32_t* rounds_out, int* check_only, bool input_on_device,
-                              const std::function<uint8_t*(int, uint64_t)>& sink) {
-    if (l == 0) throw std::invalid_argument("context_length must be > 0 for l-EDS transformation");  // eds_transforms.cpp:322-324
+                              const std::function<uint8_t*(int, uint64_t)>& sink, eds_parsed* parse_only,
+                              const uint64_t* single_pair) {
+    if (l == 0 && !parse_only && !single_pair)
+        throw std::invalid_argument("context_length must be > 0 for l-EDS transformation");  // eds_transforms.cpp:322-324
     // string offsets into the EDS text are 32-bit (Length is uint32 in the reference too); the SEDS text has no such bound
     // (config 5: 13 GB of source sets for 0.1 GB of EDS)
     if (eds_bytes >= 0xfffffff0ull) throw std::invalid_argument("eds_leds_merge_host: the EDS text must be below 4 GiB (Length is uint32 in the reference too)");
@@ -872,6 +945,78 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
     if (n_str)
         LEDS_LAUNCH("k_init", k_init, G, B, d_str_start.as<uint32_t>(), d_str_end.as<uint32_t>(), d_sym_first.as<uint32_t>(), n_str, n_sym, pool, cur);
 
+    if (parse_only) {
+        // EDS::parse / parse_sources end here: hand the index, the statistics and the source id lists to the host
+        eds_parsed& o = *parse_only;
+        memset(&o, 0, sizeof(o));
+        DevBuf& d_stats = B_.d[30];  // (the emit's stack workspace: not in use on this path)
+        d_stats.reserve(sizeof(EdsStatsDev));
+        EdsStatsDev hs;
+        memset(&hs, 0, sizeof(hs));
+        hs.min_ctx = 0xffffffffu;
+        EDSB_CUDA(cudaMemcpyAsync(d_stats.p, &hs, sizeof(hs), cudaMemcpyHostToDevice, s));
+        if (n_sym) LEDS_LAUNCH("k_eds_stats", k_eds_stats, G, B, cur, pool, n_sym, d_stats.as<EdsStatsDev>());
+        unsigned long long n_ids = 0;
+        if (linear && n_str) {
+            d_off.reserve((size_t)(n_str + 1) * 8);
+            LEDS_SCAN("src_offsets", OpSum64, n_str, (SrcCountFn{d_rawbits.as<uint32_t>(), Wd, d_off.as<unsigned long long>(), d_stats.as<EdsStatsDev>()}));
+            n_ids = total_of();
+            d_kept.reserve((size_t)(n_ids + 1) * 4);
+            LEDS_LAUNCH("k_src_ids", k_src_ids, G, B, d_rawbits.as<uint32_t>(), Wd, n_str, d_off.as<unsigned long long>(), id_of,
+                        reinterpret_cast<int32_t*>(d_kept.p));
+        }
+        auto grab = [&](const void* dev, size_t bytes) -> void* {
+            void* h = malloc(bytes ? bytes : 1);
+            if (!h) throw std::bad_alloc();
+            if (bytes) {
+                const cudaError_t e = cudaMemcpyAsync(h, dev, bytes, cudaMemcpyDeviceToHost, s);
+                if (e != cudaSuccess) {
+                    free(h);
+                    throw CudaError(std::string("device to host copy: ") + cudaGetErrorString(e));
+                }
+            }
+            return h;
+        };
+        try {
+            o.text = static_cast<uint8_t*>(grab(text, n));
+            o.text_bytes = n;
+            o.str_start = static_cast<uint32_t*>(grab(d_str_start.p, (size_t)n_str * 4));
+            o.str_end = static_cast<uint32_t*>(grab(d_str_end.p, (size_t)n_str * 4));
+            o.sym_first = static_cast<uint32_t*>(grab(n_str ? d_sym_first.p : nullptr, n_str ? (size_t)(n_sym + 1) * 4 : 0));
+            if (!n_str) o.sym_first[0] = 0;
+            o.n_strings = n_str;
+            o.n_symbols = n_sym;
+            o.has_sources = linear ? 1u : 0u;
+            if (linear) {
+                o.src_off = static_cast<uint64_t*>(grab(n_str ? d_off.p : nullptr, n_str ? (size_t)n_str * 8 : 0));
+                o.src_off = static_cast<uint64_t*>(realloc(o.src_off, (size_t)(n_str + 1) * 8));
+                if (!o.src_off) throw std::bad_alloc();
+                o.src_ids = static_cast<int32_t*>(grab(d_kept.p, (size_t)n_ids * 4));
+            }
+            EDSB_CUDA(cudaMemcpyAsync(&hs, d_stats.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
+            EDSB_CUDA(cudaStreamSynchronize(s));
+            EDSB_CUDA(cudaGetLastError());
+        } catch (...) {
+            eds_parsed_free(&o);
+            throw;
+        }
+        if (linear) o.src_off[n_str] = n_ids;
+        o.total_chars = hs.total_chars;
+        o.num_degenerate_symbols = hs.num_degenerate;
+        o.num_common_chars = hs.num_common_chars;
+        o.total_change_size = hs.total_change_size;
+        o.num_empty_strings = hs.num_empty_strings;
+        o.sum_context_length = hs.sum_ctx;
+        o.num_context_blocks = hs.num_ctx_blocks;
+        o.min_context_length = hs.min_ctx == 0xffffffffu ? 0u : hs.min_ctx;
+        o.max_context_length = hs.max_ctx;
+        o.num_paths = n_paths;
+        o.max_paths_per_string = hs.max_paths_per_string;
+        o.total_paths = n_ids;
+        clk.resolve();
+        return;
+    }
+
     // ---- merge rounds (eds_transforms.cpp:335-359) -------------------------------------------------------
     d_cand.reserve((size_t)n_sym + 1);
     d_sel.reserve((size_t)n_sym + 1);
@@ -881,10 +1026,18 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
     d_off.reserve((size_t)(n_sym + 1) * 8);
     uint32_t cur_n = n_sym, rounds = 0;
     const uint32_t kMaxRounds = 10000;
+    if (single_pair && *single_pair + 1 >= (uint64_t)cur_n)  // eds.cpp:1437-1442
+        throw std::out_of_range("Position out of range: pos1=" + std::to_string(*single_pair) + ", pos2=" + std::to_string(*single_pair + 1) +
+                                ", n=" + std::to_string(cur_n));
     while (cur_n >= 2) {
         if (rounds >= kMaxRounds) throw std::runtime_error("Maximum iterations reached without convergence");
-        LEDS_LAUNCH("k_cand", k_cand, G, B, cur, pool, cur_n, l, d_cand.as<uint8_t>());
-        LEDS_SCAN("run_parity", OpMax64, cur_n, (RunFn{d_cand.as<uint8_t>(), d_sel.as<uint8_t>()}));
+        if (single_pair) {
+            if (rounds == 1) break;  // EDS::merge_adjacent: exactly this pair, once
+            LEDS_LAUNCH("k_select_one", k_select_one, G, B, d_sel.as<uint8_t>(), cur_n, (uint32_t)*single_pair);
+        } else {
+            LEDS_LAUNCH("k_cand", k_cand, G, B, cur, pool, cur_n, l, d_cand.as<uint8_t>());
+            LEDS_SCAN("run_parity", OpMax64, cur_n, (RunFn{d_cand.as<uint8_t>(), d_sel.as<uint8_t>()}));
+        }
         LEDS_SCAN("pair_list", OpSum64, cur_n, (PairListFn{d_sel.as<uint8_t>(), d_pairs_before.as<uint32_t>(), d_pair_list.as<uint32_t>()}));
         const uint32_t n_pairs = (uint32_t)total_of();
         if (check_only) {

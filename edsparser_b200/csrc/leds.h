@@ -22,7 +22,10 @@ class LedsPipeline {
     void merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const uint8_t* seds_in, uint64_t seds_bytes, uint32_t l,
                     bool compact, uint64_t max_output_bytes, eds_buffer* leds_out, eds_buffer* seds_out,
                     uint32_t* rounds_out, int* check_only = nullptr, bool input_on_device = false,
-                    const std::function<uint8_t*(int, uint64_t)>& sink = {});
+                    const std::function<uint8_t*(int, uint64_t)>& sink = {}, eds_parsed* parse_only = nullptr,
+                    const uint64_t* single_pair = nullptr);
+    // parse_only != nullptr: stop after the ingest (EDS::parse / parse_sources) and export the index + statistics
+    // single_pair != nullptr: merge exactly the symbols (*single_pair, *single_pair + 1) — EDS::merge_adjacent — and emit
     // sink(which, bytes): where result `which` (0 l-EDS, 1 SEDS) goes instead of a fresh malloc'd buffer
     // check_only != nullptr: stop after the first round's pair selection; *check_only = 1 iff no pair exists
     // input_on_device: eds_in / seds_in are device pointers (the VCF front end hands its output over in HBM)

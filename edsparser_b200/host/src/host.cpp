@@ -2,6 +2,7 @@
 // are turned back into the exception classes the reference throws. No compute happens here.
 #include <cctype>
 #include <cstdlib>
+#include <filesystem>
 #include <fstream>
 #include <iostream>
 #include <iterator>
@@ -231,17 +232,266 @@ std::pair<std::string, std::string> parse_vcf_to_leds_streaming(std::istream& vc
     return vcf_transform(vcf_stream, fasta_stream, (uint32_t)context_length, stats);
 }
 
-EDS::EDS(std::istream& eds_stream) : text_(slurp(eds_stream)) {}
-EDS::EDS(std::istream& eds_stream, std::istream& sources_stream)
-    : text_(slurp(eds_stream)), sources_(slurp(sources_stream)), has_sources_(true) {}
-EDS::EDS(const std::string& eds_text) : text_(eds_text) {}
-EDS::EDS(const std::string& eds_text, const std::string& sources_text) : text_(eds_text), sources_(sources_text), has_sources_(true) {}
+// ---- class EDS: a host-side view of what the device parsed (eds_parse_host) ------------------------------------------
+void EDS::build(const std::string& eds_text, const std::string* seds_text) {
+    eds_parsed p;
+    const eds_status rc =
+        eds_parse_host(t_session.get(), reinterpret_cast<const uint8_t*>(eds_text.data()), eds_text.size(),
+                       seds_text ? reinterpret_cast<const uint8_t*>(seds_text->data()) : nullptr, seds_text ? seds_text->size() : 0, &p);
+    if (rc != EDS_OK) rethrow(rc);
+    struct Release {
+        eds_parsed* p;
+        ~Release() { eds_parsed_free(p); }
+    } release{&p};
+    n_ = p.n_symbols;
+    m_ = p.n_strings;
+    N_ = p.total_chars;
+    is_empty_ = p.n_symbols == 0;
+    sets_.assign(n_, StringSet());
+    Metadata& md = metadata_;
+    md = Metadata();
+    md.symbol_sizes.resize(n_);
+    md.cum_set_sizes.resize(n_);
+    md.is_degenerate.resize(n_);
+    md.string_lengths.resize(m_);
+    md.cum_common_positions.assign(1, 0);
+    md.cum_degenerate_counts.assign(1, 0);
+    const char* text = reinterpret_cast<const char*>(p.text);
+    Position common = 0;
+    int degenerate_strings = 0;
+    for (size_t i = 0; i < n_; ++i) {
+        const uint32_t first = p.sym_first[i], count = p.sym_first[i + 1] - first;
+        md.symbol_sizes[i] = count;
+        md.cum_set_sizes[i] = first;
+        md.is_degenerate[i] = count > 1;
+        StringSet& set = sets_[i];
+        set.reserve(count);
+        for (uint32_t j = first; j < first + count; ++j) {
+            set.emplace_back(text + p.str_start[j], p.str_end[j] - p.str_start[j]);
+            md.string_lengths[j] = p.str_end[j] - p.str_start[j];
+        }
+        if (count > 1)
+            degenerate_strings += (int)count;
+        else
+            common += md.string_lengths[first];
+        md.cum_common_positions.push_back(common);
+        md.cum_degenerate_counts.push_back(degenerate_strings);
+    }
+    if (is_empty_) {
+        md.cum_common_positions.clear();
+        md.cum_degenerate_counts.clear();
+    }
+    md.min_context_length = p.min_context_length;
+    md.max_context_length = p.max_context_length;
+    md.avg_context_length = p.num_context_blocks ? (double)p.sum_context_length / (double)p.num_context_blocks : 0.0;
+    md.num_degenerate_symbols = p.num_degenerate_symbols;
+    md.num_common_chars = p.num_common_chars;
+    md.total_change_size = p.total_change_size;
+    md.num_empty_strings = p.num_empty_strings;
+    has_sources_ = p.has_sources != 0;
+    sources_.clear();
+    if (has_sources_) {
+        sources_.resize(m_);
+        for (size_t j = 0; j < m_; ++j) sources_[j].insert(p.src_ids + p.src_off[j], p.src_ids + p.src_off[j + 1]);
+        md.num_paths = p.num_paths;
+        md.max_paths_per_string = p.max_paths_per_string;
+        md.avg_paths_per_string = m_ ? (double)p.total_paths / (double)m_ : 0.0;
+    }
+}
+
+EDS::EDS(std::istream& eds_stream) { build(slurp(eds_stream), nullptr); }
+EDS::EDS(std::istream& eds_stream, std::istream& seds_stream) {
+    const std::string e = slurp(eds_stream), s = slurp(seds_stream);
+    build(e, &s);
+}
+EDS::EDS(const std::string& eds_string) { build(eds_string, nullptr); }
+EDS::EDS(const std::string& eds_string, const std::string& seds_string) { build(eds_string, &seds_string); }
+
+EDS EDS::from_string(const std::string& eds_string) { return EDS(eds_string); }
+EDS EDS::from_string(const std::string& eds_string, const std::string& seds_string) { return EDS(eds_string, seds_string); }
+
+namespace {
+std::string read_file(const std::filesystem::path& path, const char* what) {
+    std::ifstream in(path, std::ios::binary);
+    if (!in) throw std::runtime_error(std::string("Failed to open ") + what + " file: " + path.string());
+    return slurp(in);
+}
+}  // namespace
+
+EDS EDS::load(const std::filesystem::path& path, StoringMode mode) {
+    EDS out(read_file(path, "EDS"));
+    out.mode_ = mode;
+    return out;
+}
+
+EDS EDS::load(const std::filesystem::path& eds_path, const std::filesystem::path& seds_path, StoringMode mode) {
+    EDS out(read_file(eds_path, "EDS"), read_file(seds_path, "sEDS"));
+    out.mode_ = mode;
+    return out;
+}
+
+EDS::Statistics EDS::get_statistics() const {
+    const Metadata& md = metadata_;
+    return Statistics{md.min_context_length, md.max_context_length,  md.avg_context_length,   md.num_degenerate_symbols,
+                      md.num_common_chars,   md.total_change_size,   md.num_empty_strings,    md.num_paths,
+                      md.max_paths_per_string, md.avg_paths_per_string};
+}
+
+void EDS::print_statistics(std::ostream& os) const {
+    const Statistics st = get_statistics();
+    const char* rule = "========================================\n";
+    auto row = [&os](const char* label, auto value) {
+        std::string l(label);
+        l.resize(32, ' ');  // the reference pads its labels to column 32
+        os << l << value << "\n";
+    };
+    os << rule << "EDS Statistics\n" << rule << "Structure:\n";
+    row("  Number of sets (n):", n_);
+    row("  Total characters (N):", N_);
+    row("  Total strings (m):", m_);
+    row("  Degenerate symbols:", st.num_degenerate_symbols);
+    row("  Regular symbols:", n_ - st.num_degenerate_symbols);
+    os << "\nContext Lengths:\n";
+    row("  Minimum:", st.min_context_length);
+    row("  Maximum:", st.max_context_length);
+    row("  Average:", st.avg_context_length);
+    os << "\nVariations:\n";
+    row("  Total change size:", st.total_change_size);
+    row("  Common characters:", st.num_common_chars);
+    row("  Empty strings:", st.num_empty_strings);
+    os << "\n";
+    if (has_sources_)
+        os << "Sources: Loaded (" << sources_.size() << " strings with source info)\n";
+    else
+        os << "Sources: Not loaded\n";
+    os << rule;
+}
+
+void EDS::print(std::ostream& os) const {
+    if (mode_ == StoringMode::METADATA_ONLY)
+        throw std::runtime_error("Cannot print EDS in METADATA_ONLY mode. Load with StoringMode::FULL to access string data for printing.");
+    if (is_empty_) {
+        os << "(empty EDS)\n";
+        return;
+    }
+    os << "EDS with " << n_ << " sets, " << m_ << " total strings:\n";
+    for (size_t i = 0; i < n_; ++i) {
+        os << "Set " << i << ": {";
+        const char* sep = "";
+        for (const String& str : sets_[i]) {
+            os << sep;
+            if (str.empty()) os << "ε"; else os << '"' << str << '"';
+            sep = ", ";
+        }
+        os << "}" << (metadata_.is_degenerate[i] ? " [degenerate]" : "") << "\n";
+    }
+}
+
+namespace {
+// the EDS text of a set list: every symbol braced (FULL) or only the degenerate ones (COMPACT), eds.cpp:600-631
+void write_sets(std::ostream& os, const std::vector<StringSet>& sets, const std::vector<bool>& degenerate, bool full) {
+    for (size_t i = 0; i < sets.size(); ++i) {
+        const bool braced = full || degenerate[i];
+        if (braced) os << SET_OPEN;
+        for (size_t j = 0; j < sets[i].size(); ++j) {
+            if (j) os << SET_SEPARATOR;
+            os << sets[i][j];
+        }
+        if (braced) os << SET_CLOSE;
+    }
+}
+void write_sources(std::ostream& os, const std::vector<std::set<int>>& sources) {
+    for (const std::set<int>& ids : sources) {
+        os << SET_OPEN;
+        const char* sep = "";
+        for (int id : ids) {
+            os << sep << id;
+            sep = ",";
+        }
+        os << SET_CLOSE;
+    }
+}
+}  // namespace
+
+void EDS::save(std::ostream& os, OutputFormat format) const {
+    if (mode_ == StoringMode::METADATA_ONLY)
+        throw std::runtime_error("Cannot save EDS in METADATA_ONLY mode. Load with StoringMode::FULL to access string data for saving.");
+    write_sets(os, sets_, metadata_.is_degenerate, format == OutputFormat::FULL);
+    os << "\n";
+}
+
+void EDS::save(const std::filesystem::path& path, OutputFormat format) const {
+    std::ofstream out(path);
+    if (!out) throw std::runtime_error("Failed to open file for writing: " + path.string());
+    save(out, format);
+}
+
+void EDS::save_sources(std::ostream& os) const {
+    if (!has_sources_) throw std::runtime_error("Cannot save sources: no sources loaded");
+    write_sources(os, sources_);
+    os << "\n";
+}
+
+void EDS::save_sources(const std::filesystem::path& path) const {
+    std::ofstream out(path);
+    if (!out) throw std::runtime_error("Failed to open file for writing: " + path.string());
+    save_sources(out);
+}
+
+std::string EDS::text() const {
+    std::ostringstream os;
+    write_sets(os, sets_, metadata_.is_degenerate, true);
+    return os.str();
+}
+
+std::string EDS::sources_text() const {
+    std::ostringstream os;
+    write_sources(os, sources_);
+    return os.str();
+}
+
+void EDS::load_sources(const std::string& seds_string) {
+    const StoringMode mode = mode_;
+    build(text(), &seds_string);  // the device checks the sources against this EDS (count, syntax) as it parses them
+    mode_ = mode;
+}
+void EDS::load_sources(std::istream& is) { load_sources(slurp(is)); }
+void EDS::load_sources(const std::filesystem::path& path) { load_sources(read_file(path, "sEDS")); }
+
+const std::vector<StringSet>& EDS::get_sets() const {
+    if (mode_ == StoringMode::METADATA_ONLY)
+        throw std::runtime_error("Cannot access sets in METADATA_ONLY mode. Use read_symbol(pos) for on-demand access, or load with StoringMode::FULL");
+    return sets_;
+}
+
+StringSet EDS::read_symbol(Position pos) const {
+    if (pos >= n_) throw std::out_of_range("Position " + std::to_string(pos) + " out of range");
+    return sets_[pos];
+}
+
+EDS EDS::merge_adjacent(size_t pos1, size_t pos2) const {
+    if (pos2 != pos1 + 1)  // eds.cpp:1429-1434
+        throw std::invalid_argument("Positions must be adjacent: pos2 (" + std::to_string(pos2) + ") must equal pos1 + 1 (" +
+                                    std::to_string(pos1 + 1) + ")");
+    if (pos1 >= n_ || pos2 >= n_)  // eds.cpp:1437-1442
+        throw std::out_of_range("Position out of range: pos1=" + std::to_string(pos1) + ", pos2=" + std::to_string(pos2) +
+                                ", n=" + std::to_string(n_));
+    const std::string e = text(), s = has_sources_ ? sources_text() : std::string();
+    eds_buffer oe{nullptr, 0}, os{nullptr, 0};
+    const eds_status rc = eds_merge_adjacent_host(t_session.get(), reinterpret_cast<const uint8_t*>(e.data()), e.size(),
+                                                  has_sources_ ? reinterpret_cast<const uint8_t*>(s.data()) : nullptr, s.size(), pos1, &oe, &os);
+    if (rc != EDS_OK) rethrow(rc);
+    const std::string me(reinterpret_cast<const char*>(oe.data), oe.bytes), ms(reinterpret_cast<const char*>(os.data), os.bytes);
+    eds_buffer_free_host(&oe);
+    eds_buffer_free_host(&os);
+    return has_sources_ ? EDS(me, ms) : EDS(me);
+}
 
 bool is_leds(const EDS& eds, Length context_length) {
     if (context_length == 0) return true;  // eds_transforms.cpp:440-442
     int answer = 0;
-    const eds_status rc = eds_is_leds_host(t_session.get(), reinterpret_cast<const uint8_t*>(eds.text().data()), eds.text().size(),
-                                           context_length, &answer);
+    const std::string text = eds.text();
+    const eds_status rc = eds_is_leds_host(t_session.get(), reinterpret_cast<const uint8_t*>(text.data()), text.size(), context_length, &answer);
     if (rc != EDS_OK) rethrow(rc);
     return answer != 0;
 }

@@ -181,6 +181,42 @@ eds_status eds_leds_merge_host_view(eds_ctx* ctx, const uint8_t* eds_in, uint64_
 eds_status eds_is_leds_host(eds_ctx* ctx, const uint8_t* eds_in, uint64_t eds_bytes, uint32_t l, int* is_leds_out);
 
 /* ------------------------------------------------------------------------------------------
+ * EDS objects: EDS::parse + normalize_eds_format (eds.cpp:39-155, 831-881), EDS::parse_sources
+ * (eds.cpp:268-355), calculate_statistics / calculate_source_statistics (eds.cpp:361-505) and
+ * EDS::merge_adjacent (eds.cpp:1425-1695), run on the device. The host class `edsparser::EDS`
+ * (edsparser_b200/host/include/edsparser/formats/eds.hpp) is built from what these return.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct eds_parsed {
+    uint8_t* text;        /* the EDS text without white space (compact input stays compact), malloc'd       */
+    uint64_t text_bytes;
+    uint32_t* str_start;  /* n_strings: string j is text[str_start[j] .. str_end[j])                        */
+    uint32_t* str_end;
+    uint32_t* sym_first;  /* n_symbols + 1: symbol i holds strings sym_first[i] .. sym_first[i + 1)          */
+    uint32_t n_strings, n_symbols;
+    uint32_t has_sources;
+    uint64_t* src_off;    /* n_strings + 1 (sources given): ids of string j are src_ids[src_off[j] ..)      */
+    int32_t* src_ids;     /* ascending, duplicates removed (std::set<int> order)                            */
+    /* EDS::Statistics (eds.hpp:105-119), reduced on the device */
+    uint64_t total_chars;            /* N */
+    uint64_t num_degenerate_symbols, num_common_chars, total_change_size, num_empty_strings;
+    uint64_t sum_context_length, num_context_blocks;
+    uint32_t min_context_length, max_context_length;
+    uint64_t num_paths, max_paths_per_string, total_paths;
+} eds_parsed;
+
+/* seds == NULL: no sources. Errors carry the reference's messages (runtime_error / out_of_range). */
+eds_status eds_parse_host(eds_ctx* ctx, const uint8_t* eds, uint64_t eds_bytes, const uint8_t* seds, uint64_t seds_bytes,
+                          eds_parsed* out);
+void eds_parsed_free(eds_parsed* parsed);
+
+/* EDS::merge_adjacent(pos1, pos1 + 1): all combinations without sources, the combinations with a non-empty source
+ * intersection (a set containing 0 is universal) with them. Output in the FULL dialect of EDS::save /
+ * save_sources (trailing newline), malloc'd. The caller checks adjacency / range (the reference's messages name
+ * both positions). */
+eds_status eds_merge_adjacent_host(eds_ctx* ctx, const uint8_t* eds, uint64_t eds_bytes, const uint8_t* seds,
+                                   uint64_t seds_bytes, uint64_t pos1, eds_buffer* eds_out, eds_buffer* seds_out);
+
+/* ------------------------------------------------------------------------------------------
  * VCF front end: parse_vcf_to_eds_streaming (vcf_transforms.cpp:677-729) when l == 0,
  * parse_vcf_to_leds_streaming (vcf_transforms.cpp:735-755: the same followed by the LINEAR merge,
  * one thread, compact) when l > 0. One path id per sample column, 1-based (vcf_transforms.cpp:588).
