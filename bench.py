@@ -185,6 +185,33 @@ def workload_config(n, config=2):
             "parallelism": f"column-sharded x{n}" if n > 1 else "single GPU"}
 
 
+def pin_to_gpu_numa(index):
+    """Run this rank on the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers it allocates
+    afterwards (first touch) and its copy submissions stay on that socket: with 8 ranks streaming 1 GB each per step
+    through the host, remote-node memory is what makes the end-to-end leg stop scaling. Best effort; returns a note."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        bus = out[-12:] if len(out) >= 12 else out  # 00000000:1B:00.0 -> 0000:1b:00.0
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "numa node unknown"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"numa node {node}: no allowed cpu"
+        os.sched_setaffinity(0, cpus)
+        return f"numa node {node}, {len(cpus)} cpus"
+    except Exception as err:
+        return f"not pinned ({type(err).__name__})"
+
+
 def kernel_profile(ctx, view, steps):
     """Per-kernel CUDA-event times of `steps` transforms (profiling adds an event pair per launch)."""
     ctx.set_profiling(True)
@@ -291,6 +318,7 @@ def run_ours(args, rank, world):
     import edsparser_b200 as E
 
     local = int(os.environ.get("LOCAL_RANK", 0))
+    numa_note = pin_to_gpu_numa(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -387,7 +415,7 @@ def run_ours(args, rank, world):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": cells_step * e2e_steps / float(dt.item()), "unit": "cells/s",
                "h2d_bytes_per_step": len(shard_text) * world, "d2h_bytes_per_step": nout * world,
-               "ms_per_step": 1e3 * float(dt.item()) / e2e_steps, "steps": e2e_steps,
+               "ms_per_step": 1e3 * float(dt.item()) / e2e_steps, "steps": e2e_steps, "host_placement": numa_note,
                "api": "per rank: pinned H2D + eds_msa_transform_device + D2H into pinned host memory + eds_comm_post / eds_comm_offsets (NCCL all-gather of the byte counts, issued by the library)"}
         del pinned, dtext
     ctx.msa_synth_free()
