@@ -31,6 +31,7 @@ EXPORTS = [
     "eds_group_create", "eds_group_destroy", "eds_group_size", "eds_group_ctx", "eds_group_msa_transform_host",
     "eds_group_msa_transform_fd", "eds_nccl_unique_id", "eds_comm_create", "eds_comm_destroy", "eds_comm_post",
     "eds_comm_offsets", "eds_comm_flush", "eds_parse_host", "eds_parsed_free", "eds_merge_adjacent_host",
+    "eds_group_leds_merge_host",
 ]
 
 
@@ -131,6 +132,7 @@ class Library:
         L.eds_group_ctx.restype = vp
         L.eds_group_msa_transform_host.argtypes = [vp, vp, u64, u32, i32, u64, P(Buffer), P(Buffer), P(MsaStats)]
         L.eds_group_msa_transform_fd.argtypes = [vp, vp, u64, u32, i32, u64, i32, i32, P(u64), P(MsaStats)]
+        L.eds_group_leds_merge_host.argtypes = [vp, vp, u64, vp, u64, u32, i32, P(Buffer), P(Buffer), P(u32), P(u32)]
         L.eds_nccl_unique_id.argtypes = [vp]
         L.eds_comm_create.argtypes = [vp, vp, i32, i32, P(vp)]
         L.eds_comm_destroy.argtypes = [vp]
@@ -184,6 +186,17 @@ class Group:
         self.lib.check(self.lib.L.eds_group_msa_transform_host(self.handle, src, len(file_bytes), l, leds, halo, ctypes.byref(e),
                                                                ctypes.byref(s), st))
         return _host_bytes(self.lib, e), _host_bytes(self.lib, s), [x.as_dict() for x in st]  # (_host_bytes frees)
+
+    def leds_merge_host(self, eds, seds, l, compact=True):
+        """eds2leds over the group's devices: (l-EDS bytes, SEDS bytes or b"", rounds, shards used)."""
+        e, s = Buffer(), Buffer()
+        rounds, used = ctypes.c_uint32(), ctypes.c_uint32()
+        se = ctypes.c_char_p(bytes(eds))
+        ss = ctypes.c_char_p(bytes(seds)) if seds is not None else None
+        self.lib.check(self.lib.L.eds_group_leds_merge_host(self.handle, se, len(eds), ss, len(seds) if seds is not None else 0, l,
+                                                            1 if compact else 0, ctypes.byref(e), ctypes.byref(s), ctypes.byref(rounds),
+                                                            ctypes.byref(used)))
+        return _host_bytes(self.lib, e), _host_bytes(self.lib, s), rounds.value, used.value
 
     def msa_transform_files(self, file_bytes, l, eds_path, seds_path, leds=None, halo=0):
         leds = (1 if l > 0 else 0) if leds is None else leds

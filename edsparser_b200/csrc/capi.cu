@@ -153,6 +153,9 @@ eds_status eds_ctx_create(int device, void* stream, eds_ctx** out) {
         if (const char* fz = getenv("EDSB_FUSED_NC")) ctx->fused_nc = (uint32_t)atoi(fz);
         if (const char* fz = getenv("EDSB_FUSED_STAGES")) ctx->fused_stages = (uint32_t)atoi(fz);
         if (const char* fz = getenv("EDSB_FUSED_PW")) ctx->fused_pw = (uint32_t)atoi(fz);
+        if (const char* fz = getenv("EDSB_FUSED_PWB")) ctx->fused_pwb = (uint32_t)atoi(fz);
+        if (const char* fz = getenv("EDSB_FUSED_BULK_PCT")) ctx->fused_bulk_pct = (uint32_t)atoi(fz);
+        if (const char* fz = getenv("EDSB_FUSED_T")) ctx->fused_t = (uint32_t)atoi(fz);
         if (const char* fz = getenv("EDSB_FUSED_DW")) ctx->fused_dw = (uint32_t)atoi(fz);
         if (const char* fz = getenv("EDSB_FUSED_MODE")) ctx->fused_mode = (uint32_t)atoi(fz);
         if (const char* hm = getenv("EDSB_DEBUG_HASH_MASK")) ctx->hash_mask = strtoull(hm, nullptr, 0);

@@ -70,6 +70,9 @@ struct eds_ctx {
     uint32_t fused_nc = 0;         // EDSB_FUSED_NC: force the cluster size (0 = by row count)
     uint32_t fused_stages = 0;     // EDSB_FUSED_STAGES: cap the ring depth (0 = what fits)
     uint32_t fused_pw = 0;         // EDSB_FUSED_PW: producer warps (0 = default)
+    uint32_t fused_pwb = 0;        // EDSB_FUSED_PWB: mode 2, producer warps that issue bulk copies (0 = half)
+    uint32_t fused_bulk_pct = 0;   // EDSB_FUSED_BULK_PCT: mode 2, share of the rows fed by bulk copies (0 = 50)
+    uint32_t fused_t = 0;          // EDSB_FUSED_T: 16 or 32 chunks per tile (0 = default)
     uint32_t fused_dw = 0;         // EDSB_FUSED_DW: duty warps (0 = default)
     uint32_t fused_mode = 0;       // EDSB_FUSED_MODE: 0 = one bulk copy (TMA) per row (measured faster), 1 = 16-byte cp.async per lane
     int sm_count = 148;

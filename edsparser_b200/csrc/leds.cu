@@ -777,7 +777,7 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
                               uint32_t l, bool compact, uint64_t max_output_bytes, eds_buffer* leds_out,
                               eds_buffer* seds_out, uint32_t* rounds_out, int* check_only, bool input_on_device,
                               const std::function<uint8_t*(int, uint64_t)>& sink, eds_parsed* parse_only,
-                              const uint64_t* single_pair) {
+                              const uint64_t* single_pair, uint32_t* edge_unmerged) {
     if (l == 0 && !parse_only && !single_pair)
         throw std::invalid_argument("context_length must be > 0 for l-EDS transformation");  // eds_transforms.cpp:322-324
     // string offsets into the EDS text are 32-bit (Length is uint32 in the reference too); the SEDS text has no such bound
@@ -1068,6 +1068,21 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
         ++rounds;
     }
     if (rounds_out) *rounds_out = rounds;
+    if (edge_unmerged) {
+        // for a caller that cut the EDS inside long conserved symbols (eds_group_leds_merge_host): did the shard's first
+        // and last symbol stay the leaves they were? (a pool index below n_str is an original string)
+        *edge_unmerged = 0;
+        if (cur_n) {
+            uint32_t first[2] = {0, 0}, last[2] = {0, 0};
+            EDSB_CUDA(cudaMemcpyAsync(&first[0], cur.begin, 4, cudaMemcpyDeviceToHost, s));
+            EDSB_CUDA(cudaMemcpyAsync(&first[1], cur.count, 4, cudaMemcpyDeviceToHost, s));
+            EDSB_CUDA(cudaMemcpyAsync(&last[0], cur.begin + (cur_n - 1), 4, cudaMemcpyDeviceToHost, s));
+            EDSB_CUDA(cudaMemcpyAsync(&last[1], cur.count + (cur_n - 1), 4, cudaMemcpyDeviceToHost, s));
+            EDSB_CUDA(cudaStreamSynchronize(s));
+            if (first[1] == 1u && first[0] < n_str) *edge_unmerged |= 1u;
+            if (last[1] == 1u && last[0] < n_str) *edge_unmerged |= 2u;
+        }
+    }
     if (check_only) {  // fewer than two symbols: nothing can be merged
         *check_only = 1;
         return;

@@ -23,7 +23,8 @@ class LedsPipeline {
                     bool compact, uint64_t max_output_bytes, eds_buffer* leds_out, eds_buffer* seds_out,
                     uint32_t* rounds_out, int* check_only = nullptr, bool input_on_device = false,
                     const std::function<uint8_t*(int, uint64_t)>& sink = {}, eds_parsed* parse_only = nullptr,
-                    const uint64_t* single_pair = nullptr);
+                    const uint64_t* single_pair = nullptr, uint32_t* edge_unmerged = nullptr);
+    // edge_unmerged != nullptr: bit 0 / bit 1 = the first / last symbol of the result is an original, unmerged string
     // parse_only != nullptr: stop after the ingest (EDS::parse / parse_sources) and export the index + statistics
     // single_pair != nullptr: merge exactly the symbols (*single_pair, *single_pair + 1) — EDS::merge_adjacent — and emit
     // sink(which, bytes): where result `which` (0 l-EDS, 1 SEDS) goes instead of a fresh malloc'd buffer

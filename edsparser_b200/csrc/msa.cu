@@ -2269,9 +2269,10 @@ void MsaPipeline::plan_fused() {
 #ifdef EDSB_EMU
     DW = std::min(DW, 2u);
 #endif
+    const uint32_t T = ctx_->fused_t == 16u ? 16u : 32u;  // 16-chunk tiles lose: twice the bulk copies per byte (profiles/r02_a)
     uint32_t S = 0;
-    for (uint32_t s = 6; s >= 2; --s)
-        if (fz_smem_bytes(s, NC, RG, slot_pitch, DW) + 1024 <= ctx_->smem_optin) {
+    for (uint32_t s = 12; s >= 2; --s)
+        if (fz_smem_bytes(T, s, NC, RG, slot_pitch, DW) + 1024 <= ctx_->smem_optin) {
             S = s;
             break;
         }
@@ -2280,17 +2281,18 @@ void MsaPipeline::plan_fused() {
     // a duty warp waits for phase q of a stage's barrier by parity, which is only sound while phase q - 1 is known
     // to be complete: true when its previous tile (DW tiles back) is not older than the stage's previous use (S back)
     DW = std::min(DW, S);
-    const uint32_t n_tiles = (g.n_chunks + kFzT - 1) / kFzT;
+    const uint32_t n_tiles = (g.n_chunks + T - 1) / T;
     fz_.PW = std::max(1u, std::min(ctx_->fused_pw ? ctx_->fused_pw : 4u, kFzMaxPW));
 #ifdef EDSB_EMU
     fz_.PW = std::min(fz_.PW, 2u);
 #endif
+    fz_.T = T;
     fz_.S = S;
     fz_.DW = DW;
     fz_.NC = NC;
     fz_.RG = RG;
     fz_.slot_pitch = slot_pitch;
-    fz_.smem = fz_smem_bytes(S, NC, RG, slot_pitch, DW);
+    fz_.smem = fz_smem_bytes(T, S, NC, RG, slot_pitch, DW);
 
     // per-CTA tables, one upload: pack[NC][slot_pitch] u64 | meta[NC][8] u32 | info[NC][RG] u16
     const size_t off_meta = (size_t)NC * slot_pitch * 8, off_info = off_meta + (size_t)NC * 32;
@@ -2339,15 +2341,19 @@ void MsaPipeline::plan_fused() {
 #ifdef EDSB_EMU
     regions = 3;
 #else
-    const uint32_t key = (NC << 24) ^ (S << 16) ^ slot_pitch ^ (fz_.PW << 28) ^ (fz_.DW << 12);
+    const uint32_t key = (NC << 24) ^ (S << 16) ^ slot_pitch ^ (fz_.PW << 28) ^ (fz_.DW << 12) ^ (T << 20);
     if (fz_attr_smem_ < fz_.smem) {
-        EDSB_CUDA(cudaFuncSetAttribute(k_scan_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz_.smem));
+        EDSB_CUDA(cudaFuncSetAttribute(k_scan_fused<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz_.smem));
+        EDSB_CUDA(cudaFuncSetAttribute(k_scan_fused<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz_.smem));
         fz_attr_smem_ = fz_.smem;
     }
     if (fz_occ_key_ != key) {
         if (NC == 1) {
             int per_sm = 0;
-            EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_fused, (kFzCW + fz_.PW + fz_.DW) * 32, fz_.smem));
+            if (T == 16u)
+                EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_fused<16>, (kFzCW + fz_.PW + fz_.DW) * 32, fz_.smem));
+            else
+                EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_fused<32>, (kFzCW + fz_.PW + fz_.DW) * 32, fz_.smem));
             fz_occ_regions_ = (uint32_t)std::max(0, per_sm) * (uint32_t)ctx_->sm_count;
         } else {
             cudaLaunchConfig_t cfg;
@@ -2363,7 +2369,10 @@ void MsaPipeline::plan_fused() {
             cfg.attrs = attr;
             cfg.numAttrs = 1;
             int n = 0;
-            EDSB_CUDA(cudaOccupancyMaxActiveClusters(&n, k_scan_fused, &cfg));
+            if (T == 16u)
+                EDSB_CUDA(cudaOccupancyMaxActiveClusters(&n, k_scan_fused<16>, &cfg));
+            else
+                EDSB_CUDA(cudaOccupancyMaxActiveClusters(&n, k_scan_fused<32>, &cfg));
             fz_occ_regions_ = (uint32_t)std::max(0, n);
         }
         fz_occ_key_ = key;
@@ -2390,11 +2399,24 @@ void MsaPipeline::plan_fused() {
     f.PW = fz_.PW;
     f.DW = fz_.DW;
     f.mode = ctx_->fused_mode;
+    f.PWB = 0;
+    f.n_bulk = 0;
+    if (f.mode == 2u) {
+        // both copy engines: the first warps issue bulk copies for a share of the rows, the others cp.async for the rest
+        if (fz_.PW < 2u || fz_.T != 32u) {
+            f.mode = 0;
+        } else {
+            f.PWB = std::max(1u, std::min(fz_.PW - 1u, ctx_->fused_pwb ? ctx_->fused_pwb : fz_.PW / 2u));
+            f.n_bulk = (uint32_t)((uint64_t)slot_pitch * std::min(ctx_->fused_bulk_pct ? ctx_->fused_bulk_pct : 50u, 100u) / 100u);
+        }
+    }
     // tile t is fetched with bulk copies when vectors [32 t + dmin, 32 t + 32 + dmax] all lie inside the buffer
-    const long long T = (long long)kFzT, vmax = (long long)g.n_vec - 1;
-    f.tile_lo_ok = g.d_min_vec >= 0 ? 0 : (-g.d_min_vec + T - 1) / T;
-    const long long top = vmax - T - g.d_max_vec;
-    f.tile_hi_ok = top < 0 ? 0 : top / T + 1;
+    const long long vmax = (long long)g.n_vec - 1;
+    const long long Tl = (long long)fz_.T;
+    f.tile_lo_ok = g.d_min_vec >= 0 ? 0 : (-g.d_min_vec + Tl - 1) / Tl;
+    const long long top = vmax - Tl - g.d_max_vec;
+    f.tile_hi_ok = top < 0 ? 0 : top / Tl + 1;
+    f.T = fz_.T;
     fz_.on = true;
 }
 
@@ -2476,7 +2498,8 @@ void MsaPipeline::launch_scan(const MsaBufs& b, bool allow_fused) {
         ctx_->clock.begin("k_scan_fused");
         const uint32_t threads = (kFzCW + fz_.PW + fz_.DW) * 32, blocks = fz_.regions * fz_.NC;
 #ifdef EDSB_EMU
-        EDSB_LAUNCH(k_scan_fused, blocks, threads, fz_.smem, s, g, fzp_, b.status);
+        if (fz_.T == 16u) EDSB_LAUNCH(k_scan_fused<16>, blocks, threads, fz_.smem, s, g, fzp_, b.status);
+        else EDSB_LAUNCH(k_scan_fused<32>, blocks, threads, fz_.smem, s, g, fzp_, b.status);
 #else
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
@@ -2491,7 +2514,10 @@ void MsaPipeline::launch_scan(const MsaBufs& b, bool allow_fused) {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = fz_.NC > 1 ? 1 : 0;
-        EDSB_CUDA(cudaLaunchKernelEx(&cfg, k_scan_fused, g, fzp_, b.status));
+        if (fz_.T == 16u)
+            EDSB_CUDA(cudaLaunchKernelEx(&cfg, k_scan_fused<16>, g, fzp_, b.status));
+        else
+            EDSB_CUDA(cudaLaunchKernelEx(&cfg, k_scan_fused<32>, g, fzp_, b.status));
 #endif
         ctx_->clock.end();
         ctx_->clock.begin("k_colbits");

@@ -44,7 +44,7 @@ class MsaPipeline {
     // k_scan_fused (scan_fused.cuh): geometry of the last prepare(); on = false -> k_scan + k_stash
     struct FzPlan {
         bool on = false;
-        uint32_t S = 0, NC = 1, RG = 0, slot_pitch = 0, regions = 0, capc = 0, PW = 1, DW = 1;
+        uint32_t S = 0, NC = 1, RG = 0, slot_pitch = 0, regions = 0, capc = 0, PW = 1, DW = 1, T = 32;
         size_t smem = 0;
     } fz_;
     FzParams fzp_;

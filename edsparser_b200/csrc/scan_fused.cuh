@@ -25,34 +25,38 @@
 
 namespace edsb {
 
-template <int WS>
+// rows [first, end) of one word-shift class; a warp instruction covers 32 / T rows (lane = chunk + T * sub)
+template <int WS, int T>
 __device__ __forceinline__ void fz_rows(const uint8_t* stg, const unsigned long long* s_pack, uint32_t first, uint32_t end,
-                                        uint32_t lane, const uint4& ref, uint4& acc) {
-    uint32_t slot = first;
-    for (; slot + 4u <= end; slot += 4u) {
+                                        uint32_t chunk, uint32_t sub, const uint4& ref, uint4& acc) {
+    constexpr uint32_t kPitch = 16u * (uint32_t)T + 16u, kRows = 32u / (uint32_t)T;
+    uint32_t slot = first + sub;
+    for (; slot + 3u * kRows < end; slot += 4u * kRows) {
         uint4 lo[4], hi[4];
         uint32_t bs[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const uint8_t* row = stg + (size_t)(slot + u) * kFzPitch + 16u * lane;
+            const uint8_t* row = stg + (size_t)(slot + u * kRows) * kPitch + 16u * chunk;
             lo[u] = *reinterpret_cast<const uint4*>(row);
             hi[u] = *reinterpret_cast<const uint4*>(row + 16);
-            bs[u] = (reinterpret_cast<const uint32_t*>(s_pack)[2u * (slot + u)] & 3u) * 8u;
+            bs[u] = (reinterpret_cast<const uint32_t*>(s_pack)[2u * (slot + u * kRows)] & 3u) * 8u;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) xor_acc<WS>(lo[u], hi[u], bs[u], ref, acc);
     }
-    for (; slot < end; ++slot) {
-        const uint8_t* row = stg + (size_t)slot * kFzPitch + 16u * lane;
+    for (; slot < end; slot += kRows) {
+        const uint8_t* row = stg + (size_t)slot * kPitch + 16u * chunk;
         const uint4 lo = *reinterpret_cast<const uint4*>(row), hi = *reinterpret_cast<const uint4*>(row + 16);
         xor_acc<WS>(lo, hi, (reinterpret_cast<const uint32_t*>(s_pack)[2u * slot] & 3u) * 8u, ref, acc);
     }
 }
 
-__device__ __forceinline__ void fz_rows_aligned(const uint8_t* stg, uint32_t first, uint32_t end, uint32_t lane, const uint4& ref,
-                                                uint4& acc) {
-    for (uint32_t slot = first; slot < end; ++slot) {
-        const uint4 lo = *reinterpret_cast<const uint4*>(stg + (size_t)slot * kFzPitch + 16u * lane);
+template <int T>
+__device__ __forceinline__ void fz_rows_aligned(const uint8_t* stg, uint32_t first, uint32_t end, uint32_t chunk, uint32_t sub,
+                                                const uint4& ref, uint4& acc) {
+    constexpr uint32_t kPitch = 16u * (uint32_t)T + 16u, kRows = 32u / (uint32_t)T;
+    for (uint32_t slot = first + sub; slot < end; slot += kRows) {
+        const uint4 lo = *reinterpret_cast<const uint4*>(stg + (size_t)slot * kPitch + 16u * chunk);
         acc.x |= lo.x ^ ref.x;
         acc.y |= lo.y ^ ref.y;
         acc.z |= lo.z ^ ref.z;
@@ -66,7 +70,10 @@ __device__ __forceinline__ void fz_rows_aligned(const uint8_t* stg, uint32_t fir
 // (gaps of row 0, line breaks, window edges), stores it, lists the variable columns and copies them out of the
 // stage into its own region of the temporary stash. That is a few hundred dependent instructions per tile — more
 // than a tile's time budget — so DW warps take the tiles in rotation while the consumers stream on.
+template <int T>
 __global__ void __launch_bounds__((kFzCW + kFzMaxPW + kFzMaxDW) * 32, 1) k_scan_fused(MsaGeom g, FzParams f, MsaStatus* st) {
+    constexpr uint32_t kFzT = (uint32_t)T, kFzPitch = 16u * kFzT + 16u;
+    const uint32_t chunk = (threadIdx.x & 31) % kFzT, sub = (threadIdx.x & 31) / kFzT;
     unsigned char* smem = EDSB_DYN_SMEM();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t S = f.S, NC = f.NC, RG = f.RG, PW = f.PW, DW = f.DW;
@@ -98,7 +105,7 @@ __global__ void __launch_bounds__((kFzCW + kFzMaxPW + kFzMaxDW) * 32, 1) k_scan_
     for (uint32_t i = threadIdx.x; i < S * 32u; i += blockDim.x) red16[i] = 0u;
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < S; ++s) {
-            mbar_init(&full[s], f.mode == 0 ? PW : PW * 32u);
+            mbar_init(&full[s], (f.mode == 2u && kFzT == 32u) ? f.PWB + (PW - f.PWB) * 32u : ((f.mode == 0 || kFzT != 32u) ? PW : PW * 32u));
             mbar_init(&empty[s], kFzCW + 1);
             mbar_init(&red_full[s], kFzCW);
             mbar_init(&maskbar[2u * s], 1);
@@ -118,20 +125,20 @@ __global__ void __launch_bounds__((kFzCW + kFzMaxPW + kFzMaxDW) * 32, 1) k_scan_
             const uint32_t s = it % S;
             mbar_wait(&full[s], (it / S) & 1u);
             const uint8_t* stg = stages + (size_t)s * stage_bytes;
-            const uint4 ref = *reinterpret_cast<const uint4*>(stg + 16u * lane);  // slot 0 = row 0, shift 0
+            const uint4 ref = *reinterpret_cast<const uint4*>(stg + 16u * chunk);  // slot 0 = row 0, shift 0
             uint4 acc = make_uint4(0, 0, 0, 0);
             if (f.all_aligned) {
-                fz_rows_aligned(stg, my_lo, my_hi, lane, ref, acc);
+                fz_rows_aligned<T>(stg, my_lo, my_hi, chunk, sub, ref, acc);
             } else {
-                fz_rows<0>(stg, s_pack, max(my_lo, cls0), min(my_hi, cls1), lane, ref, acc);
-                fz_rows<1>(stg, s_pack, max(my_lo, cls1), min(my_hi, cls2), lane, ref, acc);
-                fz_rows<2>(stg, s_pack, max(my_lo, cls2), min(my_hi, cls3), lane, ref, acc);
-                fz_rows<3>(stg, s_pack, max(my_lo, cls3), min(my_hi, cls4), lane, ref, acc);
+                fz_rows<0, T>(stg, s_pack, max(my_lo, cls0), min(my_hi, cls1), chunk, sub, ref, acc);
+                fz_rows<1, T>(stg, s_pack, max(my_lo, cls1), min(my_hi, cls2), chunk, sub, ref, acc);
+                fz_rows<2, T>(stg, s_pack, max(my_lo, cls2), min(my_hi, cls3), chunk, sub, ref, acc);
+                fz_rows<3, T>(stg, s_pack, max(my_lo, cls3), min(my_hi, cls4), chunk, sub, ref, acc);
             }
             // red16[s] is zero again by now: the duty warp of the tile that last used stage s cleared it before it let
             // the stage go, and full[s] completed after that
             const uint32_t nz = nonzero_bytes16(acc);
-            if (nz) atomicOr(&red16[s * 32u + lane], nz);
+            if (nz) atomicOr(&red16[s * 32u + chunk], nz);
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&red_full[s]);
@@ -143,12 +150,20 @@ __global__ void __launch_bounds__((kFzCW + kFzMaxPW + kFzMaxDW) * 32, 1) k_scan_
         // mode 0: a lane issues one bulk copy per row it owns (UBLKCP takes uniform operands: the warp issues its
         // lanes' copies one after the other, which is why the rows are spread over PW warps);
         // mode 1: a warp copies a row with one 16-byte cp.async per lane, the 33rd vectors lane-per-row.
-        const uint32_t pw = warp - (uint32_t)kFzCW;
+        // mode 2 (T = 32): both engines at once — the first PWB warps feed slots [0, n_bulk) through bulk copies (the TMA
+        // unit takes one 528-byte copy per ~28 cycles per SM, which alone caps the kernel near 5 TB/s), the other warps
+        // feed the rest with cp.async through the load/store path.
+        const uint32_t pw_all = warp - (uint32_t)kFzCW;
+        const bool hybrid = f.mode == 2u && kFzT == 32u;
+        const bool bulk = hybrid ? pw_all < f.PWB : (f.mode == 0u || kFzT != 32u);
+        const uint32_t cut = min(f.n_bulk, nslots);
+        const uint32_t lo_slot = hybrid ? (bulk ? 0u : cut) : 0u, hi_slot = hybrid ? (bulk ? cut : nslots) : nslots;
+        const uint32_t pw = hybrid ? (bulk ? pw_all : pw_all - f.PWB) : pw_all, PWg = hybrid ? (bulk ? f.PWB : PW - f.PWB) : PW;
         const uint4* vec = reinterpret_cast<const uint4*>(g.text);
         const long long vmax = (long long)g.n_vec - 1;
         const uint8_t* base0 = g.text + g.d_min_vec * 16;  // s_off16[slot] counts 16-byte vectors from here
-        uint32_t my_slots = 0;  // slots pw * 32 + lane + 32 * PW * m of all lanes together
-        for (uint32_t base = pw * 32u; base < nslots; base += 32u * PW) my_slots += min(32u, nslots - base);
+        uint32_t my_slots = 0;  // slots lo + pw * 32 + lane + 32 * PWg * m of all lanes together
+        for (uint32_t base = lo_slot + pw * 32u; base < hi_slot; base += 32u * PWg) my_slots += min(32u, hi_slot - base);
         uint32_t it = 0;
         for (uint32_t tile = cid; tile < f.n_tiles; tile += ncl, ++it) {
             const uint32_t s = it % S;
@@ -156,31 +171,31 @@ __global__ void __launch_bounds__((kFzCW + kFzMaxPW + kFzMaxDW) * 32, 1) k_scan_
             uint8_t* dst = stages + (size_t)s * stage_bytes;
             const size_t toff = (size_t)tile * (16u * kFzT);
             if ((long long)tile >= f.tile_lo_ok && (long long)tile < f.tile_hi_ok) {
-                if (f.mode == 0) {
+                if (bulk) {
                     if (lane == 0) mbar_arrive_expect_tx(&full[s], my_slots * kFzPitch);
                     __syncwarp();
-                    for (uint32_t slot = pw * 32u + lane; slot < nslots; slot += 32u * PW)
+                    for (uint32_t slot = lo_slot + pw * 32u + lane; slot < hi_slot; slot += 32u * PWg)
                         bulk_g2s(dst + (size_t)slot * kFzPitch, reinterpret_cast<const uint8_t*>((uintptr_t)(s_pack[slot] & ~15ull)) + toff,
                                  kFzPitch, &full[s]);
                 } else {
                     // lean issue loop: one shared-memory read (the row's offset in 16-byte units), one 64-bit multiply-add
                     // and the copy per row; the destination steps by a constant
                     const uint8_t* src0 = base0 + toff + 16u * lane;
-                    auto d = smem_addr(dst + (size_t)pw * kFzPitch + 16u * lane);
+                    auto d = smem_addr(dst + (size_t)(lo_slot + pw) * kFzPitch + 16u * lane);
 #pragma unroll 4
-                    for (uint32_t slot = pw; slot < nslots; slot += PW) {
+                    for (uint32_t slot = lo_slot + pw; slot < hi_slot; slot += PWg) {
                         cp_async16_at(d, src0 + (size_t)s_off16[slot] * 16u);
-                        d += PW * kFzPitch;
+                        d += PWg * kFzPitch;
                     }
-                    for (uint32_t slot = pw * 32u + lane; slot < nslots; slot += 32u * PW)
+                    for (uint32_t slot = lo_slot + pw * 32u + lane; slot < hi_slot; slot += 32u * PWg)
                         cp_async16(dst + (size_t)slot * kFzPitch + 16u * kFzT,
                                    reinterpret_cast<const uint8_t*>((uintptr_t)(s_pack[slot] & ~15ull)) + toff + 16u * kFzT);
                     cp_async_arrive_noinc(&full[s]);
                 }
             } else {
-                for (uint32_t base = pw * 32u; base < nslots; base += 32u * PW) {
-                    const uint32_t hi_slot = min(nslots, base + 32u);
-                    for (uint32_t idx = lane; idx < (hi_slot - base) * (kFzT + 1u); idx += 32) {
+                for (uint32_t base = lo_slot + pw * 32u; base < hi_slot; base += 32u * PWg) {
+                    const uint32_t top = min(hi_slot, base + 32u);
+                    for (uint32_t idx = lane; idx < (top - base) * (kFzT + 1u); idx += 32) {
                         const uint32_t slot = base + idx / (kFzT + 1u), k = idx % (kFzT + 1u);
                         const long long d16 = (long long)((s_pack[slot] & ~15ull) - (unsigned long long)(uintptr_t)g.text) >> 4;
                         long long vi = d16 + (long long)tile * kFzT + k;
@@ -189,7 +204,7 @@ __global__ void __launch_bounds__((kFzCW + kFzMaxPW + kFzMaxDW) * 32, 1) k_scan_
                     }
                 }
                 __syncwarp();
-                if (f.mode != 0 || lane == 0) mbar_arrive(&full[s]);
+                if (!bulk || lane == 0) mbar_arrive(&full[s]);
             }
         }
     } else {
@@ -222,10 +237,11 @@ __global__ void __launch_bounds__((kFzCW + kFzMaxPW + kFzMaxDW) * 32, 1) k_scan_
             if (it % DW != dw) continue;
             const uint32_t s = it % S;
             mbar_wait(&red_full[s], (it / S) & 1u);
+            const bool live = lane < kFzT;  // lanes beyond the tile's chunks idle (16-chunk tiles)
             uint32_t nz = red16[s * 32u + lane];
             red16[s * 32u + lane] = 0u;
             const uint8_t* stg = stages + (size_t)s * stage_bytes;  // the stage is held until this warp lets go
-            const uint4 ref = *reinterpret_cast<const uint4*>(stg + 16u * lane);
+            const uint4 ref = *reinterpret_cast<const uint4*>(stg + 16u * (live ? lane : 0u));
             if (NC > 1) {
                 // partial mismatch bits of this CTA's rows -> every CTA of the cluster (distributed shared memory).
                 // 2S buffers: a peer's bits for tile it + 2S can only arrive after its duty for it + S, hence after OUR
@@ -271,9 +287,10 @@ __global__ void __launch_bounds__((kFzCW + kFzMaxPW + kFzMaxDW) * 32, 1) k_scan_
             rb += step;
             if (rb >= line) rb -= line;
             const uint32_t nl = eq_bytes16(ref, 0x0a0a0a0au);
-            if (((nl ^ expect) | (nz & expect)) & valid) bad |= (uint32_t)kBadNewlineLayout;
+            if (live && (((nl ^ expect) | (nz & expect)) & valid)) bad |= (uint32_t)kBadNewlineLayout;
+            if (!live) valid = 0u;
             const uint32_t mism = (nz | eq_bytes16(ref, 0x2d2d2d2du)) & valid & ~expect;  // differs from row 0, or row 0 is '-'
-            if (rank == 0 && j < g.n_chunks) f.mism16[j] = (uint16_t)mism;
+            if (live && rank == 0 && j < g.n_chunks) f.mism16[j] = (uint16_t)mism;
             const uint32_t cnt = (uint32_t)__popc(mism);
             const uint32_t incl = warp_inclusive_scan(cnt);
             const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);

@@ -5,8 +5,8 @@
 
 namespace edsb {
 
-constexpr uint32_t kFzT = 32;                    // 16-byte chunks per tile (lane = chunk)
-constexpr uint32_t kFzPitch = 16u * kFzT + 16u;  // bytes per staged row
+// T = 16-byte chunks per tile (32: lane = chunk; 16: two rows per warp instruction, twice the ring depth);
+// a staged row takes 16 T + 16 bytes (the aligned superset of its T chunks)
 constexpr uint32_t kFzMaxNC = 8;                 // portable cluster size
 constexpr uint32_t kFzGroupRows = 128;           // most rows of one CTA (4 per lane in the gather)
 constexpr uint32_t kFzMaxPW = 8;                 // most producer warps
@@ -26,20 +26,22 @@ struct FzParams {
     unsigned long long* tmp_col;     // [regions * capc]: p-space byte position of the slot's column
     uint32_t* region_count;          // [regions]
     uint32_t S, NC, RG, slot_pitch, n_tiles, capc, all_aligned;
+    uint32_t T;     // chunks per tile (the kernel instantiation)
     uint32_t PW;    // producer warps
     uint32_t DW;    // duty warps (mask + gather), tiles in rotation
-    uint32_t mode;  // 0: one bulk copy (TMA) per row, 1: 16-byte cp.async per lane
+    uint32_t mode;  // 0: one bulk copy (TMA) per row, 1: 16-byte cp.async per lane, 2: both (first PWB warps bulk, slots [0, n_bulk))
+    uint32_t PWB, n_bulk;
     long long tile_lo_ok, tile_hi_ok;  // tiles [lo, hi) can be fetched with bulk copies (every vector inside the buffer)
 };
 
-inline size_t fz_smem_bytes(uint32_t S, uint32_t NC, uint32_t RG, uint32_t slot_pitch, uint32_t DW) {
-    size_t b = (size_t)S * slot_pitch * kFzPitch;             // stages
+inline size_t fz_smem_bytes(uint32_t T, uint32_t S, uint32_t NC, uint32_t RG, uint32_t slot_pitch, uint32_t DW) {
+    size_t b = (size_t)S * slot_pitch * (16u * T + 16u);      // stages
     b += (size_t)S * 32 * 4;                                  // red16
     b += NC > 1 ? (size_t)2 * S * NC * 32 * 4 : 0;            // mask_in
     b += (size_t)slot_pitch * 8;                              // s_pack
     b += ((size_t)RG * 2 + 15) & ~(size_t)15;                 // s_info
     b += (((size_t)slot_pitch + 3) & ~(size_t)3) * 4;         // s_off16
-    b += (size_t)DW * 16 * kFzT * 2;                          // s_vpos
+    b += (size_t)DW * 16 * T * 2;                             // s_vpos
     b += (size_t)(5 * S) * sizeof(Mbar) + 16;                 // barriers: full, empty, red_full [S], maskbar [2S]
     return b;
 }

@@ -28,6 +28,7 @@
 #endif
 
 #include "ctx.h"
+#include "leds.h"
 #include "msa.h"
 
 namespace edsb {
@@ -134,9 +135,15 @@ eds_status guarded_shard(F&& body) {
     } catch (const edsb::CudaError& e) {
         edsb::set_last_error(e.what());
         return EDS_ERR_CUDA;
+    } catch (const edsb::BudgetError& e) {
+        edsb::set_last_error(e.what());
+        return EDS_ERR_BUDGET;
     } catch (const std::invalid_argument& e) {
         edsb::set_last_error(e.what());
         return EDS_ERR_INVALID_ARGUMENT;
+    } catch (const std::out_of_range& e) {
+        edsb::set_last_error(e.what());
+        return EDS_ERR_OUT_OF_RANGE;
     } catch (const std::bad_alloc&) {
         edsb::set_last_error("out of host memory");
         return EDS_ERR_RUNTIME;
@@ -606,3 +613,218 @@ eds_status eds_group_msa_transform_fd(eds_group* g, const uint8_t* file, uint64_
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// eds2leds over the devices of a group (symbol ranges). A merge never crosses a long conserved
+// symbol that no candidate pair ever touches, so the EDS is cut INSIDE such symbols — `{AAAAAAAA}` becomes `...{AAAA}`
+// and `{AAAA}...` — every shard is merged on its own device, and the results are joined by gluing the two halves back
+// together (their source set is kept once). Whether a cut was really inert is CHECKED, not assumed: every shard
+// reports whether its first / last symbol is still the unmerged half it was given; one touched seam and the call falls
+// back to a single-device merge of the whole text. Output bytes are those of the single-device merge either way.
+namespace {
+
+struct LedsCut {
+    uint64_t eds_at;    // byte offset inside the conserved symbol's characters where the text is cut
+    uint64_t n_strings; // strings that start before the cut (the split symbol's own string included)
+    bool braced;        // the symbol is written {…} (else bare text of the compact dialect)
+};
+
+inline bool is_space_c(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13); }
+
+// cuts near the byte positions k * n / parts; false when the text has no usable symbol near one of them
+bool plan_leds_cuts(const uint8_t* t, uint64_t n, uint32_t parts, uint32_t l, std::vector<LedsCut>& cuts) {
+    cuts.clear();
+    uint64_t strings = 0, counted = 0;  // strings that start in t[0, counted)
+    auto count_to = [&](uint64_t upto) {
+        // a string starts after '{' or ',' and at the first character of a bare run (after '}' or at the start)
+        for (uint64_t i = counted; i < upto; ++i) {
+            const uint8_t c = t[i];
+            if (c == '{' || c == ',') ++strings;
+            else if (c != '}' && (i == 0 || t[i - 1] == '}')) ++strings;
+        }
+        counted = upto;
+    };
+    uint64_t prev_cut = 0;
+    for (uint32_t k = 1; k < parts; ++k) {
+        uint64_t p = std::max<uint64_t>(n / parts * k, prev_cut + 1);
+        bool found = false;
+        // walk forward over symbols until a conserved one of at least 2 l + 2 characters turns up (bounded search)
+        for (uint64_t scanned = 0; p < n && scanned < (1u << 22) && !found;) {
+            // start of the next symbol at or after p
+            while (p < n && t[p] != '{' && !(p > 0 && t[p - 1] == '}' && t[p] != '{')) {
+                ++p;
+                ++scanned;
+            }
+            if (p >= n) break;
+            const bool braced = t[p] == '{';
+            const uint64_t body = braced ? p + 1 : p;
+            uint64_t e = body;
+            bool solid = true;
+            while (e < n && t[e] != '}' && t[e] != '{') {
+                if (t[e] == ',') solid = false;
+                ++e;
+            }
+            if (braced && (e >= n || t[e] != '}')) return false;  // malformed: let the single-device path report it
+            const uint64_t len = e - body;
+            if (solid && len >= 2ull * l + 2 && body > prev_cut) {
+                const uint64_t at = body + len / 2;
+                count_to(body + 1);  // the symbol's own string is counted (it starts at `body`, or with the '{' before it)
+                cuts.push_back(LedsCut{at, strings, braced});
+                prev_cut = at;
+                found = true;
+            } else {
+                scanned += e - p + 1;
+                p = braced ? e + 1 : e;
+            }
+        }
+        if (!found) return false;
+    }
+    return true;
+}
+
+// byte offset of the set with index `j` (its '{') in the SEDS text, scanning on from a known (offset, index) pair
+bool seds_seek(const uint8_t* s, uint64_t n, uint64_t j, uint64_t& at, uint64_t& idx) {
+    for (; at < n; ++at)
+        if (s[at] == '{') {
+            if (idx == j) return true;
+            ++idx;
+        }
+    return idx == j;
+}
+
+}  // namespace
+
+extern "C" eds_status eds_group_leds_merge_host(eds_group* g, const uint8_t* eds, uint64_t eds_bytes, const uint8_t* seds,
+                                                uint64_t seds_bytes, uint32_t l, int compact, eds_buffer* leds_out, eds_buffer* seds_out,
+                                                uint32_t* rounds_out, uint32_t* shards_used) {
+    if (leds_out) *leds_out = eds_buffer{nullptr, 0};
+    if (seds_out) *seds_out = eds_buffer{nullptr, 0};
+    if (shards_used) *shards_used = 1;
+    return guarded_shard([&] {
+        if (!g || !eds || !leds_out || !seds_out) throw std::invalid_argument("eds_group_leds_merge_host: null argument");
+        if (l == 0) throw std::invalid_argument("context_length must be > 0 for l-EDS transformation");
+        const uint32_t n = (uint32_t)g->ctx.size();
+        const bool linear = seds != nullptr;
+        auto single = [&] {
+            eds_ctx* c = g->ctx[0];
+            EDSB_CUDA(cudaSetDevice(c->device));
+            c->leds->merge_host(eds, eds_bytes, seds, seds_bytes, l, compact != 0, 0, leds_out, seds_out, rounds_out);
+        };
+        // the planner reads plain text: white space inside the text (legal, stripped by the parser) -> one device
+        uint64_t ne = eds_bytes, ns = seds_bytes;
+        while (ne && is_space_c(eds[ne - 1])) --ne;
+        while (linear && ns && is_space_c(seds[ns - 1])) --ns;
+        bool plain = n > 1 && ne >= (uint64_t)n * (4ull * l + 64);
+        for (uint64_t i = 0; plain && i < ne; ++i) plain = !is_space_c(eds[i]);
+        for (uint64_t i = 0; plain && linear && i < ns; ++i) plain = !is_space_c(seds[i]);
+        std::vector<LedsCut> cuts;
+        if (!plain || !plan_leds_cuts(eds, ne, n, l, cuts)) {
+            single();
+            return;
+        }
+        // shard texts: [cut k-1, cut k) with the split symbol closed on the left and reopened on the right
+        std::vector<std::string> se(n), ss(n);
+        std::vector<uint64_t> set_at(n + 1, 0);
+        if (linear) {
+            uint64_t at = 0, idx = 0;
+            for (uint32_t k = 1; k < n; ++k) {
+                // set index of the split symbol's string = n_strings - 1: the right shard starts with a copy of that set
+                if (!seds_seek(seds, ns, cuts[k - 1].n_strings - 1, at, idx)) {
+                    single();
+                    return;
+                }
+                set_at[k] = at;
+            }
+            set_at[n] = ns;
+        }
+        for (uint32_t k = 0; k < n; ++k) {
+            const uint64_t lo = k ? cuts[k - 1].eds_at : 0, hi = k + 1 < n ? cuts[k].eds_at : ne;
+            std::string& e = se[k];
+            if (k && cuts[k - 1].braced) e.push_back('{');
+            e.append(reinterpret_cast<const char*>(eds + lo), hi - lo);
+            if (k + 1 < n && cuts[k].braced) e.push_back('}');
+            if (linear) {
+                // sets of the strings that start in this shard; the split symbol's set opens the right shard as well
+                const uint64_t a = set_at[k];
+                uint64_t b = set_at[k + 1];
+                if (k + 1 < n) {  // include the split symbol's own set: up to and including its '}'
+                    while (b < ns && seds[b] != '}') ++b;
+                    ++b;
+                }
+                ss[k].assign(reinterpret_cast<const char*>(seds + a), b - a);
+            }
+        }
+        // one thread per device
+        std::vector<eds_buffer> oe(n, eds_buffer{nullptr, 0}), os(n, eds_buffer{nullptr, 0});
+        std::vector<uint32_t> rounds(n, 0), edges(n, 0);
+        std::vector<std::string> err(n);
+        std::vector<int> status(n, 0);
+        std::vector<std::thread> th;
+        for (uint32_t k = 0; k < n; ++k)
+            th.emplace_back([&, k] {
+                try {
+                    eds_ctx* c = g->ctx[k];
+                    EDSB_CUDA(cudaSetDevice(c->device));
+                    c->leds->merge_host(reinterpret_cast<const uint8_t*>(se[k].data()), se[k].size(),
+                                        linear ? reinterpret_cast<const uint8_t*>(ss[k].data()) : nullptr, ss[k].size(), l, compact != 0, 0,
+                                        &oe[k], &os[k], &rounds[k], nullptr, false, {}, nullptr, nullptr, &edges[k]);
+                } catch (const std::exception& e) {
+                    status[k] = 1;
+                    err[k] = e.what();
+                }
+            });
+        for (auto& t : th) t.join();
+        bool inert = true;
+        for (uint32_t k = 0; k < n; ++k) {
+            if (status[k]) inert = false;  // (an error inside a shard carries shard-local positions: redo it whole)
+            if (k > 0 && !(edges[k] & 1u)) inert = false;
+            if (k + 1 < n && !(edges[k] & 2u)) inert = false;
+        }
+        auto drop = [&] {
+            for (uint32_t k = 0; k < n; ++k) {
+                eds_buffer_free_host(&oe[k]);
+                eds_buffer_free_host(&os[k]);
+            }
+        };
+        if (!inert) {
+            drop();
+            single();
+            return;
+        }
+        // join: glue the halves (drop "}{" in the braced dialect), keep the split symbol's set once, one final newline
+        std::string je, js;
+        for (uint32_t k = 0; k < n; ++k) {
+            std::string part(reinterpret_cast<const char*>(oe[k].data), oe[k].bytes);
+            while (!part.empty() && part.back() == '\n') part.pop_back();
+            if (k > 0 && !je.empty() && je.back() == '}' && !part.empty() && part.front() == '{') {
+                je.pop_back();
+                part.erase(0, 1);
+            }
+            je += part;
+            if (linear) {
+                std::string sp(reinterpret_cast<const char*>(os[k].data), os[k].bytes);
+                while (!sp.empty() && sp.back() == '\n') sp.pop_back();
+                if (k > 0) sp.erase(0, sp.find('}') + 1);  // the copy of the split symbol's set
+                js += sp;
+            }
+        }
+        drop();
+        je.push_back('\n');
+        if (linear) js.push_back('\n');
+        uint8_t* he = static_cast<uint8_t*>(malloc(je.size() ? je.size() : 1));
+        uint8_t* hs = static_cast<uint8_t*>(malloc(js.size() ? js.size() : 1));
+        if (!he || !hs) {
+            free(he);
+            free(hs);
+            throw std::bad_alloc();
+        }
+        memcpy(he, je.data(), je.size());
+        memcpy(hs, js.data(), js.size());
+        leds_out->data = he;
+        leds_out->bytes = je.size();
+        seds_out->data = hs;
+        seds_out->bytes = linear ? js.size() : 0;
+        if (rounds_out) *rounds_out = *std::max_element(rounds.begin(), rounds.end());
+        if (shards_used) *shards_used = n;
+    });
+}

@@ -69,8 +69,6 @@ struct Session {
 };
 thread_local Session t_session;
 
-std::string slurp(std::istream& in) { return std::string(std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>()); }
-
 // one group per thread and device list, like the per-thread context
 struct GroupSession {
     eds_group* group = nullptr;
@@ -88,6 +86,9 @@ struct GroupSession {
     }
 };
 thread_local GroupSession t_group;
+
+std::string slurp(std::istream& in) { return std::string(std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>()); }
+
 
 std::pair<std::string, std::string> msa_transform(std::istream& in, uint32_t l, int leds) {
     const std::string file = slurp(in);
@@ -116,6 +117,20 @@ void merge(std::istream& input, std::ostream& output, Length l, std::istream* ph
     const std::string eds = slurp(input);
     std::string seds;
     if (phasing_in) seds = slurp(*phasing_in);
+    if (g_devices.size() > 1 && g_budget == 0) {
+        // symbol ranges over the devices of the group (cut inside long conserved symbols, verified, glued back together)
+        eds_buffer ge{nullptr, 0}, gs{nullptr, 0};
+        uint32_t r = 0, used = 0;
+        const eds_status grc = eds_group_leds_merge_host(t_group.get(), reinterpret_cast<const uint8_t*>(eds.data()), eds.size(),
+                                                         phasing_in ? reinterpret_cast<const uint8_t*>(seds.data()) : nullptr, seds.size(), l,
+                                                         compact ? 1 : 0, &ge, &gs, &r, &used);
+        if (grc != EDS_OK) rethrow(grc);
+        output.write(reinterpret_cast<const char*>(ge.data), (std::streamsize)ge.bytes);
+        if (phasing_in && phasing_out) phasing_out->write(reinterpret_cast<const char*>(gs.data), (std::streamsize)gs.bytes);
+        eds_buffer_free_host(&ge);
+        eds_buffer_free_host(&gs);
+        return;
+    }
     eds_buffer o{nullptr, 0}, so{nullptr, 0};  // views into pinned memory kept by the context: nothing to free
     uint32_t rounds = 0;
     const eds_status rc = eds_leds_merge_host_view(t_session.get(), reinterpret_cast<const uint8_t*>(eds.data()), eds.size(),

@@ -3,6 +3,7 @@
 // but the merge runs on the GPU.
 #include <filesystem>
 #include <fstream>
+#include <vector>
 
 #include "cli_common.hpp"
 #include "edsparser/transforms/eds_transforms.hpp"
@@ -21,6 +22,7 @@ static void usage() {
                  "  --full                       Use full output format with brackets on all symbols (default: compact)\n"
                  "  -t [ --threads ] arg (=1)    Number of threads for parallel processing (accepted; the merge runs on the GPU)\n"
                  "  --device arg (=0)            CUDA device to run on (B200 build)\n"
+                 "  --gpus arg (=1)              Merge symbol ranges on this many GPUs of the node, starting at --device\n"
                  "  --max-output-bytes arg (=0)  Refuse (do not truncate) a merge whose output would exceed this (0 = no limit)\n\n"
                  "MERGING METHODS (auto-detected):\n"
                  "  LINEAR:    used when --sources/-s is provided; keeps only combinations with a common source\n"
@@ -33,7 +35,7 @@ int main(int argc, char** argv) {
     try {
         const cli::Args args(argc, argv, {{"help", 'h', false}, {"input", 'i', true}, {"output", 'o', true},
                                          {"context-length", 'l', true}, {"sources", 's', true}, {"full", 0, false},
-                                         {"threads", 't', true}, {"device", 0, true}, {"max-output-bytes", 0, true}});
+                                         {"threads", 't', true}, {"device", 0, true}, {"gpus", 0, true}, {"max-output-bytes", 0, true}});
         if (args.has("help")) {
             usage();
             cli::print_performance(timer);
@@ -56,7 +58,15 @@ int main(int argc, char** argv) {
                 throw std::invalid_argument("the argument ('" + args.get("threads") + "') for option '--threads' is invalid");
             }
         }
-        if (args.has("device")) b200::set_device((int)args.to_uint("device"));
+        const int first_device = args.has("device") ? (int)args.to_uint("device") : 0;
+        b200::set_device(first_device);
+        if (args.has("gpus")) {
+            const unsigned long n = args.to_uint("gpus");
+            if (n < 1 || n > 64) throw std::invalid_argument("the argument for option '--gpus' is invalid");
+            std::vector<int> devices;
+            for (unsigned long i = 0; i < n; ++i) devices.push_back(first_device + (int)i);
+            b200::set_devices(devices);
+        }
         if (args.has("max-output-bytes")) b200::set_max_output_bytes(args.to_uint("max-output-bytes"));
 
         if (input_file.extension() != ".eds") {

@@ -291,6 +291,16 @@ eds_status eds_group_msa_transform_fd(eds_group* group, const uint8_t* file, uin
                                       uint64_t halo, int eds_fd, int seds_fd, uint64_t totals[2],
                                       eds_msa_stats* per_device_stats);
 
+/* eds2leds over the devices of a group (symbol ranges): the EDS text is cut INSIDE long conserved
+ * symbols (no candidate pair of select_independent_merge_pairs, eds_transforms.cpp:46-107, can involve a conserved
+ * symbol of >= l characters unless a neighbour collapses to a short conserved one), every shard is merged on its own
+ * device, the halves are glued back together. Every shard reports whether its seam symbols stayed unmerged; if one did
+ * not, or the text offers no such symbol near a cut, the whole text is merged on one device. The bytes are those of
+ * eds_leds_merge_host either way; *shards_used tells which way it went. seds = NULL: CARTESIAN. */
+eds_status eds_group_leds_merge_host(eds_group* group, const uint8_t* eds, uint64_t eds_bytes, const uint8_t* seds,
+                                     uint64_t seds_bytes, uint32_t l, int compact, eds_buffer* leds_out,
+                                     eds_buffer* seds_out, uint32_t* rounds_out, uint32_t* shards_used);
+
 /* eds_comm: one process PER GPU (torchrun, mpirun): rank 0 makes the 128-byte NCCL id, the launcher ships it to
  * every rank, each rank builds the communicator for its context. After every eds_msa_transform_device the rank
  * posts its byte counts (enqueued behind the transform, no host synchronisation, two posts may be in flight);

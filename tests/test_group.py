@@ -100,3 +100,53 @@ def test_group_config2_shape():
         assert g.msa_transform_host(text, 10)[:2] == one
     finally:
         g.close()
+
+
+def check_group_leds(lib, n, sizes, ls=(2, 3)):
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import bench_leds
+
+    g = lib.group(list(range(n)))
+    try:
+        sharded = 0
+        for seed, bp in enumerate(sizes, start=1):
+            e, s = bench_leds.genrandomeds_like(bp, seed=seed)
+            for l in ls:
+                for compact in (True, False):
+                    exp = oracle_lib.eds2leds(e, s, l, compact=compact)
+                    got = g.leds_merge_host(e, s, l, compact=compact)
+                    assert got[0] == exp[0] and got[1] == exp[1], (n, bp, l, compact)
+                    sharded += got[3] > 1
+        e, s = bench_leds.genrandomeds_like(sizes[0], variability=0.01, seed=9)
+        assert g.leds_merge_host(e, None, 3)[0] == oracle_lib.eds2leds(e, None, 3)[0]  # CARTESIAN
+        # white space inside the text, or nothing to cut at: one device, same bytes
+        assert g.leds_merge_host(b"{AAAA}{A,C}\n{G}{T,G}{TTTT}", b"{0}{1,2}{2,3}{0}{1,2}{2,3}{0}", 2)[:2] == \
+            oracle_lib.eds2leds(b"{AAAA}{A,C}\n{G}{T,G}{TTTT}", b"{0}{1,2}{2,3}{0}{1,2}{2,3}{0}", 2)
+        return sharded
+    finally:
+        g.close()
+
+
+def test_group_leds_emulated():
+    import emu_lib
+
+    assert check_group_leds(emu_lib.lib(), 3, sizes=(2500,), ls=(3,)) >= 1
+
+
+@pytest.mark.gpu
+def test_group_leds_on_devices():
+    """eds2leds over symbol ranges (cuts inside long conserved symbols, verified seams) == the oracle; on a one-GPU box the
+    group has one device and the call takes the single-device path."""
+    import ctypes
+
+    import edsparser_b200 as E
+
+    lib = E.load()
+    cudart = ctypes.CDLL("libcudart.so")
+    n_dev = ctypes.c_int(0)
+    cudart.cudaGetDeviceCount(ctypes.byref(n_dev))
+    n = max(1, min(4, n_dev.value))
+    sharded = check_group_leds(lib, n, sizes=(200_000, 1_000_000), ls=(3, 10))
+    assert n == 1 or sharded >= 1
