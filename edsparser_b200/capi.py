@@ -63,10 +63,10 @@ class MsaStats(ctypes.Structure):
                 ("n_variable", ctypes.c_uint64), ("n_alternatives", ctypes.c_uint64),
                 ("first_open_col", ctypes.c_uint64), ("eds_bytes", ctypes.c_uint64), ("seds_bytes", ctypes.c_uint64),
                 ("eds_lead_bytes", ctypes.c_uint64), ("tail_open_common", ctypes.c_uint32),
-                ("gpu_launches", ctypes.c_uint32), ("retries", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+                ("gpu_launches", ctypes.c_uint32), ("retries", ctypes.c_uint32), ("n_hashed_symbols", ctypes.c_uint32)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class VcfStats(ctypes.Structure):

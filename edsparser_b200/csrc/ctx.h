@@ -62,7 +62,7 @@ struct eds_ctx {
     bool own_stream = false;
     // side streams + events: independent kernels of one transform overlap (fork/join by events, no host sync)
     cudaStream_t aux[2] = {nullptr, nullptr};
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool serial = false;  // EDSB_DEBUG_SERIAL=1: everything on the main stream
     // k_scan_fused (scan + variable-column gather in one pass, scan_fused.cuh); EDSB_FUSED=0 selects k_scan + k_stash
     bool fused = true;

@@ -68,6 +68,47 @@ struct StripFn {
     }
 };
 
+// White-space census of a text, 16 bytes per load: how many white-space bytes and where the first one is. Files end with
+// a newline and hold none inside, so the usual answer is "only at the end": the text is then used where it lies, minus
+// its tail, and the compaction pass (StripFn: read + write of every byte) is skipped.
+struct SpaceCensus {
+    unsigned long long count, first;
+};
+
+__device__ __forceinline__ uint32_t space_bytes4(uint32_t w) {  // bit k = byte k is ' ' or 9..13
+    // quick reject: no byte below 0x21 (the haszero trick on w - 0x21..)
+    if (!((w - 0x21212121u) & ~w & 0x80808080u)) return 0u;
+    uint32_t m = 0;
+    for (uint32_t k = 0; k < 4u; ++k) m |= (is_space((uint8_t)(w >> (8u * k))) ? 1u : 0u) << k;
+    return m;
+}
+
+__global__ void __launch_bounds__(256) k_space_census(const uint8_t* t, unsigned long long n, SpaceCensus* out) {
+    unsigned long long cnt = 0, first = ~0ull;
+    const unsigned long long n16 = n / 16u;
+    const uint4* v = reinterpret_cast<const uint4*>(t);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint4 x = ldg_nc(v + i);
+        const uint32_t m = space_bytes4(x.x) | (space_bytes4(x.y) << 4) | (space_bytes4(x.z) << 8) | (space_bytes4(x.w) << 12);
+        if (m) {
+            cnt += (unsigned long long)__popc(m);
+            first = min(first, i * 16u + (unsigned long long)(__ffs((int)m) - 1));
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (unsigned long long i = n16 * 16u; i < n; ++i)
+            if (is_space(t[i])) {
+                ++cnt;
+                first = min(first, i);
+            }
+    cnt = warp_sum(cnt);
+    for (int d = 16; d > 0; d >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, d));
+    if ((threadIdx.x & 31) == 0 && (cnt || first != ~0ull)) {
+        atomicAdd(&out->count, cnt);
+        atomicMin(&out->first, first);
+    }
+}
+
 // ---- EDS text: brace depth -------------------------------------------------------------------------
 struct DepthFn {
     const uint8_t* t;
@@ -857,10 +898,31 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
         if (eds_bytes) EDSB_CUDA(cudaMemcpyAsync(d_raw.p, eds_in, eds_bytes, in_kind, s));
         raw = d_raw.as<uint8_t>();
     }
-    d_text.reserve(eds_bytes + 16);
-    uint8_t* text = d_text.as<uint8_t>();
-    LEDS_SCAN("strip_eds", OpSum64, eds_bytes, (StripFn{raw, text}));
-    const uint32_t n = (uint32_t)total_of();
+    // white space only at the end (or none): the text is used where it lies; else it is compacted (eds.cpp:46)
+    DevBuf& d_census = B_.d[31];  // (the emit's big-copy list: not in use yet)
+    d_census.reserve(2 * sizeof(SpaceCensus) + sizeof(BigCopy));
+    auto census = [&](const char* name, const uint8_t* t, uint64_t bytes, SpaceCensus& h) {
+        SpaceCensus* d = d_census.as<SpaceCensus>();
+        h.count = 0;
+        h.first = ~0ull;
+        EDSB_CUDA(cudaMemcpyAsync(d, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+        if (bytes) LEDS_LAUNCH(name, k_space_census, G, 256, t, (unsigned long long)bytes, d);
+        EDSB_CUDA(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, s));
+        EDSB_CUDA(cudaStreamSynchronize(s));
+    };
+    SpaceCensus ce;
+    census("census_eds", raw, eds_bytes, ce);
+    uint8_t* text;
+    uint32_t n;
+    if (ce.count == 0 || ce.first + ce.count == eds_bytes) {
+        text = const_cast<uint8_t*>(raw);  // (read only from here on)
+        n = (uint32_t)(ce.count ? ce.first : eds_bytes);
+    } else {
+        d_text.reserve(eds_bytes + 16);
+        text = d_text.as<uint8_t>();
+        LEDS_SCAN("strip_eds", OpSum64, eds_bytes, (StripFn{raw, text}));
+        n = (uint32_t)total_of();
+    }
 
     uint32_t n_str = 0, n_sym = 0;
     if (n) {
@@ -891,10 +953,19 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
             if (seds_bytes) EDSB_CUDA(cudaMemcpyAsync(d_sraw.p, seds_in, seds_bytes, in_kind, s));
             sraw = d_sraw.as<uint8_t>();
         }
-        d_stext.reserve(seds_bytes + 16);
-        uint8_t* stext = d_stext.as<uint8_t>();
-        LEDS_SCAN("strip_seds", OpSum64, seds_bytes, (StripFn{sraw, stext}));
-        const unsigned long long ns = total_of();
+        SpaceCensus cs;
+        census("census_seds", sraw, seds_bytes, cs);
+        const uint8_t* stext;
+        unsigned long long ns;
+        if (cs.count == 0 || cs.first + cs.count == seds_bytes) {
+            stext = sraw;
+            ns = cs.count ? cs.first : seds_bytes;
+        } else {
+            d_stext.reserve(seds_bytes + 16);
+            LEDS_SCAN("strip_seds", OpSum64, seds_bytes, (StripFn{sraw, d_stext.as<uint8_t>()}));
+            stext = d_stext.as<uint8_t>();
+            ns = total_of();
+        }
         if (ns == 0) throw std::runtime_error("sEDS input is empty");
         const uint32_t pw = kMaxPathId / 32;
         d_present.reserve((size_t)pw * 4);

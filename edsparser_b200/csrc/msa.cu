@@ -468,18 +468,47 @@ __device__ __forceinline__ uint32_t sym_lower_bound(const uint32_t* sym, uint32_
     return lo;
 }
 
-// k_finalize: owned symbol range and what happens at the shard's two edges (one thread).
+// first index in [0, n) whose (masked) entry is >= key, by the whole warp: 32 probes per step instead of one
+__device__ __forceinline__ uint32_t warp_lower_bound(const uint32_t* a, uint32_t n, uint32_t key, uint32_t mask) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t lo = 0, hi = n;  // answer in [lo, hi]
+    while (hi - lo > 32u) {
+        const uint32_t step = (hi - lo + 31u) / 32u;
+        const uint32_t at = lo + lane * step;  // lane 0 probes lo
+        const bool below = at < hi && (a[at] & mask) < key;
+        const uint32_t m = __ballot_sync(0xffffffffu, below);
+        // entries are sorted: the lanes that answer "below" form a prefix
+        const uint32_t cnt = (uint32_t)__popc(m);
+        if (cnt == 0) {
+            hi = lo;  // a[lo] >= key
+        } else {
+            const uint32_t new_lo = lo + (cnt - 1u) * step + 1u;
+            const uint32_t new_hi = cnt < 32u ? min(hi, lo + cnt * step) : hi;
+            lo = new_lo;
+            hi = new_hi;
+        }
+    }
+    const uint32_t at = lo + lane;
+    const bool below = at < hi && (a[at] & mask) < key;
+    return lo + (uint32_t)__popc(__ballot_sync(0xffffffffu, below));
+}
+
+// k_finalize: owned symbol range and what happens at the shard's two edges (one warp; the four searches are 32-ary).
 __global__ void k_finalize(MsaGeom g, MsaBufs b) {
     MsaStatus* st = b.status;
-    if (st->abort || threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (st->abort || blockIdx.x != 0 || threadIdx.x >= 32) return;
     const uint32_t n_runs = st->n_runs, n_syms = st->n_syms;
     const uint32_t* sym = b.sym;
     const uint32_t* runs = b.runs;
     const bool leds = g.leds && g.l > 0;
     const bool right_open = g.col_begin + g.ncols < g.total_cols;  // the alignment continues past the window
     uint32_t fail = 0;
-    const uint32_t k_lo = sym_lower_bound(sym, n_syms, g.own_lo);
-    const uint32_t k_hi = sym_lower_bound(sym, n_syms, g.own_hi);
+    const uint32_t k_lo = warp_lower_bound(sym, n_syms, g.own_lo, kColMask);
+    const uint32_t k_hi = warp_lower_bound(sym, n_syms, g.own_hi, kColMask);
+    const uint32_t nv = st->n_varsyms_window;
+    const uint32_t v_lo = warp_lower_bound(b.varsym, nv, k_lo, 0xffffffffu);
+    const uint32_t v_hi = warp_lower_bound(b.varsym, nv, k_hi, 0xffffffffu);
+    if (threadIdx.x != 0) return;
     uint32_t lead_lo = 0, lead_hi = 0, lead_close = 0, tail_open = 0;
 
     if (leds && g.col_begin > 0 && n_runs > 0) {
@@ -505,22 +534,8 @@ __global__ void k_finalize(MsaGeom g, MsaBufs b) {
             }
         }
     }
-    // owned slice of the variable-symbol list
-    {
-        const uint32_t nv = st->n_varsyms_window;
-        uint32_t lo = 0, hi = nv;
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (b.varsym[mid] < k_lo) lo = mid + 1; else hi = mid;
-        }
-        st->v_lo = lo;
-        hi = nv;
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (b.varsym[mid] < k_hi) lo = mid + 1; else hi = mid;
-        }
-        st->v_hi = lo;
-    }
+    st->v_lo = v_lo;
+    st->v_hi = v_hi;
     st->k_lo = k_lo;
     st->k_hi = k_hi;
     st->lead_lo = lead_lo;
@@ -848,30 +863,33 @@ __device__ __forceinline__ uint32_t eq_mask32(const uint32_t (&v)[8], uint32_t c
     return m;
 }
 
-// Single-column symbol, many rows: a LANE owns 32 consecutive rows — one word of every alternative's row bitset.
-// It peels its distinct residues off in order of first row (one SIMD byte compare over its 32 bytes per distinct
-// residue: the compare IS the bitset word), the warp merges the lanes' lists in lane order (= row order) into the
-// symbol's residue list, and every lane stores its words under the merged numbering: 128-byte coalesced stores.
-// ~600 warp instructions per 1024 rows instead of 32 dependent ballot rounds. False: more than 8 residues or a
-// NUL byte -> the symbol goes to the hashed warp path (k_group2).
-__device__ bool group_single_warp(const MsaGeom& g, const MsaBufs& b, uint32_t k, uint32_t s, uint32_t& nalts) {
-    nalts = 0;
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t slot0 = first_slot(b, s);
-    const uint8_t* col = b.stash + (size_t)slot0 * g.Rp;
+// Single-column symbols, rows across lanes: a LANE owns 32 consecutive rows — one word of every alternative's row
+// bitset — and a GROUP of GL lanes (GL = R/32 rounded up to a power of two, at most 32) owns a symbol, so a warp
+// handles 32 / GL symbols at once (100 rows: 8 symbols per warp; 1000 rows: one). A lane peels its distinct residues
+// off in order of first row (one SIMD byte compare over its 32 bytes per distinct residue: the compare IS the bitset
+// word), the group merges its lanes' lists in lane order (= row order) into the symbol's residue list, and every lane
+// stores its words under the merged numbering (coalesced). Every collective is executed by all 32 lanes (groups never
+// diverge around one). ok = false: more than 8 residues or a NUL byte -> the symbol goes to the hashed row path.
+__device__ void group_single_lanes(const MsaGeom& g, const MsaBufs& b, bool active, uint32_t k, uint32_t s, uint32_t GL,
+                                   uint32_t& nalts, bool& ok_out) {
+    const uint32_t lane = threadIdx.x & 31, gl = lane & (GL - 1u), gbase = lane & ~(GL - 1u);
+    const uint32_t gmask = GL >= 32u ? 0xffffffffu : (((1u << GL) - 1u) << gbase);
     const uint32_t Rw = g.Rp >> 5;
-    uint32_t* rowbits = b.rowbits ? b.rowbits + (size_t)slot0 * 8u * Rw : nullptr;
+    const uint32_t slot0 = active ? first_slot(b, s) : 0u;
+    const uint8_t* col = b.stash + (size_t)slot0 * g.Rp;
+    uint32_t* rowbits = b.rowbits + (size_t)slot0 * 8u * Rw;
     Seen G;
     G.lo = G.hi = G.n = 0;
-    bool ok = true;
-    if (rowbits && Rw > 32u) {
+    bool ok = active;
+    if (Rw > GL) {
         // deeper than 1024 rows: a residue first seen in a later chunk has no words for the earlier chunks
-        for (uint32_t i = lane; i < 8u * Rw; i += 32) rowbits[i] = 0u;
+        if (active)
+            for (uint32_t i = gl; i < 8u * Rw; i += GL) rowbits[i] = 0u;
         __syncwarp();
     }
-    for (uint32_t w0 = 0; w0 < Rw; w0 += 32) {
-        const uint32_t w = w0 + lane;
-        const bool have = w < Rw;
+    for (uint32_t w0 = 0; w0 < Rw; w0 += GL) {
+        const uint32_t w = w0 + gl;
+        const bool have = ok && w < Rw;
         uint32_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (have) {
             const uint4 a = *reinterpret_cast<const uint4*>(col + (size_t)w * 32u), c = *reinterpret_cast<const uint4*>(col + (size_t)w * 32u + 16u);
@@ -896,33 +914,29 @@ __device__ bool group_single_warp(const MsaGeom& g, const MsaBufs& b, uint32_t k
             }
         }
         if (remaining) lane_ok = false;  // a ninth residue
-        if (__any_sync(0xffffffffu, !lane_ok)) {
-            ok = false;
-            break;
-        }
-        // merge in lane order: the lowest lane that holds a residue the list does not know appends its news
+        if (__ballot_sync(0xffffffffu, !lane_ok) & gmask) ok = false;
+        // merge in lane order: the lowest lane of the group that holds a residue the list does not know appends its news
         for (;;) {
             bool news = false;
-            for (uint32_t j = 0; j < L.n; ++j) news = news || seen_lookup(G, seen_byte(L, j)) == 8u;
-            const uint32_t pending = __ballot_sync(0xffffffffu, news);
-            if (!pending) break;
-            const int src = __ffs((int)pending) - 1;
-            const uint32_t slo = __shfl_sync(0xffffffffu, L.lo, src), shi = __shfl_sync(0xffffffffu, L.hi, src);
-            const uint32_t sn = __shfl_sync(0xffffffffu, L.n, src);
+            if (ok && have)
+                for (uint32_t j = 0; j < L.n; ++j) news = news || seen_lookup(G, seen_byte(L, j)) == 8u;
+            const uint32_t pending_all = __ballot_sync(0xffffffffu, news);
+            if (!pending_all) break;
+            const uint32_t pending = pending_all & gmask;
+            const int src = pending ? __ffs((int)pending) - 1 : (int)lane;
             Seen src_list;
-            src_list.lo = slo;
-            src_list.hi = shi;
-            src_list.n = sn;
-            for (uint32_t j = 0; j < sn; ++j) {
-                const uint32_t ch = seen_byte(src_list, j);
-                if (seen_lookup(G, ch) == 8u) {
-                    if (G.n >= 8u) ok = false; else seen_index(G, ch);
+            src_list.lo = __shfl_sync(0xffffffffu, L.lo, src);
+            src_list.hi = __shfl_sync(0xffffffffu, L.hi, src);
+            src_list.n = __shfl_sync(0xffffffffu, L.n, src);
+            if (pending)
+                for (uint32_t j = 0; j < src_list.n; ++j) {
+                    const uint32_t ch = seen_byte(src_list, j);
+                    if (seen_lookup(G, ch) == 8u) {
+                        if (G.n >= 8u) ok = false; else seen_index(G, ch);
+                    }
                 }
-            }
-            if (!ok) break;
         }
-        if (!ok) break;
-        if (rowbits && have) {
+        if (have && ok) {
             // words of this lane under the merged numbering
 #pragma unroll
             for (uint32_t a = 0; a < 8u; ++a) {
@@ -936,49 +950,55 @@ __device__ bool group_single_warp(const MsaGeom& g, const MsaBufs& b, uint32_t k
             }
         }
     }
-    if (!ok) {
-        if (b.seen && lane == 0) b.seen[(size_t)slot0 * 3u + 2u] = 0xffu;  // queued as wide: k_emit_var skips it
-        return false;
+    if (active && gl == 0u) {
+        if (!ok) {
+            b.seen[(size_t)slot0 * 3u + 2u] = 0xffu;  // on the hashed row path: k_emit_var skips it
+        } else {
+            b.seen[(size_t)slot0 * 3u] = G.lo;
+            b.seen[(size_t)slot0 * 3u + 1u] = G.hi;
+            b.seen[(size_t)slot0 * 3u + 2u] = G.n;
+            uint32_t chars = 0;
+            for (uint32_t a = 0; a < G.n; ++a) chars += seen_byte(G, a) != (uint32_t)'-';
+            b.sym_nalts[k] = G.n;
+            b.sym_edsz[k] = 2ull + chars + (G.n - 1u);
+        }
     }
-    if (b.seen && lane == 0) {
-        b.seen[(size_t)slot0 * 3u] = G.lo;
-        b.seen[(size_t)slot0 * 3u + 1u] = G.hi;
-        b.seen[(size_t)slot0 * 3u + 2u] = G.n;
-    }
-    if (lane == 0) {
-        uint32_t chars = 0;
-        for (uint32_t a = 0; a < G.n; ++a) chars += seen_byte(G, a) != (uint32_t)'-';
-        b.sym_nalts[k] = G.n;
-        b.sym_edsz[k] = 2ull + chars + (G.n - 1u);
-    }
-    nalts = G.n;  // warp-uniform: the caller must not read sym_nalts back (no fence between lanes)
-    return true;
+    nalts = ok ? G.n : 0u;
+    ok_out = ok;
 }
 
 // k_group: single-column symbols — lane per symbol (registers only) when narrow_ok, else warp per symbol with
 // rows across lanes; everything else is queued for k_group2 (two variable columns already give up to 25
 // alternatives, more than the 8-entry residue list holds).
-__global__ void k_group(MsaGeom g, MsaBufs b, uint32_t narrow_ok) {
+__global__ void k_group(MsaGeom g, MsaBufs b, uint32_t narrow_ok, uint32_t group_lanes) {
     MsaStatus* st = b.status;
     if (st->abort || st->halo_fail) return;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const uint32_t v_lo = st->v_lo, v_hi = st->v_hi;
     unsigned long long alts_here = 0;
     if (narrow_ok != 1u) {
-        // many rows (or a test switch): a warp per symbol, symbols strided over all warps of the grid so that every
-        // warp has one dependent chain (symbol -> slot -> column) in flight instead of 32 in a row
-        for (uint32_t v = v_lo + blockIdx.x * wpb + warp; v < v_hi; v += gridDim.x * wpb) {
-            const uint32_t k = b.varsym[v];
-            const uint32_t s = b.sym[k] & kColMask, en = b.sym[k + 1] & kColMask;
-            bool wide = true;
-            if (en - s == 1u && narrow_ok != 2u) {  // narrow_ok 2: tests force the wide path
-                uint32_t na;
-                if (group_single_warp(g, b, k, s, na)) {
-                    wide = false;
-                    if (lane == 0) alts_here += na;
+        // rows across lanes: a group of GL lanes per symbol, 32 / GL symbols per warp, batches strided over the grid
+        const uint32_t GL = group_lanes, NS = 32u / GL, sub = lane / GL;
+        for (uint32_t v0 = v_lo + (blockIdx.x * wpb + warp) * NS; v0 < v_hi; v0 += gridDim.x * wpb * NS) {
+            const uint32_t v = v0 + sub;
+            bool active = v < v_hi && narrow_ok != 2u;  // narrow_ok 2: tests send every symbol down the hashed path
+            uint32_t k = 0, s = 0;
+            if (active) {
+                k = b.varsym[v];
+                s = b.sym[k] & kColMask;
+                active = (b.sym[k + 1] & kColMask) - s == 1u;  // multi-column symbols: k_group3 takes them
+            }
+            uint32_t na;
+            bool ok;
+            group_single_lanes(g, b, active, k, s, GL, na, ok);
+            if (active && (lane & (GL - 1u)) == 0u) {
+                if (ok) {
+                    alts_here += na;
+                } else {  // more than 8 residues, or a NUL byte: hashed row path
+                    b.hardlist[atomicAdd(&st->n_hard, 1u)] = k;
+                    b.emitlist[atomicAdd(&st->n_emit2, 1u)] = k;
                 }
             }
-            if (wide && lane == 0) b.widelist[atomicAdd(&st->n_wide, 1u)] = k;
         }
     } else
     for (uint32_t v0 = v_lo + (blockIdx.x * wpb + warp) * 32u; v0 < v_hi; v0 += gridDim.x * wpb * 32u) {
@@ -990,7 +1010,7 @@ __global__ void k_group(MsaGeom g, MsaBufs b, uint32_t narrow_ok) {
             s = b.sym[k] & kColMask;
             en = b.sym[k + 1] & kColMask;
         }
-        uint32_t cls = !have ? 0u : (en - s == 1u ? 1u : 3u);
+        uint32_t cls = !have ? 0u : (en - s == 1u ? 1u : 0u);  // multi-column symbols: k_group3 takes them
         if (cls == 1u) {
             Seen sn;
             if (narrow_scan(b.stash + (size_t)first_slot(b, s) * g.Rp, g.R, sn)) {
@@ -1004,7 +1024,8 @@ __global__ void k_group(MsaGeom g, MsaBufs b, uint32_t narrow_ok) {
                 cls = 3u;
             }
         }
-        list_append(b.widelist, &st->n_wide, cls == 3u, k);
+        list_append(b.hardlist, &st->n_hard, cls == 3u, k);
+        list_append(b.emitlist, &st->n_emit2, cls == 3u, k);
     }
     alts_here = warp_sum(alts_here);
     if (lane == 0 && alts_here) atomicAdd(&st->n_alts, alts_here);
@@ -1276,17 +1297,22 @@ __device__ bool group_tuple(const MsaGeom& g, const MsaBufs& b, const TupleScrat
     return true;
 }
 
-// k_group3: the queued multi-column symbols, warp per symbol; what the tuple formulation takes goes to easylist
-// (k_emit3), the rest to hardlist (k_group2 / k_emit2).
-__global__ void k_group3(MsaGeom g, MsaBufs b, uint32_t per_warp_smem, uint32_t force_hard, uint32_t emit_by_rows) {
+// k_group3: the multi-column symbols (it finds them itself — 32 symbols per warp look, so it runs beside k_group on
+// its own stream), warp per symbol; what the tuple formulation takes goes to easylist (k_emit3) or, with few rows,
+// emitlist; the rest to hardlist (k_group2 / k_emit2). all_symbols (a test switch): single-column symbols too.
+__global__ void k_group3(MsaGeom g, MsaBufs b, uint32_t per_warp_smem, uint32_t force_hard, uint32_t emit_by_rows, uint32_t all_symbols) {
     MsaStatus* st = b.status;
     if (st->abort || st->halo_fail) return;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const TupleScratch t = tuple_scratch(EDSB_DYN_SMEM() + (size_t)warp * per_warp_smem);
-    const uint32_t n_wide = st->n_wide;
+    const uint32_t v_lo = st->v_lo, v_hi = st->v_hi;
     unsigned long long alts_here = 0;
-    for (uint32_t item = blockIdx.x * wpb + warp; item < n_wide; item += gridDim.x * wpb) {
-        const uint32_t kw = b.widelist[item];
+    for (uint32_t v0 = v_lo + (blockIdx.x * wpb + warp) * 32u; v0 < v_hi; v0 += gridDim.x * wpb * 32u) {
+        const uint32_t v = v0 + lane;
+        const uint32_t kmine = v < v_hi ? b.varsym[v] : 0u;
+        const bool mine = v < v_hi && (all_symbols || (b.sym[kmine + 1] & kColMask) - (b.sym[kmine] & kColMask) > 1u);
+      for (uint32_t todo = __ballot_sync(0xffffffffu, mine); todo; todo &= todo - 1u) {
+        const uint32_t kw = __shfl_sync(0xffffffffu, kmine, __ffs((int)todo) - 1);
         uint32_t na = 0;
         const bool ok = !force_hard && group_tuple(g, b, t, kw, na);
         if (lane == 0) {
@@ -1301,6 +1327,7 @@ __global__ void k_group3(MsaGeom g, MsaBufs b, uint32_t per_warp_smem, uint32_t 
             }
         }
         __syncwarp();
+      }
     }
     if (lane == 0 && alts_here) atomicAdd(&st->n_alts, alts_here);
 }
@@ -1753,22 +1780,44 @@ __device__ __forceinline__ void stage_id(uint8_t* stage, uint32_t q, unsigned lo
 #endif
 }
 
-// Single-column symbol from what k_group left behind (row bitsets + residue list): EDS text from the list; the SEDS
-// segment of the WHOLE symbol — every alternative's "{ids}" — is laid out in the warp's stage at the output's own
-// 16-byte phase and leaves with aligned 16-byte stores. A lane owns word w of every alternative, i.e. rows
-// 32 w .. 32 w + 31: every row is in exactly one alternative, so every lane renders exactly 32 ids — a balanced
-// ~400 warp instructions per 1024 rows, one scan per alternative, one copy-out per symbol. (stage: the symbol's
-// SEDS bytes + 32; alignments deeper than 1024 rows take one more round per 1024 rows.)
-__device__ bool emit_single_from_bits(const MsaGeom& g, const MsaBufs& b, uint32_t k, uint32_t s, uint8_t* stage) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t slot0 = first_slot(b, s), Rw = g.Rp >> 5;
+template <typename T>
+__device__ __forceinline__ T group_inclusive_scan(T v, uint32_t GL, uint32_t gl) {
+    for (uint32_t d = 1; d < GL; d <<= 1) {
+        const T o = __shfl_up_sync(0xffffffffu, v, d);
+        if (gl >= d) v += o;
+    }
+    return v;
+}
+
+template <typename T>
+__device__ __forceinline__ T group_sum(T v, uint32_t GL) {
+    for (uint32_t d = GL >> 1; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, (int)d);
+    return v;
+}
+
+// Single-column symbols from what k_group left behind (row bitsets + residue list), a group of GL lanes per symbol:
+// EDS text from the list; the SEDS segment of the WHOLE symbol — every alternative's "{ids}" — is laid out in the
+// group's stage at the output's own 16-byte phase and leaves with aligned 16-byte stores. A lane owns word w of every
+// alternative, i.e. rows 32 w .. 32 w + 31: every row is in exactly one alternative, so every lane renders exactly 32
+// ids — balanced, one scan per alternative, one copy-out per symbol. All collectives are executed by all 32 lanes.
+// (stage: the symbol's SEDS bytes + 32; alignments deeper than 32 GL rows take one more round per 32 GL rows.)
+__device__ void emit_single_lanes(const MsaGeom& g, const MsaBufs& b, bool active, uint32_t k, uint32_t s, uint32_t GL, uint8_t* stage) {
+    const uint32_t lane = threadIdx.x & 31, gl = lane & (GL - 1u), gbase = lane & ~(GL - 1u);
+    const uint32_t Rw = g.Rp >> 5;
+    const uint32_t slot0 = active ? first_slot(b, s) : 0u;
     Seen sn;
-    sn.lo = b.seen[(size_t)slot0 * 3u];
-    sn.hi = b.seen[(size_t)slot0 * 3u + 1u];
-    sn.n = b.seen[(size_t)slot0 * 3u + 2u];
-    if (sn.n > 8u) return false;  // queued as wide by k_group
+    sn.lo = sn.hi = sn.n = 0;
+    if (active) {
+        sn.lo = b.seen[(size_t)slot0 * 3u];
+        sn.hi = b.seen[(size_t)slot0 * 3u + 1u];
+        sn.n = b.seen[(size_t)slot0 * 3u + 2u];
+        if (sn.n > 8u) {  // on the hashed row path
+            active = false;
+            sn.n = 0;
+        }
+    }
     const uint32_t* rowbits = b.rowbits + (size_t)slot0 * 8u * Rw;
-    if (lane == 0) {
+    if (active && gl == 0u) {
         uint8_t* eds = b.eds_out + b.eds_off[k];
         *eds++ = '{';
         for (uint32_t a = 0; a < sn.n; ++a) {
@@ -1778,24 +1827,23 @@ __device__ bool emit_single_from_bits(const MsaGeom& g, const MsaBufs& b, uint32
         }
         *eds = '}';
     }
-    const unsigned long long so = b.seds_off[k];
+    const unsigned long long so = active ? b.seds_off[k] : 0ull;
     const uint32_t phase = (uint32_t)(so & 15u);
     // bytes of every alternative (all words), hence where each starts in the stage
     uint32_t start[8], fill[8];  // fill[a]: bytes of alternative a placed by the rounds so far
     uint32_t run = phase;
 #pragma unroll
     for (uint32_t a = 0; a < 8u; ++a) {
-        start[a] = fill[a] = 0;
-        if (a < sn.n) {
-            uint32_t bytes = 0;
-            for (uint32_t w = lane; w < Rw; w += 32) bytes += word_id_bytes(w, rowbits[a * Rw + w]);
-            bytes = warp_sum(bytes);
-            start[a] = run;
-            run += 1u + bytes;  // '{' + "id," each; the last ',' becomes '}'
-        }
+        uint32_t bytes = 0;
+        if (a < sn.n)
+            for (uint32_t w = gl; w < Rw; w += GL) bytes += word_id_bytes(w, rowbits[a * Rw + w]);
+        bytes = group_sum(bytes, GL);
+        start[a] = run;
+        fill[a] = 0;
+        if (a < sn.n) run += 1u + bytes;  // '{' + "id," each; the last ',' becomes '}'
     }
-    for (uint32_t w0 = 0; w0 < Rw; w0 += 32) {
-        const uint32_t w = w0 + lane;
+    for (uint32_t w0 = 0; w0 < Rw; w0 += GL) {
+        const uint32_t w = w0 + gl;
         // id widths of this lane's word: ids below `pow` are wl wide, the others wl + 1 (a word spans at most one power of ten)
         const uint32_t lo_id = w * 32u + 1u, wl = decimal_width(lo_id);
         uint32_t pow = 10;
@@ -1803,53 +1851,55 @@ __device__ bool emit_single_from_bits(const MsaGeom& g, const MsaBufs& b, uint32
         const uint32_t lowmask = pow - lo_id >= 32u ? 0xffffffffu : low_bits(pow - lo_id);
 #pragma unroll
         for (uint32_t a = 0; a < 8u; ++a) {
-            if (a < sn.n) {
-                const uint32_t v = w < Rw ? rowbits[a * Rw + w] : 0u;
-                const uint32_t mine = word_bytes_fast(v, lowmask, wl);
-                const uint32_t incl = warp_inclusive_scan(mine);
-                uint32_t q = start[a] + 1u + fill[a] + (incl - mine);
-                for (uint32_t rem = v; rem; rem &= rem - 1u) {
-                    const uint32_t id = w * 32u + (uint32_t)__ffs((int)rem);
-                    const unsigned long long e = __ldg(b.id_text + id);
-                    uint32_t dw = (uint32_t)(e >> 56);
-                    if (dw) {
-                        stage_id(stage, q, e, dw);
-                    } else {  // more than six digits
-                        dw = decimal_width(id);
-                        write_decimal(stage + q, id, dw);
-                        stage[q + dw] = (uint8_t)',';
-                    }
-                    q += dw + 1u;
+            const uint32_t v = (a < sn.n && w < Rw) ? rowbits[a * Rw + w] : 0u;
+            const uint32_t mine = word_bytes_fast(v, lowmask, wl);
+            const uint32_t incl = group_inclusive_scan(mine, GL, gl);
+            uint32_t q = start[a] + 1u + fill[a] + (incl - mine);
+            for (uint32_t rem = v; rem; rem &= rem - 1u) {
+                const uint32_t id = w * 32u + (uint32_t)__ffs((int)rem);
+                const unsigned long long e = __ldg(b.id_text + id);
+                uint32_t dw = (uint32_t)(e >> 56);
+                if (dw) {
+                    stage_id(stage, q, e, dw);
+                } else {  // more than six digits
+                    dw = decimal_width(id);
+                    write_decimal(stage + q, id, dw);
+                    stage[q + dw] = (uint8_t)',';
                 }
-                fill[a] += __shfl_sync(0xffffffffu, incl, 31);
+                q += dw + 1u;
             }
+            fill[a] += __shfl_sync(0xffffffffu, incl, (int)(gbase + GL - 1u));
         }
     }
     __syncwarp();
-    if (lane < sn.n) {
+    // braces of alternative a by lane a of the group (groups of fewer than 8 lanes: lanes take several)
+    for (uint32_t a0 = gl; a0 < 8u; a0 += GL) {
         uint32_t st0 = 0, fl = 0;
 #pragma unroll
         for (uint32_t a = 0; a < 8u; ++a)
-            if (a == lane) {
+            if (a == a0) {
                 st0 = start[a];
                 fl = fill[a];
             }
-        stage[st0] = (uint8_t)'{';
-        stage[st0 + fl] = (uint8_t)'}';
-    }
-    __syncwarp();
-    // copy out [phase, run): aligned 16-byte stores, bytes at the two ragged ends
-    uint8_t* const dst = b.seds_out + (so - phase);
-    for (uint32_t j = lane * 16u; j < run; j += 512u) {
-        if (j >= phase && j + 16u <= run) {
-            *reinterpret_cast<uint4*>(dst + j) = *reinterpret_cast<const uint4*>(stage + j);
-        } else {
-            const uint32_t lo_b = j > phase ? j : phase, hi_b = j + 16u < run ? j + 16u : run;
-            for (uint32_t i = lo_b; i < hi_b; ++i) dst[i] = stage[i];
+        if (a0 < sn.n) {
+            stage[st0] = (uint8_t)'{';
+            stage[st0 + fl] = (uint8_t)'}';
         }
     }
     __syncwarp();
-    return true;
+    // copy out [phase, run): aligned 16-byte stores, bytes at the two ragged ends
+    if (active) {
+        uint8_t* const dst = b.seds_out + (so - phase);
+        for (uint32_t j = gl * 16u; j < run; j += GL * 16u) {
+            if (j >= phase && j + 16u <= run) {
+                *reinterpret_cast<uint4*>(dst + j) = *reinterpret_cast<const uint4*>(stage + j);
+            } else {
+                const uint32_t lo_b = j > phase ? j : phase, hi_b = j + 16u < run ? j + 16u : run;
+                for (uint32_t i = lo_b; i < hi_b; ++i) dst[i] = stage[i];
+            }
+        }
+    }
+    __syncwarp();
 }
 
 __device__ bool emit_single_warp(const MsaGeom& g, const MsaBufs& b, uint32_t k, uint32_t s) {
@@ -1941,16 +1991,31 @@ __global__ void k_emit_var(MsaGeom g, MsaBufs b, uint32_t per_warp_smem, uint32_
     if (st->abort || st->halo_fail) return;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     if (nb == 0u) {
-        // too many rows for per-lane segments: warp per symbol, rows across lanes
-        // per_warp_smem != 0: the id-list stage of this warp (idlist.cuh) and the bitsets k_group left in b.rowbits
+        // rows across lanes: a group of GL lanes per symbol (the bitsets k_group left in b.rowbits), 32 / GL symbols per
+        // warp; per_warp_smem = the groups' stages. Without the bitsets / a stage: round 1's row-parallel form.
         uint8_t* stage = (per_warp_smem && b.rowbits) ? EDSB_DYN_SMEM() + (size_t)warp * per_warp_smem : nullptr;
         const uint32_t v_lo = st->v_lo, v_hi = st->v_hi;
+        if (stage) {
+            const uint32_t GL = seg_pitch, NS = 32u / GL, sub = lane / GL;  // (seg_pitch carries the group width here)
+            uint8_t* my_stage = stage + (size_t)sub * (per_warp_smem / NS);
+            for (uint32_t v0 = v_lo + (blockIdx.x * wpb + warp) * NS; v0 < v_hi; v0 += gridDim.x * wpb * NS) {
+                const uint32_t v = v0 + sub;
+                bool active = v < v_hi;
+                uint32_t k = 0, s = 0;
+                if (active) {
+                    k = b.varsym[v];
+                    s = b.sym[k] & kColMask;
+                    active = (b.sym[k + 1] & kColMask) - s == 1u;
+                }
+                emit_single_lanes(g, b, active, k, s, GL, my_stage);
+            }
+            return;
+        }
         for (uint32_t v = v_lo + blockIdx.x * wpb + warp; v < v_hi; v += gridDim.x * wpb) {
             const uint32_t k = b.varsym[v];
             const uint32_t s = b.sym[k] & kColMask, en = b.sym[k + 1] & kColMask;
             if (en - s == 1u) {
-                if (stage) emit_single_from_bits(g, b, k, s, stage);
-                else emit_single_warp(g, b, k, s);
+                emit_single_warp(g, b, k, s);
                 __syncwarp();
             }
         }
@@ -2622,11 +2687,14 @@ void MsaPipeline::run_once(MsaBufs& b) {
         if (best) nb = 32;
     }
     const uint32_t narrow_ok = ctx_->narrow_off == 2 ? 2u : (nb ? 1u : 0u);  // 1 lane per symbol, 0 rows across lanes, 2 all wide
+    // rows across lanes: lanes per symbol = words of a row bitset, rounded up to a power of two (at most a warp)
+    const uint32_t group_lanes = std::min(32u, pow2_ceil(g.Rp >> 5));
     size_t ev_warp_smem = (2048 + (size_t)nb * seg_pitch + 15) & ~(size_t)15;
     size_t ev_smem = narrow_ok ? evw * ev_warp_smem + (((size_t)g.R * 4 + 15) & ~(size_t)15) : 0;
     if (narrow_ok == 0u && b.rowbits) {
         // rows across lanes: one id-list stage per warp; the row bitsets come from k_group through global memory
-        const size_t per_warp = (size_t)((8 + g.sum_id_width + g.R + 32 + 15) & ~15ull);  // a symbol's whole SEDS segment + phase
+        // a symbol's whole SEDS segment + phase, for each of the 32 / GL symbols a warp renders at once
+        const size_t per_warp = (size_t)((8 + g.sum_id_width + g.R + 32 + 15) & ~15ull) * (32u / group_lanes);
         evw = kSymWarps;
         while (evw > 1 && evw * per_warp > smem_budget / 2) evw >>= 1;
         ev_warp_smem = evw * per_warp <= smem_budget ? per_warp : 0;
@@ -2708,14 +2776,18 @@ void MsaPipeline::run_once(MsaBufs& b) {
         d_ws_.reserve(need);
         b.group_ws = d_ws_.as<uint8_t>();
     }
-    after(s, s1, ctx_->ev[1]);  // join: stash ready
+    // the stash is ready on s1 (k_restash / k_stash ran there): the multi-column symbols start right behind it on s1,
+    // the single-column ones on the main stream once it has seen the stash; they join before the hashed row path
+    after(s, s1, ctx_->ev[1]);   // main stream: the stash is ready
+    after(s1, s, ctx_->ev[7]);   // side stream: the symbol list and the owned range are ready (k_finalize)
+    ctx_->clock.begin("k_group3", s1);
+    EDSB_LAUNCH(k_group3, sms * (uint32_t)g3_occ, g3w * 32u, g3_smem, s1, g, b, (uint32_t)g3_warp_smem,
+                (ctx_->narrow_off == 2 || ctx_->tuple_off) ? 1u : 0u, g.R <= 160u ? 1u : 0u, ctx_->narrow_off == 2 ? 1u : 0u);
+    ctx_->clock.end();
     ctx_->clock.begin("k_group");
-    EDSB_LAUNCH(k_group, sms * (uint32_t)std::max(1, g1_occ), kPartThreads, 0, s, g, b, narrow_ok);
+    EDSB_LAUNCH(k_group, sms * (uint32_t)std::max(1, g1_occ), kPartThreads, 0, s, g, b, narrow_ok, group_lanes);
     ctx_->clock.end();
-    ctx_->clock.begin("k_group3");
-    EDSB_LAUNCH(k_group3, sms * (uint32_t)g3_occ, g3w * 32u, g3_smem, s, g, b, (uint32_t)g3_warp_smem,
-                (ctx_->narrow_off == 2 || ctx_->tuple_off) ? 1u : 0u, g.R <= 160u ? 1u : 0u);
-    ctx_->clock.end();
+    after(s, s1, ctx_->ev[6]);   // join: k_group3 done
     ctx_->clock.begin("k_group2");
     EDSB_LAUNCH(k_group2, g2_blocks, gw * 32u, group_smem, s, g, b, Rq, T, group_global ? 1u : 0u, group_stage,
                 (uint32_t)group_warp_smem);
@@ -2736,7 +2808,8 @@ void MsaPipeline::run_once(MsaBufs& b) {
     ctx_->clock.end();
     if (narrow_ok != 2u) {
         ctx_->clock.begin("k_emit_var");
-        EDSB_LAUNCH(k_emit_var, sms * (uint32_t)std::max(1, ev_occ), evw * 32u, ev_smem, s, g, b, (uint32_t)ev_warp_smem, nb, seg_pitch);
+        EDSB_LAUNCH(k_emit_var, sms * (uint32_t)std::max(1, ev_occ), evw * 32u, ev_smem, s, g, b, (uint32_t)ev_warp_smem, nb,
+                    nb ? seg_pitch : group_lanes);
         ctx_->clock.end();
     }
     ctx_->clock.begin("k_emit3", s2);
@@ -2810,6 +2883,7 @@ void MsaPipeline::transform(const eds_msa_view& view, uint32_t l, int leds, eds_
         stats->tail_open_common = st.tail_open;
         stats->gpu_launches = ctx_->clock.launches;
         stats->retries = retries;
+        stats->n_hashed_symbols = st.n_hard;
     }
 }
 

@@ -114,7 +114,7 @@ typedef struct eds_msa_stats {
     uint32_t tail_open_common; /* 1: the last owned symbol is conserved and continues in the next shard */
     uint32_t gpu_launches;    /* kernels launched by this call (retries included)                 */
     uint32_t retries;         /* pipeline re-runs after a scratch/output buffer had to grow       */
-    uint32_t reserved;
+    uint32_t n_hashed_symbols; /* multi-column symbols that took the hashed row path (outside the tuple form's envelope) */
 } eds_msa_stats;
 
 /* Whole pipeline on one device, input already in device memory.

@@ -43,8 +43,7 @@ def test_group_emulated():
     import emu_lib
 
     lib = emu_lib.lib()
-    check_group(lib, 1, n_cases=1, max_cols=120)
-    check_group(lib, 3, n_cases=2, max_cols=120)
+    check_group(lib, 3, n_cases=1, max_cols=100)
 
 
 def test_comm_single_rank_emulated():
@@ -132,7 +131,7 @@ def check_group_leds(lib, n, sizes, ls=(2, 3)):
 def test_group_leds_emulated():
     import emu_lib
 
-    assert check_group_leds(emu_lib.lib(), 3, sizes=(2500,), ls=(3,)) >= 1
+    assert check_group_leds(emu_lib.lib(), 3, sizes=(1500,), ls=(3,)) >= 1
 
 
 @pytest.mark.gpu
