@@ -81,7 +81,11 @@ struct eds_ctx {
     uint32_t scan_blocks_per_sm = 0;  // 0 = default
     uint32_t scan_row_slices = 0;     // tests (EDSB_DEBUG_ROW_SLICES): force k_scan's row split; 0 = automatic
     int tuple_off = 0;   // tests (EDSB_DEBUG_TUPLE_OFF): every multi-column symbol on the hashed row path
-    int narrow_off = 0;  // tests (EDSB_DEBUG_NARROW_OFF): 1 = no lane-per-symbol path, 2 = every symbol on the hashed warp path
+    // single-column symbols (EDSB_DEBUG_NARROW_OFF): 0 (default) = lane per symbol up to 160 rows, rows across lanes (a lane
+    // group per symbol) beyond; 1 = rows across lanes at every row count (config 2: k_emit_var 0.116 -> 0.068 ms but
+    // k_group 0.026 -> 0.044 and the three emit kernels crowd each other: step 0.545 -> 0.585 ms, profiles/r02_b);
+    // 2 = every symbol on the hashed warp path (tests)
+    int narrow_off = 0;
     uint64_t hash_mask = ~0ull;       // tests narrow it (EDSB_HASH_MASK) to exercise the exact-compare fallback
     edsb::KernelClock clock;
     edsb::MsaPipeline* msa = nullptr;

@@ -165,6 +165,46 @@ struct EventFn {
     }
 };
 
+// Depth and events in ONE scan (two packed sums): a = strings | symbols << 32, b = opens | closes << 32. The depth
+// before a character is opens - closes of its prefix; nothing is written per byte.
+struct EdsFn {
+    const uint8_t* t;
+    uint32_t* str_start;
+    uint32_t* str_end;
+    uint32_t* sym_first;
+    LedsStatus* st;
+    __device__ U64x2 value(unsigned long long i) const {
+        const uint8_t c = t[i];
+        const bool open = c == (uint8_t)'{', close = c == (uint8_t)'}';
+        // a bare run starts right after a '}' or at the start of the text (depth is 0 there in any well-formed text;
+        // a malformed one is reported by the depth check below before the events are used)
+        const bool e0 = !open && !close && (i == 0 || t[i - 1] == (uint8_t)'}');
+        const bool e1 = open || c == (uint8_t)',';
+        return U64x2{(unsigned long long)(e0 + e1) | ((open || e0) ? 1ull << 32 : 0ull),
+                     (open ? 1ull : 0ull) | (close ? 1ull << 32 : 0ull)};
+    }
+    __device__ void apply(unsigned long long i, U64x2 prefix, U64x2) const {
+        const uint8_t c = t[i];
+        const long long d = (long long)(prefix.b & 0xffffffffull) - (long long)(prefix.b >> 32);
+        if ((c == (uint8_t)'{' && d != 0) || (c == (uint8_t)'}' && d != 1) || d < 0 || d > 1) atomicOr(&st->err, (uint32_t)kErrEdsSyntax);
+        const bool open = c == (uint8_t)'{', close = c == (uint8_t)'}';
+        const bool e0 = !open && !close && (i == 0 || t[i - 1] == (uint8_t)'}');
+        const bool e1 = open || c == (uint8_t)',';
+        uint32_t j = (uint32_t)prefix.a;
+        const uint32_t si = (uint32_t)(prefix.a >> 32);
+        if (open || e0) sym_first[si] = j;
+        if (e0) {
+            str_start[j] = (uint32_t)i;
+            if (j > 0) str_end[j - 1] = (uint32_t)i - 1u;  // the previous string closed with the '}' before us
+            ++j;
+        }
+        if (e1) {
+            str_start[j] = (uint32_t)i + 1u;
+            if (j > 0) str_end[j - 1] = (c == (uint8_t)',') ? (uint32_t)i : (uint32_t)i - ((i > 0 && t[i - 1] == (uint8_t)'}') ? 1u : 0u);
+        }
+    }
+};
+
 __global__ void k_close_strings(const uint8_t* t, uint32_t n, uint32_t* str_end, uint32_t n_str, uint32_t* sym_first, uint32_t n_sym) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         if (n_str) str_end[n_str - 1] = n - ((n > 0 && t[n - 1] == (uint8_t)'}') ? 1u : 0u);
@@ -847,7 +887,7 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
 
     // grow-only device buffers owned by the pipeline: a second call of similar size allocates nothing
     Bufs& B_ = *bufs_;
-    DevBuf &d_raw = B_.d[0], &d_text = B_.d[1], &d_depth = B_.d[2], &d_part = B_.d[3], &d_status = B_.d[4], &d_sraw = B_.d[5],
+    DevBuf &d_raw = B_.d[0], &d_text = B_.d[1], &d_part = B_.d[3], &d_status = B_.d[4], &d_sraw = B_.d[5],
            &d_stext = B_.d[6], &d_str_start = B_.d[7], &d_str_end = B_.d[8], &d_sym_first = B_.d[9], &d_present = B_.d[12], &d_rank = B_.d[13], &d_idof = B_.d[14], &d_rawbits = B_.d[15],
            &d_cand = B_.d[16], &d_sel = B_.d[17], &d_pairs_before = B_.d[18], &d_pair_list = B_.d[19], &d_kept = B_.d[20],
            &d_off = B_.d[21], &d_falt_off = B_.d[22], &d_falt_pool = B_.d[23], &d_falt_flags = B_.d[24], &d_eds_off = B_.d[25],
@@ -856,7 +896,7 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
     DevBuf* d_tab = &B_.d[32];  // 4 entries
     Keep<uint32_t>&p_left = B_.k[0], &p_right = B_.k[1], &p_len = B_.k[2], &p_bits = B_.k[3];
 
-    d_part.reserve((size_t)(P + 1) * 8);
+    d_part.reserve((size_t)(P + 1) * 16);  // (the fused EDS scan carries two sums per partition)
     unsigned long long* part = d_part.as<unsigned long long>();
     d_status.reserve(sizeof(LedsStatus));
     LedsStatus* st = d_status.as<LedsStatus>();
@@ -926,20 +966,22 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
 
     uint32_t n_str = 0, n_sym = 0;
     if (n) {
-        d_depth.reserve(n);
-        LEDS_SCAN("eds_depth", OpSum64, n, (DepthFn{text, d_depth.as<uint8_t>(), st}));
-        const unsigned long long oc = total_of();
-        status_now();
-        if ((hst.err & kErrEdsSyntax) || (uint32_t)oc != (uint32_t)(oc >> 32))
-            throw std::runtime_error(explain_eds_error(strip_host(host_view(eds_in, eds_bytes), eds_bytes)));
+        // depth (validation) and events (strings, symbols) in one scan over the text: two packed sums
         d_str_start.reserve((size_t)(n + 2) * 4);
         d_str_end.reserve((size_t)(n + 2) * 4);
         d_sym_first.reserve((size_t)(n + 2) * 4);
-        const EventFn ev{text, d_depth.as<uint8_t>(), d_str_start.as<uint32_t>(), d_str_end.as<uint32_t>(), d_sym_first.as<uint32_t>()};
-        LEDS_SCAN("eds_events", OpSum64, n, ev);
-        const unsigned long long tot = total_of();
-        n_str = (uint32_t)tot;
-        n_sym = (uint32_t)(tot >> 32);
+        U64x2* part2 = reinterpret_cast<U64x2*>(part);
+        clk.begin("eds_scan");
+        device_scan<OpSum64x2>(s, P, n, EdsFn{text, d_str_start.as<uint32_t>(), d_str_end.as<uint32_t>(), d_sym_first.as<uint32_t>(), st}, part2);
+        clk.end();
+        ++clk.launches;
+        U64x2 tot2{0, 0};
+        EDSB_CUDA(cudaMemcpyAsync(&tot2, part2 + P, sizeof(tot2), cudaMemcpyDeviceToHost, s));
+        status_now();
+        if ((hst.err & kErrEdsSyntax) || (uint32_t)tot2.b != (uint32_t)(tot2.b >> 32))
+            throw std::runtime_error(explain_eds_error(strip_host(host_view(eds_in, eds_bytes), eds_bytes)));
+        n_str = (uint32_t)tot2.a;
+        n_sym = (uint32_t)(tot2.a >> 32);
         LEDS_LAUNCH("k_close_strings", k_close_strings, 1, 32, text, n, d_str_end.as<uint32_t>(), n_str, d_sym_first.as<uint32_t>(), n_sym);
     }
 

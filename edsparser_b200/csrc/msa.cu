@@ -870,8 +870,8 @@ __device__ __forceinline__ uint32_t eq_mask32(const uint32_t (&v)[8], uint32_t c
 // word), the group merges its lanes' lists in lane order (= row order) into the symbol's residue list, and every lane
 // stores its words under the merged numbering (coalesced). Every collective is executed by all 32 lanes (groups never
 // diverge around one). ok = false: more than 8 residues or a NUL byte -> the symbol goes to the hashed row path.
-__device__ void group_single_lanes(const MsaGeom& g, const MsaBufs& b, bool active, uint32_t k, uint32_t s, uint32_t GL,
-                                   uint32_t& nalts, bool& ok_out) {
+template <uint32_t GL>
+__device__ void group_single_lanes(const MsaGeom& g, const MsaBufs& b, bool active, uint32_t k, uint32_t s, uint32_t& nalts, bool& ok_out) {
     const uint32_t lane = threadIdx.x & 31, gl = lane & (GL - 1u), gbase = lane & ~(GL - 1u);
     const uint32_t gmask = GL >= 32u ? 0xffffffffu : (((1u << GL) - 1u) << gbase);
     const uint32_t Rw = g.Rp >> 5;
@@ -988,9 +988,16 @@ __global__ void k_group(MsaGeom g, MsaBufs b, uint32_t narrow_ok, uint32_t group
                 s = b.sym[k] & kColMask;
                 active = (b.sym[k + 1] & kColMask) - s == 1u;  // multi-column symbols: k_group3 takes them
             }
-            uint32_t na;
-            bool ok;
-            group_single_lanes(g, b, active, k, s, GL, na, ok);
+            uint32_t na = 0;
+            bool ok = false;
+            switch (GL) {  // (warp-uniform)
+                case 1: group_single_lanes<1>(g, b, active, k, s, na, ok); break;
+                case 2: group_single_lanes<2>(g, b, active, k, s, na, ok); break;
+                case 4: group_single_lanes<4>(g, b, active, k, s, na, ok); break;
+                case 8: group_single_lanes<8>(g, b, active, k, s, na, ok); break;
+                case 16: group_single_lanes<16>(g, b, active, k, s, na, ok); break;
+                default: group_single_lanes<32>(g, b, active, k, s, na, ok); break;
+            }
             if (active && (lane & (GL - 1u)) == 0u) {
                 if (ok) {
                     alts_here += na;
@@ -1297,22 +1304,31 @@ __device__ bool group_tuple(const MsaGeom& g, const MsaBufs& b, const TupleScrat
     return true;
 }
 
-// k_group3: the multi-column symbols (it finds them itself — 32 symbols per warp look, so it runs beside k_group on
-// its own stream), warp per symbol; what the tuple formulation takes goes to easylist (k_emit3) or, with few rows,
-// emitlist; the rest to hardlist (k_group2 / k_emit2). all_symbols (a test switch): single-column symbols too.
-__global__ void k_group3(MsaGeom g, MsaBufs b, uint32_t per_warp_smem, uint32_t force_hard, uint32_t emit_by_rows, uint32_t all_symbols) {
+// k_widelist: the owned multi-column symbols (all_symbols, a test switch: every owned variable symbol) -> widelist.
+__global__ void k_widelist(MsaGeom g, MsaBufs b, uint32_t all_symbols) {
+    MsaStatus* st = b.status;
+    if (st->abort || st->halo_fail) return;
+    const uint32_t v_lo = st->v_lo, v_hi = st->v_hi;
+    for (uint32_t v0 = v_lo + ((blockIdx.x * blockDim.x + threadIdx.x) & ~31u); v0 < v_hi; v0 += gridDim.x * blockDim.x) {
+        const uint32_t v = v0 + (threadIdx.x & 31);
+        const uint32_t k = v < v_hi ? b.varsym[v] : 0u;
+        const bool wide = v < v_hi && (all_symbols || (b.sym[k + 1] & kColMask) - (b.sym[k] & kColMask) > 1u);
+        list_append(b.widelist, &st->n_wide, wide, k);
+    }
+}
+
+// k_group3: the multi-column symbols of widelist, warp per symbol, on its own stream beside k_group; what the tuple
+// formulation takes goes to easylist (k_emit3) or, with few rows, emitlist; the rest to hardlist (k_group2 / k_emit2).
+__global__ void k_group3(MsaGeom g, MsaBufs b, uint32_t per_warp_smem, uint32_t force_hard, uint32_t emit_by_rows) {
     MsaStatus* st = b.status;
     if (st->abort || st->halo_fail) return;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const TupleScratch t = tuple_scratch(EDSB_DYN_SMEM() + (size_t)warp * per_warp_smem);
-    const uint32_t v_lo = st->v_lo, v_hi = st->v_hi;
+    const uint32_t n_wide = st->n_wide;
     unsigned long long alts_here = 0;
-    for (uint32_t v0 = v_lo + (blockIdx.x * wpb + warp) * 32u; v0 < v_hi; v0 += gridDim.x * wpb * 32u) {
-        const uint32_t v = v0 + lane;
-        const uint32_t kmine = v < v_hi ? b.varsym[v] : 0u;
-        const bool mine = v < v_hi && (all_symbols || (b.sym[kmine + 1] & kColMask) - (b.sym[kmine] & kColMask) > 1u);
-      for (uint32_t todo = __ballot_sync(0xffffffffu, mine); todo; todo &= todo - 1u) {
-        const uint32_t kw = __shfl_sync(0xffffffffu, kmine, __ffs((int)todo) - 1);
+    {
+      for (uint32_t item = blockIdx.x * wpb + warp; item < n_wide; item += gridDim.x * wpb) {
+        const uint32_t kw = b.widelist[item];
         uint32_t na = 0;
         const bool ok = !force_hard && group_tuple(g, b, t, kw, na);
         if (lane == 0) {
@@ -1780,8 +1796,9 @@ __device__ __forceinline__ void stage_id(uint8_t* stage, uint32_t q, unsigned lo
 #endif
 }
 
-template <typename T>
-__device__ __forceinline__ T group_inclusive_scan(T v, uint32_t GL, uint32_t gl) {
+template <uint32_t GL, typename T>
+__device__ __forceinline__ T group_inclusive_scan(T v, uint32_t gl) {
+#pragma unroll
     for (uint32_t d = 1; d < GL; d <<= 1) {
         const T o = __shfl_up_sync(0xffffffffu, v, d);
         if (gl >= d) v += o;
@@ -1789,8 +1806,9 @@ __device__ __forceinline__ T group_inclusive_scan(T v, uint32_t GL, uint32_t gl)
     return v;
 }
 
-template <typename T>
-__device__ __forceinline__ T group_sum(T v, uint32_t GL) {
+template <uint32_t GL, typename T>
+__device__ __forceinline__ T group_sum(T v) {
+#pragma unroll
     for (uint32_t d = GL >> 1; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, (int)d);
     return v;
 }
@@ -1801,7 +1819,8 @@ __device__ __forceinline__ T group_sum(T v, uint32_t GL) {
 // alternative, i.e. rows 32 w .. 32 w + 31: every row is in exactly one alternative, so every lane renders exactly 32
 // ids — balanced, one scan per alternative, one copy-out per symbol. All collectives are executed by all 32 lanes.
 // (stage: the symbol's SEDS bytes + 32; alignments deeper than 32 GL rows take one more round per 32 GL rows.)
-__device__ void emit_single_lanes(const MsaGeom& g, const MsaBufs& b, bool active, uint32_t k, uint32_t s, uint32_t GL, uint8_t* stage) {
+template <uint32_t GL>
+__device__ void emit_single_lanes(const MsaGeom& g, const MsaBufs& b, bool active, uint32_t k, uint32_t s, uint8_t* stage) {
     const uint32_t lane = threadIdx.x & 31, gl = lane & (GL - 1u), gbase = lane & ~(GL - 1u);
     const uint32_t Rw = g.Rp >> 5;
     const uint32_t slot0 = active ? first_slot(b, s) : 0u;
@@ -1829,17 +1848,20 @@ __device__ void emit_single_lanes(const MsaGeom& g, const MsaBufs& b, bool activ
     }
     const unsigned long long so = active ? b.seds_off[k] : 0ull;
     const uint32_t phase = (uint32_t)(so & 15u);
+    uint32_t amax = sn.n;  // most alternatives of any symbol of this warp (warp-uniform loop bound)
+    for (int d = 16; d > 0; d >>= 1) amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, d));
     // bytes of every alternative (all words), hence where each starts in the stage
     uint32_t start[8], fill[8];  // fill[a]: bytes of alternative a placed by the rounds so far
     uint32_t run = phase;
 #pragma unroll
     for (uint32_t a = 0; a < 8u; ++a) {
+        start[a] = run;
+        fill[a] = 0;
+        if (a >= amax) continue;
         uint32_t bytes = 0;
         if (a < sn.n)
             for (uint32_t w = gl; w < Rw; w += GL) bytes += word_id_bytes(w, rowbits[a * Rw + w]);
-        bytes = group_sum(bytes, GL);
-        start[a] = run;
-        fill[a] = 0;
+        bytes = group_sum<GL>(bytes);
         if (a < sn.n) run += 1u + bytes;  // '{' + "id," each; the last ',' becomes '}'
     }
     for (uint32_t w0 = 0; w0 < Rw; w0 += GL) {
@@ -1851,9 +1873,10 @@ __device__ void emit_single_lanes(const MsaGeom& g, const MsaBufs& b, bool activ
         const uint32_t lowmask = pow - lo_id >= 32u ? 0xffffffffu : low_bits(pow - lo_id);
 #pragma unroll
         for (uint32_t a = 0; a < 8u; ++a) {
+            if (a >= amax) continue;
             const uint32_t v = (a < sn.n && w < Rw) ? rowbits[a * Rw + w] : 0u;
             const uint32_t mine = word_bytes_fast(v, lowmask, wl);
-            const uint32_t incl = group_inclusive_scan(mine, GL, gl);
+            const uint32_t incl = group_inclusive_scan<GL>(mine, gl);
             uint32_t q = start[a] + 1u + fill[a] + (incl - mine);
             for (uint32_t rem = v; rem; rem &= rem - 1u) {
                 const uint32_t id = w * 32u + (uint32_t)__ffs((int)rem);
@@ -2007,7 +2030,14 @@ __global__ void k_emit_var(MsaGeom g, MsaBufs b, uint32_t per_warp_smem, uint32_
                     s = b.sym[k] & kColMask;
                     active = (b.sym[k + 1] & kColMask) - s == 1u;
                 }
-                emit_single_lanes(g, b, active, k, s, GL, my_stage);
+                switch (GL) {  // (warp-uniform)
+                    case 1: emit_single_lanes<1>(g, b, active, k, s, my_stage); break;
+                    case 2: emit_single_lanes<2>(g, b, active, k, s, my_stage); break;
+                    case 4: emit_single_lanes<4>(g, b, active, k, s, my_stage); break;
+                    case 8: emit_single_lanes<8>(g, b, active, k, s, my_stage); break;
+                    case 16: emit_single_lanes<16>(g, b, active, k, s, my_stage); break;
+                    default: emit_single_lanes<32>(g, b, active, k, s, my_stage); break;
+                }
             }
             return;
         }
@@ -2780,9 +2810,12 @@ void MsaPipeline::run_once(MsaBufs& b) {
     // the single-column ones on the main stream once it has seen the stash; they join before the hashed row path
     after(s, s1, ctx_->ev[1]);   // main stream: the stash is ready
     after(s1, s, ctx_->ev[7]);   // side stream: the symbol list and the owned range are ready (k_finalize)
+    ctx_->clock.begin("k_widelist", s1);
+    EDSB_LAUNCH(k_widelist, sms * 2u, kPartThreads, 0, s1, g, b, ctx_->narrow_off == 2 ? 1u : 0u);
+    ctx_->clock.end();
     ctx_->clock.begin("k_group3", s1);
     EDSB_LAUNCH(k_group3, sms * (uint32_t)g3_occ, g3w * 32u, g3_smem, s1, g, b, (uint32_t)g3_warp_smem,
-                (ctx_->narrow_off == 2 || ctx_->tuple_off) ? 1u : 0u, g.R <= 160u ? 1u : 0u, ctx_->narrow_off == 2 ? 1u : 0u);
+                (ctx_->narrow_off == 2 || ctx_->tuple_off) ? 1u : 0u, g.R <= 160u ? 1u : 0u);
     ctx_->clock.end();
     ctx_->clock.begin("k_group");
     EDSB_LAUNCH(k_group, sms * (uint32_t)std::max(1, g1_occ), kPartThreads, 0, s, g, b, narrow_ok, group_lanes);
@@ -2812,9 +2845,11 @@ void MsaPipeline::run_once(MsaBufs& b) {
                     nb ? seg_pitch : group_lanes);
         ctx_->clock.end();
     }
-    ctx_->clock.begin("k_emit3", s2);
-    EDSB_LAUNCH(k_emit3, sms * (uint32_t)e3_occ, e3w * 32u, e3_smem, s2, g, b, (uint32_t)e3_warp_smem);
-    ctx_->clock.end();
+    if (g.R > 160u) {  // with few rows k_group3 hands its symbols to k_emit2 (easylist stays empty)
+        ctx_->clock.begin("k_emit3", s2);
+        EDSB_LAUNCH(k_emit3, sms * (uint32_t)e3_occ, e3w * 32u, e3_smem, s2, g, b, (uint32_t)e3_warp_smem);
+        ctx_->clock.end();
+    }
     ctx_->clock.begin("k_emit2", s2);
     EDSB_LAUNCH(k_emit2, e2_blocks, ew * 32u, emit_smem, s2, g, b, Rq, emit_global ? 1u : 0u, emit_stage,
                 (uint32_t)emit_warp_smem);

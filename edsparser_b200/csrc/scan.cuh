@@ -15,6 +15,15 @@ struct OpSum64 {
     static __device__ __forceinline__ V identity() { return 0ull; }
     static __device__ __forceinline__ V combine(V a, V b) { return a + b; }
 };
+// two packed sums scanned together (eds2leds: strings | symbols << 32 and opens | closes << 32 in ONE pass over the text)
+struct U64x2 {
+    unsigned long long a, b;
+};
+struct OpSum64x2 {
+    typedef U64x2 V;
+    static __device__ __forceinline__ V identity() { return U64x2{0ull, 0ull}; }
+    static __device__ __forceinline__ V combine(V x, V y) { return U64x2{x.a + y.a, x.b + y.b}; }
+};
 struct OpMax64 {
     typedef unsigned long long V;
     static __device__ __forceinline__ V identity() { return 0ull; }
@@ -29,12 +38,17 @@ constexpr int kScanBlock = 256;
 constexpr int kScanItems = 8;
 #endif
 
+__device__ __forceinline__ unsigned long long shfl_up_v(unsigned long long v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ U64x2 shfl_up_v(U64x2 v, int d) {
+    return U64x2{__shfl_up_sync(0xffffffffu, v.a, d), __shfl_up_sync(0xffffffffu, v.b, d)};
+}
+
 template <typename Op>
 __device__ __forceinline__ typename Op::V warp_scan_incl(typename Op::V v) {
     const unsigned lane = threadIdx.x & 31;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        typename Op::V o = __shfl_up_sync(0xffffffffu, v, d);
+        typename Op::V o = shfl_up_v(v, d);
         if (lane >= (unsigned)d) v = Op::combine(o, v);
     }
     return v;
@@ -46,7 +60,7 @@ __device__ __forceinline__ typename Op::V block_scan_excl(typename Op::V v, type
     typedef typename Op::V V;
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     const V inc = warp_scan_incl<Op>(v);
-    V excl = __shfl_up_sync(0xffffffffu, inc, 1);
+    V excl = shfl_up_v(inc, 1);
     if (lane == 0) excl = Op::identity();
     __syncthreads();
     if (lane == 31) smem[wid] = inc;
@@ -54,7 +68,7 @@ __device__ __forceinline__ typename Op::V block_scan_excl(typename Op::V v, type
     if (wid == 0) {
         const V w = lane < nw ? smem[lane] : Op::identity();
         const V winc = warp_scan_incl<Op>(w);
-        V wex = __shfl_up_sync(0xffffffffu, winc, 1);
+        V wex = shfl_up_v(winc, 1);
         if (lane == 0) wex = Op::identity();
         smem[lane] = wex;
         if (lane == 31) smem[32] = winc;

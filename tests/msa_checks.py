@@ -176,7 +176,7 @@ def check_wide_alphabet(ctx, seed=21, n_cases=8):
         assert ctx.msa_transform_host(text, l)[:2] == oracle_lib.msa2eds(text, l), (seed, i, l, text)
 
 
-def check_narrow_off(lib, seed=12, n_cases=15):
+def check_narrow_off(lib, seed=12, n_cases=15, wide_cases=3):
     """EDSB_DEBUG_NARROW_OFF=1: single-column symbols take the rows-across-lanes path (what large R uses);
     =2: every variable symbol goes through the hashed warp-per-symbol path."""
     for mode in ("1", "2"):
@@ -187,20 +187,22 @@ def check_narrow_off(lib, seed=12, n_cases=15):
             del os.environ["EDSB_DEBUG_NARROW_OFF"]
         try:
             check_random_against_oracle(ctx, seed, n_cases, max_rows=70, max_cols=100, ls=(0, 2, 10))
-            check_wide_alphabet(ctx, n_cases=3)
+            check_wide_alphabet(ctx, n_cases=wide_cases)
         finally:
             ctx.close()
 
 
-def check_row_slices(lib, seed=14, n_cases=15):
-    """EDSB_DEBUG_ROW_SLICES=n: k_scan splits the rows into n slices that OR their mismatch bits together
-    (what a narrow column shard of a deep alignment uses)."""
-    for slices in ("2", "5"):
+def check_row_slices(lib, seed=14, n_cases=15, settings=("2", "5")):
+    """EDSB_DEBUG_ROW_SLICES=n: k_scan (the two-pass form, EDSB_FUSED=0) splits the rows into n slices that OR their
+    mismatch bits together (what a narrow column shard of an alignment too deep for the fused scan uses)."""
+    for slices in settings:
         os.environ["EDSB_DEBUG_ROW_SLICES"] = slices
+        os.environ["EDSB_FUSED"] = "0"
         try:
             ctx = lib.context()
         finally:
             del os.environ["EDSB_DEBUG_ROW_SLICES"]
+            del os.environ["EDSB_FUSED"]
         try:
             check_random_against_oracle(ctx, seed, n_cases, max_rows=40, max_cols=120, ls=(0, 3, 10))
         finally:
