@@ -31,7 +31,7 @@ EXPORTS = [
     "eds_group_create", "eds_group_destroy", "eds_group_size", "eds_group_ctx", "eds_group_msa_transform_host",
     "eds_group_msa_transform_fd", "eds_nccl_unique_id", "eds_comm_create", "eds_comm_destroy", "eds_comm_post",
     "eds_comm_offsets", "eds_comm_flush", "eds_parse_host", "eds_parsed_free", "eds_merge_adjacent_host",
-    "eds_group_leds_merge_host",
+    "eds_group_leds_merge_host", "eds_leds_merge_device_in", "eds_genrandomeds_device",
 ]
 
 
@@ -133,6 +133,8 @@ class Library:
         L.eds_group_msa_transform_host.argtypes = [vp, vp, u64, u32, i32, u64, P(Buffer), P(Buffer), P(MsaStats)]
         L.eds_group_msa_transform_fd.argtypes = [vp, vp, u64, u32, i32, u64, i32, i32, P(u64), P(MsaStats)]
         L.eds_group_leds_merge_host.argtypes = [vp, vp, u64, vp, u64, u32, i32, P(Buffer), P(Buffer), P(u32), P(u32)]
+        L.eds_leds_merge_device_in.argtypes = [vp, vp, u64, vp, u64, u32, i32, u64, P(Buffer), P(Buffer), P(u32)]
+        L.eds_genrandomeds_device.argtypes = [vp, u64, u32, u32, u64, P(Buffer), P(Buffer)]
         L.eds_nccl_unique_id.argtypes = [vp]
         L.eds_comm_create.argtypes = [vp, vp, i32, i32, P(vp)]
         L.eds_comm_destroy.argtypes = [vp]
@@ -315,6 +317,21 @@ class Context:
         self.lib.L.eds_msa_index_free(ctypes.byref(idx))
         del keep
         return out
+
+    def genrandomeds_device(self, ref_size, variability_ppm=100_000, paths=4, seed=1):
+        """genrandomeds-shaped EDS + SEDS text generated in device memory: (eds Buffer, seds Buffer), owned by the ctx."""
+        e, s = Buffer(), Buffer()
+        self.lib.check(self.lib.L.eds_genrandomeds_device(self.handle, ref_size, variability_ppm, paths, seed, ctypes.byref(e),
+                                                          ctypes.byref(s)))
+        return e, s
+
+    def leds_merge_device_in(self, eds_buf, seds_buf, l, compact=True, max_output_bytes=0):
+        """eds2leds on text already in device memory: (l-EDS bytes, SEDS bytes, rounds)."""
+        o, so, rounds = Buffer(), Buffer(), ctypes.c_uint32()
+        self.lib.check(self.lib.L.eds_leds_merge_device_in(self.handle, eds_buf.data, eds_buf.bytes, seds_buf.data if seds_buf else None,
+                                                           seds_buf.bytes if seds_buf else 0, l, 1 if compact else 0, max_output_bytes,
+                                                           ctypes.byref(o), ctypes.byref(so), ctypes.byref(rounds)))
+        return _host_bytes(self.lib, o), _host_bytes(self.lib, so), rounds.value
 
     def msa_transform_host(self, text, l=0, leds=None):
         """bytes of a .msa file -> (eds bytes, seds bytes, stats dict); l == 0 and leds None -> plain EDS."""

@@ -453,6 +453,37 @@ eds_status eds_leds_merge_host_view(eds_ctx* ctx, const uint8_t* eds_in, uint64_
     return rc;
 }
 
+eds_status eds_leds_merge_device_in(eds_ctx* ctx, const uint8_t* eds_dev, uint64_t eds_bytes, const uint8_t* seds_dev,
+                                    uint64_t seds_bytes, uint32_t l, int compact, uint64_t max_output_bytes,
+                                    eds_buffer* leds_out, eds_buffer* seds_out, uint32_t* rounds_out) {
+    if (leds_out) *leds_out = eds_buffer{nullptr, 0};
+    if (seds_out) *seds_out = eds_buffer{nullptr, 0};
+    eds_status rc = guarded([&] {
+        use_device(ctx);
+        if (!eds_dev || !leds_out || !seds_out) throw std::invalid_argument("eds_leds_merge_device_in: null argument");
+        if ((reinterpret_cast<uintptr_t>(eds_dev) | reinterpret_cast<uintptr_t>(seds_dev)) & 15u)
+            throw std::invalid_argument("eds_leds_merge_device_in: inputs must be 16-byte aligned");
+        ctx->leds->merge_host(eds_dev, eds_bytes, seds_dev, seds_bytes, l, compact != 0, max_output_bytes, leds_out, seds_out,
+                              rounds_out, nullptr, true);
+    });
+    if (rc != EDS_OK) {
+        if (leds_out) eds_buffer_free_host(leds_out);
+        if (seds_out) eds_buffer_free_host(seds_out);
+    }
+    return rc;
+}
+
+eds_status eds_genrandomeds_device(eds_ctx* ctx, uint64_t ref_size, uint32_t variability_ppm, uint32_t paths, uint64_t seed,
+                                   eds_buffer* eds_out, eds_buffer* seds_out) {
+    if (eds_out) *eds_out = eds_buffer{nullptr, 0};
+    if (seds_out) *seds_out = eds_buffer{nullptr, 0};
+    return guarded([&] {
+        use_device(ctx);
+        if (!eds_out || !seds_out) throw std::invalid_argument("eds_genrandomeds_device: null argument");
+        ctx->leds->genrandomeds(ref_size, variability_ppm, paths, seed, eds_out, seds_out);
+    });
+}
+
 eds_status eds_parse_host(eds_ctx* ctx, const uint8_t* eds, uint64_t eds_bytes, const uint8_t* seds, uint64_t seds_bytes,
                           eds_parsed* out) {
     if (out) memset(out, 0, sizeof(*out));

@@ -843,7 +843,7 @@ struct Keep {
 }  // namespace
 
 struct LedsPipeline::Bufs {
-    DevBuf d[36];
+    DevBuf d[40];
     Keep<uint32_t> k[4];
     ~Bufs() {
         for (DevBuf& b : d) b.release();
@@ -1273,6 +1273,149 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
     seds_out->bytes = seds_bytes_out;
 #undef LEDS_SCAN
 #undef LEDS_LAUNCH
+}
+
+// =====================================================================================================================
+// genrandomeds on the device (reference tool src/cpp/tools/genrandomeds.cpp:221-352): an EDS + SEDS
+// pair of the tool's SHAPE generated straight into HBM — reference of `n` random bases, a position is a variant site
+// with probability ppm / 10^6, a site has 2..4 alternatives (the reference base first; the others 70 % SNP, 15 %
+// insertion of the base + 1..10 random bases, 15 % the empty string), P paths, alternative k carried by path k + 1 and
+// every further path by a random alternative, conserved runs carry {0}; no trailing newline. The reference tool draws
+// from libstdc++'s mt19937 stream, which is sequential; here every position is keyed on (seed, position) through
+// splitmix64, so any slice can be produced anywhere (edsparser_b200/synth.py::genrandomeds is the numpy statement of
+// the same function, pinned to this kernel in the tests). One scan: per-position (EDS bytes | SEDS bytes << 32).
+__device__ __forceinline__ unsigned long long gmix64(unsigned long long x) {
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+
+struct GenSite {
+    unsigned long long h;
+    uint32_t base;    // index into ACGT
+    uint32_t n_alts;  // 0: not a site
+};
+
+struct GenFn {
+    unsigned long long n, seed;
+    uint32_t ppm, P;
+    uint8_t* eds;
+    uint8_t* seds;
+    __device__ __forceinline__ GenSite site(unsigned long long i) const {
+        GenSite g;
+        g.h = gmix64(seed ^ gmix64(i));
+        g.base = (uint32_t)(g.h & 3u);
+        const bool is = ((g.h >> 8) % 1000000ull) < ppm;
+        g.n_alts = is ? min(P, 2u + (uint32_t)((g.h >> 40) % 3ull)) : 0u;
+        return g;
+    }
+    // alternative k >= 1 of a site: length, and its characters through out(j, ch)
+    template <typename Out>
+    __device__ __forceinline__ uint32_t alt(const GenSite& g, uint32_t k, Out out) const {
+        const unsigned long long hk = gmix64(g.h ^ gmix64(k));
+        const uint32_t r = (uint32_t)(hk % 100ull);
+        if (r < 70u) {  // SNP: another base
+            out(0u, (uint8_t)"ACGT"[(g.base + 1u + (uint32_t)((hk >> 8) % 3ull)) & 3u]);
+            return 1u;
+        }
+        if (r < 85u) {  // insertion: the base, then 1..10 random bases
+            const uint32_t extra = 1u + (uint32_t)((hk >> 16) % 10ull);
+            out(0u, (uint8_t)"ACGT"[g.base]);
+            for (uint32_t j = 0; j < extra; ++j) out(1u + j, (uint8_t)"ACGT"[gmix64(hk + j) & 3u]);
+            return 1u + extra;
+        }
+        return 0u;  // deletion: the empty string
+    }
+    __device__ __forceinline__ uint32_t alt_of_path(const GenSite& g, uint32_t p) const {  // p = 1..P
+        return p <= g.n_alts ? p - 1u : (uint32_t)(gmix64(g.h ^ gmix64(100ull + p)) % g.n_alts);
+    }
+    __device__ unsigned long long value(unsigned long long i) const {
+        const GenSite g = site(i);
+        if (!g.n_alts) {
+            const bool first = i == 0 || site(i - 1).n_alts != 0, last = i + 1 == n || site(i + 1).n_alts != 0;
+            return (unsigned long long)(1u + first + last) | ((unsigned long long)(first ? 3u : 0u) << 32);
+        }
+        uint32_t e = 2u + 1u + (g.n_alts - 1u);  // braces, the reference base, separators
+        for (uint32_t k = 1; k < g.n_alts; ++k) e += alt(g, k, [](uint32_t, uint8_t) {});
+        uint32_t sb = 2u * g.n_alts;  // braces of every set
+        for (uint32_t p = 1; p <= P; ++p) sb += decimal_width(p) + 1u;  // "id," (the last ',' of a set is its '}')
+        sb -= g.n_alts;
+        return (unsigned long long)e | ((unsigned long long)sb << 32);
+    }
+    __device__ void apply(unsigned long long i, unsigned long long prefix, unsigned long long) const {
+        const GenSite g = site(i);
+        uint8_t* e = eds + (prefix & 0xffffffffull);
+        uint8_t* sd = seds + (prefix >> 32);
+        if (!g.n_alts) {
+            const bool first = i == 0 || site(i - 1).n_alts != 0, last = i + 1 == n || site(i + 1).n_alts != 0;
+            if (first) {
+                *e++ = '{';
+                sd[0] = '{';
+                sd[1] = '0';
+                sd[2] = '}';
+            }
+            *e++ = (uint8_t)"ACGT"[g.base];
+            if (last) *e = '}';
+            return;
+        }
+        *e++ = '{';
+        *e++ = (uint8_t)"ACGT"[g.base];
+        for (uint32_t k = 1; k < g.n_alts; ++k) {
+            *e++ = ',';
+            e += alt(g, k, [e](uint32_t j, uint8_t ch) { e[j] = ch; });
+        }
+        *e = '}';
+        for (uint32_t k = 0; k < g.n_alts; ++k) {
+            *sd++ = '{';
+            for (uint32_t p = 1; p <= P; ++p)
+                if (alt_of_path(g, p) == k) {
+                    const uint32_t w = decimal_width(p);
+                    write_decimal(sd, p, w);
+                    sd[w] = ',';
+                    sd += w + 1u;
+                }
+            sd[-1] = '}';
+        }
+    }
+};
+
+void LedsPipeline::genrandomeds(uint64_t n, uint32_t ppm, uint32_t paths, uint64_t seed, eds_buffer* eds_out, eds_buffer* seds_out) {
+    if (n == 0 || n >= 0xfffffff0ull / 3) throw std::invalid_argument("eds_genrandomeds_device: reference size out of range");
+    if (paths < 2 || paths > 1000000) throw std::invalid_argument("eds_genrandomeds_device: need 2 .. 10^6 paths");
+    if (ppm > 1000000) throw std::invalid_argument("eds_genrandomeds_device: variability above 1");
+    cudaStream_t s = ctx_->stream;
+    const uint32_t sms = (uint32_t)ctx_->sm_count;
+    const unsigned P = std::max(1u, std::min(ctx_->partitions ? ctx_->partitions : sms * 4u, 4096u));
+    Bufs& B_ = *bufs_;
+    DevBuf &d_part = B_.d[3], &d_eds = B_.d[36], &d_seds = B_.d[37];
+    d_part.reserve((size_t)(P + 1) * 16);
+    unsigned long long* part = d_part.as<unsigned long long>();
+    // sizes first (the reduce pass of the scan), then the text
+    GenFn fn{n, seed, ppm, paths, nullptr, nullptr};
+    auto reduce = k_part_reduce<OpSum64, GenFn>;
+    EDSB_LAUNCH(reduce, P, kScanBlock, 0, s, (unsigned long long)n, fn, part);
+    std::vector<unsigned long long> h(P);
+    EDSB_CUDA(cudaMemcpyAsync(h.data(), part, (size_t)P * 8, cudaMemcpyDeviceToHost, s));
+    EDSB_CUDA(cudaStreamSynchronize(s));
+    unsigned long long eb = 0, sb = 0;
+    for (unsigned long long v : h) {
+        eb += v & 0xffffffffull;
+        sb += v >> 32;
+    }
+    if (eb >= 0xfffffff0ull || sb >= 0xfffffff0ull) throw std::invalid_argument("eds_genrandomeds_device: output above 4 GiB");
+    d_eds.reserve(eb + 16);
+    d_seds.reserve(sb + 16);
+    fn.eds = d_eds.as<uint8_t>();
+    fn.seds = d_seds.as<uint8_t>();
+    auto apply = k_part_apply<OpSum64, GenFn>;
+    EDSB_LAUNCH(apply, P, kScanBlock, 0, s, (unsigned long long)n, fn, part);
+    EDSB_CUDA(cudaStreamSynchronize(s));
+    EDSB_CUDA(cudaGetLastError());
+    eds_out->data = d_eds.as<uint8_t>();
+    eds_out->bytes = eb;
+    seds_out->data = d_seds.as<uint8_t>();
+    seds_out->bytes = sb;
 }
 
 }  // namespace edsb

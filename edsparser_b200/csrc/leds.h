@@ -31,6 +31,9 @@ class LedsPipeline {
     // check_only != nullptr: stop after the first round's pair selection; *check_only = 1 iff no pair exists
     // input_on_device: eds_in / seds_in are device pointers (the VCF front end hands its output over in HBM)
 
+    // genrandomeds-shaped EDS + SEDS text generated in device memory (buffers owned by the pipeline until the next call)
+    void genrandomeds(uint64_t n, uint32_t ppm, uint32_t paths, uint64_t seed, eds_buffer* eds_out, eds_buffer* seds_out);
+
    private:
     struct Bufs;
     eds_ctx* ctx_;

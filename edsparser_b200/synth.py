@@ -56,3 +56,51 @@ def fasta_window(n_rows, total_cols, line_width=80, col_begin=0, col_count=None,
         out += seg.tobytes()
         out += b"\n"
     return bytes(out)
+
+
+def genrandomeds(ref_size, variability_ppm=100_000, paths=4, seed=1):
+    """numpy statement of eds_genrandomeds_device (csrc/leds.cu GenFn): the same (seed, position)-keyed generator,
+    position by position. Returns (eds bytes, seds bytes). For sizes a Python loop finishes (tests)."""
+    M = (1 << 64) - 1
+
+    def mix(x):
+        x = (x + 0x9E3779B97F4A7C15) & M
+        x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & M
+        x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & M
+        return x ^ (x >> 31)
+
+    def site(i):
+        h = mix(seed ^ mix(i))
+        base = h & 3
+        is_site = ((h >> 8) % 1000000) < variability_ppm
+        return h, base, (min(paths, 2 + (h >> 40) % 3) if is_site else 0)
+
+    def alt(h, base, k):
+        hk = mix(h ^ mix(k))
+        r = hk % 100
+        if r < 70:
+            return "ACGT"[(base + 1 + (hk >> 8) % 3) & 3]
+        if r < 85:
+            extra = 1 + (hk >> 16) % 10
+            return "ACGT"[base] + "".join("ACGT"[mix((hk + j) & M) & 3] for j in range(extra))
+        return ""
+
+    eds, seds = [], []
+    sites = [site(i) for i in range(ref_size)]
+    for i, (h, base, n_alts) in enumerate(sites):
+        if not n_alts:
+            first = i == 0 or sites[i - 1][2] != 0
+            last = i + 1 == ref_size or sites[i + 1][2] != 0
+            if first:
+                eds.append("{")
+                seds.append("{0}")
+            eds.append("ACGT"[base])
+            if last:
+                eds.append("}")
+            continue
+        alts = ["ACGT"[base]] + [alt(h, base, k) for k in range(1, n_alts)]
+        eds.append("{" + ",".join(alts) + "}")
+        owner = [p - 1 if p <= n_alts else mix(h ^ mix(100 + p)) % n_alts for p in range(1, paths + 1)]
+        for k in range(n_alts):
+            seds.append("{" + ",".join(str(p) for p in range(1, paths + 1) if owner[p - 1] == k) + "}")
+    return "".join(eds).encode(), "".join(seds).encode()

@@ -176,6 +176,21 @@ eds_status eds_leds_merge_host_view(eds_ctx* ctx, const uint8_t* eds_in, uint64_
                                     uint64_t seds_bytes, uint32_t l, int compact, uint64_t max_output_bytes,
                                     eds_buffer* leds_out, eds_buffer* seds_out, uint32_t* rounds_out);
 
+/* The same merge with the inputs ALREADY in device memory (16-byte aligned, e.g. eds_genrandomeds_device's output):
+ * host text out. */
+eds_status eds_leds_merge_device_in(eds_ctx* ctx, const uint8_t* eds_dev, uint64_t eds_bytes, const uint8_t* seds_dev,
+                                    uint64_t seds_bytes, uint32_t l, int compact, uint64_t max_output_bytes,
+                                    eds_buffer* leds_out, eds_buffer* seds_out, uint32_t* rounds_out);
+
+/* genrandomeds on the device (reference tool src/cpp/tools/genrandomeds.cpp:221-352; BASELINE config 3's generator):
+ * an EDS + SEDS pair of the tool's shape — n random bases, a position is a variant site with probability
+ * variability_ppm / 10^6, 2..4 alternatives per site (reference base first; 70 % SNP, 15 % insertion of 1..10 bases,
+ * 15 % empty), `paths` paths, conserved runs carry {0}, no trailing newline — written straight into device memory
+ * owned by the ctx (valid until the next call). Keyed on (seed, position) with a counter-based generator, not the
+ * tool's sequential mt19937 stream: shape-compatible, not stream-compatible. */
+eds_status eds_genrandomeds_device(eds_ctx* ctx, uint64_t ref_size, uint32_t variability_ppm, uint32_t paths, uint64_t seed,
+                                   eds_buffer* eds_out, eds_buffer* seds_out);
+
 /* is_leds (eds_transforms.cpp:439-468): 1 iff no interior non-degenerate symbol is shorter than l and no
  * two degenerate symbols are adjacent (l = 0: always 1). Parsed and tested on the device. */
 eds_status eds_is_leds_host(eds_ctx* ctx, const uint8_t* eds_in, uint64_t eds_bytes, uint32_t l, int* is_leds_out);

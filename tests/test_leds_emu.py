@@ -36,3 +36,16 @@ def test_long_strings_and_many_paths(ctx):
 
 def test_msa_pipeline(ctx):
     leds_checks.check_msa_pipeline(ctx, n_cases=2)
+
+
+def test_genrandomeds_device_matches_numpy(ctx):
+    """eds_genrandomeds_device (genrandomeds-shaped EDS + SEDS generated on the device) == its numpy statement, and the
+    merge of that device-resident text == the oracle."""
+    import oracle_lib
+    from edsparser_b200 import synth
+
+    for n, ppm, paths, seed in ((400, 100_000, 4, 1), (300, 300_000, 3, 2), (250, 0, 4, 5)):
+        e, s = ctx.genrandomeds_device(n, ppm, paths, seed)
+        got = (ctx.download(e), ctx.download(s))
+        assert got == synth.genrandomeds(n, ppm, paths, seed)
+        assert ctx.leds_merge_device_in(e, s, 3)[:2] == oracle_lib.eds2leds(got[0], got[1], 3)

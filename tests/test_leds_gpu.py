@@ -38,3 +38,20 @@ def test_long_strings_and_many_paths(ctx):
 
 def test_msa_pipeline(ctx):
     leds_checks.check_msa_pipeline(ctx, n_cases=20)
+
+
+def test_genrandomeds_device(ctx):
+    """genrandomeds on the device (SURVEY 8f row 3): bytes == the numpy statement of the same counter-based generator;
+    the device-resident pair goes through eds_leds_merge_device_in == the oracle; config-3 size generates and merges."""
+    import oracle_lib
+    from edsparser_b200 import synth
+
+    for n, ppm, paths, seed in ((20_000, 100_000, 4, 1), (5_000, 400_000, 7, 2), (3_000, 10_000, 2, 3)):
+        e, s = ctx.genrandomeds_device(n, ppm, paths, seed)
+        got = (ctx.download(e), ctx.download(s))
+        assert got == synth.genrandomeds(n, ppm, paths, seed)
+        assert ctx.leds_merge_device_in(e, s, 10)[:2] == oracle_lib.eds2leds(got[0], got[1], 10)
+    e, s = ctx.genrandomeds_device(100_000_000, 100_000, 4, 1)  # BASELINE config 3's size, straight into HBM
+    assert e.bytes > 250_000_000 and s.bytes > 200_000_000
+    out, sout, rounds = ctx.leds_merge_device_in(e, s, 10)
+    assert rounds >= 1 and ctx.is_leds(out, 10)

@@ -28,4 +28,13 @@ for i in range(6):
             continue
         got = ctx.leds_merge_host(eds, seds, l)
         assert got[:2] == exp
+fa = b">chr1\nACGTACGTACGT\n"
+vcf = (b"##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS1\tS2\n"
+       b"chr1\t5\t.\tA\tC\t.\t.\t.\tGT\t0|1\t0|0\nchr1\t5\t.\tA\tG\t.\t.\t.\tGT\t0|0\t0|1\n")
+for l in (0, 3):
+    assert ctx.vcf_transform_host(vcf, fa, l)[:2] == oracle_lib.vcf2eds(vcf, fa, l)[:2]
+v = ctx.msa_synth(1000, 4000, 80, seed=3, variable_ppm=20000)   # clusters of 8 CTAs, tuple grouping, staged emit
+t = ctx.download(E.Buffer(v.text, v.text_bytes))
+e, s, st = ctx.msa_transform_device(v, 10)
+assert (ctx.download(e), ctx.download(s)) == oracle_lib.msa2eds(t, 10)
 print("sanitize run ok")
