@@ -2246,7 +2246,7 @@ MsaPipeline::~MsaPipeline() {
 }
 
 uint32_t MsaPipeline::partitions() const {
-    uint32_t p = ctx_->partitions ? ctx_->partitions : 592u;  // 4 blocks per SM on 148 SMs
+    uint32_t p = ctx_->partitions ? ctx_->partitions : 4u * (uint32_t)ctx_->sm_count;  // 4 blocks per SM: 592 on a B200
     return std::max(1u, std::min(p, 4096u));
 }
 

@@ -1,5 +1,8 @@
 // TEST INFRASTRUCTURE ONLY — see cuda_emu.h. Thread pool that plays the threads of one block.
 #include "cuda_emu.h"
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace emu {
 
@@ -89,10 +92,15 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
     s.dyn_smem = dyn.data();
     Pool& p = pool();
     p.ensure(n);
+    static const bool trace = getenv("EMU_TRACE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
     for (unsigned z = 0; z < grid.z; ++z)
         for (unsigned y = 0; y < grid.y; ++y)
             for (unsigned x = 0; x < grid.x; ++x) p.run_block(body, dim3(x, y, z), n);
     s.dyn_smem = nullptr;
+    if (trace)
+        fprintf(stderr, "emu launch grid %u block %u smem %zu: %.1f ms\n", grid.x * grid.y * grid.z, n, smem,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
 }
 
 }  // namespace emu

@@ -176,7 +176,7 @@ def check_wide_alphabet(ctx, seed=21, n_cases=8):
         assert ctx.msa_transform_host(text, l)[:2] == oracle_lib.msa2eds(text, l), (seed, i, l, text)
 
 
-def check_narrow_off(lib, seed=12, n_cases=15, wide_cases=3):
+def check_narrow_off(lib, seed=12, n_cases=15, wide_cases=3, max_rows=70, ls=(0, 2, 10)):
     """EDSB_DEBUG_NARROW_OFF=1: single-column symbols take the rows-across-lanes path (what large R uses);
     =2: every variable symbol goes through the hashed warp-per-symbol path."""
     for mode in ("1", "2"):
@@ -186,7 +186,7 @@ def check_narrow_off(lib, seed=12, n_cases=15, wide_cases=3):
         finally:
             del os.environ["EDSB_DEBUG_NARROW_OFF"]
         try:
-            check_random_against_oracle(ctx, seed, n_cases, max_rows=70, max_cols=100, ls=(0, 2, 10))
+            check_random_against_oracle(ctx, seed, n_cases, max_rows=max_rows, max_cols=100, ls=ls)
             check_wide_alphabet(ctx, n_cases=wide_cases)
         finally:
             ctx.close()

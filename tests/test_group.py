@@ -43,7 +43,7 @@ def test_group_emulated():
     import emu_lib
 
     lib = emu_lib.lib()
-    check_group(lib, 3, n_cases=1, max_cols=100)
+    check_group(lib, 3, n_cases=4, max_cols=150)
 
 
 def test_comm_single_rank_emulated():

@@ -39,7 +39,7 @@ def test_bad_inputs(ctx):
 
 
 def test_hash_collision_fallback():
-    msa_checks.check_hash_collision_fallback(emu_lib.lib(), n_cases=2)
+    msa_checks.check_hash_collision_fallback(emu_lib.lib(), n_cases=6)
 
 
 def test_wide_alphabet(ctx):
@@ -47,11 +47,11 @@ def test_wide_alphabet(ctx):
 
 
 def test_narrow_path_off():
-    msa_checks.check_narrow_off(emu_lib.lib(), n_cases=1, wide_cases=1)
+    msa_checks.check_narrow_off(emu_lib.lib(), n_cases=6, wide_cases=2)
 
 
 def test_row_sliced_scan():
-    msa_checks.check_row_slices(emu_lib.lib(), n_cases=1, settings=("5",))
+    msa_checks.check_row_slices(emu_lib.lib(), n_cases=6)
 
 
 def test_shards(ctx):
