@@ -31,7 +31,7 @@ EXPORTS = [
     "eds_group_create", "eds_group_destroy", "eds_group_size", "eds_group_ctx", "eds_group_msa_transform_host",
     "eds_group_msa_transform_fd", "eds_nccl_unique_id", "eds_comm_create", "eds_comm_destroy", "eds_comm_post",
     "eds_comm_offsets", "eds_comm_flush", "eds_parse_host", "eds_parsed_free", "eds_merge_adjacent_host",
-    "eds_group_leds_merge_host", "eds_leds_merge_device_in", "eds_genrandomeds_device",
+    "eds_group_leds_merge_host", "eds_group_vcf_transform_host", "eds_leds_merge_device_in", "eds_genrandomeds_device",
 ]
 
 
@@ -133,6 +133,7 @@ class Library:
         L.eds_group_msa_transform_host.argtypes = [vp, vp, u64, u32, i32, u64, P(Buffer), P(Buffer), P(MsaStats)]
         L.eds_group_msa_transform_fd.argtypes = [vp, vp, u64, u32, i32, u64, i32, i32, P(u64), P(MsaStats)]
         L.eds_group_leds_merge_host.argtypes = [vp, vp, u64, vp, u64, u32, i32, P(Buffer), P(Buffer), P(u32), P(u32)]
+        L.eds_group_vcf_transform_host.argtypes = L.eds_vcf_transform_host.argtypes + [P(u32)]
         L.eds_leds_merge_device_in.argtypes = [vp, vp, u64, vp, u64, u32, i32, u64, P(Buffer), P(Buffer), P(u32)]
         L.eds_genrandomeds_device.argtypes = [vp, u64, u32, u32, u64, P(Buffer), P(Buffer)]
         L.eds_nccl_unique_id.argtypes = [vp]
@@ -199,6 +200,32 @@ class Group:
                                                             1 if compact else 0, ctypes.byref(e), ctypes.byref(s), ctypes.byref(rounds),
                                                             ctypes.byref(used)))
         return _host_bytes(self.lib, e), _host_bytes(self.lib, s), rounds.value, used.value
+
+    def vcf_transform_host(self, vcf, fasta, l=0):
+        """vcf2eds over the group's devices: (eds, seds, stats dict, SV line offsets, shards used)."""
+        va, vn, k1 = _as_pointer(vcf)
+        fa, fn, k2 = _as_pointer(fasta)
+        e, s, st = Buffer(), Buffer(), VcfStats()
+        sv, nsv, used = ctypes.POINTER(ctypes.c_uint64)(), ctypes.c_uint64(), ctypes.c_uint32()
+        self.lib.check(self.lib.L.eds_group_vcf_transform_host(self.handle, va, vn, fa, fn, l, ctypes.byref(e), ctypes.byref(s),
+                                                               ctypes.byref(st), ctypes.byref(sv), ctypes.byref(nsv), ctypes.byref(used)))
+        del k1, k2
+        lines = [int(sv[i]) for i in range(nsv.value)]
+        if nsv.value:
+            ctypes.CDLL(None).free(sv)
+        return _host_bytes(self.lib, e), _host_bytes(self.lib, s), st.as_dict(), lines, used.value
+
+    def vcf_transform_host_raw(self, vcf_addr, vcf_n, fa_addr, fa_n, l=0, keep=False):
+        """The bare C call on (address, length) pairs: ((eds bytes, seds bytes), stats, shards used[, eds, seds])."""
+        e, s, st, used = Buffer(), Buffer(), VcfStats(), ctypes.c_uint32()
+        self.lib.check(self.lib.L.eds_group_vcf_transform_host(self.handle, vcf_addr, vcf_n, fa_addr, fa_n, l, ctypes.byref(e),
+                                                               ctypes.byref(s), ctypes.byref(st), None, None, ctypes.byref(used)))
+        sizes = (int(e.bytes), int(s.bytes))
+        if keep:
+            return sizes, st.as_dict(), used.value, _host_bytes(self.lib, e), _host_bytes(self.lib, s)
+        self.lib.L.eds_buffer_free_host(ctypes.byref(e))
+        self.lib.L.eds_buffer_free_host(ctypes.byref(s))
+        return sizes, st.as_dict(), used.value
 
     def msa_transform_files(self, file_bytes, l, eds_path, seds_path, leds=None, halo=0):
         leds = (1 if l > 0 else 0) if leds is None else leds

@@ -30,6 +30,7 @@
 #include "ctx.h"
 #include "leds.h"
 #include "msa.h"
+#include "vcf.h"
 
 namespace edsb {
 void set_last_error(const std::string& msg);  // capi.cu
@@ -322,7 +323,12 @@ eds_status eds_group_create(const int* devices, int n_devices, eds_group** out) 
                 EDSB_CUDA(cudaMallocHost(&g->h_counts[i], (size_t)(2 + 2 * n_devices) * 8));
             }
 #ifndef EDSB_EMU
-            if (n_devices > 1) {
+            // repeated device ids (several contexts sharing a device: tests on a one-GPU box) -> no communicator, the
+            // byte counts are exchanged on the host
+            std::vector<int> uniq(g->devices);
+            std::sort(uniq.begin(), uniq.end());
+            const bool distinct = std::adjacent_find(uniq.begin(), uniq.end()) == uniq.end();
+            if (n_devices > 1 && distinct) {
                 Nccl& n = nccl();
                 if (!n.ok) throw edsb::CudaError(n.why);
                 g->comm.assign(n_devices, nullptr);
@@ -827,4 +833,323 @@ extern "C" eds_status eds_group_leds_merge_host(eds_group* g, const uint8_t* eds
         if (rounds_out) *rounds_out = *std::max_element(rounds.begin(), rounds.end());
         if (shards_used) *shards_used = n;
     });
+}
+
+// =====================================================================================================================
+// vcf2eds over the devices of a group (ranges of record lines). Every device gets a slice of the
+// VCF's lines and the whole FASTA record; the slices meet once in the middle of the transform (VcfShardHook):
+//   * the order of records that share a position comes from the reference's ONE unstable std::sort over all records
+//     (vcf_transforms.cpp:715-718), so that very call is made once over every slice's positions and each slice takes
+//     its part of the permutation;
+//   * no group of overlapping records may span a cut (largest record end of the slices before <= first POS - 1), and
+//     the sorted order must keep every record inside its own slice;
+//   * slice k renders the reference bases from its first group to the next slice's first group.
+// Anything else — a slice without records, an error in a slice (its positions are slice-local), a spanning group —
+// and the whole input runs on the first device, which also produces the reference's error texts. l > 0: the joined
+// text goes through eds_group_leds_merge_host (parse_vcf_to_leds_streaming :750-752 = transform, then LINEAR merge).
+namespace {
+
+struct VcfMeet {
+    std::mutex m;
+    std::condition_variable cv;
+    uint32_t n = 1, arrived = 0;
+    bool done = false, ok = true;
+    std::vector<char> here;
+    std::vector<const std::vector<uint64_t>*> pos;
+    std::vector<uint64_t> max_end, n_bases, lo, hi;
+    std::vector<std::vector<uint32_t>> perm;
+
+    explicit VcfMeet(uint32_t n_) : n(n_), here(n_, 0), pos(n_, nullptr), max_end(n_, 0), n_bases(n_, 0), lo(n_, 0), hi(n_, 0), perm(n_) {}
+
+    void solve() {
+        uint64_t total = 0;
+        for (uint32_t k = 0; k < n; ++k) {
+            if (!pos[k] || pos[k]->empty() || n_bases[k] != n_bases[0]) {
+                ok = false;
+                return;
+            }
+            total += pos[k]->size();
+        }
+        if (total >= 0xfffffff0ull) {
+            ok = false;
+            return;
+        }
+        std::vector<std::pair<uint64_t, uint32_t>> keyed(total);
+        bool unsorted = false;
+        uint64_t at = 0, prev = 0;
+        for (uint32_t k = 0; k < n; ++k)
+            for (uint64_t p : *pos[k]) {
+                if (at && p <= prev) unsorted = true;
+                prev = p;
+                keyed[at] = {p, (uint32_t)at};
+                ++at;
+            }
+        // the same call, comparator and sequence as the single-device transform (vcf.cu) and the reference make
+        if (unsorted)
+            std::sort(keyed.begin(), keyed.end(),
+                      [](const std::pair<uint64_t, uint32_t>& a, const std::pair<uint64_t, uint32_t>& b) { return a.first < b.first; });
+        uint64_t base = 0, end_before = 0;
+        std::vector<uint64_t> first_pos(n, 0);
+        for (uint32_t k = 0; k < n; ++k) {
+            const uint64_t cnt = pos[k]->size();
+            first_pos[k] = keyed[base].first;
+            if (k && (first_pos[k] == 0 || end_before > first_pos[k] - 1)) {
+                ok = false;  // a group of overlapping records spans the cut
+                return;
+            }
+            if (unsorted) {
+                perm[k].resize(cnt);
+                for (uint64_t j = 0; j < cnt; ++j) {
+                    const uint64_t idx = keyed[base + j].second;
+                    if (idx < base || idx >= base + cnt) {
+                        ok = false;  // the sort moves a record into another slice
+                        return;
+                    }
+                    perm[k][j] = (uint32_t)(idx - base);
+                }
+            }
+            end_before = std::max(end_before, max_end[k]);
+            base += cnt;
+        }
+        for (uint32_t k = 0; k < n; ++k) {
+            lo[k] = k ? first_pos[k] - 1 : 0;
+            hi[k] = k + 1 < n ? first_pos[k + 1] - 1 : n_bases[0];
+        }
+    }
+
+    // returns false when the slices cannot be joined (every caller sees the same answer)
+    bool arrive(uint32_t k, const std::vector<uint64_t>* p, uint64_t me, uint64_t nb, bool failed) {
+        std::unique_lock<std::mutex> lk(m);
+        if (here[k]) return ok;
+        here[k] = 1;
+        pos[k] = p;
+        max_end[k] = me;
+        n_bases[k] = nb;
+        if (failed) ok = false;
+        if (++arrived == n) {
+            if (ok) solve();
+            done = true;
+            cv.notify_all();
+        } else {
+            cv.wait(lk, [&] { return done; });
+        }
+        return ok;
+    }
+};
+
+struct VcfCannotShard : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+struct VcfSliceHook : edsb::VcfShardHook {
+    VcfMeet* meet;
+    uint32_t k;
+    VcfSliceHook(VcfMeet* m, uint32_t k_) : meet(m), k(k_) {}
+    void exchange(const std::vector<uint64_t>& pos, uint64_t max_end, uint64_t n_bases, std::vector<uint32_t>* perm, uint64_t* ref_lo,
+                  uint64_t* ref_hi) override {
+        if (!meet->arrive(k, &pos, max_end, n_bases, false)) throw VcfCannotShard("the VCF slices cannot be joined");
+        *perm = std::move(meet->perm[k]);
+        *ref_lo = meet->lo[k];
+        *ref_hi = meet->hi[k];
+    }
+};
+
+// POS and the 0-based end of the record line at `at` (CHROM \t POS \t ID \t REF \t ...); false: not a plain record line
+bool vcf_line_span(const uint8_t* t, uint64_t n, uint64_t at, uint64_t& pos, uint64_t& end) {
+    if (at >= n || t[at] == '#' || t[at] == '\n') return false;
+    uint64_t i = at;
+    auto skip_field = [&]() {
+        while (i < n && t[i] != '\t' && t[i] != '\n') ++i;
+        if (i >= n || t[i] != '\t') return false;
+        ++i;
+        return true;
+    };
+    if (!skip_field()) return false;
+    pos = 0;
+    uint64_t digits = 0;
+    while (i < n && t[i] >= '0' && t[i] <= '9' && digits < 18) {
+        pos = pos * 10 + (t[i] - '0');
+        ++i;
+        ++digits;
+    }
+    if (!digits || pos == 0 || i >= n || t[i] != '\t') return false;
+    ++i;
+    if (!skip_field()) return false;
+    const uint64_t ref0 = i;
+    while (i < n && t[i] != '\t' && t[i] != '\n') ++i;
+    if (i == ref0) return false;
+    end = pos - 1 + (i - ref0);
+    return true;
+}
+
+}  // namespace
+
+extern "C" eds_status eds_group_vcf_transform_host(eds_group* g, const uint8_t* vcf, uint64_t vcf_bytes, const uint8_t* fasta,
+                                                   uint64_t fasta_bytes, uint32_t l, eds_buffer* eds_out, eds_buffer* seds_out,
+                                                   eds_vcf_stats* stats, uint64_t** sv_lines, uint64_t* n_sv_lines,
+                                                   uint32_t* shards_used) {
+    if (eds_out) *eds_out = eds_buffer{nullptr, 0};
+    if (seds_out) *seds_out = eds_buffer{nullptr, 0};
+    if (sv_lines) *sv_lines = nullptr;
+    if (n_sv_lines) *n_sv_lines = 0;
+    if (shards_used) *shards_used = 1;
+    if (!g || g->ctx.empty() || !eds_out || !seds_out || (!vcf && vcf_bytes) || (!fasta && fasta_bytes)) {
+        edsb::set_last_error("eds_group_vcf_transform_host: null argument");
+        return EDS_ERR_INVALID_ARGUMENT;
+    }
+    const uint32_t n = (uint32_t)g->ctx.size();
+    auto single = [&]() { return eds_vcf_transform_host(g->ctx[0], vcf, vcf_bytes, fasta, fasta_bytes, l, eds_out, seds_out, stats, sv_lines, n_sv_lines); };
+    if (n < 2 || vcf_bytes < (uint64_t)n * 64) return single();
+
+    // ---- cuts: the first line start at or after k / n of the bytes where the record does not touch the one before it
+    std::vector<uint64_t> cut(n + 1, 0);
+    cut[n] = vcf_bytes;
+    for (uint32_t k = 1; k < n; ++k) {
+        uint64_t at = (uint64_t)((unsigned __int128)vcf_bytes * k / n);
+        at = std::max(at, cut[k - 1] + 1);
+        bool found = false;
+        for (int tries = 0; tries < 256 && at < vcf_bytes; ++tries) {
+            const void* nl = memchr(vcf + at, '\n', (size_t)(vcf_bytes - at));
+            if (!nl) break;
+            const uint64_t line = (uint64_t)(static_cast<const uint8_t*>(nl) - vcf) + 1;  // a line starts here
+            if (line >= vcf_bytes) break;
+            // the line before it
+            uint64_t before = line - 1;
+            while (before > 0 && vcf[before - 1] != '\n') --before;
+            uint64_t p0, e0, p1, e1;
+            if (vcf_line_span(vcf, vcf_bytes, before, p0, e0) && vcf_line_span(vcf, vcf_bytes, line, p1, e1) && p1 > p0 && e0 <= p1 - 1) {
+                cut[k] = line;
+                found = true;
+                break;
+            }
+            at = line;
+        }
+        if (!found) return single();
+    }
+
+    struct Slice {
+        eds_buffer de{nullptr, 0}, ds{nullptr, 0};
+        eds_vcf_stats st;
+        std::vector<uint64_t> sv;
+        int status = 0;
+    };
+    std::vector<Slice> slice(n);
+    VcfMeet meet(n);
+    Barrier bar;
+    bar.n = n;
+    uint8_t *h_eds = nullptr, *h_seds = nullptr;
+    uint64_t etot = 0, stot = 0;
+    bool all_ok = false;
+    std::vector<std::thread> th;
+    for (uint32_t k = 0; k < n; ++k)
+        th.emplace_back([&, k] {
+            Slice& me = slice[k];
+            memset(&me.st, 0, sizeof(me.st));
+            eds_ctx* c = g->ctx[k];
+            try {
+                EDSB_CUDA(cudaSetDevice(c->device));
+                const uint64_t bytes = cut[k + 1] - cut[k];
+                c->vcf_in[0].reserve(bytes + 16);
+                c->vcf_in[1].reserve(fasta_bytes + 16);
+                EDSB_CUDA(cudaMemcpyAsync(c->vcf_in[0].p, vcf + cut[k], bytes, cudaMemcpyHostToDevice, c->stream));
+                if (fasta_bytes) EDSB_CUDA(cudaMemcpyAsync(c->vcf_in[1].p, fasta, fasta_bytes, cudaMemcpyHostToDevice, c->stream));
+                VcfSliceHook hook(&meet, k);
+                c->vcf->transform_device(c->vcf_in[0].as<uint8_t>(), bytes, c->vcf_in[1].as<uint8_t>(), fasta_bytes, &me.de, &me.ds, &me.st,
+                                         &me.sv, &hook);
+            } catch (const std::exception&) {
+                me.status = 1;
+            }
+            meet.arrive(k, nullptr, 0, 0, true);  // no-op when the slice has been to the meeting point
+            bar.wait();
+            if (k == 0) {
+                all_ok = meet.ok;
+                for (uint32_t i = 0; i < n; ++i) all_ok = all_ok && slice[i].status == 0;
+                if (all_ok) {
+                    for (uint32_t i = 0; i < n; ++i) {
+                        etot += slice[i].de.bytes;
+                        stot += slice[i].ds.bytes;
+                    }
+                    h_eds = static_cast<uint8_t*>(malloc(etot ? etot : 1));
+                    h_seds = static_cast<uint8_t*>(malloc(stot ? stot : 1));
+                    if (!h_eds || !h_seds) all_ok = false;
+                }
+            }
+            bar.wait();
+            if (!all_ok) return;
+            uint64_t eo = 0, so = 0;
+            for (uint32_t i = 0; i < k; ++i) {
+                eo += slice[i].de.bytes;
+                so += slice[i].ds.bytes;
+            }
+            cudaError_t e = cudaSuccess;
+            if (me.de.bytes) e = cudaMemcpyAsync(h_eds + eo, me.de.data, me.de.bytes, cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess && me.ds.bytes) e = cudaMemcpyAsync(h_seds + so, me.ds.data, me.ds.bytes, cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            if (e != cudaSuccess) me.status = 2;
+        });
+    for (auto& t : th) t.join();
+    for (uint32_t i = 0; i < n; ++i) all_ok = all_ok && slice[i].status == 0;
+    if (!all_ok) {
+        free(h_eds);
+        free(h_seds);
+        for (uint32_t i = 0; i < n; ++i) cudaGetLastError();
+        return single();
+    }
+    eds_vcf_stats tot;
+    memset(&tot, 0, sizeof(tot));
+    std::vector<uint64_t> sv_all;
+    for (uint32_t i = 0; i < n; ++i) {
+        const eds_vcf_stats& s = slice[i].st;
+        tot.total_variants += s.total_variants;
+        tot.processed_variants += s.processed_variants;
+        tot.skipped_malformed += s.skipped_malformed;
+        tot.skipped_unsupported_sv += s.skipped_unsupported_sv;
+        tot.variant_groups += s.variant_groups;
+        tot.n_lines += s.n_lines;
+        tot.n_alleles += s.n_alleles;
+        tot.n_haplotype_slots += s.n_haplotype_slots;
+        tot.n_samples_max = std::max(tot.n_samples_max, s.n_samples_max);
+        tot.gpu_launches += s.gpu_launches;
+        tot.retries += s.retries;
+        tot.host_sorted = std::max(tot.host_sorted, s.host_sorted);
+        tot.n_bases = s.n_bases;
+        for (uint64_t at : slice[i].sv) sv_all.push_back(at + cut[i]);
+    }
+    tot.eds_bytes = etot;
+    tot.seds_bytes = stot;
+    if (sv_lines && n_sv_lines && !sv_all.empty()) {
+        *sv_lines = static_cast<uint64_t*>(malloc(sv_all.size() * sizeof(uint64_t)));
+        if (!*sv_lines) {
+            free(h_eds);
+            free(h_seds);
+            edsb::set_last_error("out of host memory");
+            return EDS_ERR_RUNTIME;
+        }
+        memcpy(*sv_lines, sv_all.data(), sv_all.size() * sizeof(uint64_t));
+        *n_sv_lines = sv_all.size();
+    }
+    if (shards_used) *shards_used = n;
+    if (l == 0) {
+        eds_out->data = h_eds;
+        eds_out->bytes = etot;
+        seds_out->data = h_seds;
+        seds_out->bytes = stot;
+        if (stats) *stats = tot;
+        return EDS_OK;
+    }
+    uint32_t rounds = 0, merged_on = 1;
+    const eds_status rc = eds_group_leds_merge_host(g, h_eds, etot, h_seds, stot, l, 1, eds_out, seds_out, &rounds, &merged_on);
+    free(h_eds);
+    free(h_seds);
+    if (rc != EDS_OK) {
+        if (sv_lines && *sv_lines) {
+            free(*sv_lines);
+            *sv_lines = nullptr;
+            *n_sv_lines = 0;
+        }
+        return rc;
+    }
+    tot.leds_rounds = rounds;
+    if (stats) *stats = tot;
+    return EDS_OK;
 }

@@ -50,6 +50,7 @@ struct VcfStatus {
     u64 max_tokens;  // largest number of sample columns seen by k_gt
     uint32_t unsorted, pad;
     u64 first_tokens;
+    u64 max_end;     // largest 0-based end of a record (sharded runs: no group may span a cut)
 };
 
 __device__ __forceinline__ bool is_space(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13); }
@@ -395,9 +396,11 @@ __global__ void k_alleles(const uint8_t* t, const Rec* recs, u64 n_rec, u64* al_
 // position order already strict? records inside the reference?
 __global__ void k_rec_check(const Rec* recs, u64 n_rec, u64* pos_out, VcfStatus* st) {
     const u64 n_bases = st->fa_err ? 0 : st->fa_rec_end - st->fa_seq_start - st->fa_nl;
+    u64 my_end = 0;
     for (u64 k = gtid(); k < n_rec; k += gthreads()) {
         const u64 pos = recs[k].pos;
         pos_out[k] = pos;
+        if (pos) my_end = max(my_end, pos - 1 + (u64)recs[k].ref_len);
         if (k && pos <= recs[k - 1].pos) st->unsorted = 1;
         uint32_t err = 0;
         if (pos == 0) err = kVcfPosZero;
@@ -407,6 +410,9 @@ __global__ void k_rec_check(const Rec* recs, u64 n_rec, u64* pos_out, VcfStatus*
             atomicMin(&st->bad_line, recs[k].line_start);
         }
     }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) my_end = max(my_end, __shfl_xor_sync(0xffffffffu, my_end, d));
+    if ((threadIdx.x & 31) == 0 && my_end) atomicMax(&st->max_end, my_end);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -821,17 +827,18 @@ struct OutFn {
     uint32_t n_groups, common_extra;  // 2 for "{}" around the text, 3 for "{0}"
     uint32_t text;                    // 1: count the text itself
     u64* off;
+    u64 ref_lo;                       // first reference base of this run (0 unless sharded)
     __device__ u64 value(u64 g) const {
-        const u64 clen = g_from[g] - (g ? g_to[g - 1] : 0ull);
+        const u64 clen = g_from[g] - (g ? g_to[g - 1] : ref_lo);
         return (clen ? (text ? clen : 0ull) + common_extra : 0ull) + (g < n_groups ? g_bytes[g] : 0ull);
     }
     __device__ void apply(u64 g, u64 prefix, u64) const { off[g] = prefix; }
 };
 
 // common text: thread per 16 reference positions, group lookup by binary search, then a linear walk
-__global__ void k_emit_ref(Fasta fa, u64 n_bases, const u64* g_from, const u64* g_to, uint32_t n_groups, const u64* eds_off,
-                           uint8_t* out) {
-    for (u64 q0 = gtid() * 16; q0 < n_bases; q0 += gthreads() * 16) {
+__global__ void k_emit_ref(Fasta fa, u64 ref_lo, u64 n_bases, const u64* g_from, const u64* g_to, uint32_t n_groups,
+                           const u64* eds_off, uint8_t* out) {
+    for (u64 q0 = ref_lo + gtid() * 16; q0 < n_bases; q0 += gthreads() * 16) {
         // g = number of groups that start at or before q0
         uint32_t lo = 0, hi = n_groups;
         while (lo < hi) {
@@ -843,7 +850,7 @@ __global__ void k_emit_ref(Fasta fa, u64 n_bases, const u64* g_from, const u64* 
         const u64 q1 = q0 + 16 < n_bases ? q0 + 16 : n_bases;
         for (u64 q = q0; q < q1; ++q) {
             while (g < n_groups && g_from[g] <= q) ++g;
-            const u64 cursor = g ? g_to[g - 1] : 0ull;
+            const u64 cursor = g ? g_to[g - 1] : ref_lo;
             if (q >= cursor) out[eds_off[g] + 1 + (q - cursor)] = fa.at(q);
         }
     }
@@ -853,14 +860,14 @@ __global__ void k_emit_ref(Fasta fa, u64 n_bases, const u64* g_from, const u64* 
 __global__ void k_emit_groups(const uint8_t* t, Fasta fa, GroupView gv, const uint32_t* g_first, uint32_t n_groups,
                               const u64* canon, const uint32_t* hap_len, const uint8_t* kept, const uint32_t* slot_bits,
                               const uint32_t* slot_seds, uint32_t W, uint32_t stage_bytes, const u64* id_text,
-                              const u64* eds_off, const u64* seds_off, uint8_t* out, uint8_t* sout) {
+                              const u64* eds_off, const u64* seds_off, uint8_t* out, uint8_t* sout, u64 ref_lo) {
     const unsigned lane = threadIdx.x & 31;
     const u64 warp = gtid() >> 5, n_warps = gthreads() >> 5;
     uint8_t* const stage = EDSB_DYN_SMEM() + (size_t)(threadIdx.x >> 5) * stage_bytes;
     for (u64 g64 = warp; g64 <= n_groups; g64 += n_warps) {
         const uint32_t g = (uint32_t)g64;
         u64 eo = eds_off[g], so = seds_off[g];
-        const u64 clen = gv.g_from[g] - (g ? gv.g_to[g - 1] : 0ull);
+        const u64 clen = gv.g_from[g] - (g ? gv.g_to[g - 1] : ref_lo);
         if (clen) {
             if (lane == 0) {
                 out[eo] = (uint8_t)'{';
@@ -927,7 +934,7 @@ VcfPipeline::~VcfPipeline() { delete bufs_; }
 
 void VcfPipeline::transform_device(const uint8_t* vcf, uint64_t vcf_bytes, const uint8_t* fasta, uint64_t fasta_bytes,
                                    eds_buffer* eds_out, eds_buffer* seds_out, eds_vcf_stats* stats,
-                                   std::vector<uint64_t>* sv_lines) {
+                                   std::vector<uint64_t>* sv_lines, VcfShardHook* hook) {
     if ((reinterpret_cast<uintptr_t>(vcf) | reinterpret_cast<uintptr_t>(fasta)) & 15u)
         throw std::invalid_argument("eds_vcf_transform_device: buffers must be 16-byte aligned");
     cudaStream_t s = ctx_->stream;
@@ -1079,6 +1086,14 @@ void VcfPipeline::transform_device(const uint8_t* vcf, uint64_t vcf_bytes, const
     u64 n_slots = 0, max_samples = 0;
     uint32_t W = 1;
     uint32_t host_sorted = 0, retries = 0;
+    u64 ref_lo = 0, ref_hi = n_bases;
+    if (hook && !n_rec) {
+        std::vector<uint32_t> none;
+        uint64_t lo = 0, hi = n_bases;
+        hook->exchange(std::vector<uint64_t>(), 0, n_bases, &none, &lo, &hi);
+        ref_lo = lo;
+        ref_hi = hi;
+    }
     if (n_rec) {
         // ---- sample columns (main stream) || position order (side stream + host) -------------------------------
         d_al_off.reserve((size_t)n_rows * 8);
@@ -1106,7 +1121,29 @@ void VcfPipeline::transform_device(const uint8_t* vcf, uint64_t vcf_bytes, const
                 ++retries;
             }
         };
-        if (hst.unsorted) {
+        if (hook) {
+            // sharded: the order comes from the one sort over every slice's records, made where the slices meet
+            std::vector<uint64_t> h_pos(n_rec);
+            EDSB_CUDA(cudaMemcpyAsync(h_pos.data(), d_pos.p, (size_t)n_rec * 8, cudaMemcpyDeviceToHost, s));
+            EDSB_CUDA(cudaStreamSynchronize(s));
+            std::vector<uint32_t> h_perm;
+            bool met = false;
+            run_gt([&]() {
+                if (met) return;
+                met = true;
+                uint64_t lo = 0, hi = n_bases;
+                hook->exchange(h_pos, hst.max_end, n_bases, &h_perm, &lo, &hi);
+                ref_lo = lo;
+                ref_hi = hi;
+            });
+            if (h_perm.empty()) {
+                VCF_LAUNCH("k_iota", k_iota, G, B, 0, rec_of, n_rec);
+            } else {
+                host_sorted = 1;
+                EDSB_CUDA(cudaMemcpyAsync(rec_of, h_perm.data(), (size_t)n_rec * 4, cudaMemcpyHostToDevice, s));
+                EDSB_CUDA(cudaStreamSynchronize(s));
+            }
+        } else if (hst.unsorted) {
             // std::sort is unstable (:715-718): the order of records that share a position is whatever that very
             // call leaves, so the same call (same comparator, same sequence) is made on the host while k_gt runs
             host_sorted = 1;
@@ -1155,7 +1192,7 @@ void VcfPipeline::transform_device(const uint8_t* vcf, uint64_t vcf_bytes, const
     uint32_t* rec_of = d_rec_of.as<uint32_t>();
     u64 *g_from = d_gfrom.as<u64>(), *g_to = d_gto.as<u64>();
     VCF_LAUNCH("k_group_info", k_group_info, G, B, 0, recs, rec_of, d_incl.as<u64>(), d_gfirst.as<uint32_t>(), n_groups, n_rec,
-               n_bases, g_from, g_to);
+               ref_hi, g_from, g_to);
     const GroupView gv{recs, rec_of, d_slot_base.as<u64>(), d_al_off.as<u64>(), d_al_len.as<uint32_t>(), g_from, g_to};
     if (n_groups) {
         d_canon.reserve((size_t)n_slots * 8);
@@ -1168,16 +1205,16 @@ void VcfPipeline::transform_device(const uint8_t* vcf, uint64_t vcf_bytes, const
                    d_bits.as<uint32_t>(), W, d_canon.as<u64>(), d_hap_len.as<uint32_t>(), d_slot_bits.as<uint32_t>(),
                    d_slot_seds.as<uint32_t>(), d_kept.as<uint8_t>(), d_geds.as<u64>(), d_gseds.as<u64>());
     }
-    VCF_SCAN("eds_offsets", OpSum64, (u64)n_groups + 1, (OutFn{g_from, g_to, d_geds.as<u64>(), n_groups, 2u, 1u, d_eds_off.as<u64>()}));
+    VCF_SCAN("eds_offsets", OpSum64, (u64)n_groups + 1, (OutFn{g_from, g_to, d_geds.as<u64>(), n_groups, 2u, 1u, d_eds_off.as<u64>(), ref_lo}));
     const u64 eds_total = total_of();
-    VCF_SCAN("seds_offsets", OpSum64, (u64)n_groups + 1, (OutFn{g_from, g_to, d_gseds.as<u64>(), n_groups, 3u, 0u, d_seds_off.as<u64>()}));
+    VCF_SCAN("seds_offsets", OpSum64, (u64)n_groups + 1, (OutFn{g_from, g_to, d_gseds.as<u64>(), n_groups, 3u, 0u, d_seds_off.as<u64>(), ref_lo}));
     const u64 seds_total = total_of();
 
     // ---- emit ------------------------------------------------------------------------------------------------------
     d_out.reserve(eds_total + 16);
     d_sout.reserve(seds_total + 16);
-    if (n_bases)
-        VCF_LAUNCH("k_emit_ref", k_emit_ref, G, B, 0, fa, n_bases, g_from, g_to, n_groups, d_eds_off.as<u64>(), d_out.as<uint8_t>());
+    if (ref_hi > ref_lo)
+        VCF_LAUNCH("k_emit_ref", k_emit_ref, G, B, 0, fa, ref_lo, ref_hi, g_from, g_to, n_groups, d_eds_off.as<u64>(), d_out.as<uint8_t>());
     {
         const uint32_t stage_bytes = id_list_stage_bytes((u64)W * 32u);
         const uint32_t wpb = std::max<uint32_t>(1u, std::min<uint32_t>(B / 32u, (40u * 1024u) / stage_bytes));
@@ -1190,7 +1227,7 @@ void VcfPipeline::transform_device(const uint8_t* vcf, uint64_t vcf_bytes, const
         VCF_LAUNCH("k_emit_groups", k_emit_groups, grid, wpb * 32, (size_t)stage_bytes * wpb, vcf, fa, gv, d_gfirst.as<uint32_t>(),
                    n_groups, d_canon.as<u64>(), d_hap_len.as<uint32_t>(), d_kept.as<uint8_t>(), d_slot_bits.as<uint32_t>(),
                    d_slot_seds.as<uint32_t>(), W, stage_bytes, d_id_text.as<u64>(), d_eds_off.as<u64>(), d_seds_off.as<u64>(),
-                   d_out.as<uint8_t>(), d_sout.as<uint8_t>());
+                   d_out.as<uint8_t>(), d_sout.as<uint8_t>(), ref_lo);
     }
     EDSB_CUDA(cudaStreamSynchronize(s));
     EDSB_CUDA(cudaGetLastError());

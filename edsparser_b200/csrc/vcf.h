@@ -13,6 +13,19 @@ struct BadVcf : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
 
+// Sharded run (shard.cu): every device transforms a slice of the record lines. The tie order of records that share a
+// position comes from ONE sort over ALL records (the reference's std::sort is unstable: vcf_transforms.cpp:715-718), and a
+// slice only renders the reference bases of its own range, so the slices meet in the middle of the transform.
+struct VcfShardHook {
+    virtual ~VcfShardHook() {}
+    // Called exactly once per transform, after the slice's records are known (genotype kernel in flight). pos: POS of
+    // the slice's records in file order; max_end: largest 0-based record end. Blocks until every slice has arrived.
+    // Out: perm (empty = file order) = the slice's records in the global order, indices local to the slice;
+    // [ref_lo, ref_hi) = the reference bases this slice renders. Throws when the slices cannot be joined.
+    virtual void exchange(const std::vector<uint64_t>& pos, uint64_t max_end, uint64_t n_bases, std::vector<uint32_t>* perm,
+                          uint64_t* ref_lo, uint64_t* ref_hi) = 0;
+};
+
 class VcfPipeline {
    public:
     explicit VcfPipeline(eds_ctx* ctx);
@@ -25,7 +38,7 @@ class VcfPipeline {
     // skipped for an unsupported symbolic ALT, in file order (the caller prints the reference's warnings).
     void transform_device(const uint8_t* vcf, uint64_t vcf_bytes, const uint8_t* fasta, uint64_t fasta_bytes,
                           eds_buffer* eds_out, eds_buffer* seds_out, eds_vcf_stats* stats,
-                          std::vector<uint64_t>* sv_lines);
+                          std::vector<uint64_t>* sv_lines, VcfShardHook* hook = nullptr);
 
    private:
     struct Bufs;

@@ -190,8 +190,12 @@ std::pair<std::string, std::string> vcf_transform(std::istream& vcf_stream, std:
     eds_vcf_stats st{};
     uint64_t* sv = nullptr;
     uint64_t n_sv = 0;
-    const eds_status rc = eds_vcf_transform_host_view(t_session.get(), reinterpret_cast<const uint8_t*>(vcf.data()), vcf.size(),
-                                                      reinterpret_cast<const uint8_t*>(fasta.data()), fasta.size(), l, &e, &s, &st, &sv, &n_sv);
+    const bool sharded = g_devices.size() > 1;  // slices of the record lines over the devices of the group (malloc'd results)
+    const eds_status rc =
+        sharded ? eds_group_vcf_transform_host(t_group.get(), reinterpret_cast<const uint8_t*>(vcf.data()), vcf.size(),
+                                               reinterpret_cast<const uint8_t*>(fasta.data()), fasta.size(), l, &e, &s, &st, &sv, &n_sv, nullptr)
+                : eds_vcf_transform_host_view(t_session.get(), reinterpret_cast<const uint8_t*>(vcf.data()), vcf.size(),
+                                              reinterpret_cast<const uint8_t*>(fasta.data()), fasta.size(), l, &e, &s, &st, &sv, &n_sv);
     for (uint64_t i = 0; i < n_sv; ++i) warn_skipped_sv(vcf, sv[i]);
     std::free(sv);
     if (stats && (rc == EDS_OK || st.total_variants)) {  // the reference fills the counters before the merge can throw
@@ -202,7 +206,13 @@ std::pair<std::string, std::string> vcf_transform(std::istream& vcf_stream, std:
         stats->variant_groups = st.variant_groups;
     }
     if (rc != EDS_OK) rethrow(rc);
-    return {std::string(reinterpret_cast<const char*>(e.data), e.bytes), std::string(reinterpret_cast<const char*>(s.data), s.bytes)};
+    std::pair<std::string, std::string> out{std::string(reinterpret_cast<const char*>(e.data), e.bytes),
+                                            std::string(reinterpret_cast<const char*>(s.data), s.bytes)};
+    if (sharded) {
+        eds_buffer_free_host(&e);
+        eds_buffer_free_host(&s);
+    }
+    return out;
 }
 
 }  // namespace

@@ -19,7 +19,9 @@ static void usage() {
                  "  -o [ --output ] arg               Output EDS file (default: <input>.eds)\n"
                  "  -s [ --sources ] arg              Output source file (default: <output>.seds)\n"
                  "  -l [ --context-length ] arg (=0)  Create l-EDS with minimum context length (0 = regular EDS)\n"
-                 "  --device arg (=0)                 CUDA device to run on (B200 build)\n\n"
+                 "  --device arg (=0)                 CUDA device to run on (B200 build)\n"
+                 "  --gpus arg (=1)                   Slice the record lines over this many GPUs of the node,\n"
+                 "                                    starting at --device (B200 build)\n\n"
                  "One path per sample column (1-based, VCF order); both alleles of a diploid genotype count.\n"
                  "SNPs, indels, <DEL>, <INS> and multi-allelic sites are supported; overlapping records are merged\n"
                  "into one symbol; other symbolic alleles and malformed lines are skipped and counted.\n\n"
@@ -33,7 +35,7 @@ int main(int argc, char** argv) {
     timer.start();
     try {
         const cli::Args args(argc, argv, {{"help", 'h', false}, {"input", 'i', true}, {"reference", 'r', true}, {"output", 'o', true},
-                                         {"sources", 's', true}, {"context-length", 'l', true}, {"device", 0, true}});
+                                         {"sources", 's', true}, {"context-length", 'l', true}, {"device", 0, true}, {"gpus", 0, true}});
         if (args.has("help")) {
             usage();
             cli::print_performance(timer);
@@ -48,7 +50,15 @@ int main(int argc, char** argv) {
         const unsigned long l_arg = args.has("context-length") ? args.to_uint("context-length") : 0;
         if (l_arg > 0xfffffffful) throw std::invalid_argument("the argument for option '--context-length' is invalid");
         const Length context_length = (Length)l_arg;
-        if (args.has("device")) b200::set_device((int)args.to_uint("device"));
+        const int first_device = args.has("device") ? (int)args.to_uint("device") : 0;
+        b200::set_device(first_device);
+        if (args.has("gpus")) {
+            const unsigned long n = args.to_uint("gpus");
+            if (n < 1 || n > 64) throw std::invalid_argument("the argument for option '--gpus' is invalid");
+            std::vector<int> devices;
+            for (unsigned long i = 0; i < n; ++i) devices.push_back(first_device + (int)i);
+            b200::set_devices(devices);
+        }
 
         if (input_file.extension() != ".vcf") {
             std::cerr << "Error: Input file must be a VCF file (.vcf)\n";

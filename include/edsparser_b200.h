@@ -316,6 +316,18 @@ eds_status eds_group_leds_merge_host(eds_group* group, const uint8_t* eds, uint6
                                      uint64_t seds_bytes, uint32_t l, int compact, eds_buffer* leds_out,
                                      eds_buffer* seds_out, uint32_t* rounds_out, uint32_t* shards_used);
 
+/* vcf2eds over the devices of a group: slices of the VCF's record lines, one per device, each
+ * with the whole FASTA record; the slices meet once inside the transform (one sort of all positions for the tie order
+ * of the reference's unstable std::sort, vcf_transforms.cpp:715-718; no overlapping group may span a cut; each slice
+ * renders the reference bases up to the next slice's first group). Arguments and results as eds_vcf_transform_host
+ * (vcf_transforms.cpp:677-755); l > 0 runs eds_group_leds_merge_host on the joined text. Input the slices cannot be
+ * joined on (a slice without records, a spanning group, an error) runs on the group's first device.
+ * shards_used (optional): devices that took part. */
+eds_status eds_group_vcf_transform_host(eds_group* group, const uint8_t* vcf, uint64_t vcf_bytes, const uint8_t* fasta,
+                                        uint64_t fasta_bytes, uint32_t l, eds_buffer* eds_out, eds_buffer* seds_out,
+                                        eds_vcf_stats* stats, uint64_t** sv_lines, uint64_t* n_sv_lines,
+                                        uint32_t* shards_used);
+
 /* eds_comm: one process PER GPU (torchrun, mpirun): rank 0 makes the 128-byte NCCL id, the launcher ships it to
  * every rank, each rank builds the communicator for its context. After every eds_msa_transform_device the rank
  * posts its byte counts (enqueued behind the transform, no host synchronisation, two posts may be in flight);

@@ -167,3 +167,27 @@ def test_msa2eds_gpus_option(tmp_path):
         assert (tmp_path / "shape_l10.seds").read_bytes() == exp[1]
     rc, so, err = run("msa2eds", "-i", str(src), "--gpus", "0")
     assert rc == 1 and "--gpus" in err
+
+
+@pytest.mark.gpu
+def test_vcf2eds_gpus_option(tmp_path):
+    """vcf2eds --gpus N: slices of the record lines over N devices == the one-device run (N = the box's devices, at most
+    4; on a one-GPU box the option still goes through the group entry point with one device)."""
+    import torch
+    import vcf_checks
+
+    vcf, fa = vcf_checks.synth_vcf(300_000, 8000, 50, seed=4)
+    (tmp_path / "s.vcf").write_bytes(vcf)
+    (tmp_path / "s.fa").write_bytes(fa)
+    for l in (0, 5):
+        ext = "leds" if l else "eds"
+        rc, so, err = run("vcf2eds", "-i", str(tmp_path / "s.vcf"), "-r", str(tmp_path / "s.fa"), "-l", str(l), "-o", str(tmp_path / f"one.{ext}"))
+        assert rc == 0, err
+        for n in sorted({1, min(2, torch.cuda.device_count()), min(4, torch.cuda.device_count())}):
+            rc, so, err = run("vcf2eds", "-i", str(tmp_path / "s.vcf"), "-r", str(tmp_path / "s.fa"), "-l", str(l), "-o",
+                              str(tmp_path / f"g{n}.{ext}"), "--gpus", str(n))
+            assert rc == 0, err
+            assert (tmp_path / f"g{n}.{ext}").read_bytes() == (tmp_path / f"one.{ext}").read_bytes()
+            assert (tmp_path / f"g{n}.seds").read_bytes() == (tmp_path / "one.seds").read_bytes()
+    rc, so, err = run("vcf2eds", "-i", str(tmp_path / "s.vcf"), "-r", str(tmp_path / "s.fa"), "--gpus", "0")
+    assert rc == 1 and "--gpus" in err

@@ -149,3 +149,74 @@ def test_group_leds_on_devices():
     n = max(1, min(4, n_dev.value))
     sharded = check_group_leds(lib, n, sizes=(200_000, 1_000_000), ls=(3, 10))
     assert n == 1 or sharded >= 1
+
+
+def check_group_vcf(lib, devices, n_random, synth_sizes, ls=(0, 3)):
+    """eds_group_vcf_transform_host == the single-device transform == the oracle: random pairs (overlaps, ties, malformed
+    lines: whatever cannot be sliced falls back to one device) and the config-5 generator (sliced for real)."""
+    import random
+
+    import vcf_checks
+
+    rng = random.Random(11)
+    n = len(devices)
+    g = lib.group(devices)
+    ctx = lib.context()
+    try:
+        sliced = 0
+        for i in range(n_random):
+            vcf, fa = vcf_checks.make_golden_vcf.random_pair(rng, n_ref=300, n_sites=40, n_samples=5)
+            for l in ls:
+                try:
+                    exp = ctx.vcf_transform_host(vcf, fa, l)
+                except Exception as err:
+                    with pytest.raises(type(err)) as ei:
+                        g.vcf_transform_host(vcf, fa, l)
+                    assert str(ei.value) == str(err)
+                    continue
+                got = g.vcf_transform_host(vcf, fa, l)
+                assert got[:2] == exp[:2], (i, l)
+                assert vcf_checks.stats_line(got[2]) == vcf_checks.stats_line(exp[2])
+                assert got[3] == exp[3]
+                sliced += got[4] > 1
+        sorted_on_host = 0
+        for seed, (bases, sites, samples, overlap) in enumerate(synth_sizes, start=1):
+            vcf, fa = vcf_checks.synth_vcf(bases, sites, samples, seed=seed, overlap_frac=overlap)
+            for l in ls:
+                exp = ctx.vcf_transform_host(vcf, fa, l)
+                got = g.vcf_transform_host(vcf, fa, l)
+                assert got[:2] == exp[:2], (bases, l)
+                assert vcf_checks.stats_line(got[2]) == vcf_checks.stats_line(exp[2])
+                assert got[2]["host_sorted"] == exp[2]["host_sorted"]
+                sliced += got[4] > 1
+                sorted_on_host += got[4] > 1 and got[2]["host_sorted"]
+            if bases <= 4000:
+                o = oracle_lib.vcf2eds(vcf, fa, 0)
+                assert g.vcf_transform_host(vcf, fa, 0)[:2] == (o[0], o[1])
+        assert sliced > 0 and sorted_on_host > 0  # ties went through the one sort over all slices
+    finally:
+        ctx.close()
+        g.close()
+
+
+def test_group_vcf_emulated():
+    import emu_lib
+
+    check_group_vcf(emu_lib.lib(), [0, 1], n_random=3, synth_sizes=((2000, 60, 6, 0.01), (2000, 80, 5, 0.3)))
+
+
+@pytest.mark.gpu
+def test_group_vcf_on_devices():
+    import ctypes
+
+    import edsparser_b200 as E
+
+    lib = E.load()
+    cudart = ctypes.CDLL("libcudart.so")
+    n_dev = ctypes.c_int(0)
+    cudart.cudaGetDeviceCount(ctypes.byref(n_dev))
+    # fewer devices than slices: the slices share a device, each with its own context (eds_group takes repeated ids:
+    # no NCCL communicator then, the counts are exchanged on the host)
+    for n in (2, 4):
+        check_group_vcf(lib, [i % n_dev.value for i in range(n)], n_random=12,
+                        synth_sizes=((4000, 120, 8, 0.2), (200_000, 6000, 64, 0.01), (1_000_000, 20_000, 300, 0.01)))

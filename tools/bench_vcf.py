@@ -110,6 +110,27 @@ def main():
                     ctx.vcf_transform_host_view_raw(pv.data_ptr(), len(vcf), pf.data_ptr(), len(fa), l)
                     ts.append(time.perf_counter() - t0)
                 line["host_to_host_view_l%d_ms" % l] = round(min(ts) * 1e3, 2)
+            n_gpus = int(os.environ.get("EDSB_VCF_GPUS", "0"))
+            if n_gpus > 1:
+                # slices of the record lines over n_gpus devices (eds_group_vcf_transform_host): same bytes, host to host
+                import hashlib
+
+                g = E.load().group(list(range(n_gpus)))
+                try:
+                    for l in (0, 10):
+                        one = ctx.vcf_transform_host_view(pv, pf, l)
+                        sz, st_g, used, ge, gs = g.vcf_transform_host_raw(pv.data_ptr(), len(vcf), pf.data_ptr(), len(fa), l, keep=True)
+                        same = hashlib.sha256(ge).digest() == hashlib.sha256(one[0]).digest() and hashlib.sha256(gs).digest() == hashlib.sha256(one[1]).digest()
+                        del one, ge, gs
+                        ts = []
+                        for _ in range(1 if big else 3):
+                            t0 = time.perf_counter()
+                            g.vcf_transform_host_raw(pv.data_ptr(), len(vcf), pf.data_ptr(), len(fa), l)
+                            ts.append(time.perf_counter() - t0)
+                        line["group%d_l%d" % (n_gpus, l)] = {"host_to_host_ms": round(min(ts) * 1e3, 2), "shards_used": used,
+                                                              "byte_equal_to_one_device": bool(same)}
+                finally:
+                    g.close()
             line["host_to_host"] = ("eds_vcf_transform_host: pinned input, H2D + kernels + D2H into fresh malloc'd strings; "
                                     "_view: eds_vcf_transform_host_view, results in pinned memory kept by the context")
             del pv, pf
