@@ -9,7 +9,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-PRODUCT_SO = os.path.join(HERE, "libedsparser_b200.so")
+PRODUCT_SO = os.environ.get("EDSB_LIBRARY") or os.path.join(HERE, "libedsparser_b200.so")  # (another build of the same sources)
 
 EDS_OK = 0
 EDS_ERR_INVALID_ARGUMENT = 1
@@ -31,7 +31,7 @@ EXPORTS = [
     "eds_group_create", "eds_group_destroy", "eds_group_size", "eds_group_ctx", "eds_group_msa_transform_host",
     "eds_group_msa_transform_fd", "eds_nccl_unique_id", "eds_comm_create", "eds_comm_destroy", "eds_comm_post",
     "eds_comm_offsets", "eds_comm_flush", "eds_parse_host", "eds_parsed_free", "eds_merge_adjacent_host",
-    "eds_group_leds_merge_host", "eds_group_vcf_transform_host", "eds_leds_merge_device_in", "eds_genrandomeds_device",
+    "eds_group_leds_merge_host", "eds_group_vcf_transform_host", "eds_group_vcf_transform_host_view", "eds_leds_merge_device_in", "eds_genrandomeds_device",
 ]
 
 
@@ -134,6 +134,7 @@ class Library:
         L.eds_group_msa_transform_fd.argtypes = [vp, vp, u64, u32, i32, u64, i32, i32, P(u64), P(MsaStats)]
         L.eds_group_leds_merge_host.argtypes = [vp, vp, u64, vp, u64, u32, i32, P(Buffer), P(Buffer), P(u32), P(u32)]
         L.eds_group_vcf_transform_host.argtypes = L.eds_vcf_transform_host.argtypes + [P(u32)]
+        L.eds_group_vcf_transform_host_view.argtypes = L.eds_group_vcf_transform_host.argtypes
         L.eds_leds_merge_device_in.argtypes = [vp, vp, u64, vp, u64, u32, i32, u64, P(Buffer), P(Buffer), P(u32)]
         L.eds_genrandomeds_device.argtypes = [vp, u64, u32, u32, u64, P(Buffer), P(Buffer)]
         L.eds_nccl_unique_id.argtypes = [vp]
@@ -214,6 +215,25 @@ class Group:
         if nsv.value:
             ctypes.CDLL(None).free(sv)
         return _host_bytes(self.lib, e), _host_bytes(self.lib, s), st.as_dict(), lines, used.value
+
+    def vcf_transform_host_view(self, vcf, fasta, l=0):
+        """Like vcf_transform_host through eds_group_vcf_transform_host_view (pinned views, copied into bytes here)."""
+        va, vn, k1 = _as_pointer(vcf)
+        fa, fn, k2 = _as_pointer(fasta)
+        e, s, st, used = Buffer(), Buffer(), VcfStats(), ctypes.c_uint32()
+        self.lib.check(self.lib.L.eds_group_vcf_transform_host_view(self.handle, va, vn, fa, fn, l, ctypes.byref(e), ctypes.byref(s),
+                                                                    ctypes.byref(st), None, None, ctypes.byref(used)))
+        del k1, k2
+        eds = bytes((ctypes.c_ubyte * e.bytes).from_address(e.data)) if e.bytes else b""
+        seds = bytes((ctypes.c_ubyte * s.bytes).from_address(s.data)) if s.bytes else b""
+        return eds, seds, st.as_dict(), used.value
+
+    def vcf_transform_host_view_raw(self, vcf_addr, vcf_n, fa_addr, fa_n, l=0):
+        """The bare C call of the view form: ((eds bytes, seds bytes), stats, shards used); nothing to free."""
+        e, s, st, used = Buffer(), Buffer(), VcfStats(), ctypes.c_uint32()
+        self.lib.check(self.lib.L.eds_group_vcf_transform_host_view(self.handle, vcf_addr, vcf_n, fa_addr, fa_n, l, ctypes.byref(e),
+                                                                    ctypes.byref(s), ctypes.byref(st), None, None, ctypes.byref(used)))
+        return (int(e.bytes), int(s.bytes)), st.as_dict(), used.value
 
     def vcf_transform_host_raw(self, vcf_addr, vcf_n, fa_addr, fa_n, l=0, keep=False):
         """The bare C call on (address, length) pairs: ((eds bytes, seds bytes), stats, shards used[, eds, seds])."""

@@ -34,8 +34,14 @@ struct OpMax64 {
 constexpr int kScanBlock = 64;
 constexpr int kScanItems = 2;
 #else
-constexpr int kScanBlock = 256;
-constexpr int kScanItems = 8;
+#ifndef EDSB_SCAN_BLOCK
+#define EDSB_SCAN_BLOCK 256
+#endif
+#ifndef EDSB_SCAN_ITEMS
+#define EDSB_SCAN_ITEMS 8
+#endif
+constexpr int kScanBlock = EDSB_SCAN_BLOCK;
+constexpr int kScanItems = EDSB_SCAN_ITEMS;
 #endif
 
 __device__ __forceinline__ unsigned long long shfl_up_v(unsigned long long v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }

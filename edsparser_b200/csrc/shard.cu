@@ -177,6 +177,19 @@ struct eds_group {
     std::vector<edsb::DevBuf> window;   // per device: the window's rows, 16-byte aligned pitch
     std::vector<uint64_t*> d_counts;    // per device: 2 + 2 n
     std::vector<uint64_t*> h_counts;    // per device, pinned: 2 + 2 n
+    void* host_out[2] = {nullptr, nullptr};  // pinned results of the *_view calls, grow-only
+    size_t host_out_cap[2] = {0, 0};
+    uint8_t* view_slot(int which, uint64_t bytes) {
+        if (host_out_cap[which] < bytes + 1) {
+            if (host_out[which]) cudaFreeHost(host_out[which]);
+            host_out[which] = nullptr;
+            host_out_cap[which] = 0;
+            const size_t want = ((bytes + bytes / 8 + 4096) / 4096) * 4096;
+            EDSB_CUDA(cudaMallocHost(&host_out[which], want));  // unified addressing: every device of the group can write it
+            host_out_cap[which] = want;
+        }
+        return static_cast<uint8_t*>(host_out[which]);
+    }
 };
 
 extern "C" {
@@ -353,6 +366,8 @@ void eds_group_destroy(eds_group* g) {
         if (i < g->h_counts.size() && g->h_counts[i]) cudaFreeHost(g->h_counts[i]);
         eds_ctx_destroy(g->ctx[i]);
     }
+    for (int which = 0; which < 2; ++which)
+        if (g->host_out[which]) cudaFreeHost(g->host_out[which]);
     delete g;
 }
 
@@ -984,10 +999,10 @@ bool vcf_line_span(const uint8_t* t, uint64_t n, uint64_t at, uint64_t& pos, uin
 
 }  // namespace
 
-extern "C" eds_status eds_group_vcf_transform_host(eds_group* g, const uint8_t* vcf, uint64_t vcf_bytes, const uint8_t* fasta,
-                                                   uint64_t fasta_bytes, uint32_t l, eds_buffer* eds_out, eds_buffer* seds_out,
-                                                   eds_vcf_stats* stats, uint64_t** sv_lines, uint64_t* n_sv_lines,
-                                                   uint32_t* shards_used) {
+namespace {
+eds_status group_vcf_transform(eds_group* g, const uint8_t* vcf, uint64_t vcf_bytes, const uint8_t* fasta, uint64_t fasta_bytes,
+                               uint32_t l, eds_buffer* eds_out, eds_buffer* seds_out, eds_vcf_stats* stats, uint64_t** sv_lines,
+                               uint64_t* n_sv_lines, uint32_t* shards_used, bool view) {
     if (eds_out) *eds_out = eds_buffer{nullptr, 0};
     if (seds_out) *seds_out = eds_buffer{nullptr, 0};
     if (sv_lines) *sv_lines = nullptr;
@@ -998,7 +1013,13 @@ extern "C" eds_status eds_group_vcf_transform_host(eds_group* g, const uint8_t* 
         return EDS_ERR_INVALID_ARGUMENT;
     }
     const uint32_t n = (uint32_t)g->ctx.size();
-    auto single = [&]() { return eds_vcf_transform_host(g->ctx[0], vcf, vcf_bytes, fasta, fasta_bytes, l, eds_out, seds_out, stats, sv_lines, n_sv_lines); };
+    auto single = [&]() {
+        return view ? eds_vcf_transform_host_view(g->ctx[0], vcf, vcf_bytes, fasta, fasta_bytes, l, eds_out, seds_out, stats, sv_lines, n_sv_lines)
+                    : eds_vcf_transform_host(g->ctx[0], vcf, vcf_bytes, fasta, fasta_bytes, l, eds_out, seds_out, stats, sv_lines, n_sv_lines);
+    };
+    auto drop = [&](uint8_t* p) {
+        if (!view) free(p);
+    };
     if (n < 2 || vcf_bytes < (uint64_t)n * 64) return single();
 
     // ---- cuts: the first line start at or after k / n of the bytes where the record does not touch the one before it
@@ -1069,8 +1090,17 @@ extern "C" eds_status eds_group_vcf_transform_host(eds_group* g, const uint8_t* 
                         etot += slice[i].de.bytes;
                         stot += slice[i].ds.bytes;
                     }
-                    h_eds = static_cast<uint8_t*>(malloc(etot ? etot : 1));
-                    h_seds = static_cast<uint8_t*>(malloc(stot ? stot : 1));
+                    if (view) {
+                        try {
+                            h_eds = g->view_slot(0, etot);
+                            h_seds = g->view_slot(1, stot);
+                        } catch (const std::exception&) {
+                            all_ok = false;
+                        }
+                    } else {
+                        h_eds = static_cast<uint8_t*>(malloc(etot ? etot : 1));
+                        h_seds = static_cast<uint8_t*>(malloc(stot ? stot : 1));
+                    }
                     if (!h_eds || !h_seds) all_ok = false;
                 }
             }
@@ -1090,8 +1120,8 @@ extern "C" eds_status eds_group_vcf_transform_host(eds_group* g, const uint8_t* 
     for (auto& t : th) t.join();
     for (uint32_t i = 0; i < n; ++i) all_ok = all_ok && slice[i].status == 0;
     if (!all_ok) {
-        free(h_eds);
-        free(h_seds);
+        drop(h_eds);
+        drop(h_seds);
         for (uint32_t i = 0; i < n; ++i) cudaGetLastError();
         return single();
     }
@@ -1120,8 +1150,8 @@ extern "C" eds_status eds_group_vcf_transform_host(eds_group* g, const uint8_t* 
     if (sv_lines && n_sv_lines && !sv_all.empty()) {
         *sv_lines = static_cast<uint64_t*>(malloc(sv_all.size() * sizeof(uint64_t)));
         if (!*sv_lines) {
-            free(h_eds);
-            free(h_seds);
+            drop(h_eds);
+            drop(h_seds);
             edsb::set_last_error("out of host memory");
             return EDS_ERR_RUNTIME;
         }
@@ -1138,9 +1168,28 @@ extern "C" eds_status eds_group_vcf_transform_host(eds_group* g, const uint8_t* 
         return EDS_OK;
     }
     uint32_t rounds = 0, merged_on = 1;
-    const eds_status rc = eds_group_leds_merge_host(g, h_eds, etot, h_seds, stot, l, 1, eds_out, seds_out, &rounds, &merged_on);
-    free(h_eds);
-    free(h_seds);
+    eds_status rc = eds_group_leds_merge_host(g, h_eds, etot, h_seds, stot, l, 1, eds_out, seds_out, &rounds, &merged_on);
+    drop(h_eds);
+    drop(h_seds);
+    if (rc == EDS_OK && view) {
+        // the merged text back into the group's pinned slots (the intermediate they held has been consumed)
+        rc = guarded_shard([&] {
+            EDSB_CUDA(cudaSetDevice(g->ctx[0]->device));
+            uint8_t* pe = g->view_slot(0, eds_out->bytes);
+            uint8_t* ps = g->view_slot(1, seds_out->bytes);
+            memcpy(pe, eds_out->data, eds_out->bytes);
+            memcpy(ps, seds_out->data, seds_out->bytes);
+            const uint64_t nb[2] = {eds_out->bytes, seds_out->bytes};
+            eds_buffer_free_host(eds_out);
+            eds_buffer_free_host(seds_out);
+            *eds_out = eds_buffer{pe, nb[0]};
+            *seds_out = eds_buffer{ps, nb[1]};
+        });
+        if (rc != EDS_OK) {
+            eds_buffer_free_host(eds_out);
+            eds_buffer_free_host(seds_out);
+        }
+    }
     if (rc != EDS_OK) {
         if (sv_lines && *sv_lines) {
             free(*sv_lines);
@@ -1152,4 +1201,19 @@ extern "C" eds_status eds_group_vcf_transform_host(eds_group* g, const uint8_t* 
     tot.leds_rounds = rounds;
     if (stats) *stats = tot;
     return EDS_OK;
+}
+}  // namespace
+
+extern "C" eds_status eds_group_vcf_transform_host(eds_group* g, const uint8_t* vcf, uint64_t vcf_bytes, const uint8_t* fasta,
+                                                   uint64_t fasta_bytes, uint32_t l, eds_buffer* eds_out, eds_buffer* seds_out,
+                                                   eds_vcf_stats* stats, uint64_t** sv_lines, uint64_t* n_sv_lines,
+                                                   uint32_t* shards_used) {
+    return group_vcf_transform(g, vcf, vcf_bytes, fasta, fasta_bytes, l, eds_out, seds_out, stats, sv_lines, n_sv_lines, shards_used, false);
+}
+
+extern "C" eds_status eds_group_vcf_transform_host_view(eds_group* g, const uint8_t* vcf, uint64_t vcf_bytes, const uint8_t* fasta,
+                                                        uint64_t fasta_bytes, uint32_t l, eds_buffer* eds_out, eds_buffer* seds_out,
+                                                        eds_vcf_stats* stats, uint64_t** sv_lines, uint64_t* n_sv_lines,
+                                                        uint32_t* shards_used) {
+    return group_vcf_transform(g, vcf, vcf_bytes, fasta, fasta_bytes, l, eds_out, seds_out, stats, sv_lines, n_sv_lines, shards_used, true);
 }

@@ -328,6 +328,14 @@ eds_status eds_group_vcf_transform_host(eds_group* group, const uint8_t* vcf, ui
                                         eds_vcf_stats* stats, uint64_t** sv_lines, uint64_t* n_sv_lines,
                                         uint32_t* shards_used);
 
+/* Same call; the results are VIEWS into pinned host memory (owned by the group when the slices were joined, by the first
+ * device's context when the input ran whole there): valid until the next *_view call on this group, never freed by the
+ * caller. Every device copies its slice over its own PCIe link straight into the one pinned pair. */
+eds_status eds_group_vcf_transform_host_view(eds_group* group, const uint8_t* vcf, uint64_t vcf_bytes, const uint8_t* fasta,
+                                             uint64_t fasta_bytes, uint32_t l, eds_buffer* eds_out, eds_buffer* seds_out,
+                                             eds_vcf_stats* stats, uint64_t** sv_lines, uint64_t* n_sv_lines,
+                                             uint32_t* shards_used);
+
 /* eds_comm: one process PER GPU (torchrun, mpirun): rank 0 makes the 128-byte NCCL id, the launcher ships it to
  * every rank, each rank builds the communicator for its context. After every eds_msa_transform_device the rank
  * posts its byte counts (enqueued behind the transform, no host synchronisation, two posts may be in flight);

@@ -176,6 +176,7 @@ def check_group_vcf(lib, devices, n_random, synth_sizes, ls=(0, 3)):
                     continue
                 got = g.vcf_transform_host(vcf, fa, l)
                 assert got[:2] == exp[:2], (i, l)
+                assert g.vcf_transform_host_view(vcf, fa, l)[:2] == exp[:2]
                 assert vcf_checks.stats_line(got[2]) == vcf_checks.stats_line(exp[2])
                 assert got[3] == exp[3]
                 sliced += got[4] > 1
@@ -186,6 +187,7 @@ def check_group_vcf(lib, devices, n_random, synth_sizes, ls=(0, 3)):
                 exp = ctx.vcf_transform_host(vcf, fa, l)
                 got = g.vcf_transform_host(vcf, fa, l)
                 assert got[:2] == exp[:2], (bases, l)
+                assert g.vcf_transform_host_view(vcf, fa, l)[:2] == exp[:2]
                 assert vcf_checks.stats_line(got[2]) == vcf_checks.stats_line(exp[2])
                 assert got[2]["host_sorted"] == exp[2]["host_sorted"]
                 sliced += got[4] > 1
