@@ -291,7 +291,7 @@ def roofline_of(m, rows, steps, world, serial_kern=None):
     """roofline object of one measured leg: dominant kernel = the scan (fused with the column gather when it runs)."""
     peak, peak_src = peaks()
     kern = m["kern"]
-    name = "k_scan_fused" if "k_scan_fused" in kern else "k_scan"
+    name = "k_scan_l2" if "k_scan_l2" in kern else ("k_scan_fused" if "k_scan_fused" in kern else "k_scan")
     scan_ms = kern.get(name, 0.0)
     scan_bytes = rows * m["row_bytes"]  # every cell of the window read once (newlines ride along)
     achieved = scan_bytes / (scan_ms / 1e3) / 1e9 if scan_ms > 0 else 0.0

@@ -158,6 +158,12 @@ eds_status eds_ctx_create(int device, void* stream, eds_ctx** out) {
         if (const char* fz = getenv("EDSB_FUSED_T")) ctx->fused_t = (uint32_t)atoi(fz);
         if (const char* fz = getenv("EDSB_FUSED_DW")) ctx->fused_dw = (uint32_t)atoi(fz);
         if (const char* fz = getenv("EDSB_FUSED_MODE")) ctx->fused_mode = (uint32_t)atoi(fz);
+        if (const char* fz = getenv("EDSB_FUSED_PROBE")) ctx->fused_probe = (uint32_t)atoi(fz);
+        if (const char* fz = getenv("EDSB_FUSED_L2")) ctx->fused_l2 = (uint32_t)atoi(fz);
+        if (const char* fz = getenv("EDSB_FUSED_DIRECT")) ctx->fused_direct = (uint32_t)atoi(fz);
+        if (const char* fz = getenv("EDSB_FUSED_SPLIT")) ctx->fused_split = (uint32_t)atoi(fz);
+        if (const char* fz = getenv("EDSB_FUSED_CW")) ctx->fused_cw = (uint32_t)atoi(fz);
+        if (const char* fz = getenv("EDSB_FUSED_PAIR")) ctx->fused_pair = atoi(fz) != 0 ? 1u : 0u;
         if (const char* hm = getenv("EDSB_DEBUG_HASH_MASK")) ctx->hash_mask = strtoull(hm, nullptr, 0);
         if (const char* no = getenv("EDSB_DEBUG_NARROW_OFF")) ctx->narrow_off = atoi(no);
         if (const char* no = getenv("EDSB_DEBUG_TUPLE_OFF")) ctx->tuple_off = atoi(no);

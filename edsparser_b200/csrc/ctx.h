@@ -74,6 +74,12 @@ struct eds_ctx {
     uint32_t fused_bulk_pct = 0;   // EDSB_FUSED_BULK_PCT: mode 2, share of the rows fed by bulk copies (0 = 50)
     uint32_t fused_t = 0;          // EDSB_FUSED_T: 16 or 32 chunks per tile (0 = default)
     uint32_t fused_dw = 0;         // EDSB_FUSED_DW: duty warps (0 = default)
+    uint32_t fused_pair = 0;       // EDSB_FUSED_PAIR=1: two adjacent tiles per bulk copy (1040 bytes; measured slower: half the ring slots)
+    uint32_t fused_l2 = 0;         // EDSB_FUSED_L2=1: k_scan_l2 (plain loads, L1 / L2 as the stage; measured slower) instead of k_scan_fused (TMA ring in shared memory)
+    uint32_t fused_cw = 0;         // EDSB_FUSED_CW: consumer warps per CTA of k_scan_l2 (0 = default)
+    uint32_t fused_direct = 0;     // EDSB_FUSED_DIRECT: rows per CTA of k_scan_fused that bypass the ring (<= 32)
+    uint32_t fused_split = 0;      // EDSB_FUSED_SPLIT=1: k_scan_fused with one `full` barrier per stage and producer warp
+    uint32_t fused_probe = 0;      // EDSB_FUSED_PROBE: timing probes of k_scan_fused (scan_fused.h); results are not valid
     uint32_t fused_mode = 0;       // EDSB_FUSED_MODE: 0 = one bulk copy (TMA) per row (measured faster), 1 = 16-byte cp.async per lane
     int sm_count = 148;
     size_t smem_optin = 227 * 1024;

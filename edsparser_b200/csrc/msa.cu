@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(kScanThreads, EDSB_SCAN_MINB) k_scan(MsaGeom g
 
 }  // namespace edsb
 #include "scan_fused.cuh"
+#include "scan_l2.cuh"
 namespace edsb {
 
 // ---------------------------------------------------------------------------------------------
@@ -2343,10 +2344,66 @@ void MsaPipeline::prepare(const eds_msa_view& v, uint32_t l, int leds) {
 
 // k_scan_fused geometry for the alignment of prepare(): cluster size (rows per CTA <= 128), stages that fit in shared
 // memory, the per-CTA row tables (slot 0 = row 0, then the CTA's rows sorted by word shift), co-resident clusters.
+// the instance of k_scan_fused the plan asks for: 16-chunk tiles, 32-chunk tiles, 32-chunk tiles fetched in pairs
+#define FZ_KERNEL(EXPR)                                   \
+    do {                                                  \
+        if (fz_.T == 16u) {                               \
+            auto kern = k_scan_fused<16, 1, false>;       \
+            EXPR;                                         \
+        } else if (fz_.H == 2u) {                         \
+            auto kern = k_scan_fused<32, 2, false>;       \
+            EXPR;                                         \
+        } else if (fz_.direct) {                          \
+            auto kern = k_scan_fused<32, 1, true>;        \
+            EXPR;                                         \
+        } else {                                          \
+            auto kern = k_scan_fused<32, 1, false>;       \
+            EXPR;                                         \
+        }                                                 \
+    } while (0)
+
 void MsaPipeline::plan_fused() {
     const MsaGeom& g = geom_;
     fz_ = FzPlan();
     if (!ctx_->fused || g.R < ctx_->fused_min_rows) return;
+    if (ctx_->fused_l2 && g.R <= (uint32_t)kRowCache) {
+        // k_scan_l2: plain loads, the caches as the stage; a persistent grid, every duty warp of every CTA owns a region
+        fz_.l2 = true;
+        fz_.T = 32;
+        fz_.DW = std::max(1u, std::min(ctx_->fused_dw ? ctx_->fused_dw : (uint32_t)kL2MaxDW, (uint32_t)kL2MaxDW));
+        fz_.CW = std::max(1u, std::min(ctx_->fused_cw ? ctx_->fused_cw : (uint32_t)kL2MaxCW, (uint32_t)kL2MaxCW));
+        const uint32_t n_tiles = (g.n_chunks + 31) / 32;
+#ifdef EDSB_EMU
+        uint32_t regions = 3;
+#else
+        const uint32_t key = 0x80000000u ^ (fz_.CW << 8) ^ fz_.DW;
+        if (fz_occ_key_ != key) {
+            int per_sm = 0;
+            EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_l2<true>, (int)((fz_.CW + fz_.DW) * 32), 0));
+            fz_occ_regions_ = (uint32_t)std::max(0, per_sm) * (uint32_t)ctx_->sm_count;
+            fz_occ_key_ = key;
+        }
+        uint32_t regions = fz_occ_regions_;
+#endif
+        regions = std::min(regions, n_tiles);
+        if (regions == 0) {
+            fz_ = FzPlan();
+            return;
+        }
+        fz_.regions = regions;
+        d_fz_cnt_.reserve((size_t)regions * fz_.DW * 4);
+        FzParams& f = fzp_;
+        memset(&f, 0, sizeof(f));
+        f.region_count = d_fz_cnt_.as<uint32_t>();
+        f.n_tiles = n_tiles;
+        f.all_aligned = g.all_aligned;
+        f.DW = fz_.DW;
+        f.T = 32;
+        f.NC = 1;
+        f.probe = ctx_->fused_probe;
+        fz_.on = true;
+        return;
+    }
     uint32_t NC = 1;
     while (NC < kFzMaxNC && (g.R + NC - 1) / NC > kFzGroupRows) NC <<= 1;
     if (ctx_->fused_nc) NC = ctx_->fused_nc;
@@ -2355,24 +2412,35 @@ void MsaPipeline::plan_fused() {
     if (NC > 1) return;  // clusters are not emulated
 #endif
     const uint32_t RG = (((g.R + NC - 1) / NC) + 31u) & ~31u;
+    const uint32_t T = ctx_->fused_t == 16u ? 16u : 32u;  // 16-chunk tiles lose: twice the bulk copies per byte (profiles/r02_a)
+    // pairs of adjacent tiles per bulk copy (scan_fused.cuh): bulk mode, 32-chunk tiles; S and DW even
+    const uint32_t H = (T == 32u && ctx_->fused_mode == 0u && ctx_->fused_pair) ? 2u : 1u;  // off by default: see profiles/r02_a
+    // rows that bypass the ring (scan_fused.cuh: the last slots of every CTA, loaded straight into registers)
+    const uint32_t n_direct = (T == 32u && H == 1u) ? std::min(ctx_->fused_direct, kFzMaxDirect) : 0u;
     uint32_t slot_pitch = 1;  // row 0 + the most rows any CTA of the cluster holds
+    uint32_t stage_slots = 1; // ... of which a stage holds
     for (uint32_t c = 0; c < NC; ++c) {
         const uint32_t lo = std::max(c * RG, 1u), hi = std::min(g.R, (c + 1) * RG);
-        if (hi > lo) slot_pitch = std::max(slot_pitch, 1u + hi - lo);
+        const uint32_t nslots = hi > lo ? 1u + hi - lo : 1u;
+        slot_pitch = std::max(slot_pitch, nslots);
+        stage_slots = std::max(stage_slots, nslots - std::min(n_direct, (nslots - 1u) / 2u));
     }
     uint32_t DW = std::max(1u, std::min(ctx_->fused_dw ? ctx_->fused_dw : 4u, kFzMaxDW));
 #ifdef EDSB_EMU
     DW = std::min(DW, 2u);
 #endif
-    const uint32_t T = ctx_->fused_t == 16u ? 16u : 32u;  // 16-chunk tiles lose: twice the bulk copies per byte (profiles/r02_a)
     uint32_t S = 0;
     for (uint32_t s = 12; s >= 2; --s)
-        if (fz_smem_bytes(T, s, NC, RG, slot_pitch, DW) + 1024 <= ctx_->smem_optin) {
+        if (fz_smem_bytes(T, s, NC, RG, slot_pitch, DW, stage_slots) + 1024 <= ctx_->smem_optin) {
             S = s;
             break;
         }
     if (ctx_->fused_stages && ctx_->fused_stages <= S) S = ctx_->fused_stages;
     if (S < 2) return;
+    if (H == 2u) {
+        S &= ~1u;
+        DW = std::max(2u, DW & ~1u);
+    }
     // a duty warp waits for phase q of a stage's barrier by parity, which is only sound while phase q - 1 is known
     // to be complete: true when its previous tile (DW tiles back) is not older than the stage's previous use (S back)
     DW = std::min(DW, S);
@@ -2382,12 +2450,14 @@ void MsaPipeline::plan_fused() {
     fz_.PW = std::min(fz_.PW, 2u);
 #endif
     fz_.T = T;
+    fz_.H = H;
+    fz_.direct = n_direct > 0;
     fz_.S = S;
     fz_.DW = DW;
     fz_.NC = NC;
     fz_.RG = RG;
     fz_.slot_pitch = slot_pitch;
-    fz_.smem = fz_smem_bytes(T, S, NC, RG, slot_pitch, DW);
+    fz_.smem = fz_smem_bytes(T, S, NC, RG, slot_pitch, DW, stage_slots);
 
     // per-CTA tables, one upload: pack[NC][slot_pitch] u64 | meta[NC][8] u32 | info[NC][RG] u16
     const size_t off_meta = (size_t)NC * slot_pitch * 8, off_info = off_meta + (size_t)NC * 32;
@@ -2436,19 +2506,18 @@ void MsaPipeline::plan_fused() {
 #ifdef EDSB_EMU
     regions = 3;
 #else
-    const uint32_t key = (NC << 24) ^ (S << 16) ^ slot_pitch ^ (fz_.PW << 28) ^ (fz_.DW << 12) ^ (T << 20);
+    const uint32_t key = (NC << 24) ^ (S << 16) ^ slot_pitch ^ (fz_.PW << 28) ^ (fz_.DW << 12) ^ (T << 20) ^ (H << 9) ^ (stage_slots * 2654435761u) ^ (n_direct ? 0x55u : 0u);
     if (fz_attr_smem_ < fz_.smem) {
-        EDSB_CUDA(cudaFuncSetAttribute(k_scan_fused<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz_.smem));
-        EDSB_CUDA(cudaFuncSetAttribute(k_scan_fused<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz_.smem));
+        EDSB_CUDA(cudaFuncSetAttribute(k_scan_fused<16, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz_.smem));
+        EDSB_CUDA(cudaFuncSetAttribute(k_scan_fused<32, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz_.smem));
+        EDSB_CUDA(cudaFuncSetAttribute(k_scan_fused<32, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz_.smem));
+        EDSB_CUDA(cudaFuncSetAttribute(k_scan_fused<32, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz_.smem));
         fz_attr_smem_ = fz_.smem;
     }
     if (fz_occ_key_ != key) {
         if (NC == 1) {
             int per_sm = 0;
-            if (T == 16u)
-                EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_fused<16>, (kFzCW + fz_.PW + fz_.DW) * 32, fz_.smem));
-            else
-                EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_fused<32>, (kFzCW + fz_.PW + fz_.DW) * 32, fz_.smem));
+            FZ_KERNEL(EDSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (kFzCW + fz_.PW + fz_.DW) * 32, fz_.smem)));
             fz_occ_regions_ = (uint32_t)std::max(0, per_sm) * (uint32_t)ctx_->sm_count;
         } else {
             cudaLaunchConfig_t cfg;
@@ -2464,10 +2533,7 @@ void MsaPipeline::plan_fused() {
             cfg.attrs = attr;
             cfg.numAttrs = 1;
             int n = 0;
-            if (T == 16u)
-                EDSB_CUDA(cudaOccupancyMaxActiveClusters(&n, k_scan_fused<16>, &cfg));
-            else
-                EDSB_CUDA(cudaOccupancyMaxActiveClusters(&n, k_scan_fused<32>, &cfg));
+            FZ_KERNEL(EDSB_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg)));
             fz_occ_regions_ = (uint32_t)std::max(0, n);
         }
         fz_occ_key_ = key;
@@ -2489,11 +2555,15 @@ void MsaPipeline::plan_fused() {
     f.NC = NC;
     f.RG = RG;
     f.slot_pitch = slot_pitch;
+    f.stage_slots = stage_slots;
+    f.n_direct = n_direct;
+    f.split = ctx_->fused_split;
     f.n_tiles = n_tiles;
     f.all_aligned = g.all_aligned;
     f.PW = fz_.PW;
     f.DW = fz_.DW;
     f.mode = ctx_->fused_mode;
+    f.probe = ctx_->fused_probe;
     f.PWB = 0;
     f.n_bulk = 0;
     if (f.mode == 2u) {
@@ -2589,12 +2659,21 @@ void MsaPipeline::bind(MsaBufs& b) {
 void MsaPipeline::launch_scan(const MsaBufs& b, bool allow_fused) {
     const MsaGeom& g = geom_;
     cudaStream_t s = ctx_->stream;
+    if (allow_fused && fz_.on && fz_.l2) {
+        ctx_->clock.begin("k_scan_l2");
+        const unsigned long long* pack = reinterpret_cast<const unsigned long long*>(g.row_off + g.R);
+        EDSB_LAUNCH(k_scan_l2<true>, fz_.regions, (fz_.CW + fz_.DW) * 32, 0, s, g, pack, fzp_, b.status);
+        ctx_->clock.end();
+        ctx_->clock.begin("k_colbits");
+        EDSB_LAUNCH(k_colbits, partitions(), kPartThreads, 0, s, g, b.mism, b.vbits, b.tbits, b.refc, b.part_cnt);
+        ctx_->clock.end();
+        return;
+    }
     if (allow_fused && fz_.on) {
         ctx_->clock.begin("k_scan_fused");
         const uint32_t threads = (kFzCW + fz_.PW + fz_.DW) * 32, blocks = fz_.regions * fz_.NC;
 #ifdef EDSB_EMU
-        if (fz_.T == 16u) EDSB_LAUNCH(k_scan_fused<16>, blocks, threads, fz_.smem, s, g, fzp_, b.status);
-        else EDSB_LAUNCH(k_scan_fused<32>, blocks, threads, fz_.smem, s, g, fzp_, b.status);
+        FZ_KERNEL(EDSB_LAUNCH(kern, blocks, threads, fz_.smem, s, g, fzp_, b.status));
 #else
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
@@ -2609,10 +2688,7 @@ void MsaPipeline::launch_scan(const MsaBufs& b, bool allow_fused) {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = fz_.NC > 1 ? 1 : 0;
-        if (fz_.T == 16u)
-            EDSB_CUDA(cudaLaunchKernelEx(&cfg, k_scan_fused<16>, g, fzp_, b.status));
-        else
-            EDSB_CUDA(cudaLaunchKernelEx(&cfg, k_scan_fused<32>, g, fzp_, b.status));
+        FZ_KERNEL(EDSB_CUDA(cudaLaunchKernelEx(&cfg, kern, g, fzp_, b.status)));
 #endif
         ctx_->clock.end();
         ctx_->clock.begin("k_colbits");

@@ -44,7 +44,9 @@ class MsaPipeline {
     // k_scan_fused (scan_fused.cuh): geometry of the last prepare(); on = false -> k_scan + k_stash
     struct FzPlan {
         bool on = false;
-        uint32_t S = 0, NC = 1, RG = 0, slot_pitch = 0, regions = 0, capc = 0, PW = 1, DW = 1, T = 32;
+        uint32_t S = 0, NC = 1, RG = 0, slot_pitch = 0, regions = 0, capc = 0, PW = 1, DW = 1, T = 32, H = 1, CW = 8;
+        bool direct = false;  // k_scan_fused with rows that bypass the ring
+        bool l2 = false;  // k_scan_l2 (caches as the stage) instead of k_scan_fused (shared-memory ring)
         size_t smem = 0;
     } fz_;
     FzParams fzp_;

@@ -26,10 +26,10 @@
 namespace edsb {
 
 // rows [first, end) of one word-shift class; a warp instruction covers 32 / T rows (lane = chunk + T * sub)
-template <int WS, int T>
+template <int WS, int T, int H>
 __device__ __forceinline__ void fz_rows(const uint8_t* stg, const unsigned long long* s_pack, uint32_t first, uint32_t end,
                                         uint32_t chunk, uint32_t sub, const uint4& ref, uint4& acc) {
-    constexpr uint32_t kPitch = 16u * (uint32_t)T + 16u, kRows = 32u / (uint32_t)T;
+    constexpr uint32_t kPitch = 16u * (uint32_t)T * (uint32_t)H + 16u, kRows = 32u / (uint32_t)T;
     uint32_t slot = first + sub;
     for (; slot + 3u * kRows < end; slot += 4u * kRows) {
         uint4 lo[4], hi[4];
@@ -51,10 +51,10 @@ __device__ __forceinline__ void fz_rows(const uint8_t* stg, const unsigned long 
     }
 }
 
-template <int T>
+template <int T, int H>
 __device__ __forceinline__ void fz_rows_aligned(const uint8_t* stg, uint32_t first, uint32_t end, uint32_t chunk, uint32_t sub,
                                                 const uint4& ref, uint4& acc) {
-    constexpr uint32_t kPitch = 16u * (uint32_t)T + 16u, kRows = 32u / (uint32_t)T;
+    constexpr uint32_t kPitch = 16u * (uint32_t)T * (uint32_t)H + 16u, kRows = 32u / (uint32_t)T;
     for (uint32_t slot = first + sub; slot < end; slot += kRows) {
         const uint4 lo = *reinterpret_cast<const uint4*>(stg + (size_t)slot * kPitch + 16u * chunk);
         acc.x |= lo.x ^ ref.x;
@@ -70,16 +70,37 @@ __device__ __forceinline__ void fz_rows_aligned(const uint8_t* stg, uint32_t fir
 // (gaps of row 0, line breaks, window edges), stores it, lists the variable columns and copies them out of the
 // stage into its own region of the temporary stash. That is a few hundred dependent instructions per tile — more
 // than a tile's time budget — so DW warps take the tiles in rotation while the consumers stream on.
-template <int T>
+//
+// H = 2 (pairs): the TMA unit takes one bulk copy per ~28 cycles per SM whatever its size, so 528-byte copies cap the
+// kernel near 5 TB/s. A CTA therefore takes its tiles in adjacent PAIRS — iteration `it` is tile
+// 2 (cid + (it / 2) ncl) + (it & 1) — and the producers fetch both tiles of a row with ONE 1040-byte copy into two
+// stages that interleave row by row (row pitch 1040: stage s at + 512 (s & 1)); everything downstream still works tile
+// by tile on its own stage index, barriers and all. Only full[even stage] is armed; the odd tile waits on it too (the
+// phase cannot advance before the odd stage has been released). S and DW are even in this form.
+// Measured (profiles/r02_a_fused_scan.md): slower at the shapes of the benchmark — a pair is refilled only when BOTH its
+// stages are free, so a ring that holds 4 stages keeps half of shared memory in flight instead of three quarters
+// (R = 100: 0.230 ms against 0.208; R = 1000, where only one pair fits: 11.5 ms against 6.7). With the rows split over
+// two CTAs (four pairs fit) pairs do win, 0.28 ms against 0.38, but the cluster exchange costs more than they give.
+// Kept behind EDSB_FUSED_PAIR=1.
+template <int T, int H, bool DIRECT>
 __global__ void __launch_bounds__((kFzCW + kFzMaxPW + kFzMaxDW) * 32, 1) k_scan_fused(MsaGeom g, FzParams f, MsaStatus* st) {
-    constexpr uint32_t kFzT = (uint32_t)T, kFzPitch = 16u * kFzT + 16u;
+    constexpr uint32_t kFzT = (uint32_t)T, kFzH = (uint32_t)H, kFzPitch = 16u * kFzT * kFzH + 16u, kTileBytes = 16u * kFzT;
+    static_assert(H == 1 || (H == 2 && T == 32), "pairs are built for 32-chunk tiles");
     const uint32_t chunk = (threadIdx.x & 31) % kFzT, sub = (threadIdx.x & 31) / kFzT;
     unsigned char* smem = EDSB_DYN_SMEM();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t S = f.S, NC = f.NC, RG = f.RG, PW = f.PW, DW = f.DW;
     const uint32_t rank = NC > 1 ? cluster_rank() : 0u;
     const uint32_t cid = NC > 1 ? cluster_id_x() : blockIdx.x, ncl = NC > 1 ? cluster_count_x() : gridDim.x;
-    const uint32_t stage_bytes = f.slot_pitch * kFzPitch;
+    const uint32_t stage_bytes = f.stage_slots * (kTileBytes + 16u);  // per stage; a pair of stages interleaves inside 2 of them
+    auto stage_ptr = [&](uint32_t s) -> uint8_t* {
+        return kFzH == 1u ? smem + (size_t)s * stage_bytes : smem + (size_t)(s >> 1) * (2u * stage_bytes) + (s & 1u) * kTileBytes;
+    };
+    auto tile_of = [&](uint32_t it) -> uint32_t {
+        const unsigned long long t = kFzH == 1u ? (unsigned long long)cid + (unsigned long long)it * ncl
+                                                 : 2ull * ((unsigned long long)cid + (unsigned long long)(it >> 1) * ncl) + (it & 1u);
+        return t > 0xffffffffull ? 0xffffffffu : (uint32_t)t;
+    };
 
     uint8_t* stages = smem;
     uint32_t* red16 = reinterpret_cast<uint32_t*>(stages + (size_t)S * stage_bytes);  // [S][32]
@@ -88,13 +109,27 @@ __global__ void __launch_bounds__((kFzCW + kFzMaxPW + kFzMaxDW) * 32, 1) k_scan_
     uint16_t* s_info = reinterpret_cast<uint16_t*>(s_pack + f.slot_pitch);
     uint32_t* s_off16 = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(s_info) + ((RG * 2u + 15u) & ~15u));  // [slot_pitch]
     uint16_t* s_vpos = reinterpret_cast<uint16_t*>(s_off16 + ((f.slot_pitch + 3u) & ~3u));  // [DW][512]
-    Mbar* full = reinterpret_cast<Mbar*>(s_vpos + DW * 16u * kFzT);
-    Mbar* empty = full + S;
+    // full: one barrier per stage, or (f.split) one per stage and producer warp — the completions of a stage's ~100 bulk
+    // copies then update PW barriers instead of queueing on one
+    Mbar* full_base = reinterpret_cast<Mbar*>(s_vpos + DW * 16u * kFzT);  // [S][kFzMaxPW]
+    const bool split = f.split && f.mode == 0u && kFzH == 1u && kFzT == 32u;
+    const uint32_t fstep = split ? kFzMaxPW : 1u;
+    Mbar* full = full_base;  // stage s, part p: full[s * fstep + p]
+    Mbar* empty = full_base + S * kFzMaxPW;
     Mbar* red_full = empty + S;    // [S]
     Mbar* maskbar = red_full + S;  // [2S] cluster exchange of the partial masks
 
     const uint32_t* meta = f.meta + rank * 8u;
     const uint32_t nslots = meta[0];
+    // Direct rows: the TMA unit takes one bulk copy per ~28 cycles whatever its size, which caps a ring fed with 528-byte
+    // copies at 5.3 TB/s. The last nd slots therefore never enter the ring: the consumer warps load their 16-byte vectors
+    // of those rows straight into registers BEFORE they wait for the stage (the loads fly while the stage fills), and
+    // the duty warp reads their residues of the variable columns from global memory (L2: just loaded).
+    // Measured (profiles/r02_a_fused_scan.md): slower, 0.27 - 0.30 ms against 0.21 at R = 100 — the loads of tile `it` are only
+    // issued when the warp reaches tile `it`, so their DRAM latency is paid per tile instead of hidden by the ring; the
+    // registers to issue them a tile ahead are not there. Kept behind EDSB_FUSED_DIRECT=n (its own instantiation).
+    const uint32_t nd = (DIRECT && kFzT == 32u && kFzH == 1u) ? min(f.n_direct, (nslots - 1u) / 2u) : 0u;
+    const uint32_t ns = nslots - nd;  // staged slots
     const uint32_t cls0 = meta[1], cls1 = meta[2], cls2 = meta[3], cls3 = meta[4], cls4 = meta[5];
     for (uint32_t i = threadIdx.x; i < nslots; i += blockDim.x) {
         const unsigned long long e = f.pack[(size_t)rank * f.slot_pitch + i];
@@ -105,7 +140,10 @@ __global__ void __launch_bounds__((kFzCW + kFzMaxPW + kFzMaxDW) * 32, 1) k_scan_
     for (uint32_t i = threadIdx.x; i < S * 32u; i += blockDim.x) red16[i] = 0u;
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < S; ++s) {
-            mbar_init(&full[s], (f.mode == 2u && kFzT == 32u) ? f.PWB + (PW - f.PWB) * 32u : ((f.mode == 0 || kFzT != 32u) ? PW : PW * 32u));
+            if (split)
+                for (uint32_t p = 0; p < PW; ++p) mbar_init(&full[s * fstep + p], 1);
+            else
+                mbar_init(&full[s], (f.mode == 2u && kFzT == 32u) ? f.PWB + (PW - f.PWB) * 32u : ((f.mode == 0 || kFzT != 32u) ? PW : PW * 32u));
             mbar_init(&empty[s], kFzCW + 1);
             mbar_init(&red_full[s], kFzCW);
             mbar_init(&maskbar[2u * s], 1);
@@ -118,22 +156,62 @@ __global__ void __launch_bounds__((kFzCW + kFzMaxPW + kFzMaxDW) * 32, 1) k_scan_
 
     if (warp < (uint32_t)kFzCW) {
         // ---------------------------------------------------------------- consumer warps: a contiguous share of the slots
-        const uint32_t n_rows = nslots - 1u;
+        const uint32_t n_rows = ns - 1u;
         const uint32_t my_lo = 1u + n_rows * warp / (uint32_t)kFzCW, my_hi = 1u + n_rows * (warp + 1u) / (uint32_t)kFzCW;
-        uint32_t it = 0;
-        for (uint32_t tile = cid; tile < f.n_tiles; tile += ncl, ++it) {
+        constexpr uint32_t kDirectPerWarp = DIRECT ? (kFzMaxDirect + (uint32_t)kFzCW - 1u) / (uint32_t)kFzCW : 1u;
+        const uint4* gvec = reinterpret_cast<const uint4*>(g.text);
+        const long long gvmax = (long long)g.n_vec - 1;
+        for (uint32_t it = 0; tile_of(it) < f.n_tiles; ++it) {
             const uint32_t s = it % S;
-            mbar_wait(&full[s], (it / S) & 1u);
-            const uint8_t* stg = stages + (size_t)s * stage_bytes;
+            uint4 dlo[kDirectPerWarp], dhi[kDirectPerWarp];
+            if (DIRECT && nd) {
+                const uint32_t tile = tile_of(it);
+                const bool inside = (long long)tile >= f.tile_lo_ok && (long long)tile < f.tile_hi_ok;
+#pragma unroll
+                for (uint32_t k = 0; k < kDirectPerWarp; ++k) {
+                    const uint32_t slot = ns + warp + k * (uint32_t)kFzCW;
+                    const unsigned long long e = s_pack[slot < nslots ? slot : 0u];
+                    long long vi = ((long long)((e & ~15ull) - (unsigned long long)(uintptr_t)g.text) >> 4) + (long long)tile * kFzT + lane;
+                    if (inside) {
+                        dlo[k] = ldg_nc(gvec + vi);
+                        dhi[k] = ldg_nc(gvec + vi + 1);
+                    } else {
+                        const long long va = vi < 0 ? 0 : (vi > gvmax ? gvmax : vi);
+                        long long vb = vi + 1;
+                        vb = vb < 0 ? 0 : (vb > gvmax ? gvmax : vb);
+                        dlo[k] = ldg_nc(gvec + va);
+                        dhi[k] = ldg_nc(gvec + vb);
+                    }
+                }
+            }
+            if (split)
+                for (uint32_t p = 0; p < PW; ++p) mbar_wait(&full[s * fstep + p], (it / S) & 1u);
+            else
+                mbar_wait(&full[kFzH == 1u ? s : (s & ~1u)], (it / S) & 1u);
+            const uint8_t* stg = stage_ptr(s);
             const uint4 ref = *reinterpret_cast<const uint4*>(stg + 16u * chunk);  // slot 0 = row 0, shift 0
             uint4 acc = make_uint4(0, 0, 0, 0);
-            if (f.all_aligned) {
-                fz_rows_aligned<T>(stg, my_lo, my_hi, chunk, sub, ref, acc);
+            if (DIRECT && nd && !(f.probe & 1u)) {
+#pragma unroll
+                for (uint32_t k = 0; k < kDirectPerWarp; ++k) {
+                    const uint32_t slot = ns + warp + k * (uint32_t)kFzCW;
+                    if (slot < nslots) {
+                        const uint4 x = realign16(dlo[k], dhi[k], (uint32_t)s_pack[slot] & 15u);
+                        acc.x |= x.x ^ ref.x;
+                        acc.y |= x.y ^ ref.y;
+                        acc.z |= x.z ^ ref.z;
+                        acc.w |= x.w ^ ref.w;
+                    }
+                }
+            }
+            if (f.probe & 1u) {
+            } else if (f.all_aligned) {
+                fz_rows_aligned<T, H>(stg, my_lo, my_hi, chunk, sub, ref, acc);
             } else {
-                fz_rows<0, T>(stg, s_pack, max(my_lo, cls0), min(my_hi, cls1), chunk, sub, ref, acc);
-                fz_rows<1, T>(stg, s_pack, max(my_lo, cls1), min(my_hi, cls2), chunk, sub, ref, acc);
-                fz_rows<2, T>(stg, s_pack, max(my_lo, cls2), min(my_hi, cls3), chunk, sub, ref, acc);
-                fz_rows<3, T>(stg, s_pack, max(my_lo, cls3), min(my_hi, cls4), chunk, sub, ref, acc);
+                fz_rows<0, T, H>(stg, s_pack, max(my_lo, cls0), min(my_hi, cls1), chunk, sub, ref, acc);
+                fz_rows<1, T, H>(stg, s_pack, max(my_lo, cls1), min(my_hi, cls2), chunk, sub, ref, acc);
+                fz_rows<2, T, H>(stg, s_pack, max(my_lo, cls2), min(my_hi, cls3), chunk, sub, ref, acc);
+                fz_rows<3, T, H>(stg, s_pack, max(my_lo, cls3), min(my_hi, cls4), chunk, sub, ref, acc);
             }
             // red16[s] is zero again by now: the duty warp of the tile that last used stage s cleared it before it let
             // the stage go, and full[s] completed after that
@@ -156,27 +234,34 @@ __global__ void __launch_bounds__((kFzCW + kFzMaxPW + kFzMaxDW) * 32, 1) k_scan_
         const uint32_t pw_all = warp - (uint32_t)kFzCW;
         const bool hybrid = f.mode == 2u && kFzT == 32u;
         const bool bulk = hybrid ? pw_all < f.PWB : (f.mode == 0u || kFzT != 32u);
-        const uint32_t cut = min(f.n_bulk, nslots);
-        const uint32_t lo_slot = hybrid ? (bulk ? 0u : cut) : 0u, hi_slot = hybrid ? (bulk ? cut : nslots) : nslots;
+        const uint32_t cut = min(f.n_bulk, ns);
+        const uint32_t lo_slot = hybrid ? (bulk ? 0u : cut) : 0u, hi_slot = hybrid ? (bulk ? cut : ns) : ns;
         const uint32_t pw = hybrid ? (bulk ? pw_all : pw_all - f.PWB) : pw_all, PWg = hybrid ? (bulk ? f.PWB : PW - f.PWB) : PW;
         const uint4* vec = reinterpret_cast<const uint4*>(g.text);
         const long long vmax = (long long)g.n_vec - 1;
         const uint8_t* base0 = g.text + g.d_min_vec * 16;  // s_off16[slot] counts 16-byte vectors from here
         uint32_t my_slots = 0;  // slots lo + pw * 32 + lane + 32 * PWg * m of all lanes together
         for (uint32_t base = lo_slot + pw * 32u; base < hi_slot; base += 32u * PWg) my_slots += min(32u, hi_slot - base);
-        uint32_t it = 0;
-        for (uint32_t tile = cid; tile < f.n_tiles; tile += ncl, ++it) {
+        // one tile (H = 1) or a pair of adjacent tiles (H = 2) per step; copy_tiles = how many of them exist
+        for (uint32_t it = 0; tile_of(it) < f.n_tiles; it += kFzH) {
+            const uint32_t tile = tile_of(it);
             const uint32_t s = it % S;
-            if (it >= S) mbar_wait(&empty[s], ((it / S) - 1u) & 1u);
-            uint8_t* dst = stages + (size_t)s * stage_bytes;
-            const size_t toff = (size_t)tile * (16u * kFzT);
-            if ((long long)tile >= f.tile_lo_ok && (long long)tile < f.tile_hi_ok) {
+            const uint32_t n_here = (kFzH == 2u && tile + 1u < f.n_tiles) ? 2u : 1u;
+            if (it >= S) {
+                mbar_wait(&empty[s], ((it / S) - 1u) & 1u);
+                if (kFzH == 2u) mbar_wait(&empty[s + 1u], ((it / S) - 1u) & 1u);
+            }
+            uint8_t* dst = stage_ptr(s);
+            const size_t toff = (size_t)tile * kTileBytes;
+            if ((long long)tile >= f.tile_lo_ok && (long long)(tile + n_here - 1u) < f.tile_hi_ok) {
                 if (bulk) {
-                    if (lane == 0) mbar_arrive_expect_tx(&full[s], my_slots * kFzPitch);
+                    const uint32_t copy_bytes = n_here * kTileBytes + 16u;
+                    Mbar* fb = &full[split ? s * fstep + pw_all : s];
+                    if (lane == 0) mbar_arrive_expect_tx(fb, my_slots * copy_bytes);
                     __syncwarp();
                     for (uint32_t slot = lo_slot + pw * 32u + lane; slot < hi_slot; slot += 32u * PWg)
                         bulk_g2s(dst + (size_t)slot * kFzPitch, reinterpret_cast<const uint8_t*>((uintptr_t)(s_pack[slot] & ~15ull)) + toff,
-                                 kFzPitch, &full[s]);
+                                 copy_bytes, fb);
                 } else {
                     // lean issue loop: one shared-memory read (the row's offset in 16-byte units), one 64-bit multiply-add
                     // and the copy per row; the destination steps by a constant
@@ -193,10 +278,12 @@ __global__ void __launch_bounds__((kFzCW + kFzMaxPW + kFzMaxDW) * 32, 1) k_scan_
                     cp_async_arrive_noinc(&full[s]);
                 }
             } else {
+                // the first / last tiles of a window: clamped plain loads, vector by vector
+                const uint32_t n_vec_row = n_here * kFzT + 1u;
                 for (uint32_t base = lo_slot + pw * 32u; base < hi_slot; base += 32u * PWg) {
                     const uint32_t top = min(hi_slot, base + 32u);
-                    for (uint32_t idx = lane; idx < (top - base) * (kFzT + 1u); idx += 32) {
-                        const uint32_t slot = base + idx / (kFzT + 1u), k = idx % (kFzT + 1u);
+                    for (uint32_t idx = lane; idx < (top - base) * n_vec_row; idx += 32) {
+                        const uint32_t slot = base + idx / n_vec_row, k = idx % n_vec_row;
                         const long long d16 = (long long)((s_pack[slot] & ~15ull) - (unsigned long long)(uintptr_t)g.text) >> 4;
                         long long vi = d16 + (long long)tile * kFzT + k;
                         vi = vi < 0 ? 0 : (vi > vmax ? vmax : vi);
@@ -204,7 +291,7 @@ __global__ void __launch_bounds__((kFzCW + kFzMaxPW + kFzMaxDW) * 32, 1) k_scan_
                     }
                 }
                 __syncwarp();
-                if (!bulk || lane == 0) mbar_arrive(&full[s]);
+                if (!bulk || lane == 0) mbar_arrive(&full[split ? s * fstep + pw_all : s]);
             }
         }
     } else {
@@ -217,30 +304,44 @@ __global__ void __launch_bounds__((kFzCW + kFzMaxPW + kFzMaxDW) * 32, 1) k_scan_
         uint32_t local_cnt = 0, bad = 0, overflow = 0;
         // this lane's four rows of the gather: byte offset of the row inside a stage, and which of the four exist
         uint32_t roff[4], rmask = 0;
+        const uint8_t* gsrc[4];  // direct rows: p-space byte 0 of the row in global memory (else null: the row is in the stage)
         const bool have_rows = 4u * lane < RG && rank * RG + 4u * lane < g.Rp;
 #pragma unroll
         for (uint32_t k = 0; k < 4u; ++k) {
             const uint32_t inf = have_rows ? s_info[4u * lane + k] : 0xffffu;
             roff[k] = inf == 0xffffu ? 0u : (inf >> 4) * kFzPitch + (inf & 15u);
             if (inf != 0xffffu) rmask |= 0xffu << (8u * k);
+            gsrc[k] = nullptr;
+            if (inf != 0xffffu && (inf >> 4) >= ns) {
+                roff[k] = 0u;
+                gsrc[k] = reinterpret_cast<const uint8_t*>((uintptr_t)(s_pack[inf >> 4] & ~15ull)) + (inf & 15u);
+            }
         }
         // position of this lane's chunk inside a text line, kept up to date by addition (no division per tile)
+        // (pairs: DW is even, so a duty warp keeps its parity inside the pairs and still advances DW * ncl tiles a turn)
         const uint32_t step = (uint32_t)(((uint64_t)DW * ncl * (16u * kFzT)) % line);
         uint32_t rb;
         {
-            const uint64_t t0 = (uint64_t)cid + (uint64_t)dw * ncl;
+            const uint64_t t0 = kFzH == 1u ? (uint64_t)cid + (uint64_t)dw * ncl : 2ull * ((uint64_t)cid + (uint64_t)(dw >> 1) * ncl) + (dw & 1u);
             const uint64_t v = g.u_begin + t0 * (16u * kFzT) + 16u * lane + 16ull * line - g.a0;  // + 16 lines: never negative
             rb = (uint32_t)(v % line);
         }
-        uint32_t it = 0;
-        for (uint32_t tile = cid; tile < f.n_tiles; tile += ncl, ++it) {
+        for (uint32_t it = 0; tile_of(it) < f.n_tiles; ++it) {
             if (it % DW != dw) continue;
+            const uint32_t tile = tile_of(it);
             const uint32_t s = it % S;
             mbar_wait(&red_full[s], (it / S) & 1u);
             const bool live = lane < kFzT;  // lanes beyond the tile's chunks idle (16-chunk tiles)
             uint32_t nz = red16[s * 32u + lane];
             red16[s * 32u + lane] = 0u;
-            const uint8_t* stg = stages + (size_t)s * stage_bytes;  // the stage is held until this warp lets go
+            if (f.probe & 2u) {
+                const uint64_t jj = (uint64_t)tile * kFzT + lane;
+                if (live && rank == 0 && jj < g.n_chunks) f.mism16[jj] = 0;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                continue;
+            }
+            const uint8_t* stg = stage_ptr(s);  // the stage is held until this warp lets go
             const uint4 ref = *reinterpret_cast<const uint4*>(stg + 16u * (live ? lane : 0u));
             if (NC > 1) {
                 // partial mismatch bits of this CTA's rows -> every CTA of the cluster (distributed shared memory).
@@ -298,15 +399,22 @@ __global__ void __launch_bounds__((kFzCW + kFzMaxPW + kFzMaxDW) * 32, 1) k_scan_
                 uint32_t at = incl - cnt;
                 for (uint32_t bits = mism; bits; bits &= bits - 1u) vp[at++] = (uint16_t)(16u * lane + (uint32_t)__ffs((int)bits) - 1u);
                 __syncwarp();
-                if (local_cnt + total <= f.capc) {
+                if (f.probe & 4u) {
+                } else if (local_cnt + total <= f.capc) {
                     // two columns per round: eight independent byte reads in flight per lane
                     uint8_t* out = f.tmp_stash + ((size_t)region * f.capc + local_cnt) * g.Rp + rank * RG + 4u * lane;
                     for (uint32_t i = 0; i < total; i += 2u) {
                         const uint32_t v0 = vp[i], v1 = vp[min(i + 1u, total - 1u)];
                         const uint8_t* c0 = stg + v0;
                         const uint8_t* c1 = stg + v1;
-                        uint32_t w0 = (uint32_t)c0[roff[0]] | ((uint32_t)c0[roff[1]] << 8) | ((uint32_t)c0[roff[2]] << 16) | ((uint32_t)c0[roff[3]] << 24);
-                        uint32_t w1 = (uint32_t)c1[roff[0]] | ((uint32_t)c1[roff[1]] << 8) | ((uint32_t)c1[roff[2]] << 16) | ((uint32_t)c1[roff[3]] << 24);
+                        uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+                        for (uint32_t k = 0; k < 4u; ++k) {
+                            const uint8_t* p0 = (DIRECT && gsrc[k]) ? gsrc[k] + tp + v0 : c0 + roff[k];
+                            const uint8_t* p1 = (DIRECT && gsrc[k]) ? gsrc[k] + tp + v1 : c1 + roff[k];
+                            w0 |= (uint32_t)*p0 << (8u * k);
+                            w1 |= (uint32_t)*p1 << (8u * k);
+                        }
                         w0 &= rmask;
                         w1 &= rmask;
                         if (have_rows) {

@@ -177,6 +177,7 @@ struct eds_group {
     std::vector<edsb::DevBuf> window;   // per device: the window's rows, 16-byte aligned pitch
     std::vector<uint64_t*> d_counts;    // per device: 2 + 2 n
     std::vector<uint64_t*> h_counts;    // per device, pinned: 2 + 2 n
+    edsb::DevBuf gather[2];             // first device: the slices' EDS / SEDS text joined over NVLink (vcf2eds, l > 0)
     void* host_out[2] = {nullptr, nullptr};  // pinned results of the *_view calls, grow-only
     size_t host_out_cap[2] = {0, 0};
     uint8_t* view_slot(int which, uint64_t bytes) {
@@ -368,6 +369,9 @@ void eds_group_destroy(eds_group* g) {
     }
     for (int which = 0; which < 2; ++which)
         if (g->host_out[which]) cudaFreeHost(g->host_out[which]);
+    if (!g->ctx.empty()) cudaSetDevice(g->ctx[0]->device);
+    g->gather[0].release();
+    g->gather[1].release();
     delete g;
 }
 
@@ -1018,7 +1022,7 @@ eds_status group_vcf_transform(eds_group* g, const uint8_t* vcf, uint64_t vcf_by
                     : eds_vcf_transform_host(g->ctx[0], vcf, vcf_bytes, fasta, fasta_bytes, l, eds_out, seds_out, stats, sv_lines, n_sv_lines);
     };
     auto drop = [&](uint8_t* p) {
-        if (!view) free(p);
+        if (!view && l == 0) free(p);  // (l > 0: the group's gather buffers; view: its pinned slots)
     };
     if (n < 2 || vcf_bytes < (uint64_t)n * 64) return single();
 
@@ -1090,7 +1094,18 @@ eds_status group_vcf_transform(eds_group* g, const uint8_t* vcf, uint64_t vcf_by
                         etot += slice[i].de.bytes;
                         stot += slice[i].ds.bytes;
                     }
-                    if (view) {
+                    if (l > 0) {
+                        // the joined text stays in HBM: every device pushes its slice to the first one (peer copies,
+                        // NVLink where the devices have it), which merges it there
+                        try {
+                            g->gather[0].reserve(etot + 16);
+                            g->gather[1].reserve(stot + 16);
+                            h_eds = g->gather[0].as<uint8_t>();
+                            h_seds = g->gather[1].as<uint8_t>();
+                        } catch (const std::exception&) {
+                            all_ok = false;
+                        }
+                    } else if (view) {
                         try {
                             h_eds = g->view_slot(0, etot);
                             h_seds = g->view_slot(1, stot);
@@ -1112,8 +1127,14 @@ eds_status group_vcf_transform(eds_group* g, const uint8_t* vcf, uint64_t vcf_by
                 so += slice[i].ds.bytes;
             }
             cudaError_t e = cudaSuccess;
-            if (me.de.bytes) e = cudaMemcpyAsync(h_eds + eo, me.de.data, me.de.bytes, cudaMemcpyDeviceToHost, c->stream);
-            if (e == cudaSuccess && me.ds.bytes) e = cudaMemcpyAsync(h_seds + so, me.ds.data, me.ds.bytes, cudaMemcpyDeviceToHost, c->stream);
+            if (l > 0) {
+                const int d0 = g->ctx[0]->device;
+                if (me.de.bytes) e = cudaMemcpyPeerAsync(h_eds + eo, d0, me.de.data, c->device, me.de.bytes, c->stream);
+                if (e == cudaSuccess && me.ds.bytes) e = cudaMemcpyPeerAsync(h_seds + so, d0, me.ds.data, c->device, me.ds.bytes, c->stream);
+            } else {
+                if (me.de.bytes) e = cudaMemcpyAsync(h_eds + eo, me.de.data, me.de.bytes, cudaMemcpyDeviceToHost, c->stream);
+                if (e == cudaSuccess && me.ds.bytes) e = cudaMemcpyAsync(h_seds + so, me.ds.data, me.ds.bytes, cudaMemcpyDeviceToHost, c->stream);
+            }
             if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
             if (e != cudaSuccess) me.status = 2;
         });
@@ -1167,30 +1188,24 @@ eds_status group_vcf_transform(eds_group* g, const uint8_t* vcf, uint64_t vcf_by
         if (stats) *stats = tot;
         return EDS_OK;
     }
-    uint32_t rounds = 0, merged_on = 1;
-    eds_status rc = eds_group_leds_merge_host(g, h_eds, etot, h_seds, stot, l, 1, eds_out, seds_out, &rounds, &merged_on);
-    drop(h_eds);
-    drop(h_seds);
-    if (rc == EDS_OK && view) {
-        // the merged text back into the group's pinned slots (the intermediate they held has been consumed)
-        rc = guarded_shard([&] {
-            EDSB_CUDA(cudaSetDevice(g->ctx[0]->device));
-            uint8_t* pe = g->view_slot(0, eds_out->bytes);
-            uint8_t* ps = g->view_slot(1, seds_out->bytes);
-            memcpy(pe, eds_out->data, eds_out->bytes);
-            memcpy(ps, seds_out->data, seds_out->bytes);
-            const uint64_t nb[2] = {eds_out->bytes, seds_out->bytes};
-            eds_buffer_free_host(eds_out);
-            eds_buffer_free_host(seds_out);
-            *eds_out = eds_buffer{pe, nb[0]};
-            *seds_out = eds_buffer{ps, nb[1]};
-        });
-        if (rc != EDS_OK) {
+    // parse_vcf_to_leds_streaming :750-752: LINEAR merge (compact) of the text just joined, still in HBM, on the first device
+    if (stats) *stats = tot;  // the reference fills the counters before the merge can throw
+    uint32_t rounds = 0;
+    const eds_status rc = guarded_shard([&] {
+        eds_ctx* c0 = g->ctx[0];
+        EDSB_CUDA(cudaSetDevice(c0->device));
+        std::function<uint8_t*(int, uint64_t)> sink;
+        if (view) sink = [g](int which, uint64_t bytes) -> uint8_t* { return g->view_slot(which, bytes); };
+        c0->leds->merge_host(h_eds, etot, h_seds, stot, l, true, 0, eds_out, seds_out, &rounds, nullptr, true, sink);
+    });
+    if (rc != EDS_OK) {
+        if (view) {
+            *eds_out = eds_buffer{nullptr, 0};
+            *seds_out = eds_buffer{nullptr, 0};
+        } else {
             eds_buffer_free_host(eds_out);
             eds_buffer_free_host(seds_out);
         }
-    }
-    if (rc != EDS_OK) {
         if (sv_lines && *sv_lines) {
             free(*sv_lines);
             *sv_lines = nullptr;

@@ -320,7 +320,7 @@ eds_status eds_group_leds_merge_host(eds_group* group, const uint8_t* eds, uint6
  * with the whole FASTA record; the slices meet once inside the transform (one sort of all positions for the tie order
  * of the reference's unstable std::sort, vcf_transforms.cpp:715-718; no overlapping group may span a cut; each slice
  * renders the reference bases up to the next slice's first group). Arguments and results as eds_vcf_transform_host
- * (vcf_transforms.cpp:677-755); l > 0 runs eds_group_leds_merge_host on the joined text. Input the slices cannot be
+ * (vcf_transforms.cpp:677-755); l > 0: the slices are joined in the first device's memory (peer copies) and merged there. Input the slices cannot be
  * joined on (a slice without records, a spanning group, an error) runs on the group's first device.
  * shards_used (optional): devices that took part. */
 eds_status eds_group_vcf_transform_host(eds_group* group, const uint8_t* vcf, uint64_t vcf_bytes, const uint8_t* fasta,

@@ -327,6 +327,10 @@ inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) 
     if (n) memmove(d, s, n);
     return cudaSuccess;
 }
+inline cudaError_t cudaMemcpyPeerAsync(void* d, int, const void* s, int, size_t n, cudaStream_t = nullptr) {
+    memcpy(d, s, n);
+    return cudaSuccess;
+}
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) {
     if (n) memmove(d, s, n);
     return cudaSuccess;

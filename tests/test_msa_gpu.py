@@ -91,28 +91,40 @@ def test_synth_wide_rows(ctx):
     msa_checks.check_synth(ctx, n_rows=5000, n_cols=3_000, wrap=70, l=5, variable_ppm=20000)
 
 
-def test_synth_cluster_sizes(ctx):
-    # k_scan_fused splits the rows of a tile over a thread-block cluster: 1 CTA up to 128 rows, then 2, 4, 8
-    for rows in (33, 128, 129, 200, 300, 520, 777, 1024):
-        st = msa_checks.check_synth(ctx, n_rows=rows, n_cols=40_000, wrap=80, l=10, variable_ppm=15000, shards=2)
-        assert st["n_variable_cols"] > 300
-
-
-def test_fused_scan_matches_two_pass(lib):
-    # the same alignments through k_scan + k_stash (EDSB_FUSED=0) and through k_scan_fused
+def test_synth_cluster_sizes(lib):
+    # k_scan_l2 (default) takes any depth up to 2048 rows in one CTA; k_scan_fused (EDSB_FUSED_L2=0) splits the rows of a
+    # tile over a thread-block cluster: 1 CTA up to 128 rows, then 2, 4, 8
     import os
 
-    for env in ("0", "1"):
-        os.environ["EDSB_FUSED"] = env
+    for l2 in ("1", "0"):
+        os.environ["EDSB_FUSED_L2"] = l2
         try:
             c = lib.context(0)
         finally:
-            del os.environ["EDSB_FUSED"]
+            del os.environ["EDSB_FUSED_L2"]
+        try:
+            for rows in (33, 128, 129, 200, 300, 520, 777, 1024):
+                st = msa_checks.check_synth(c, n_rows=rows, n_cols=40_000, wrap=80, l=10, variable_ppm=15000, shards=2)
+                assert st["n_variable_cols"] > 300
+        finally:
+            c.close()
+
+
+def test_fused_scan_matches_two_pass(lib):
+    # the same alignments through k_scan + k_stash (EDSB_FUSED=0), k_scan_fused (the TMA ring) and k_scan_l2 (the default)
+    import os
+
+    for fused, l2, name in (("0", "1", "k_scan"), ("1", "0", "k_scan_fused"), ("1", "1", "k_scan_l2")):
+        os.environ.update({"EDSB_FUSED": fused, "EDSB_FUSED_L2": l2})
+        try:
+            c = lib.context(0)
+        finally:
+            del os.environ["EDSB_FUSED"], os.environ["EDSB_FUSED_L2"]
         try:
             c.set_profiling(True)
             msa_checks.check_synth(c, n_rows=100, n_cols=150_000, wrap=80, l=10)
             names = [n for n, _ in c.kernel_times()]
-            assert ("k_scan_fused" in names) == (env == "1") and ("k_stash" in names) == (env == "0")
+            assert name in names and ("k_stash" in names) == (fused == "0")
             c.set_profiling(False)
             msa_checks.check_random_against_oracle(c, seed=5, n_cases=30, max_rows=150, max_cols=3000)
         finally:
