@@ -57,6 +57,7 @@ eds_status guarded(F&& body) {
 void use_device(eds_ctx* ctx) {
     if (!ctx) throw std::invalid_argument("null eds_ctx");
     EDSB_CUDA(cudaSetDevice(ctx->device));
+    (void)cudaGetLastError();  // a non-sticky error some earlier call of this thread left behind is not this call's
 }
 
 uint8_t* to_host(eds_ctx* ctx, const eds_buffer& dev) {

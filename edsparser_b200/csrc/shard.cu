@@ -359,6 +359,11 @@ eds_status eds_group_create(const int* devices, int n_devices, eds_group** out) 
 
 void eds_group_destroy(eds_group* g) {
     if (!g) return;
+    if (!g->ctx.empty() && g->ctx[0]) {  // buffers of the first device, while its context is still there
+        cudaSetDevice(g->ctx[0]->device);
+        g->gather[0].release();
+        g->gather[1].release();
+    }
     for (size_t i = 0; i < g->ctx.size(); ++i) {
         cudaSetDevice(g->ctx[i]->device);
         if (i < g->comm.size() && g->comm[i]) nccl().CommDestroy(g->comm[i]);
@@ -369,9 +374,6 @@ void eds_group_destroy(eds_group* g) {
     }
     for (int which = 0; which < 2; ++which)
         if (g->host_out[which]) cudaFreeHost(g->host_out[which]);
-    if (!g->ctx.empty()) cudaSetDevice(g->ctx[0]->device);
-    g->gather[0].release();
-    g->gather[1].release();
     delete g;
 }
 
