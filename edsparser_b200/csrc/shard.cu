@@ -161,12 +161,16 @@ struct eds_comm {
     eds_ctx* ctx = nullptr;
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
-    static constexpr int kRing = 2;
-    uint64_t* h_mine[kRing] = {nullptr, nullptr};  // pinned: this rank's (eds, seds) bytes
-    uint64_t* h_all[kRing] = {nullptr, nullptr};   // pinned: everyone's, as gathered
-    uint64_t* d_mine = nullptr;                    // device: kRing x 2
-    uint64_t* d_all = nullptr;                     // device: kRing x 2 x world
-    cudaEvent_t done[kRing] = {nullptr, nullptr};
+    static constexpr int kRing = 4;
+    uint64_t* h_mine[kRing] = {};  // pinned: this rank's (eds, seds) bytes
+    uint64_t* h_all[kRing] = {};   // pinned: everyone's, as gathered
+    uint64_t* d_mine = nullptr;    // device: kRing x 2
+    uint64_t* d_all = nullptr;     // device: kRing x 2 x world
+    cudaEvent_t done[kRing] = {};
+    // The counts are host values (the transform has returned them), so the exchange depends on nothing the context's
+    // stream still holds: it runs on a stream of its own and the next transform does not queue behind the all-gather
+    // (which would make every step wait for the slowest rank).
+    cudaStream_t side = nullptr;
     uint64_t posted = 0;
 };
 
@@ -230,6 +234,7 @@ eds_status eds_comm_create(eds_ctx* ctx, const uint8_t id[128], int rank, int wo
                 EDSB_CUDA(cudaMallocHost(&c->h_all[i], (size_t)world * 16));
                 EDSB_CUDA(cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming));
             }
+            EDSB_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
             EDSB_CUDA(cudaMalloc(&c->d_mine, eds_comm::kRing * 16));
             EDSB_CUDA(cudaMalloc(&c->d_all, (size_t)eds_comm::kRing * world * 16));
         } catch (...) {
@@ -244,7 +249,9 @@ void eds_comm_destroy(eds_comm* c) {
     if (!c) return;
     cudaSetDevice(c->ctx->device);
     cudaStreamSynchronize(c->ctx->stream);
+    if (c->side) cudaStreamSynchronize(c->side);
     if (c->comm) nccl().CommDestroy(c->comm);
+    if (c->side) cudaStreamDestroy(c->side);
     for (int i = 0; i < eds_comm::kRing; ++i) {
         if (c->h_mine[i]) cudaFreeHost(c->h_mine[i]);
         if (c->h_all[i]) cudaFreeHost(c->h_all[i]);
@@ -262,7 +269,7 @@ eds_status eds_comm_post(eds_comm* c, uint64_t eds_bytes, uint64_t seds_bytes) {
         if (!c) throw std::invalid_argument("eds_comm_post: null comm");
         EDSB_CUDA(cudaSetDevice(c->ctx->device));
         const int k = (int)(c->posted % eds_comm::kRing);
-        cudaStream_t s = c->ctx->stream;
+        cudaStream_t s = c->side;
         if (c->posted >= (uint64_t)eds_comm::kRing) EDSB_CUDA(cudaEventSynchronize(c->done[k]));  // the post that used this slot
         c->h_mine[k][0] = eds_bytes;
         c->h_mine[k][1] = seds_bytes;
@@ -305,7 +312,10 @@ eds_status eds_comm_offsets(eds_comm* c, uint64_t out[4]) {
 eds_status eds_comm_flush(eds_comm* c) {
     return guarded_shard([&] {
         if (!c) throw std::invalid_argument("eds_comm_flush: null comm");
-        // the posts were enqueued on the context's own stream: they are ordered before anything enqueued from now on
+        if (c->posted == 0) return;
+        EDSB_CUDA(cudaSetDevice(c->ctx->device));
+        // the posts run on the comm's own stream: the context's stream waits for the last one (they complete in order)
+        EDSB_CUDA(cudaStreamWaitEvent(c->ctx->stream, c->done[(c->posted - 1) % eds_comm::kRing], 0));
     });
 }
 

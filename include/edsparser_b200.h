@@ -338,8 +338,9 @@ eds_status eds_group_vcf_transform_host_view(eds_group* group, const uint8_t* vc
 
 /* eds_comm: one process PER GPU (torchrun, mpirun): rank 0 makes the 128-byte NCCL id, the launcher ships it to
  * every rank, each rank builds the communicator for its context. After every eds_msa_transform_device the rank
- * posts its byte counts (enqueued behind the transform, no host synchronisation, two posts may be in flight);
- * eds_comm_offsets waits for the last post and returns {eds offset, seds offset, eds total, seds total}. */
+ * posts its byte counts (host values by then: the exchange runs on the comm's own stream beside the next transform,
+ * no host synchronisation, four posts may be in flight); eds_comm_offsets waits for the last post and returns
+ * {eds offset, seds offset, eds total, seds total}; eds_comm_flush makes the context's stream wait for it. */
 typedef struct eds_comm eds_comm;
 eds_status eds_nccl_unique_id(uint8_t out[128]);
 eds_status eds_comm_create(eds_ctx* ctx, const uint8_t id[128], int rank, int world, eds_comm** out);

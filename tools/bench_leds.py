@@ -152,6 +152,8 @@ def main():
     sizes = [int(x) for x in sys.argv[1:]] or [20_000, 100_000, 1_000_000]
     check_up_to = int(os.environ.get("EDSB_LEDS_CHECK_BP", "20000000"))  # the oracle port is linear: ~0.5 s per Mbp
     ctx = E.load().context(0)
+    if os.environ.get("EDSB_PARTITIONS"):  # A/B of the scan partition count (default: 4 per SM)
+        ctx.set_tuning(int(os.environ["EDSB_PARTITIONS"]), 0)
     L = 10
     for n in sizes:
         eds, seds = genrandomeds_like(n)
