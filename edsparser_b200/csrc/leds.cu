@@ -878,7 +878,7 @@ void LedsPipeline::merge_host(const uint8_t* eds_in, uint64_t eds_bytes, const u
     KernelClock& clk = ctx_->clock;
     clk.reset();
     const uint32_t sms = (uint32_t)ctx_->sm_count;
-    const unsigned P = std::max(1u, std::min(ctx_->partitions ? ctx_->partitions : sms * 4u, 4096u));
+    const unsigned P = std::max(1u, std::min(ctx_->partitions ? ctx_->partitions : sms * 8u, 4096u));
 #ifdef EDSB_EMU
     const uint32_t G = 2u, B = kScanBlock;  // few OS threads per emulated launch
 #else
@@ -1386,7 +1386,7 @@ void LedsPipeline::genrandomeds(uint64_t n, uint32_t ppm, uint32_t paths, uint64
     if (ppm > 1000000) throw std::invalid_argument("eds_genrandomeds_device: variability above 1");
     cudaStream_t s = ctx_->stream;
     const uint32_t sms = (uint32_t)ctx_->sm_count;
-    const unsigned P = std::max(1u, std::min(ctx_->partitions ? ctx_->partitions : sms * 4u, 4096u));
+    const unsigned P = std::max(1u, std::min(ctx_->partitions ? ctx_->partitions : sms * 8u, 4096u));
     Bufs& B_ = *bufs_;
     DevBuf &d_part = B_.d[3], &d_eds = B_.d[36], &d_seds = B_.d[37];
     d_part.reserve((size_t)(P + 1) * 16);

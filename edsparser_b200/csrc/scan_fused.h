@@ -15,7 +15,10 @@ constexpr uint32_t kFzMaxDirect = 32;            // most rows of a CTA that bypa
 #ifdef EDSB_EMU
 constexpr int kFzCW = 2;
 #else
-constexpr int kFzCW = 8;
+#ifndef EDSB_FZ_CW
+#define EDSB_FZ_CW 8
+#endif
+constexpr int kFzCW = EDSB_FZ_CW;  // consumer warps
 #endif
 
 struct FzParams {

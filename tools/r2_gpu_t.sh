@@ -1,15 +1,12 @@
 #!/bin/bash
 mkdir -p gpurun_out
-true
-rc=0
-echo "pytest rc=$rc" >> gpurun_out/r2t_pytest.log
-tail -3 gpurun_out/r2t_pytest.log
-if [ $rc -ne 0 ]; then grep -n "Error\|assert" gpurun_out/r2t_pytest.log | head -20; exit 1; fi
-timeout 300 python tools/sweep_fused.py 100 10000000 $1 > gpurun_out/r2t_sweep_r100.jsonl 2> gpurun_out/r2t_sweep_r100.err
-timeout 300 python tools/sweep_fused.py 1000 3000000 $1 > gpurun_out/r2t_sweep_r1000.jsonl 2> gpurun_out/r2t_sweep_r1000.err
-python - <<'PY'
-import json
-for f in ('r100','r1000'):
-    for l in open('gpurun_out/r2t_sweep_%s.jsonl' % f):
-        d=json.loads(l); k=d.pop('kernels',{}); d.pop('cols'); print(d)
+for v in "" cw6 cw12 cw16; do
+  if [ -n "$v" ]; then export EDSB_LIBRARY=$PWD/build/variants/lib$v.so; fi
+  timeout 200 python tools/sweep_fused.py 100 10000000 none > gpurun_out/r2t_cw_$v.jsonl 2> gpurun_out/r2t_cw_$v.err
+  timeout 200 python tools/sweep_fused.py 1000 3000000 none >> gpurun_out/r2t_cw_$v.jsonl 2>> gpurun_out/r2t_cw_$v.err
+  python - "$v" <<'PY'
+import json,sys
+for l in open('gpurun_out/r2t_cw_%s.jsonl' % sys.argv[1]):
+    d=json.loads(l); d.pop('kernels',None); d.pop('cols',None); print(sys.argv[1] or 'cw8', d)
 PY
+done

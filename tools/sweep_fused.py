@@ -43,7 +43,9 @@ def main():
     ring = {"EDSB_FUSED": 1, "EDSB_FUSED_L2": 0}  # k_scan_fused (TMA ring), the default
     settings = [{"EDSB_FUSED": 0}, ring]
     what = sys.argv[3:]
-    if "probe" in what:
+    if "none" in what:
+        pass
+    elif "probe" in what:
         # where the time goes: the same kernel with a phase left out (results are not valid)
         settings += [dict(ring, EDSB_FUSED_PROBE=p) for p in (1, 2, 3, 4)]
     elif "split" in what:
