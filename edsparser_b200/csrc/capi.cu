@@ -168,6 +168,7 @@ eds_status eds_ctx_create(int device, void* stream, eds_ctx** out) {
         if (const char* hm = getenv("EDSB_DEBUG_HASH_MASK")) ctx->hash_mask = strtoull(hm, nullptr, 0);
         if (const char* no = getenv("EDSB_DEBUG_NARROW_OFF")) ctx->narrow_off = atoi(no);
         if (const char* no = getenv("EDSB_DEBUG_TUPLE_OFF")) ctx->tuple_off = atoi(no);
+        if (const char* no = getenv("EDSB_DEBUG_GROUP_CTA")) ctx->group_cta = (uint32_t)atoi(no);
         if (const char* rs = getenv("EDSB_DEBUG_ROW_SLICES")) ctx->scan_row_slices = (uint32_t)atoi(rs);
         ctx->msa = new edsb::MsaPipeline(ctx);
         ctx->leds = new edsb::LedsPipeline(ctx);

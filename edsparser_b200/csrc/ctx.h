@@ -79,6 +79,7 @@ struct eds_ctx {
     uint32_t fused_cw = 0;         // EDSB_FUSED_CW: consumer warps per CTA of k_scan_l2 (0 = default)
     uint32_t fused_direct = 0;     // EDSB_FUSED_DIRECT: rows per CTA of k_scan_fused that bypass the ring (<= 32)
     uint32_t fused_split = 0;      // EDSB_FUSED_SPLIT=1: k_scan_fused with one `full` barrier per stage and producer warp
+    uint32_t group_cta = 1;        // EDSB_DEBUG_GROUP_CTA: k_group2 gives a symbol a whole block when the symbols are few (1), never (0), always (2)
     uint32_t fused_probe = 0;      // EDSB_FUSED_PROBE: timing probes of k_scan_fused (scan_fused.h); results are not valid
     uint32_t fused_mode = 0;       // EDSB_FUSED_MODE: 0 = one bulk copy (TMA) per row (measured faster), 1 = 16-byte cp.async per lane
     int sm_count = 148;

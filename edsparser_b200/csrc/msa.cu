@@ -710,8 +710,17 @@ struct GroupScratch {
     uint32_t T, stage_bytes;
 };
 
+// CTA = false: one warp groups the symbol (many symbols in flight). CTA = true: the whole block does — the symbols that
+// reach this path at R = 1000 are a few hundred wide ones, fewer than there are blocks, and a warp alone needs ~0.5 ms
+// for the widest (every lane walks R / 32 strings of up to kStageCols characters three times).
+template <bool CTA>
 __device__ void group_wide(const MsaGeom& g, const MsaBufs& b, const GroupScratch& sc, uint32_t k) {
     const uint32_t lane = threadIdx.x & 31;
+    const uint32_t tid = CTA ? threadIdx.x : lane, nthr = CTA ? blockDim.x : 32u;
+    auto sync = [&]() {
+        if (CTA) __syncthreads();
+        else __syncwarp();
+    };
     const uint32_t T = sc.T;
     unsigned long long* hrow = sc.hrow;
     uint32_t *len = sc.len, *lead = sc.lead, *tab = sc.tab;
@@ -719,11 +728,22 @@ __device__ void group_wide(const MsaGeom& g, const MsaBufs& b, const GroupScratc
     const uint32_t s = e & kColMask, en = b.sym[k + 1] & kColMask;
     const uint32_t slot0 = first_slot(b, s);
     RowWalk w{b.vbits, b.refc, b.stash, g.Rp, sc.cdesc, sc.stage, s, false};
-    w.staged = stage_symbol(g, b, s, en, slot0, sc.cdesc, sc.stage, sc.stage_bytes);
+    if (CTA) {
+        __shared__ uint32_t s_staged;
+        __syncthreads();  // the previous symbol's readers of the scratch are done
+        if (threadIdx.x < 32u) {
+            const bool st = stage_symbol(g, b, s, en, slot0, sc.cdesc, sc.stage, sc.stage_bytes);
+            if (lane == 0) s_staged = st ? 1u : 0u;
+        }
+        __syncthreads();
+        w.staged = s_staged != 0u;
+    } else {
+        w.staged = stage_symbol(g, b, s, en, slot0, sc.cdesc, sc.stage, sc.stage_bytes);
+    }
     const bool exact = (en - s) <= 7u && g.hash_mask == ~0ull;  // the key IS the string: no verification needed
 
-    for (uint32_t i = lane; i < T; i += 32) tab[i] = kEmptySlot;
-    for (uint32_t r = lane; r < g.R; r += 32) {
+    for (uint32_t i = tid; i < T; i += nthr) tab[i] = kEmptySlot;
+    for (uint32_t r = tid; r < g.R; r += nthr) {
         uint32_t c = s, slot = slot0, n = 0;
         unsigned long long h;
         int ch;
@@ -745,8 +765,8 @@ __device__ void group_wide(const MsaGeom& g, const MsaBufs& b, const GroupScratc
         hrow[r] = h;
         len[r] = n;
     }
-    __syncwarp();
-    for (uint32_t r = lane; r < g.R; r += 32) {
+    sync();
+    for (uint32_t r = tid; r < g.R; r += nthr) {
         const unsigned long long h = hrow[r];
         uint32_t slot = (uint32_t)((h ^ (h >> 32)) * 0x9e3779b1u >> 7) & (T - 1u);
         for (;;) {
@@ -760,18 +780,19 @@ __device__ void group_wide(const MsaGeom& g, const MsaBufs& b, const GroupScratc
         }
         lead[r] = slot;
     }
-    __syncwarp();
+    sync();
     uint32_t collided = 0;
-    for (uint32_t r = lane; r < g.R; r += 32) {
+    for (uint32_t r = tid; r < g.R; r += nthr) {
         const uint32_t m = tab[lead[r]];
         if (!exact && m != r && (len[m] != len[r] || !rows_equal(w, m, r, s, en, slot0))) collided = 1;
         lead[r] = m;
     }
-    collided = __any_sync(0xffffffffu, collided);
-    __syncwarp();
+    if (CTA) collided = (uint32_t)__syncthreads_or((int)collided);
+    else collided = __any_sync(0xffffffffu, collided);
+    sync();
     if (collided) {
         // exact fallback: first earlier row with the same string
-        for (uint32_t r = lane; r < g.R; r += 32) {
+        for (uint32_t r = tid; r < g.R; r += nthr) {
             uint32_t m = r;
             for (uint32_t r2 = 0; r2 < r; ++r2) {
                 if (len[r2] == len[r] && hrow[r2] == hrow[r] && rows_equal(w, r2, r, s, en, slot0)) {
@@ -781,30 +802,75 @@ __device__ void group_wide(const MsaGeom& g, const MsaBufs& b, const GroupScratc
             }
             lead[r] = m;
         }
-        __syncwarp();
+        sync();
     }
     // number the alternatives by first row; tab[0..R) is reused as "alternative of leader row"
     uint32_t nalts = 0;
     unsigned long long lensum = 0;
-    for (uint32_t r0 = 0; r0 < g.R; r0 += 32) {
-        const uint32_t r = r0 + lane;
-        const bool isl = r < g.R && lead[r] == r;
-        const uint32_t mask = __ballot_sync(0xffffffffu, isl);
-        if (isl) {
-            tab[r] = nalts + (uint32_t)__popc(mask & lanemask_lt());
-            lensum += len[r];
+    if (!CTA) {
+        for (uint32_t r0 = 0; r0 < g.R; r0 += 32) {
+            const uint32_t r = r0 + lane;
+            const bool isl = r < g.R && lead[r] == r;
+            const uint32_t mask = __ballot_sync(0xffffffffu, isl);
+            if (isl) {
+                tab[r] = nalts + (uint32_t)__popc(mask & lanemask_lt());
+                lensum += len[r];
+            }
+            if (lane == 0) b.leadmask[(size_t)slot0 * (g.Rp >> 5) + (r0 >> 5)] = mask;
+            nalts += (uint32_t)__popc(mask);
         }
-        if (lane == 0) b.leadmask[(size_t)slot0 * (g.Rp >> 5) + (r0 >> 5)] = mask;
-        nalts += (uint32_t)__popc(mask);
+        __syncwarp();
+        for (uint32_t r = lane; r < g.R; r += 32) store_alt(g, b.altid, (size_t)slot0 * g.Rp + r, tab[lead[r]]);
+        lensum = warp_sum(lensum);
+    } else {
+        // chunks of 32 rows over the warps: leaders per chunk -> exclusive offsets (kept behind the R entries of tab that
+        // the numbering writes: T = 2 Rq >= R + R / 32) -> numbers
+        __shared__ unsigned long long s_lensum;
+        __shared__ uint32_t s_nalts;
+        const uint32_t warp = threadIdx.x >> 5, nw = blockDim.x >> 5, nchunks = (g.R + 31u) >> 5;
+        uint32_t* cnt = tab + (T >> 1);
+        if (threadIdx.x == 0) s_lensum = 0ull;
+        for (uint32_t ck = warp; ck < nchunks; ck += nw) {
+            const uint32_t r = ck * 32u + lane;
+            const uint32_t mask = __ballot_sync(0xffffffffu, r < g.R && lead[r] == r);
+            if (lane == 0) {
+                cnt[ck] = (uint32_t)__popc(mask);
+                b.leadmask[(size_t)slot0 * (g.Rp >> 5) + ck] = mask;
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t carry = 0;
+            for (uint32_t c0 = 0; c0 < nchunks; c0 += 32) {
+                const uint32_t v = c0 + lane < nchunks ? cnt[c0 + lane] : 0u;
+                const uint32_t inc = warp_inclusive_scan(v);
+                if (c0 + lane < nchunks) cnt[c0 + lane] = carry + inc - v;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) s_nalts = carry;
+        }
+        __syncthreads();
+        for (uint32_t ck = warp; ck < nchunks; ck += nw) {
+            const uint32_t r = ck * 32u + lane;
+            const bool isl = r < g.R && lead[r] == r;
+            const uint32_t mask = __ballot_sync(0xffffffffu, isl);
+            if (isl) {
+                tab[r] = cnt[ck] + (uint32_t)__popc(mask & lanemask_lt());
+                lensum += len[r];
+            }
+        }
+        lensum = warp_sum(lensum);
+        if (lane == 0 && lensum) atomicAdd(&s_lensum, lensum);
+        __syncthreads();
+        for (uint32_t r = threadIdx.x; r < g.R; r += blockDim.x) store_alt(g, b.altid, (size_t)slot0 * g.Rp + r, tab[lead[r]]);
+        nalts = s_nalts;
+        lensum = s_lensum;
     }
-    __syncwarp();
-    for (uint32_t r = lane; r < g.R; r += 32) store_alt(g, b.altid, (size_t)slot0 * g.Rp + r, tab[lead[r]]);
-    lensum = warp_sum(lensum);
-    if (lane == 0) {
+    if (tid == 0) {
         b.sym_nalts[k] = nalts;
         b.sym_edsz[k] = 2ull + lensum + (unsigned long long)(nalts - 1u);
     }
-    __syncwarp();
+    sync();
 }
 
 __device__ __forceinline__ void list_append(uint32_t* list, uint32_t* counter, bool mine, uint32_t k) {
@@ -1042,7 +1108,7 @@ __global__ void k_group(MsaGeom g, MsaBufs b, uint32_t narrow_ok, uint32_t group
 
 // k_group2: the queued symbols, warp per symbol, evenly strided over the list.
 __global__ void k_group2(MsaGeom g, MsaBufs b, uint32_t Rq, uint32_t T, uint32_t use_global, uint32_t stage_bytes,
-                         uint32_t per_warp_smem) {
+                         uint32_t per_warp_smem, uint32_t cta_ok) {
     MsaStatus* st = b.status;
     if (st->abort || st->halo_fail) return;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -1059,9 +1125,26 @@ __global__ void k_group2(MsaGeom g, MsaBufs b, uint32_t Rq, uint32_t T, uint32_t
     sc.stage_bytes = use_global ? 0u : stage_bytes;
     const uint32_t n_wide = st->n_hard;
     unsigned long long alts_here = 0;
+    if (cta_ok == 2u || (cta_ok && n_wide <= 2u * gridDim.x)) {
+        // few symbols: a block each, in the first warp's scratch
+        unsigned char* base0 = use_global ? b.group_ws + ((size_t)blockIdx.x * wpb) * ((size_t)Rq * 16u + (size_t)T * 4u) : EDSB_DYN_SMEM();
+        sc.hrow = reinterpret_cast<unsigned long long*>(base0);
+        sc.len = reinterpret_cast<uint32_t*>(sc.hrow + Rq);
+        sc.lead = sc.len + Rq;
+        sc.tab = sc.lead + Rq;
+        sc.stage = reinterpret_cast<uint8_t*>(sc.tab + T);
+        sc.cdesc = reinterpret_cast<uint16_t*>(sc.stage + stage_bytes);
+        for (uint32_t item = blockIdx.x; item < n_wide; item += gridDim.x) {
+            const uint32_t kw = b.hardlist[item];
+            group_wide<true>(g, b, sc, kw);
+            if (threadIdx.x == 0) alts_here += b.sym_nalts[kw];
+        }
+        if (threadIdx.x == 0 && alts_here) atomicAdd(&st->n_alts, alts_here);
+        return;
+    }
     for (uint32_t item = blockIdx.x * wpb + warp; item < n_wide; item += gridDim.x * wpb) {
         const uint32_t kw = b.hardlist[item];
-        group_wide(g, b, sc, kw);
+        group_wide<false>(g, b, sc, kw);
         if (lane == 0) alts_here += b.sym_nalts[kw];
     }
     if (lane == 0 && alts_here) atomicAdd(&st->n_alts, alts_here);
@@ -2899,7 +2982,7 @@ void MsaPipeline::run_once(MsaBufs& b) {
     after(s, s1, ctx_->ev[6]);   // join: k_group3 done
     ctx_->clock.begin("k_group2");
     EDSB_LAUNCH(k_group2, g2_blocks, gw * 32u, group_smem, s, g, b, Rq, T, group_global ? 1u : 0u, group_stage,
-                (uint32_t)group_warp_smem);
+                (uint32_t)group_warp_smem, ctx_->group_cta);
     ctx_->clock.end();
 
     ctx_->clock.begin("k_size_count");

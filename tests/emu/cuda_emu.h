@@ -143,6 +143,17 @@ inline T exchange(T v, int src_lane) {
 #define gridDim (emu::state().grid)
 
 inline void __syncthreads() { emu::state().block_bar.wait(); }
+// block-wide OR of a predicate: accumulate, barrier, read, barrier, (one thread) reset, barrier
+inline int __syncthreads_or(int pred) {
+    static std::atomic<int> acc{0};
+    if (pred) acc.store(1, std::memory_order_relaxed);
+    emu::state().block_bar.wait();
+    const int v = acc.load(std::memory_order_relaxed);
+    emu::state().block_bar.wait();
+    if (emu::tls.lin == 0) acc.store(0, std::memory_order_relaxed);
+    emu::state().block_bar.wait();
+    return v;
+}
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::my_warp().bar.wait(); }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 

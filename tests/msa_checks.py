@@ -192,6 +192,32 @@ def check_narrow_off(lib, seed=12, n_cases=15, wide_cases=3, max_rows=70, ls=(0,
             ctx.close()
 
 
+def check_group_cta(lib, seed=21, n_cases=8, max_rows=70):
+    """EDSB_DEBUG_GROUP_CTA=2 with EDSB_DEBUG_NARROW_OFF=2: every variable symbol goes through the hashed path with a whole
+    block per symbol (what the few wide symbols of a deep alignment get); =0: a warp per symbol."""
+    for mode in ("2", "0"):
+        os.environ.update({"EDSB_DEBUG_GROUP_CTA": mode, "EDSB_DEBUG_NARROW_OFF": "2"})
+        try:
+            ctx = lib.context()
+        finally:
+            del os.environ["EDSB_DEBUG_GROUP_CTA"], os.environ["EDSB_DEBUG_NARROW_OFF"]
+        try:
+            check_random_against_oracle(ctx, seed, n_cases, max_rows=max_rows, max_cols=120, ls=(0, 3, 10))
+            check_wide_alphabet(ctx, n_cases=2)
+        finally:
+            ctx.close()
+    # forced hash collisions (exact fallback search) through the block form
+    os.environ.update({"EDSB_DEBUG_GROUP_CTA": "2", "EDSB_DEBUG_NARROW_OFF": "2", "EDSB_DEBUG_HASH_MASK": "0x3"})
+    try:
+        ctx = lib.context()
+    finally:
+        del os.environ["EDSB_DEBUG_GROUP_CTA"], os.environ["EDSB_DEBUG_NARROW_OFF"], os.environ["EDSB_DEBUG_HASH_MASK"]
+    try:
+        check_random_against_oracle(ctx, seed + 1, max(2, n_cases // 2), max_rows=max_rows, max_cols=120, ls=(0, 10))
+    finally:
+        ctx.close()
+
+
 def check_row_slices(lib, seed=14, n_cases=15, settings=("2", "5")):
     """EDSB_DEBUG_ROW_SLICES=n: k_scan (the two-pass form, EDSB_FUSED=0) splits the rows into n slices that OR their
     mismatch bits together (what a narrow column shard of an alignment too deep for the fused scan uses)."""

@@ -50,6 +50,10 @@ def test_narrow_path_off():
     msa_checks.check_narrow_off(emu_lib.lib(), n_cases=6, wide_cases=2)
 
 
+def test_group_block_per_symbol():
+    msa_checks.check_group_cta(emu_lib.lib(), n_cases=4, max_rows=50)
+
+
 def test_row_sliced_scan():
     msa_checks.check_row_slices(emu_lib.lib(), n_cases=6)
 

@@ -129,3 +129,14 @@ def test_fused_scan_matches_two_pass(lib):
             msa_checks.check_random_against_oracle(c, seed=5, n_cases=30, max_rows=150, max_cols=3000)
         finally:
             c.close()
+
+
+def test_group_block_per_symbol(lib):
+    msa_checks.check_group_cta(lib, n_cases=25, max_rows=300)
+    # a deep alignment with wide symbols: the few symbols the tuple form does not take get a block each
+    c = lib.context(0)
+    try:
+        st = msa_checks.check_synth(c, n_rows=1000, n_cols=60_000, wrap=80, l=10, variable_ppm=40000, shards=1)
+        assert st["n_hashed_symbols"] > 0
+    finally:
+        c.close()

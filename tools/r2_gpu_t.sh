@@ -1,12 +1,14 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for v in "" cw6 cw12 cw16; do
-  if [ -n "$v" ]; then export EDSB_LIBRARY=$PWD/build/variants/lib$v.so; fi
-  timeout 200 python tools/sweep_fused.py 100 10000000 none > gpurun_out/r2t_cw_$v.jsonl 2> gpurun_out/r2t_cw_$v.err
-  timeout 200 python tools/sweep_fused.py 1000 3000000 none >> gpurun_out/r2t_cw_$v.jsonl 2>> gpurun_out/r2t_cw_$v.err
-  python - "$v" <<'PY'
+timeout 400 python -m pytest tests/test_msa_gpu.py -q -m gpu -x > gpurun_out/r2t_pytest.log 2>&1
+rc=$?; echo "pytest rc=$rc"; tail -3 gpurun_out/r2t_pytest.log
+if [ $rc -ne 0 ]; then grep -n "^E " gpurun_out/r2t_pytest.log | head; exit 1; fi
+for m in 1 0; do
+  EDSB_DEBUG_GROUP_CTA=$m timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/r2t_bench_cta$m.json 2> gpurun_out/r2t_bench_cta$m.err
+  python - $m <<'PY'
 import json,sys
-for l in open('gpurun_out/r2t_cw_%s.jsonl' % sys.argv[1]):
-    d=json.loads(l); d.pop('kernels',None); d.pop('cols',None); print(sys.argv[1] or 'cw8', d)
+l=[x for x in open('gpurun_out/r2t_bench_cta%s.json' % sys.argv[1]) if x.startswith('{')][-1]
+d=json.loads(l); c=d['config4']; k=c['roofline']['kernels_ms_serial']
+print('cta', sys.argv[1], 'config2', round(d['ms_per_step'],4), 'config4', round(c['ms_per_step'],3), {x:k[x] for x in ('k_group','k_group2','k_group3','k_emit2','k_emit_var','k_emit3')})
 PY
 done
