@@ -224,6 +224,9 @@ def kernel_profile(ctx, view, steps):
     return {k: v / steps for k, v in acc.items()}
 
 
+NO_EXCHANGE = os.environ.get("EDSB_BENCH_NO_EXCHANGE") == "1"  # diagnosis only: a line measured this way is not a bench value
+
+
 def measure_device(lib, ctx, dist, dev, rank, world, rows, cols_per_gpu, steps, warmup, exchange):
     """Device-resident leg: window [rank] of a rows x (world * cols_per_gpu) alignment generated in HBM, `steps`
     transforms timed with CUDA events (max over ranks), then the per-kernel profile. Returns a dict (rank-local)."""
@@ -258,7 +261,8 @@ def measure_device(lib, ctx, dist, dev, rank, world, rows, cols_per_gpu, steps, 
             lib.check(rc)
         # file offsets of this rank's slices: all-gather of the byte counts, issued behind the transform; the host
         # reads them once, before it writes (exchange.offsets() after the loop)
-        exchange.post(c_e.bytes, c_s.bytes)
+        if not NO_EXCHANGE:
+            exchange.post(c_e.bytes, c_s.bytes)
 
     def barrier():
         if world > 1:
@@ -355,7 +359,7 @@ def run_ours(args, rank, world):
     warmup = max(args.warmup, 3)
     sampler = ClockSampler(local) if rank == 0 else None
     m = measure_device(lib, ctx, dist, dev, rank, world, R, C_PER_GPU, args.steps, warmup, exchange)
-    my_offsets = exchange.offsets()  # (eds offset, seds offset, eds total, seds total) of this rank's slices
+    my_offsets = (0, 0, 0, 0) if NO_EXCHANGE else exchange.offsets()  # (eds offset, seds offset, eds total, seds total) of this rank's slices
     clocks = sampler.stop() if sampler else None
     view, ms_total, out_bytes = m["view"], m["ms_total"], m["out_bytes"]
     cells_step = R * C_PER_GPU * world

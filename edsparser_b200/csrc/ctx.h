@@ -80,6 +80,8 @@ struct eds_ctx {
     uint32_t fused_direct = 0;     // EDSB_FUSED_DIRECT: rows per CTA of k_scan_fused that bypass the ring (<= 32)
     uint32_t fused_split = 0;      // EDSB_FUSED_SPLIT=1: k_scan_fused with one `full` barrier per stage and producer warp
     uint32_t group_cta = 1;        // EDSB_DEBUG_GROUP_CTA: k_group2 gives a symbol a whole block when the symbols are few (1), never (0), always (2)
+    uint32_t peer_headroom = 0;    // bytes of shared memory per SM the fused scan leaves free (set by eds_comm_create: the all-gather's
+                                   // kernel must fit beside the persistent scan CTAs, or it holds an SM's CTA back until its peers arrive)
     uint32_t fused_probe = 0;      // EDSB_FUSED_PROBE: timing probes of k_scan_fused (scan_fused.h); results are not valid
     uint32_t fused_mode = 0;       // EDSB_FUSED_MODE: 0 = one bulk copy (TMA) per row (measured faster), 1 = 16-byte cp.async per lane
     int sm_count = 148;

@@ -2518,6 +2518,15 @@ void MsaPipeline::plan_fused() {
             S = s;
             break;
         }
+    // a communicator posts its all-gather beside the next scan: its kernel needs room on the SMs this persistent grid
+    // fills, or one of our CTAs starts only when the slowest peer has arrived (8 GPUs: 0.67 -> 0.61 ms per config-2 step).
+    // Not at the price of a ring shallower than three stages.
+    if (ctx_->peer_headroom)
+        for (uint32_t s = S; s >= 3; --s)
+            if (fz_smem_bytes(T, s, NC, RG, slot_pitch, DW, stage_slots) + 1024 + ctx_->peer_headroom <= ctx_->smem_optin) {
+                S = s;
+                break;
+            }
     if (ctx_->fused_stages && ctx_->fused_stages <= S) S = ctx_->fused_stages;
     if (S < 2) return;
     if (H == 2u) {

@@ -228,6 +228,9 @@ eds_status eds_comm_create(eds_ctx* ctx, const uint8_t id[128], int rank, int wo
                 ncclUniqueId uid;
                 memcpy(uid.internal, id, 128);
                 nccl_check(n.CommInitRank(&c->comm, world, uid, rank), "ncclCommInitRank");
+                // msa.cu plan_fused: the scan leaves room for the all-gather's kernel (EDSB_PEER_HEADROOM=bytes, 0 = none)
+                const char* ph = getenv("EDSB_PEER_HEADROOM");
+                ctx->peer_headroom = ph ? (uint32_t)atoi(ph) : 56u * 1024u;
             }
             for (int i = 0; i < eds_comm::kRing; ++i) {
                 EDSB_CUDA(cudaMallocHost(&c->h_mine[i], 16));

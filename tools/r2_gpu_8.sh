@@ -1,12 +1,18 @@
 #!/bin/bash
 mkdir -p gpurun_out
 N=$(nvidia-smi -L | wc -l)
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/r2_8_bench_n$N.json 2> gpurun_out/r2_8_bench_n$N.err
-echo "bench N=$N rc=$?"
-python - $N <<'PY'
+run() {
+  tag=$1; shift
+  env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $N --steps 30 --warmup 3 --no-config4 > gpurun_out/r2_8_$tag.json 2> gpurun_out/r2_8_$tag.err
+  python - $tag <<'PY'
 import json,sys
-l=[x for x in open('gpurun_out/r2_8_bench_n%s.json' % sys.argv[1]) if x.startswith('{')][-1]
-d=json.loads(l)
-print('N', d['n_gpus'], 'ms', d['ms_per_step'], 'value', d['value'], 'e2e', d['e2e']['value'], d['e2e'].get('ms_per_step'), 'config4', d.get('config4',{}).get('ms_per_step'), d.get('config4',{}).get('roofline',{}).get('step',{}).get('frac'))
+try:
+    l=[x for x in open('gpurun_out/r2_8_%s.json' % sys.argv[1]) if x.startswith('{')][-1]
+    d=json.loads(l)
+    print(sys.argv[1], 'N', d['n_gpus'], 'ms', round(d['ms_per_step'],4), 'value', d['value'])
+except Exception as e:
+    print(sys.argv[1], 'failed', e)
 PY
-timeout 200 python -m pytest tests/test_group.py -q -m gpu -k "group_on_devices or config2" 2>&1 | tail -2
+}
+run base A=1
+run noex EDSB_BENCH_NO_EXCHANGE=1
