@@ -5,6 +5,8 @@
 
 #include <iomanip>
 #include <iostream>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -86,6 +88,16 @@ inline void print_performance(edsparser::Timer& timer) {
     std::cerr << "[Performance] Runtime: " << std::fixed << std::setprecision(2) << timer.elapsed_seconds() << "s";
     if (memory_mb > 0.0) std::cerr << " | Peak Memory: " << std::fixed << std::setprecision(1) << memory_mb << " MB";
     std::cerr << "\n";
+}
+
+// End of a tool: everything the tool wrote is flushed (its file streams are closed by now), then the process leaves
+// WITHOUT running static destructors — tearing the CUDA context down costs 0.3 - 0.4 s of a run whose device work takes
+// milliseconds, and the operating system reclaims it all anyway.
+[[noreturn]] inline void finish(int rc) {
+    std::cout.flush();
+    std::cerr.flush();
+    fflush(nullptr);
+    _Exit(rc);
 }
 
 }  // namespace cli

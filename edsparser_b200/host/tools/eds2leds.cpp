@@ -29,7 +29,7 @@ static void usage() {
                  "  CARTESIAN: used when no source file is provided; cross-product of alternatives\n\n";
 }
 
-int main(int argc, char** argv) {
+static int run(int argc, char** argv) {
     Timer timer;
     timer.start();
     try {
@@ -122,3 +122,5 @@ int main(int argc, char** argv) {
         return 1;
     }
 }
+
+int main(int argc, char** argv) { cli::finish(run(argc, argv)); }

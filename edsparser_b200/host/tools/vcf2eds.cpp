@@ -30,7 +30,7 @@ static void usage() {
                  "  l-EDS (with -l): <input_base>_l<N>.leds, <input_base>_l<N>.seds (VCF -> EDS -> LINEAR merge)\n\n";
 }
 
-int main(int argc, char** argv) {
+static int run(int argc, char** argv) {
     Timer timer;
     timer.start();
     try {
@@ -133,3 +133,5 @@ int main(int argc, char** argv) {
         return 1;
     }
 }
+
+int main(int argc, char** argv) { cli::finish(run(argc, argv)); }
