@@ -204,7 +204,7 @@ def check_group_vcf(lib, devices, n_random, synth_sizes, ls=(0, 3)):
 def test_group_vcf_emulated():
     import emu_lib
 
-    check_group_vcf(emu_lib.lib(), [0, 1], n_random=3, synth_sizes=((2000, 60, 6, 0.01), (2000, 80, 5, 0.3)))
+    check_group_vcf(emu_lib.lib(), [0, 1], n_random=2, synth_sizes=((1500, 50, 5, 0.3),))
 
 
 @pytest.mark.gpu

@@ -14,8 +14,8 @@ def ctx():
 
 
 def test_golden_subset(ctx):
-    n, n_err = leds_checks.check_golden(ctx, stride=8)  # (the GPU tier runs all of them)
-    assert n >= 60 and n_err >= 2
+    n, n_err = leds_checks.check_golden(ctx, stride=10)  # (the GPU tier runs all of them)
+    assert n >= 48 and n_err >= 2
 
 
 def test_survey_vectors(ctx):
